@@ -1,0 +1,160 @@
+/*
+ * sdb200.h — C ABI of the B200-native Asynchronous-Score-Distillation step library (libsdb200.so).
+ *
+ * The reference (theEricMa/ScaleDreamer) has no FFI of its own: its hot path calls un-vendored Python
+ * extensions (nerfacc, tiny-cuda-nn, diffusers/cuDNN). Each entry point below is what a threestudio plugin
+ * would bind instead of those calls; the reference call site it replaces is cited as file:line relative to
+ * the reference tree. All pointers are DEVICE pointers unless stated otherwise; all buffers are owned by the
+ * caller (torch-allocated); every function enqueues work on `stream` (a cudaStream_t passed as void*) and
+ * returns 0 on success or a negative error code (message via sdb_last_error()). No function synchronises.
+ */
+#ifndef SDB200_H
+#define SDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_OK 0
+#define SDB_ERR_ARG -1
+#define SDB_ERR_CUDA -2
+#define SDB_ERR_UNSUPPORTED -3
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+const char* sdb_last_error(void);            /* thread-local message of the last failing call */
+int sdb_abi_version(void);                   /* bumped on any signature change */
+unsigned long long sdb_launch_count(void);   /* kernels launched by this library so far (host counter) */
+
+/* ---- multiresolution hash grid (tiny-cuda-nn "HashGrid"; threestudio/models/networks.py:55-64) ------- */
+typedef struct {
+  int n_levels;              /* 16 for the field, 4 for the environment map */
+  int n_features_per_level;  /* must be 2 */
+  int log2_hashmap_size;
+  int base_resolution;
+  float per_level_scale;
+} sdb_grid_cfg;
+
+/* Number of (n_features-wide) entries the grid owns; host-only helper. */
+long long sdb_grid_num_entries(const sdb_grid_cfg* cfg);
+/* Per-level resolved geometry, host-only helper: fills res/size/offset/hashed[n_levels] and scale[n_levels]. */
+int sdb_grid_describe(const sdb_grid_cfg* cfg, float* scale, uint32_t* res, uint32_t* size, uint32_t* offset,
+                      uint32_t* hashed);
+
+/* out[n, 2*n_levels] = encode(x01[n,3]); replaces tcnn.Encoding.forward (networks.py:63-64). */
+int sdb_hashgrid_forward(const sdb_grid_cfg* cfg, const float* table, const float* x01, int n, float* out,
+                         void* stream);
+/* g_table += scatter(g_out); replaces tcnn's kernel_grid_backward. g_table must be pre-zeroed by the caller. */
+int sdb_hashgrid_backward(const sdb_grid_cfg* cfg, const float* x01, const float* g_out, int n, float* g_table,
+                          void* stream);
+
+/* ---- iNGP field = hash grid + two bias-free 32-64-{1,3} ReLU MLPs + environment map ------------------ */
+typedef struct {
+  /* geometry "implicit-volume" (threestudio/models/geometry/implicit_volume.py:19-207) */
+  sdb_grid_cfg grid;
+  const float* table;        /* geometry.encoding params, [entries, 2] fp32 */
+  const float* w1_density;   /* geometry.density_network.layers.0.weight [64,32] */
+  const float* w2_density;   /* geometry.density_network.layers.2.weight [1,64]  */
+  const float* w1_feature;   /* geometry.feature_network.layers.0.weight [64,32] */
+  const float* w2_feature;   /* geometry.feature_network.layers.2.weight [3,64]  */
+  float radius;
+  int density_bias_type;     /* 0 const, 1 blob_magic3d, 2 blob_dreamfusion */
+  float density_bias_const;
+  float density_blob_scale;
+  float density_blob_std;
+  int density_activation;    /* 0 softplus, 1 exp, 2 trunc_exp */
+  float fd_normal_eps;       /* finite_difference_normal_eps */
+  /* material "no-material" (threestudio/models/materials/no_material.py:41-54) */
+  int color_activation;      /* 0 sigmoid, 1 sigmoid-mipnerf */
+  /* background "neural-environment-map-background" (…/background/neural_environment_map_background.py:46-67) */
+  sdb_grid_cfg bg_grid;
+  const float* bg_table;     /* background.encoding params */
+  const float* bg_w1;        /* background.network.layers.0.weight [16,8]  */
+  const float* bg_w2;        /* background.network.layers.2.weight [16,16] */
+  const float* bg_w3;        /* background.network.layers.4.weight [3,16]  */
+  int bg_color_activation;
+} sdb_field;
+
+typedef struct {
+  float* table;
+  float* w1_density;
+  float* w2_density;
+  float* w1_feature;
+  float* w2_feature;
+  float* bg_table;
+  float* bg_w1;
+  float* bg_w2;
+  float* bg_w3;
+} sdb_field_grads;            /* all accumulate (+=); caller zeroes */
+
+/* geometry.forward / forward_density on arbitrary points (implicit_volume.py:109-207).
+ * features / normal may be NULL. features are pre-activation (the material applies the colour activation). */
+int sdb_field_forward(const sdb_field* field, const float* points, int n, float* density, float* features,
+                      float* normal, void* stream);
+
+/* ---- occupancy grid (nerfacc.OccGridEstimator, nerf_volume_renderer.py:60-65,430-444) ---------------- */
+/* occs[cell] = max(occs[cell]*decay, sigma(x_cell)*step) for the listed cells (x = cell corner + rand*cell),
+ * then bits = occs > min(mean(occs), occ_thre) and *occ_mean = mean(occs). n_cells may be 0 (binarize only). */
+int sdb_occgrid_update(const sdb_field* field, const int* cell_idx, const float* cell_rand, int n_cells,
+                       int resolution, float render_step_size, float ema_decay, float occ_thre, float* occs,
+                       uint32_t* occ_bits, float* occ_mean, void* stream);
+
+/* ---- fused renderer (NeRFVolumeRenderer.forward, nerf_volume_renderer.py:118-428) -------------------- */
+typedef struct {
+  float render_step_size;   /* 1.732*2*radius/num_samples_per_ray (:66-68) */
+  float near_plane;
+  float far_plane;
+  int prune;                /* grid_prune && prune_alpha_threshold: visibility pruning by the sigma pass */
+  float alpha_thre;         /* 0.01 (:177); clipped on device by *occ_mean as nerfacc does */
+  float early_stop_eps;     /* nerfacc default 1e-4 */
+  int grid_resolution;      /* 32 */
+  int output_normal;        /* material.requires_normal: fill packed normal */
+} sdb_march_cfg;
+
+typedef struct {
+  int* counter;             /* [1] out: number of kept samples */
+  int capacity;
+  int* ray_indices;         /* [cap] */
+  float* t_starts;          /* [cap] */
+  float* t_ends;            /* [cap] */
+  float* weights;           /* [cap] */
+  float* density;           /* [cap] */
+  float* rgb;               /* [cap,3] */
+  float* normal;            /* [cap,3] or NULL */
+} sdb_packed_samples;         /* optional training extras (:375-386); order is not sorted by ray */
+
+/* rays_o/rays_d [n_rays,3]; jitter [n_rays] in [0,1) or NULL (eval); bg_override [n_images,3] or NULL;
+ * occ_bits [res^3/32]; occ_mean [1] or NULL; work [1] int scratch.
+ * Outputs comp_rgb/comp_rgb_fg/comp_rgb_bg [n_rays,3], opacity/depth/z_variance [n_rays]. packed may be NULL. */
+int sdb_render_nerf_forward(const sdb_field* field, const sdb_march_cfg* march, const uint32_t* occ_bits,
+                            const float* occ_mean, const float* rays_o, const float* rays_d, const float* jitter,
+                            const float* bg_override, int n_rays, int rays_per_image, float* comp_rgb,
+                            float* comp_rgb_fg, float* comp_rgb_bg, float* opacity, float* depth, float* z_variance,
+                            const sdb_packed_samples* packed, int* work, void* stream);
+
+/* Backward of the above w.r.t. every field parameter. g_opacity / g_depth may be NULL.
+ * comp_rgb_fg / comp_rgb_bg / opacity / depth are the tensors the forward produced. */
+int sdb_render_nerf_backward(const sdb_field* field, const sdb_field_grads* grads, const sdb_march_cfg* march,
+                             const uint32_t* occ_bits, const float* occ_mean, const float* rays_o,
+                             const float* rays_d, const float* jitter, const float* bg_override, int n_rays,
+                             int rays_per_image, const float* comp_rgb_fg, const float* comp_rgb_bg,
+                             const float* opacity, const float* depth, const float* g_comp_rgb,
+                             const float* g_opacity, const float* g_depth, int* work, void* stream);
+
+/* rays from cameras (threestudio/utils/ops.py:183-269 get_ray_directions + get_rays):
+ * c2w [B,4,4], fovy [B] (radians) -> rays_o, rays_d [B,H,W,3] (normalised). */
+int sdb_raygen(const float* c2w, const float* fovy, int n_images, int height, int width, float* rays_o,
+               float* rays_d, void* stream);
+
+/* ---- optimizer (threestudio/systems/utils.py:34-53 -> torch.optim.AdamW / Adam) ----------------------- */
+/* One fused step over a flat fp32 parameter block. grad_scale multiplies the gradient (1/world_size after
+ * the all-reduce). step is the 1-based step count for bias correction. */
+int sdb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H */

@@ -1,0 +1,392 @@
+// extern "C" entry points of include/sdb200.h: argument validation, hash-grid geometry resolution and
+// dispatch to the sm_100a kernels. No torch types cross this boundary.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/sdb200.h"
+#include "render_types.cuh"
+
+unsigned long long g_sdb_launch_count = 0ull;
+static thread_local char g_err[512] = "";
+
+void sdb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_render_fwd(const FieldMeta&, const FieldPtrs&, const MarchMeta&, const RayIO&, const PackedOut&,
+                      cudaStream_t);
+int launch_render_bwd(const FieldMeta&, const FieldPtrs&, const FieldGrads&, const MarchMeta&, const RayIO&,
+                      cudaStream_t);
+int launch_field_eval(const FieldMeta&, const FieldPtrs&, const float*, int, float*, float*, float*, cudaStream_t);
+int launch_hashgrid_fwd(const GridMeta&, const float*, const float*, int, float*, cudaStream_t);
+int launch_hashgrid_bwd(const GridMeta&, const float*, const float*, int, float*, cudaStream_t);
+int launch_occ_update(const FieldMeta&, const FieldPtrs&, const int*, const float*, int, int, float, float, float,
+                      float*, uint32_t*, float*, cudaStream_t);
+
+// tiny-cuda-nn GridEncoding level geometry (restated; see oracle/render_oracle.py::grid_meta).
+static int resolve_grid(const sdb_grid_cfg* c, GridMeta* gm) {
+  if (!c || c->n_levels < 1 || c->n_levels > kMaxLevels) {
+    sdb_set_error("grid: n_levels must be in [1,%d]", kMaxLevels);
+    return SDB_ERR_ARG;
+  }
+  if (c->n_features_per_level != 2) {
+    sdb_set_error("grid: only n_features_per_level=2 is implemented (got %d)", c->n_features_per_level);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  if (c->log2_hashmap_size < 1 || c->log2_hashmap_size > 28) {
+    sdb_set_error("grid: log2_hashmap_size out of range");
+    return SDB_ERR_ARG;
+  }
+  memset(gm, 0, sizeof(*gm));
+  gm->n_levels = c->n_levels;
+  const uint32_t max_params = 1u << c->log2_hashmap_size;
+  uint32_t offset = 0;
+  const double log2_pls = std::log2((double)c->per_level_scale);
+  for (int l = 0; l < c->n_levels; ++l) {
+    const float scale = (float)(std::exp2((double)l * log2_pls) * (double)c->base_resolution - 1.0);
+    const uint32_t res = (uint32_t)std::ceil(scale) + 1u;
+    const unsigned long long dense = (unsigned long long)res * res * res;
+    unsigned long long n = (dense + 7ull) / 8ull * 8ull;  // tcnn: next_multiple(res^3, 8) then min(., 2^log2)
+    if (n > max_params) n = max_params;
+    gm->scale[l] = scale;
+    gm->res[l] = res;
+    gm->size[l] = (uint32_t)n;
+    gm->offset[l] = offset;
+    gm->hashed[l] = dense > n ? 1u : 0u;
+    offset += (uint32_t)n;
+  }
+  return SDB_OK;
+}
+
+static int resolve_field(const sdb_field* f, FieldMeta* fm, FieldPtrs* fp, bool need_bg) {
+  if (!f) {
+    sdb_set_error("field is NULL");
+    return SDB_ERR_ARG;
+  }
+  int rc = resolve_grid(&f->grid, &fm->grid);
+  if (rc) return rc;
+  if (f->grid.n_levels * f->grid.n_features_per_level != kEncDim) {
+    sdb_set_error("field: encoding width must be %d (n_levels*n_features), got %d", kEncDim,
+                  f->grid.n_levels * f->grid.n_features_per_level);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  if (need_bg) {
+    rc = resolve_grid(&f->bg_grid, &fm->bg_grid);
+    if (rc) return rc;
+    if (f->bg_grid.n_levels != 4) {
+      sdb_set_error("field: environment-map grid must have 4 levels (got %d)", f->bg_grid.n_levels);
+      return SDB_ERR_UNSUPPORTED;
+    }
+    if (!f->bg_table || !f->bg_w1 || !f->bg_w2 || !f->bg_w3) {
+      sdb_set_error("field: background pointers are NULL");
+      return SDB_ERR_ARG;
+    }
+  } else {
+    memset(&fm->bg_grid, 0, sizeof(fm->bg_grid));
+  }
+  if (!f->table || !f->w1_density || !f->w2_density || !f->w1_feature || !f->w2_feature) {
+    sdb_set_error("field: geometry pointers are NULL");
+    return SDB_ERR_ARG;
+  }
+  if (!(f->radius > 0.f)) {
+    sdb_set_error("field: radius must be > 0");
+    return SDB_ERR_ARG;
+  }
+  if (f->density_bias_type < 0 || f->density_bias_type > 2 || f->density_activation < 0 ||
+      f->density_activation > 2 || f->color_activation < 0 || f->color_activation > 1) {
+    sdb_set_error("field: unknown bias/activation enum");
+    return SDB_ERR_UNSUPPORTED;
+  }
+  fm->radius = f->radius;
+  fm->bias_type = f->density_bias_type;
+  fm->bias_const = f->density_bias_const;
+  fm->blob_scale = f->density_blob_scale;
+  fm->blob_std = f->density_blob_std;
+  fm->density_act = f->density_activation;
+  fm->color_act = f->color_activation;
+  fm->bg_color_act = f->bg_color_activation;
+  fm->fd_eps = f->fd_normal_eps > 0.f ? f->fd_normal_eps : 0.01f;
+  fp->table = f->table;
+  fp->w1d = f->w1_density;
+  fp->w2d = f->w2_density;
+  fp->w1f = f->w1_feature;
+  fp->w2f = f->w2_feature;
+  fp->bg_table = f->bg_table;
+  fp->bg_w1 = f->bg_w1;
+  fp->bg_w2 = f->bg_w2;
+  fp->bg_w3 = f->bg_w3;
+  return SDB_OK;
+}
+
+static int resolve_march(const sdb_march_cfg* c, MarchMeta* m) {
+  if (!c || !(c->render_step_size > 0.f)) {
+    sdb_set_error("march: render_step_size must be > 0");
+    return SDB_ERR_ARG;
+  }
+  if (c->grid_resolution < 1 || c->grid_resolution > 32) {
+    sdb_set_error("march: grid_resolution must be in [1,32]");
+    return SDB_ERR_UNSUPPORTED;
+  }
+  m->step = c->render_step_size;
+  m->near_plane = c->near_plane;
+  m->far_plane = c->far_plane;
+  m->prune = c->prune;
+  m->alpha_thre = c->alpha_thre;
+  m->early_stop_eps = c->early_stop_eps;
+  m->grid_res = c->grid_resolution;
+  m->output_normal = c->output_normal;
+  return SDB_OK;
+}
+
+namespace {
+
+__global__ void raygen_kernel(const float* __restrict__ c2w, const float* __restrict__ fovy, int B, int H, int W,
+                              float* __restrict__ rays_o, float* __restrict__ rays_d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H * W) return;
+  const int b = i / (H * W), rem = i % (H * W), y = rem / W, x = rem % W;
+  const float focal = 0.5f * (float)H / tanf(0.5f * fovy[b]);
+  const float dx = ((float)x + 0.5f - 0.5f * (float)W) / focal;
+  const float dy = -((float)y + 0.5f - 0.5f * (float)H) / focal;
+  const float dz = -1.f;
+  const float* m = c2w + 16 * b;
+  float rx = dx * m[0] + dy * m[1] + dz * m[2];
+  float ry = dx * m[4] + dy * m[5] + dz * m[6];
+  float rz = dx * m[8] + dy * m[9] + dz * m[10];
+  const float inv = 1.f / fmaxf(sqrtf(rx * rx + ry * ry + rz * rz), 1e-12f);
+  rays_d[3 * i + 0] = rx * inv;
+  rays_d[3 * i + 1] = ry * inv;
+  rays_d[3 * i + 2] = rz * inv;
+  rays_o[3 * i + 0] = m[3];
+  rays_o[3 * i + 1] = m[7];
+  rays_o[3 * i + 2] = m[11];
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    float pi = p[i];
+    pi *= (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sdb_last_error(void) { return g_err; }
+int sdb_abi_version(void) { return 1; }
+unsigned long long sdb_launch_count(void) { return g_sdb_launch_count; }
+
+long long sdb_grid_num_entries(const sdb_grid_cfg* cfg) {
+  GridMeta gm;
+  if (resolve_grid(cfg, &gm)) return -1;
+  return (long long)gm.offset[gm.n_levels - 1] + gm.size[gm.n_levels - 1];
+}
+
+int sdb_grid_describe(const sdb_grid_cfg* cfg, float* scale, uint32_t* res, uint32_t* size, uint32_t* offset,
+                      uint32_t* hashed) {
+  GridMeta gm;
+  int rc = resolve_grid(cfg, &gm);
+  if (rc) return rc;
+  for (int l = 0; l < gm.n_levels; ++l) {
+    if (scale) scale[l] = gm.scale[l];
+    if (res) res[l] = gm.res[l];
+    if (size) size[l] = gm.size[l];
+    if (offset) offset[l] = gm.offset[l];
+    if (hashed) hashed[l] = gm.hashed[l];
+  }
+  return SDB_OK;
+}
+
+int sdb_hashgrid_forward(const sdb_grid_cfg* cfg, const float* table, const float* x01, int n, float* out,
+                         void* stream) {
+  GridMeta gm;
+  int rc = resolve_grid(cfg, &gm);
+  if (rc) return rc;
+  SDB_CHECK_ARG(gm.n_levels == 16 || gm.n_levels == 4, "hashgrid: n_levels must be 16 or 4");
+  SDB_CHECK_ARG(table && x01 && out && n >= 0, "hashgrid_forward: bad arguments");
+  if (n == 0) return SDB_OK;
+  return launch_hashgrid_fwd(gm, table, x01, n, out, (cudaStream_t)stream);
+}
+
+int sdb_hashgrid_backward(const sdb_grid_cfg* cfg, const float* x01, const float* g_out, int n, float* g_table,
+                          void* stream) {
+  GridMeta gm;
+  int rc = resolve_grid(cfg, &gm);
+  if (rc) return rc;
+  SDB_CHECK_ARG(gm.n_levels == 16 || gm.n_levels == 4, "hashgrid: n_levels must be 16 or 4");
+  SDB_CHECK_ARG(x01 && g_out && g_table && n >= 0, "hashgrid_backward: bad arguments");
+  if (n == 0) return SDB_OK;
+  return launch_hashgrid_bwd(gm, x01, g_out, n, g_table, (cudaStream_t)stream);
+}
+
+int sdb_field_forward(const sdb_field* field, const float* points, int n, float* density, float* features,
+                      float* normal, void* stream) {
+  FieldMeta fm;
+  FieldPtrs fp;
+  int rc = resolve_field(field, &fm, &fp, false);
+  if (rc) return rc;
+  SDB_CHECK_ARG(points && density && n >= 0, "field_forward: bad arguments");
+  if (n == 0) return SDB_OK;
+  return launch_field_eval(fm, fp, points, n, density, features, normal, (cudaStream_t)stream);
+}
+
+int sdb_occgrid_update(const sdb_field* field, const int* cell_idx, const float* cell_rand, int n_cells,
+                       int resolution, float render_step_size, float ema_decay, float occ_thre, float* occs,
+                       uint32_t* occ_bits, float* occ_mean, void* stream) {
+  FieldMeta fm;
+  FieldPtrs fp;
+  int rc = resolve_field(field, &fm, &fp, false);
+  if (rc) return rc;
+  SDB_CHECK_ARG(resolution >= 1 && resolution <= 32, "occgrid: resolution must be in [1,32]");
+  SDB_CHECK_ARG(occs && occ_bits && occ_mean && n_cells >= 0, "occgrid: bad arguments");
+  SDB_CHECK_ARG(n_cells == 0 || (cell_idx && cell_rand), "occgrid: cell list is NULL");
+  return launch_occ_update(fm, fp, cell_idx, cell_rand, n_cells, resolution, render_step_size, ema_decay, occ_thre,
+                           occs, occ_bits, occ_mean, (cudaStream_t)stream);
+}
+
+int sdb_render_nerf_forward(const sdb_field* field, const sdb_march_cfg* march, const uint32_t* occ_bits,
+                            const float* occ_mean, const float* rays_o, const float* rays_d, const float* jitter,
+                            const float* bg_override, int n_rays, int rays_per_image, float* comp_rgb,
+                            float* comp_rgb_fg, float* comp_rgb_bg, float* opacity, float* depth, float* z_variance,
+                            const sdb_packed_samples* packed, int* work, void* stream) {
+  FieldMeta fm;
+  FieldPtrs fp;
+  MarchMeta mm;
+  int rc = resolve_field(field, &fm, &fp, true);
+  if (rc) return rc;
+  rc = resolve_march(march, &mm);
+  if (rc) return rc;
+  SDB_CHECK_ARG(occ_bits && rays_o && rays_d && work, "render_forward: NULL input");
+  SDB_CHECK_ARG(comp_rgb && comp_rgb_fg && comp_rgb_bg && opacity && depth && z_variance,
+                "render_forward: NULL output");
+  SDB_CHECK_ARG(n_rays >= 0 && rays_per_image > 0, "render_forward: bad ray counts");
+  if (n_rays == 0) return SDB_OK;
+  RayIO io;
+  memset(&io, 0, sizeof(io));
+  io.rays_o = rays_o;
+  io.rays_d = rays_d;
+  io.jitter = jitter;
+  io.bg_override = bg_override;
+  io.occ_bits = occ_bits;
+  io.occ_mean = occ_mean;
+  io.n_rays = n_rays;
+  io.rays_per_image = rays_per_image;
+  io.comp_rgb = comp_rgb;
+  io.comp_rgb_fg = comp_rgb_fg;
+  io.comp_rgb_bg = comp_rgb_bg;
+  io.opacity = opacity;
+  io.depth = depth;
+  io.z_variance = z_variance;
+  io.work_counter = work;
+  PackedOut pk;
+  memset(&pk, 0, sizeof(pk));
+  if (packed && packed->counter) {
+    SDB_CHECK_ARG(packed->capacity >= 0 && packed->ray_indices && packed->t_starts && packed->t_ends &&
+                      packed->weights && packed->density && packed->rgb,
+                  "render_forward: packed sample buffers are NULL");
+    pk.counter = packed->counter;
+    pk.capacity = packed->capacity;
+    pk.ray_idx = packed->ray_indices;
+    pk.t_start = packed->t_starts;
+    pk.t_end = packed->t_ends;
+    pk.weight = packed->weights;
+    pk.density = packed->density;
+    pk.rgb = packed->rgb;
+    pk.normal = packed->normal;
+  }
+  return launch_render_fwd(fm, fp, mm, io, pk, (cudaStream_t)stream);
+}
+
+int sdb_render_nerf_backward(const sdb_field* field, const sdb_field_grads* grads, const sdb_march_cfg* march,
+                             const uint32_t* occ_bits, const float* occ_mean, const float* rays_o,
+                             const float* rays_d, const float* jitter, const float* bg_override, int n_rays,
+                             int rays_per_image, const float* comp_rgb_fg, const float* comp_rgb_bg,
+                             const float* opacity, const float* depth, const float* g_comp_rgb,
+                             const float* g_opacity, const float* g_depth, int* work, void* stream) {
+  FieldMeta fm;
+  FieldPtrs fp;
+  MarchMeta mm;
+  int rc = resolve_field(field, &fm, &fp, true);
+  if (rc) return rc;
+  rc = resolve_march(march, &mm);
+  if (rc) return rc;
+  SDB_CHECK_ARG(grads && grads->table && grads->w1_density && grads->w2_density && grads->w1_feature &&
+                    grads->w2_feature && grads->bg_table && grads->bg_w1 && grads->bg_w2 && grads->bg_w3,
+                "render_backward: NULL gradient buffer");
+  SDB_CHECK_ARG(occ_bits && rays_o && rays_d && work && comp_rgb_fg && comp_rgb_bg && opacity && depth && g_comp_rgb,
+                "render_backward: NULL input");
+  SDB_CHECK_ARG(n_rays >= 0 && rays_per_image > 0, "render_backward: bad ray counts");
+  if (n_rays == 0) return SDB_OK;
+  RayIO io;
+  memset(&io, 0, sizeof(io));
+  io.rays_o = rays_o;
+  io.rays_d = rays_d;
+  io.jitter = jitter;
+  io.bg_override = bg_override;
+  io.occ_bits = occ_bits;
+  io.occ_mean = occ_mean;
+  io.n_rays = n_rays;
+  io.rays_per_image = rays_per_image;
+  io.comp_rgb_fg = const_cast<float*>(comp_rgb_fg);
+  io.comp_rgb_bg = const_cast<float*>(comp_rgb_bg);
+  io.opacity = const_cast<float*>(opacity);
+  io.depth = const_cast<float*>(depth);
+  io.g_comp_rgb = g_comp_rgb;
+  io.g_opacity = g_opacity;
+  io.g_depth = g_depth;
+  io.work_counter = work;
+  FieldGrads fg;
+  fg.table = grads->table;
+  fg.w1d = grads->w1_density;
+  fg.w2d = grads->w2_density;
+  fg.w1f = grads->w1_feature;
+  fg.w2f = grads->w2_feature;
+  fg.bg_table = grads->bg_table;
+  fg.bg_w1 = grads->bg_w1;
+  fg.bg_w2 = grads->bg_w2;
+  fg.bg_w3 = grads->bg_w3;
+  return launch_render_bwd(fm, fp, fg, mm, io, (cudaStream_t)stream);
+}
+
+int sdb_raygen(const float* c2w, const float* fovy, int n_images, int height, int width, float* rays_o,
+               float* rays_d, void* stream) {
+  SDB_CHECK_ARG(c2w && fovy && rays_o && rays_d && n_images >= 0 && height > 0 && width > 0, "raygen: bad arguments");
+  const int n = n_images * height * width;
+  if (n == 0) return SDB_OK;
+  raygen_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c2w, fovy, n_images, height, width, rays_o, rays_d);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("raygen");
+  return SDB_OK;
+}
+
+int sdb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                   void* stream) {
+  SDB_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adamw_step: bad arguments");
+  if (n == 0) return SDB_OK;
+  const float bc1 = 1.f - (float)std::pow((double)beta1, (double)step);
+  const float bc2 = 1.f - (float)std::pow((double)beta2, (double)step);
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)kNumSMs * 8);
+  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                       weight_decay, bc1, std::sqrt(bc2), grad_scale);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("adamw_step");
+  return SDB_OK;
+}
+
+}  // extern "C"

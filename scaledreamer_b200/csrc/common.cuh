@@ -1,0 +1,56 @@
+// Shared device helpers for the sm_100a ASD-step kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#define SDB_OK 0
+#define SDB_ERR_ARG -1
+#define SDB_ERR_CUDA -2
+#define SDB_ERR_UNSUPPORTED -3
+
+// Sets the thread-local last-error string (defined in capi.cu).
+void sdb_set_error(const char* fmt, ...);
+
+#define SDB_CHECK_ARG(cond, ...)                \
+  do {                                          \
+    if (!(cond)) {                              \
+      sdb_set_error(__VA_ARGS__);               \
+      return SDB_ERR_ARG;                       \
+    }                                           \
+  } while (0)
+
+#define SDB_CHECK_LAUNCH(name)                                               \
+  do {                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                    \
+    if (e__ != cudaSuccess) {                                                \
+      sdb_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return SDB_ERR_CUDA;                                                   \
+    }                                                                        \
+  } while (0)
+
+// Counts kernels launched by this library (bench.py reports it as gpu_launches).
+extern unsigned long long g_sdb_launch_count;
+#define SDB_COUNT_LAUNCH() (++g_sdb_launch_count)
+
+static constexpr int kNumSMs = 148;
+static constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+// Inclusive warp prefix sum.
+__device__ __forceinline__ float warp_scan_incl(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float n = __shfl_up_sync(kFullMask, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x / (1.f + __expf(-x)); }

@@ -1,0 +1,135 @@
+"""ctypes binding of libsdb200.so (the C ABI declared in include/sdb200.h and include/sdb200_nn.h).
+
+The product path has no CPU fallback: if the shared library is missing, or a call returns an error code,
+a RuntimeError is raised. Tensors cross the boundary as raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdb200.so")
+
+
+class GridCfgC(C.Structure):
+    _fields_ = [("n_levels", C.c_int), ("n_features_per_level", C.c_int), ("log2_hashmap_size", C.c_int),
+                ("base_resolution", C.c_int), ("per_level_scale", C.c_float)]
+
+
+class FieldC(C.Structure):
+    _fields_ = [
+        ("grid", GridCfgC), ("table", C.c_void_p), ("w1_density", C.c_void_p), ("w2_density", C.c_void_p),
+        ("w1_feature", C.c_void_p), ("w2_feature", C.c_void_p), ("radius", C.c_float),
+        ("density_bias_type", C.c_int), ("density_bias_const", C.c_float), ("density_blob_scale", C.c_float),
+        ("density_blob_std", C.c_float), ("density_activation", C.c_int), ("fd_normal_eps", C.c_float),
+        ("color_activation", C.c_int), ("bg_grid", GridCfgC), ("bg_table", C.c_void_p), ("bg_w1", C.c_void_p),
+        ("bg_w2", C.c_void_p), ("bg_w3", C.c_void_p), ("bg_color_activation", C.c_int)]
+
+
+class FieldGradsC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("table", "w1_density", "w2_density", "w1_feature", "w2_feature",
+                                          "bg_table", "bg_w1", "bg_w2", "bg_w3")]
+
+
+class MarchCfgC(C.Structure):
+    _fields_ = [("render_step_size", C.c_float), ("near_plane", C.c_float), ("far_plane", C.c_float),
+                ("prune", C.c_int), ("alpha_thre", C.c_float), ("early_stop_eps", C.c_float),
+                ("grid_resolution", C.c_int), ("output_normal", C.c_int)]
+
+
+class PackedSamplesC(C.Structure):
+    _fields_ = [("counter", C.c_void_p), ("capacity", C.c_int), ("ray_indices", C.c_void_p),
+                ("t_starts", C.c_void_p), ("t_ends", C.c_void_p), ("weights", C.c_void_p), ("density", C.c_void_p),
+                ("rgb", C.c_void_p), ("normal", C.c_void_p)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Loads libsdb200.so (built in-tree by __graft_entry__.build()). Raises if absent: no fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "scaledreamer_b200 has no CPU or PyTorch fallback for its CUDA path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.sdb_last_error.restype = C.c_char_p
+    lib.sdb_launch_count.restype = C.c_ulonglong
+    lib.sdb_grid_num_entries.restype = C.c_longlong
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+_P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argtypes; every function returns int unless listed in load() above. Pointers are void* so that
+# raw tensor addresses (python ints) are passed at full width.
+SIGNATURES = {
+    "sdb_grid_num_entries": [C.POINTER(GridCfgC)],
+    "sdb_grid_describe": [C.POINTER(GridCfgC), _P, _P, _P, _P, _P],
+    "sdb_hashgrid_forward": [C.POINTER(GridCfgC), _P, _P, _I, _P, _P],
+    "sdb_hashgrid_backward": [C.POINTER(GridCfgC), _P, _P, _I, _P, _P],
+    "sdb_field_forward": [C.POINTER(FieldC), _P, _I, _P, _P, _P, _P],
+    "sdb_occgrid_update": [C.POINTER(FieldC), _P, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P],
+    "sdb_render_nerf_forward": [C.POINTER(FieldC), C.POINTER(MarchCfgC), _P, _P, _P, _P, _P, _P, _I, _I,
+                                _P, _P, _P, _P, _P, _P, C.POINTER(PackedSamplesC), _P, _P],
+    "sdb_render_nerf_backward": [C.POINTER(FieldC), C.POINTER(FieldGradsC), C.POINTER(MarchCfgC), _P, _P, _P, _P,
+                                 _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "sdb_raygen": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "sdb_adamw_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
+}
+
+
+def _declare(lib: C.CDLL) -> None:
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.argtypes = args
+        if name != "sdb_grid_num_entries":
+            fn.restype = C.c_int
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {load().sdb_last_error().decode()}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("scaledreamer_b200 kernels need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("non-contiguous tensor passed to the C ABI")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().sdb_launch_count())
+
+
+def grid_cfg_c(cfg) -> GridCfgC:
+    """cfg: mapping/obj with the tcnn HashGrid keys."""
+    get = (lambda k: cfg[k]) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k))
+    return GridCfgC(int(get("n_levels")), int(get("n_features_per_level")), int(get("log2_hashmap_size")),
+                    int(get("base_resolution")), float(get("per_level_scale")))
+
+
+def grid_num_entries(cfg) -> int:
+    c = grid_cfg_c(cfg)
+    n = load().sdb_grid_num_entries(C.byref(c))
+    if n < 0:
+        raise RuntimeError(f"bad grid config: {load().sdb_last_error().decode()}")
+    return int(n)

@@ -1,0 +1,269 @@
+"""Host-side wrappers of the fused render kernels: tensor plumbing + torch.autograd glue.
+
+The arithmetic lives in csrc/render_fwd.cu / render_bwd.cu behind the C ABI (include/sdb200.h); this file only
+allocates outputs, fills the parameter structs and registers the backward.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import lib as L
+
+BIAS_TYPES = {"const": 0, "blob_magic3d": 1, "blob_dreamfusion": 2}
+DENSITY_ACTS = {"softplus": 0, "exp": 1, "trunc_exp": 2}
+COLOR_ACTS = {"sigmoid": 0, "sigmoid-mipnerf": 1}
+
+
+@dataclass
+class FieldSpec:
+    """Static description of the iNGP field (geometry + material + background configs, resolved)."""
+    grid: dict
+    bg_grid: dict
+    radius: float = 1.0
+    density_bias: object = "blob_magic3d"
+    density_blob_scale: float = 10.0
+    density_blob_std: float = 0.5
+    density_activation: str = "softplus"
+    fd_eps: float = 0.01
+    color_activation: str = "sigmoid"
+    bg_color_activation: str = "sigmoid"
+
+
+def _enum(table: dict, key, what: str) -> int:
+    if key not in table:
+        raise NotImplementedError(f"{what} '{key}' is not implemented by the sm_100a render kernels "
+                                  f"(supported: {sorted(table)})")
+    return table[key]
+
+
+def make_field_c(spec: FieldSpec, params: Dict[str, torch.Tensor]) -> L.FieldC:
+    """params keys: table, w1d, w2d, w1f, w2f, bg_table, bg_w1, bg_w2, bg_w3 (fp32 CUDA, contiguous)."""
+    f = L.FieldC()
+    f.grid = L.grid_cfg_c(spec.grid)
+    f.bg_grid = L.grid_cfg_c(spec.bg_grid)
+    for name, key in (("table", "table"), ("w1_density", "w1d"), ("w2_density", "w2d"), ("w1_feature", "w1f"),
+                      ("w2_feature", "w2f"), ("bg_table", "bg_table"), ("bg_w1", "bg_w1"), ("bg_w2", "bg_w2"),
+                      ("bg_w3", "bg_w3")):
+        t = params.get(key)
+        if t is not None and t.dtype != torch.float32:
+            raise RuntimeError(f"{key} must be float32")
+        setattr(f, name, L.ptr(t))
+    f.radius = float(spec.radius)
+    if isinstance(spec.density_bias, str):
+        f.density_bias_type = _enum(BIAS_TYPES, spec.density_bias, "density_bias")
+        f.density_bias_const = 0.0
+    else:
+        f.density_bias_type = 0
+        f.density_bias_const = float(spec.density_bias)
+    f.density_blob_scale = float(spec.density_blob_scale)
+    f.density_blob_std = float(spec.density_blob_std)
+    f.density_activation = _enum(DENSITY_ACTS, spec.density_activation, "density_activation")
+    f.fd_normal_eps = float(spec.fd_eps)
+    f.color_activation = _enum(COLOR_ACTS, spec.color_activation, "color_activation")
+    f.bg_color_activation = _enum(COLOR_ACTS, spec.bg_color_activation, "background color_activation")
+    return f
+
+
+@dataclass
+class MarchSpec:
+    render_step_size: float
+    near_plane: float = 0.0
+    far_plane: float = 1e10
+    prune: bool = True
+    alpha_thre: float = 0.01
+    early_stop_eps: float = 1e-4
+    grid_res: int = 32
+    output_normal: bool = False
+
+    def to_c(self) -> L.MarchCfgC:
+        return L.MarchCfgC(float(self.render_step_size), float(self.near_plane), float(min(self.far_plane, 3e38)),
+                           int(self.prune), float(self.alpha_thre), float(self.early_stop_eps), int(self.grid_res),
+                           int(self.output_normal))
+
+
+def hashgrid_forward(x01: torch.Tensor, table: torch.Tensor, grid_cfg) -> torch.Tensor:
+    lib = L.load()
+    c = L.grid_cfg_c(grid_cfg)
+    x01 = x01.contiguous().float()
+    out = torch.empty(x01.shape[0], c.n_levels * c.n_features_per_level, device=x01.device, dtype=torch.float32)
+    L.check(lib.sdb_hashgrid_forward(C.byref(c), L.ptr(table), L.ptr(x01), x01.shape[0], L.ptr(out), L.stream_ptr()),
+            "sdb_hashgrid_forward")
+    return out
+
+
+def hashgrid_backward(x01: torch.Tensor, g_out: torch.Tensor, n_entries: int, grid_cfg) -> torch.Tensor:
+    lib = L.load()
+    c = L.grid_cfg_c(grid_cfg)
+    x01 = x01.contiguous().float()
+    g_out = g_out.contiguous().float()
+    g_table = torch.zeros(n_entries, c.n_features_per_level, device=x01.device, dtype=torch.float32)
+    L.check(lib.sdb_hashgrid_backward(C.byref(c), L.ptr(x01), L.ptr(g_out), x01.shape[0], L.ptr(g_table),
+                                      L.stream_ptr()), "sdb_hashgrid_backward")
+    return g_table
+
+
+def field_forward(spec: FieldSpec, params, points: torch.Tensor, want_features=True, want_normal=False):
+    lib = L.load()
+    f = make_field_c(spec, {**params, "bg_table": params.get("bg_table"), "bg_w1": params.get("bg_w1"),
+                            "bg_w2": params.get("bg_w2"), "bg_w3": params.get("bg_w3")})
+    pts = points.reshape(-1, 3).contiguous().float()
+    n = pts.shape[0]
+    density = torch.empty(n, device=pts.device)
+    features = torch.empty(n, 3, device=pts.device) if want_features else None
+    normal = torch.empty(n, 3, device=pts.device) if want_normal else None
+    L.check(lib.sdb_field_forward(C.byref(f), L.ptr(pts), n, L.ptr(density), L.ptr(features), L.ptr(normal),
+                                  L.stream_ptr()), "sdb_field_forward")
+    return density, features, normal
+
+
+class OccGrid:
+    """Device-resident occupancy state of nerfacc.OccGridEstimator(resolution=32, levels=1)
+    (nerf_volume_renderer.py:60-65): float occs, packed binaries, running mean."""
+
+    def __init__(self, res: int, device, all_occupied: bool = False):
+        self.res = res
+        n = res ** 3
+        self.occs = torch.zeros(n, device=device)
+        self.bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device=device)
+        self.mean = torch.zeros(1, device=device)
+        if all_occupied:  # grid_prune: false
+            self.occs.fill_(1.0)
+            self.bits.fill_(-1)
+            self.mean.fill_(1.0)
+
+    def binaries(self) -> torch.Tensor:
+        """bool [res,res,res] view (x,y,z) of the packed bit-field (tests / debugging)."""
+        b = self.bits.view(-1, 1) >> torch.arange(32, device=self.bits.device, dtype=torch.int32)
+        return (b & 1).bool().reshape(-1)[: self.res ** 3].reshape(self.res, self.res, self.res)
+
+    def set_binaries(self, binary: torch.Tensor, occs: Optional[torch.Tensor] = None) -> None:
+        flat = binary.reshape(-1).to(self.bits.device).to(torch.int64)
+        pad = (-flat.numel()) % 32
+        if pad:
+            flat = torch.cat([flat, flat.new_zeros(pad)])
+        words = (flat.view(-1, 32) << torch.arange(32, device=flat.device)).sum(-1)
+        words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)
+        self.bits.copy_(words.to(torch.int32))
+        if occs is not None:
+            self.occs.copy_(occs.reshape(-1).to(self.occs.device))
+            self.mean.copy_(self.occs.mean().reshape(1))
+
+    def update(self, spec: FieldSpec, params, cell_idx: torch.Tensor, cell_rand: torch.Tensor, step_size: float,
+               ema_decay: float = 0.95, occ_thre: float = 0.01) -> None:
+        lib = L.load()
+        f = make_field_c(spec, params)
+        cell_idx = cell_idx.to(torch.int32).contiguous()
+        cell_rand = cell_rand.float().contiguous()
+        L.check(lib.sdb_occgrid_update(C.byref(f), L.ptr(cell_idx), L.ptr(cell_rand), cell_idx.numel(), self.res,
+                                       float(step_size), float(ema_decay), float(occ_thre), L.ptr(self.occs),
+                                       L.ptr(self.bits), L.ptr(self.mean), L.stream_ptr()), "sdb_occgrid_update")
+
+
+PARAM_KEYS = ("table", "w1d", "w2d", "w1f", "w2f", "bg_table", "bg_w1", "bg_w2", "bg_w3")
+
+
+def render_forward_raw(spec: FieldSpec, march: MarchSpec, params, occ: OccGrid, rays_o, rays_d, jitter, bg_override,
+                       rays_per_image: int, packed_capacity: int = 0):
+    """Runs sdb_render_nerf_forward. rays_* [Nr,3]. Returns dict of per-ray tensors (+ packed samples)."""
+    lib = L.load()
+    f = make_field_c(spec, params)
+    m = march.to_c()
+    dev = rays_o.device
+    n = rays_o.shape[0]
+    out = {k: torch.empty(n, 3, device=dev) for k in ("comp_rgb", "comp_rgb_fg", "comp_rgb_bg")}
+    out.update({k: torch.empty(n, device=dev) for k in ("opacity", "depth", "z_variance")})
+    work = torch.zeros(1, dtype=torch.int32, device=dev)
+    pk = L.PackedSamplesC()
+    packed = None
+    if packed_capacity > 0:
+        cap = packed_capacity
+        packed = {"counter": torch.zeros(1, dtype=torch.int32, device=dev),
+                  "ray_indices": torch.empty(cap, dtype=torch.int32, device=dev),
+                  "t_starts": torch.empty(cap, device=dev), "t_ends": torch.empty(cap, device=dev),
+                  "weights": torch.empty(cap, device=dev), "density": torch.empty(cap, device=dev),
+                  "rgb": torch.empty(cap, 3, device=dev),
+                  "normal": torch.empty(cap, 3, device=dev) if march.output_normal else None}
+        pk.counter = L.ptr(packed["counter"])
+        pk.capacity = cap
+        for k in ("ray_indices", "t_starts", "t_ends", "weights", "density", "rgb", "normal"):
+            setattr(pk, k, L.ptr(packed[k]))
+    L.check(lib.sdb_render_nerf_forward(
+        C.byref(f), C.byref(m), L.ptr(occ.bits), L.ptr(occ.mean), L.ptr(rays_o), L.ptr(rays_d), L.ptr(jitter),
+        L.ptr(bg_override), n, int(rays_per_image), L.ptr(out["comp_rgb"]), L.ptr(out["comp_rgb_fg"]),
+        L.ptr(out["comp_rgb_bg"]), L.ptr(out["opacity"]), L.ptr(out["depth"]), L.ptr(out["z_variance"]),
+        C.byref(pk) if packed is not None else None, L.ptr(work), L.stream_ptr()), "sdb_render_nerf_forward")
+    out["packed"] = packed
+    return out
+
+
+def render_backward_raw(spec: FieldSpec, march: MarchSpec, params, grads, occ: OccGrid, rays_o, rays_d, jitter,
+                        bg_override, rays_per_image: int, saved, g_comp_rgb, g_opacity=None, g_depth=None) -> None:
+    """Runs sdb_render_nerf_backward; accumulates into `grads` (dict keyed like params)."""
+    lib = L.load()
+    f = make_field_c(spec, params)
+    m = march.to_c()
+    g = L.FieldGradsC()
+    for name, key in (("table", "table"), ("w1_density", "w1d"), ("w2_density", "w2d"), ("w1_feature", "w1f"),
+                      ("w2_feature", "w2f"), ("bg_table", "bg_table"), ("bg_w1", "bg_w1"), ("bg_w2", "bg_w2"),
+                      ("bg_w3", "bg_w3")):
+        setattr(g, name, L.ptr(grads[key]))
+    n = rays_o.shape[0]
+    work = torch.zeros(1, dtype=torch.int32, device=rays_o.device)
+    L.check(lib.sdb_render_nerf_backward(
+        C.byref(f), C.byref(g), C.byref(m), L.ptr(occ.bits), L.ptr(occ.mean), L.ptr(rays_o), L.ptr(rays_d),
+        L.ptr(jitter), L.ptr(bg_override), n, int(rays_per_image), L.ptr(saved["comp_rgb_fg"]),
+        L.ptr(saved["comp_rgb_bg"]), L.ptr(saved["opacity"]), L.ptr(saved["depth"]), L.ptr(g_comp_rgb),
+        L.ptr(g_opacity), L.ptr(g_depth), L.ptr(work), L.stream_ptr()), "sdb_render_nerf_backward")
+
+
+class _RenderNeRF(torch.autograd.Function):
+    """comp_rgb, opacity, depth = render(params...) with the fused backward. Gradient flows to the nine field
+    parameter tensors only (rays are data)."""
+
+    @staticmethod
+    def forward(ctx, spec, march, occ, rays_o, rays_d, jitter, bg_override, rays_per_image, packed_capacity,
+                holder, *param_tensors):
+        params = dict(zip(PARAM_KEYS, param_tensors))
+        out = render_forward_raw(spec, march, params, occ, rays_o, rays_d, jitter, bg_override, rays_per_image,
+                                 packed_capacity)
+        ctx.spec, ctx.march, ctx.occ, ctx.rpi = spec, march, occ, rays_per_image
+        ctx.bits_snapshot = occ.bits.clone()  # the grid may be refreshed before backward runs
+        ctx.mean_snapshot = occ.mean.clone()
+        ctx.save_for_backward(rays_o, rays_d, jitter if jitter is not None else rays_o.new_zeros(0),
+                              bg_override if bg_override is not None else rays_o.new_zeros(0),
+                              out["comp_rgb_fg"], out["comp_rgb_bg"], out["opacity"], out["depth"], *param_tensors)
+        ctx.has_jitter, ctx.has_bg = jitter is not None, bg_override is not None
+        holder.update(out)  # non-differentiable extras (fg/bg/z_variance/packed) for the caller
+        ctx.mark_non_differentiable(out["comp_rgb_fg"], out["comp_rgb_bg"], out["z_variance"])
+        return out["comp_rgb"], out["opacity"], out["depth"]
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_op, g_depth):
+        rays_o, rays_d, jitter, bg_override, fg, bg, op, depth, *param_tensors = ctx.saved_tensors
+        params = dict(zip(PARAM_KEYS, param_tensors))
+        grads = {k: torch.zeros_like(v) for k, v in params.items()}
+        occ = ctx.occ
+        snap = OccGrid.__new__(OccGrid)
+        snap.res, snap.bits, snap.mean, snap.occs = occ.res, ctx.bits_snapshot, ctx.mean_snapshot, occ.occs
+        g_rgb = g_rgb.contiguous() if g_rgb is not None else torch.zeros_like(fg)
+        render_backward_raw(ctx.spec, ctx.march, params, grads, snap, rays_o, rays_d,
+                            jitter if ctx.has_jitter else None, bg_override if ctx.has_bg else None, ctx.rpi,
+                            {"comp_rgb_fg": fg, "comp_rgb_bg": bg, "opacity": op, "depth": depth}, g_rgb,
+                            g_op.contiguous() if g_op is not None else None,
+                            g_depth.contiguous() if g_depth is not None else None)
+        return (None,) * 10 + tuple(grads[k] for k in PARAM_KEYS)
+
+
+def render_nerf(spec, march, occ, params, rays_o, rays_d, jitter, bg_override, rays_per_image, packed_capacity=0):
+    """Differentiable fused render. Returns dict with comp_rgb / opacity / depth (grad) and the extras."""
+    holder: dict = {}
+    rgb, op, depth = _RenderNeRF.apply(spec, march, occ, rays_o.contiguous(), rays_d.contiguous(), jitter,
+                                       bg_override, rays_per_image, packed_capacity, holder,
+                                       *[params[k] for k in PARAM_KEYS])
+    out = dict(holder)
+    out["comp_rgb"], out["opacity"], out["depth"] = rgb, op, depth
+    return out
