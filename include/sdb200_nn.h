@@ -1,0 +1,85 @@
+/*
+ * sdb200_nn.h — C ABI of the dense (tensor-core) half of libsdb200.so: the frozen VAE encoder and UNet of the
+ * ASD guidance step and the kernels they are built from.
+ *
+ * The reference reaches this arithmetic through diffusers / the vendored LDM (cuDNN, cuBLAS, SDPA); each entry
+ * point cites the reference call site it replaces (paths relative to the reference tree). Activations are fp16,
+ * channels-last: an image batch is [N, H, W, C] and is at the same time the token matrix [N*H*W, C].
+ * All pointers are DEVICE pointers owned by the caller; `stream` is a cudaStream_t; return 0 or a negative code
+ * (sdb_last_error()). Nothing synchronises.
+ */
+#ifndef SDB200_NN_H
+#define SDB200_NN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_ACT_NONE 0
+#define SDB_ACT_SILU 1
+#define SDB_ACT_GELU 2
+
+/* ---- tcgen05 GEMM: out[M,N] = act(alpha * A[M,K] B[N,K]^T + bias[N] + rowbias[m / rows_per_group, N]) + residual
+ * A, B, bias, residual fp16; rowbias fp32; out fp16 or fp32 (out_fp32). Leading dimensions in elements, multiples
+ * of 8. batch > 1 repeats over z with element strides a_zs / b_zs / out_zs (0 = shared operand).
+ * Replaces nn.Linear / torch.bmm calls, e.g. extern/mvdream/ldm/modules/attention.py:49-76,163-194. */
+typedef struct {
+  const void* A;
+  long long lda;
+  const void* B;
+  long long ldb;
+  void* out;
+  long long ldc;
+  int M, N, K;
+  const void* bias;
+  const float* rowbias;
+  int rows_per_group;
+  const void* residual;
+  long long ldr;
+  float alpha;
+  int act;
+  int out_fp32;
+  int batch;
+  long long a_zs, b_zs, out_zs;
+} sdb_gemm_args;
+int sdb_gemm_f16(const sdb_gemm_args* args, void* stream);
+
+/* 3x3 stride-1 pad-1 convolution as implicit GEMM: x [N,H,W,Cin], w [Cout, 3,3,Cin] (= [Cout, 9*Cin]),
+ * out [N,H,W,Cout]; epilogue as sdb_gemm_f16 with rows_per_group = H*W (the per-image timestep-embedding add
+ * of ResBlock, openaimodel.py:262-272). Cin % 64 == 0. Replaces conv_nd(...) of openaimodel.py:203,230 and
+ * torch.nn.Conv2d of model.py:101-123. */
+int sdb_conv3x3_f16(const void* x, int n, int h, int w, int cin, const void* weight, int cout, const void* bias,
+                    const float* rowbias, const void* residual, int act, void* out, void* stream);
+
+/* Direct (CUDA-core) 3x3 conv for the 3/4/8-channel ends of the networks; x fp32 or fp16, out fp32 or fp16. */
+int sdb_conv3x3_small(const void* x, int x_fp32, const void* weight, const void* bias, void* out, int out_fp32,
+                      int n, int h, int w, int cin, int cout, void* stream);
+
+/* Multi-head attention with head_dim 64: q [B,Lq,heads*64] (row stride ldq), k/v [B,Lk,heads*64];
+ * out[b,l,h*64+d] = softmax(q_h k_h^T / 8) v_h. scores: fp16 scratch of B*heads*Lq*round_up(Lk,8) elements.
+ * Replaces CrossAttention.forward (attention.py:163-194) / diffusers AttnProcessor2_0. */
+int sdb_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                      int batch, int heads, int lq, int lk, void* scores, void* out, long long ldo, void* stream);
+
+/* GroupNorm over [N, HW, C] with optional fused SiLU (GroupNorm32 + SiLU, openaimodel.py:200-203; Normalize +
+ * nonlinearity, model.py:129-141). stats: [N, groups, 2] fp32 (sum, sum of squares) written by the forward. */
+int sdb_groupnorm_f16(const void* x, const void* gamma, const void* beta, void* y, float* stats, int n, int hw,
+                      int c, int groups, float eps, int silu, void* stream);
+/* dx of the above given dy; scratch: [N, groups, 2] fp32. */
+int sdb_groupnorm_backward_f16(const void* x, const void* gamma, const void* beta, const float* stats,
+                               const void* dy, void* dx, float* scratch, int n, int hw, int c, int groups,
+                               float eps, int silu, void* stream);
+int sdb_layernorm_f16(const void* x, const void* gamma, const void* beta, void* y, int rows, int c, float eps,
+                      void* stream);
+/* y[rows, inner] = xg[:, :inner] * gelu(xg[:, inner:]) (GEGLU, attention.py:49-57) */
+int sdb_geglu_f16(const void* xg, void* y, long long rows, int inner, void* stream);
+int sdb_upsample2x_f16(const void* x, void* y, int n, int h, int w, int c, void* stream);
+int sdb_im2col3x3s2_f16(const void* x, void* col, int n, int h, int w, int c, int pad_lo, void* stream);
+int sdb_col2im3x3s2_f16(const void* col, void* dx, int n, int h, int w, int c, int pad_lo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_NN_H */

@@ -72,7 +72,8 @@ def hashgrid_encode(x01: torch.Tensor, table: torch.Tensor, cfg: GridCfg) -> tor
     for l in range(cfg.n_levels):
         s = torch.tensor(meta["scale"][l], dtype=torch.float32)
         res, size, off = meta["res"][l], meta["size"][l], meta["offset"][l]
-        pos = x01 * s + 0.5
+        # tcnn evaluates pos = fma(scale, x, 0.5f): one rounding. Emulated exactly through float64.
+        pos = (x01.double() * s.double() + 0.5).float()
         g = torch.floor(pos)
         w = pos - g
         gi = g.to(torch.int64)

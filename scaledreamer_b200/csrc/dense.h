@@ -1,0 +1,118 @@
+// Internal C++ interface of the dense (tensor-core) half of libsdb200: the tcgen05 GEMM / implicit-conv kernel
+// plans and the element-wise / normalisation kernels the UNet and VAE executors are built from.
+// Activations are fp16, channels-last (NHWC == [tokens, C]); accumulation and statistics are fp32.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace dense {
+
+enum OperandMode : int {
+  kMatrix = 0,  // 3D map {K, rows, Z}
+  kConv3x3 = 1, // 4D map {C, W, H, N}: implicit-GEMM 3x3 stride-1 pad-1 over NHWC, K ordered (kh, kw, cin)
+  kHeads = 2,   // 4D map {d, heads, L, B}: per-head view of a [B, L, heads*d] tensor, z = b*heads + h
+};
+
+enum Act : int { kActNone = 0, kActSilu = 1, kActGelu = 2 };
+
+struct OperandGeom {
+  int mode;
+  int batched;     // kMatrix: z indexes dim 2 (else coordinate 0)
+  int heads;       // kHeads
+  int mn_major;    // B only: tile is [K rows][64 MN] (e.g. V of attention); requires BN == 64
+  int W, H;        // kConv3x3 image size
+  int bw, bh, bn;  // kConv3x3 box (bw*bh*bn == 128)
+  int cin_blocks;  // kConv3x3: Cin / 64
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_k_blocks;
+  OperandGeom a, b;
+  // epilogue: v = alpha*acc + bias[n] + rowbias[(m / rows_per_group)*N + n]; v = act(v); v += residual[m*ldr + n]
+  void* out;
+  int out_fp32;
+  long long ldc;
+  int out_zdiv;                 // output offset(z) = (z / out_zdiv)*out_zs_hi + (z % out_zdiv)*out_zs_lo
+  long long out_zs_hi, out_zs_lo;
+  const __half* bias;
+  const float* rowbias;
+  int rows_per_group;
+  const __half* residual;
+  long long ldr;
+  float alpha;
+  int act;
+};
+
+struct GemmPlan {
+  CUtensorMap ta, tb;
+  GemmParams p;
+  dim3 grid;
+  int bn;  // 64, 128 or 160
+};
+
+// dtype: 0 = fp16 (the only one wired today). dims/box innermost first; strides in BYTES for dims 1..rank-1.
+int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box);
+
+struct Epilogue {
+  void* out = nullptr;
+  int out_fp32 = 0;
+  long long ldc = 0;
+  const __half* bias = nullptr;
+  const float* rowbias = nullptr;
+  int rows_per_group = 1;
+  const __half* residual = nullptr;
+  long long ldr = 0;
+  float alpha = 1.f;
+  int act = kActNone;
+};
+
+// out[M,N] = A[M,K] * B[N,K]^T. lda/ldb in elements (multiples of 8). Optional batching over z with element strides.
+int plan_gemm(GemmPlan* plan, const __half* A, long long lda, const __half* B, long long ldb, int M, int N, int K,
+              const Epilogue& ep, int batch = 1, long long a_zs = 0, long long b_zs = 0, long long out_zs = 0);
+// out[(n,h,w), Cout] = conv3x3(x[N,H,W,Cin], w[Cout, 9*Cin]) stride 1 pad 1.
+int plan_conv3x3(GemmPlan* plan, const __half* x, int N, int H, int W, int Cin, const __half* w, int Cout,
+                 const Epilogue& ep);
+// S[b,h,Lq,Lk] = alpha * Q_h K_h^T for Q [B,Lq,heads*64] (row stride ldq), K [B,Lk,heads*64] (ldk). S row stride lds.
+int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __half* K, long long ldk, int B, int heads,
+                     int Lq, int Lk, __half* S, long long lds, float alpha);
+// O[b,Lq,h*64:(h+1)*64] = P[b,h,Lq,Lk] V_h for V [B,Lk,heads*64] (ldv); O row stride ldo.
+int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half* V, long long ldv, int B, int heads,
+                    int Lq, int Lk, __half* O, long long ldo);
+int run_gemm(const GemmPlan& plan, cudaStream_t stream);
+
+// ---- normalisation / element-wise kernels (dense_ops.cu) ------------------------------------------------
+// GroupNorm(32 groups) over NHWC fp16 with optional fused SiLU. stats: [N,32,2] fp32 scratch (sum, sumsq).
+int groupnorm_forward(const __half* x, const __half* gamma, const __half* beta, __half* y, float* stats, int N, int HW,
+                      int C, int groups, float eps, int silu, cudaStream_t s);
+// dx for y = silu?(GN(x)): needs x, gamma, beta and the forward stats; scratch2: [N,groups,2] fp32.
+int groupnorm_backward(const __half* x, const __half* gamma, const __half* beta, const float* stats, const __half* dy,
+                       __half* dx, float* scratch2, int N, int HW, int C, int groups, float eps, int silu,
+                       cudaStream_t s);
+int layernorm_forward(const __half* x, const __half* gamma, const __half* beta, __half* y, int rows, int C, float eps,
+                      cudaStream_t s);
+// in-place softmax over the first `cols` entries of each row (row stride ld); entries [cols, ld) are zeroed.
+int softmax_rows(__half* x, long long rows, int cols, long long ld, cudaStream_t s);
+int geglu(const __half* xg, __half* y, long long rows, int inner, cudaStream_t s);  // xg [rows, 2*inner]
+int silu_f32_to_f16(const float* x, __half* y, long long n, cudaStream_t s);
+int upsample_nearest2x(const __half* x, __half* y, int N, int H, int W, int C, cudaStream_t s);
+int concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* y, long long rows, cudaStream_t s);
+int add_f16(const __half* a, const __half* b, __half* y, long long n, cudaStream_t s);
+int transpose_f16(const __half* x, __half* y, int rows, int cols, cudaStream_t s);  // y[cols, rows]
+// im2col for 3x3 stride-2 convs: pad_lo = 1 (UNet Downsample, padding=1) or 0 (VAE Downsample, pad (0,1,0,1)).
+int im2col_3x3_s2(const __half* x, __half* col, int N, int H, int W, int C, int pad_lo, cudaStream_t s);
+int col2im_3x3_s2(const __half* col, __half* dx, int N, int H, int W, int C, int pad_lo, cudaStream_t s);
+// Direct (CUDA-core) 3x3 stride-1 pad-1 conv for tiny channel counts. w: [Cout, 3, 3, Cin] fp16, bias [Cout].
+int conv3x3_small(const void* x, int x_fp32, const __half* w, const __half* bias, void* y, int y_fp32, int N, int H,
+                  int W, int Cin, int Cout, cudaStream_t s);
+int timestep_embedding(const float* t, __half* out, int n, int dim, float max_period, cudaStream_t s);
+// y[rows, N] (fp32) = act?(x[rows,K]) * w[N,K]^T + bias: tiny-M linear on CUDA cores (time / camera embeddings).
+int linear_small(const __half* x, const __half* w, const __half* bias, void* y, int y_fp32, int rows, int N, int K,
+                 int silu_in, cudaStream_t s);
+
+}  // namespace dense

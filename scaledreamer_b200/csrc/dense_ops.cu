@@ -1,0 +1,697 @@
+// Normalisation and element-wise kernels of the dense path (HBM-bound; fp16 storage, fp32 math).
+// Reference semantics: GroupNorm32 / Normalize (extern/mvdream/ldm/modules/diffusionmodules/util.py:229-231,
+// model.py:46-47, attention.py:88-89), nn.LayerNorm + GEGLU (attention.py:49-57,271-273), softmax
+// (attention.py:186), nearest Upsample (openaimodel.py:109-118), timestep_embedding (util.py:165-186).
+#include "dense.h"
+
+namespace dense {
+namespace {
+
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_grad(float x) {
+  const float s = 1.f / (1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+// ---------------------------------------------------------------------------------------------- GroupNorm
+// Block = PY pixel-lanes x P channel-pair threads. Thread (py, cp) owns channel pair cp for pixels py, py+PY, ...
+// mode 0: accumulate (sum x, sum x^2); mode 1 (backward): accumulate (sum dxhat, sum dxhat*xhat).
+template <int MODE>
+__global__ void gn_reduce_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
+                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                 const float* __restrict__ stats, float* __restrict__ out, int HW, int C, int groups,
+                                 int P, int PY, int pix_per_block, float eps, int act_silu) {
+  extern __shared__ float sm[];  // [2][blockDim.x]
+  const int n = blockIdx.y;
+  const int cp = threadIdx.x % P, py = threadIdx.x / P;
+  const int cpg = C / groups;  // channels per group (even)
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(HW, p_begin + pix_per_block);
+  const int n_pairs = C / 2;
+  float a0 = 0.f, a1 = 0.f;
+  for (int c2 = cp; c2 < n_pairs; c2 += P) {  // P == n_pairs except for very wide tensors
+    float mean = 0.f, rstd = 0.f, g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
+    if (MODE == 1) {
+      const int g = (2 * c2) / cpg;
+      const float cnt = (float)HW * (float)cpg;
+      const float s = stats[(n * groups + g) * 2], ss = stats[(n * groups + g) * 2 + 1];
+      mean = s / cnt;
+      rstd = rsqrtf(fmaxf(ss / cnt - mean * mean, 0.f) + eps);
+      const float2 gg = __half22float2(reinterpret_cast<const __half2*>(gamma)[c2]);
+      const float2 bb = __half22float2(reinterpret_cast<const __half2*>(beta)[c2]);
+      g0 = gg.x, g1 = gg.y, b0 = bb.x, b1 = bb.y;
+    }
+    float s0 = 0.f, s1 = 0.f;
+    for (int p = p_begin + py; p < p_end; p += PY) {
+      const size_t off = ((size_t)n * HW + p) * n_pairs + c2;
+      const float2 v = __half22float2(reinterpret_cast<const __half2*>(x)[off]);
+      if (MODE == 0) {
+        s0 += v.x + v.y;
+        s1 += v.x * v.x + v.y * v.y;
+      } else {
+        const float2 d = __half22float2(reinterpret_cast<const __half2*>(dy)[off]);
+        const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
+        float dz0 = d.x, dz1 = d.y;
+        if (act_silu) {
+          dz0 *= silu_grad(xh0 * g0 + b0);
+          dz1 *= silu_grad(xh1 * g1 + b1);
+        }
+        const float dx0 = dz0 * g0, dx1 = dz1 * g1;
+        s0 += dx0 + dx1;
+        s1 += dx0 * xh0 + dx1 * xh1;
+      }
+    }
+    // pairs of one group are contiguous in c2: reduce through shared memory per c2-slot
+    sm[threadIdx.x] = s0;
+    sm[blockDim.x + threadIdx.x] = s1;
+    __syncthreads();
+    const int pairs_per_group = cpg / 2;
+    const int c2_base = c2 - cp;  // first pair handled in this sweep
+    // thread t < groups_in_sweep sums its group's slots over all pixel lanes
+    const int first_group = (2 * c2_base) / cpg;
+    const int sweep_pairs = min(P, n_pairs - c2_base);
+    const int groups_in_sweep = (sweep_pairs + pairs_per_group - 1) / pairs_per_group;
+    if ((int)threadIdx.x < groups_in_sweep) {
+      const int g = first_group + threadIdx.x;
+      const int lo = max(g * pairs_per_group - c2_base, 0), hi = min((g + 1) * pairs_per_group - c2_base, sweep_pairs);
+      float t0 = 0.f, t1 = 0.f;
+      for (int yy = 0; yy < PY; ++yy)
+        for (int q = lo; q < hi; ++q) {
+          t0 += sm[yy * P + q];
+          t1 += sm[blockDim.x + yy * P + q];
+        }
+      atomicAdd(&out[(n * groups + g) * 2], t0);
+      atomicAdd(&out[(n * groups + g) * 2 + 1], t1);
+    }
+    __syncthreads();
+    a0 += s0;
+    a1 += s1;
+  }
+  (void)a0;
+  (void)a1;
+}
+
+// y = act(GN(x)) (MODE 0) or dx of it (MODE 1); 8 channels (16 bytes) per thread.
+template <int MODE>
+__global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
+                                const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                const float* __restrict__ stats, const float* __restrict__ red,
+                                __half* __restrict__ y, long long total8, int HW, int C, int groups, float eps,
+                                int act_silu) {
+  const int cpg = C / groups;
+  const float cnt = (float)HW * (float)cpg;
+  const int c8n = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    const int n = (int)(i / ((long long)HW * c8n));
+    const uint4 xv = reinterpret_cast<const uint4*>(x)[i];
+    const uint4 gv = reinterpret_cast<const uint4*>(gamma)[c8];
+    const uint4 bv = reinterpret_cast<const uint4*>(beta)[c8];
+    uint4 dv = make_uint4(0, 0, 0, 0);
+    if (MODE == 1) dv = reinterpret_cast<const uint4*>(dy)[i];
+    uint4 ov;
+    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+    const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+    const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+    const __half2* dh = reinterpret_cast<const __half2*>(&dv);
+    __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c8 * 8 + 2 * e;
+      const int g = c / cpg;
+      const float s = stats[(n * groups + g) * 2], ss = stats[(n * groups + g) * 2 + 1];
+      const float mean = s / cnt;
+      const float rstd = rsqrtf(fmaxf(ss / cnt - mean * mean, 0.f) + eps);
+      const float2 xf = __half22float2(xh[e]), gf = __half22float2(gh[e]), bf = __half22float2(bh[e]);
+      const float xh0 = (xf.x - mean) * rstd, xh1 = (xf.y - mean) * rstd;
+      float o0, o1;
+      if (MODE == 0) {
+        o0 = xh0 * gf.x + bf.x;
+        o1 = xh1 * gf.y + bf.y;
+        if (act_silu) {
+          o0 = silu(o0);
+          o1 = silu(o1);
+        }
+      } else {
+        const float2 df = __half22float2(dh[e]);
+        float dz0 = df.x, dz1 = df.y;
+        if (act_silu) {
+          dz0 *= silu_grad(xh0 * gf.x + bf.x);
+          dz1 *= silu_grad(xh1 * gf.y + bf.y);
+        }
+        const float r0 = red[(n * groups + g) * 2] / cnt, r1 = red[(n * groups + g) * 2 + 1] / cnt;
+        o0 = rstd * (dz0 * gf.x - r0 - xh0 * r1);
+        o1 = rstd * (dz1 * gf.y - r0 - xh1 * r1);
+      }
+      oh[e] = __floats2half2_rn(o0, o1);
+    }
+    reinterpret_cast<uint4*>(y)[i] = ov;
+  }
+}
+
+void gn_geometry(int HW, int C, int N, int groups, int* P, int* PY, int* ppb, int* nblk) {
+  // one thread per channel pair; very wide tensors sweep in equal parts that hold whole groups
+  const int n_pairs = C / 2, ppg = C / groups / 2;
+  int d = 1;
+  while (n_pairs / d > 1024 || n_pairs % d || (n_pairs / d) % ppg) ++d;
+  const int p = n_pairs / d;
+  int py = 1;
+  while (p * py * 2 <= 256 && py * 2 <= HW) py *= 2;
+  // target ~4 waves of blocks over (N x splits)
+  int splits = (4 * kNumSMs + N - 1) / N;
+  int pix = (HW + splits - 1) / splits;
+  if (pix < py * 4) pix = py * 4;
+  if (pix > HW) pix = HW;
+  *P = p;
+  *PY = py;
+  *ppb = pix;
+  *nblk = (HW + pix - 1) / pix;
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+__global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                                 const __half* __restrict__ beta, __half* __restrict__ y, int rows, int C, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __half2* xr = reinterpret_cast<const __half2*>(x + (size_t)row * C);
+  const int n2 = C / 2;
+  float s = 0.f;
+  for (int i = lane; i < n2; i += 32) {
+    const float2 v = __half22float2(xr[i]);
+    s += v.x + v.y;
+  }
+  s = warp_sum(s);
+  const float mean = s / (float)C;
+  float ss = 0.f;
+  for (int i = lane; i < n2; i += 32) {
+    const float2 v = __half22float2(xr[i]);
+    ss += (v.x - mean) * (v.x - mean) + (v.y - mean) * (v.y - mean);
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / (float)C + eps);
+  __half2* yr = reinterpret_cast<__half2*>(y + (size_t)row * C);
+  for (int i = lane; i < n2; i += 32) {
+    const float2 v = __half22float2(xr[i]);
+    const float2 g = __half22float2(reinterpret_cast<const __half2*>(gamma)[i]);
+    const float2 b = __half22float2(reinterpret_cast<const __half2*>(beta)[i]);
+    yr[i] = __floats2half2_rn((v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- softmax
+// One 128-thread block per row; up to 4096 columns cached in registers.
+__global__ void __launch_bounds__(128) softmax_kernel(__half* __restrict__ x, int cols, long long ld) {
+  __shared__ float red[4];
+  __half* row = x + (size_t)blockIdx.x * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float v[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = tid + j * 128;
+    v[j] = c < cols ? __half2float(row[c]) : -INFINITY;
+    mx = fmaxf(mx, v[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] = tid + j * 128 < cols ? __expf(v[j] - mx) : 0.f;
+    sum += v[j];
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = tid + j * 128;
+    if (c < ld && c < 4096) row[c] = __float2half_rn(v[j] * inv);
+  }
+}
+
+__global__ void geglu_kernel(const __half* __restrict__ xg, __half* __restrict__ y, long long rows, int inner) {
+  const int i2 = inner / 2;
+  const long long total = rows * i2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / i2;
+    const int c = (int)(i - r * i2);
+    const __half2* base = reinterpret_cast<const __half2*>(xg + r * 2 * inner);
+    const float2 a = __half22float2(base[c]);
+    const float2 g = __half22float2(base[i2 + c]);
+    reinterpret_cast<__half2*>(y + r * inner)[c] = __floats2half2_rn(a.x * gelu_erf(g.x), a.y * gelu_erf(g.y));
+  }
+}
+
+__global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W, int C8) {
+  const long long total = (long long)N * 2 * H * 2 * W * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int ox = (int)(r % (2 * W));
+    r /= 2 * W;
+    const int oy = (int)(r % (2 * H));
+    const int n = (int)(r / (2 * H));
+    reinterpret_cast<uint4*>(y)[i] =
+        reinterpret_cast<const uint4*>(x)[(((long long)n * H + oy / 2) * W + ox / 2) * C8 + c];
+  }
+}
+
+__global__ void concat_kernel(const __half* __restrict__ a, int Ca8, const __half* __restrict__ b, int Cb8,
+                              __half* __restrict__ y, long long rows) {
+  const int C8 = Ca8 + Cb8;
+  const long long total = rows * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C8;
+    const int c = (int)(i - r * C8);
+    reinterpret_cast<uint4*>(y)[i] = c < Ca8 ? reinterpret_cast<const uint4*>(a)[r * Ca8 + c]
+                                             : reinterpret_cast<const uint4*>(b)[r * Cb8 + (c - Ca8)];
+  }
+}
+
+__global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ y,
+                           long long n2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<__half2*>(y)[i] =
+        __hadd2(reinterpret_cast<const __half2*>(a)[i], reinterpret_cast<const __half2*>(b)[i]);
+}
+
+__global__ void transpose_kernel(const __half* __restrict__ x, __half* __restrict__ y, int rows, int cols) {
+  __shared__ __half tile[32][34];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = by + j, c = bx + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = x[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = bx + j, r = by + threadIdx.x;
+    if (r < rows && c < cols) y[(size_t)c * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+// col[(n,oy,ox), (kh,kw,c)] = x[n, 2*oy + kh - pad_lo, 2*ox + kw - pad_lo, c] (zero outside)
+__global__ void im2col_s2_kernel(const __half* __restrict__ x, __half* __restrict__ col, int N, int H, int W, int C8,
+                                 int pad_lo) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * 9 * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const int iy = 2 * oy + tap / 3 - pad_lo, ix = 2 * ox + tap % 3 - pad_lo;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = reinterpret_cast<const uint4*>(x)[(((long long)n * H + iy) * W + ix) * C8 + c];
+    reinterpret_cast<uint4*>(col)[i] = v;
+  }
+}
+
+// dx[n,iy,ix,c] = sum over (oy,ox,tap) with 2*oy + kh - pad_lo == iy, 2*ox + kw - pad_lo == ix of col[...]
+__global__ void col2im_s2_kernel(const __half* __restrict__ col, __half* __restrict__ dx, int N, int H, int W, int C8,
+                                 int pad_lo) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * H * W * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int ix = (int)(r % W);
+    r /= W;
+    const int iy = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ty = iy + pad_lo - kh;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= Ho) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tx = ix + pad_lo - kw;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= Wo) continue;
+        const uint4 v =
+            reinterpret_cast<const uint4*>(col)[((((long long)n * Ho + oy) * Wo + ox) * 9 + kh * 3 + kw) * C8 + c];
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+        }
+      }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+    reinterpret_cast<uint4*>(dx)[i] = o;
+  }
+}
+
+// Direct 3x3 conv, small Cin (<= 8): thread = (pixel, 8 consecutive output channels).
+template <typename TIn>
+__global__ void conv_small_cin_kernel(const TIn* __restrict__ x, const __half* __restrict__ w,
+                                      const __half* __restrict__ bias, void* __restrict__ y, int y_fp32, int N, int H,
+                                      int W, int Cin, int Cout) {
+  extern __shared__ __half sw[];  // [Cout][9*Cin]
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int co8n = Cout / 8;
+  const long long total = (long long)N * H * W * co8n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % co8n);
+    long long r = i / co8n;
+    const int px = (int)(r % W);
+    r /= W;
+    const int py = (int)(r % H);
+    const int n = (int)(r / H);
+    float in[72];
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      for (int c = 0; c < Cin; ++c)
+        in[tap * Cin + c] = ok ? (float)x[(((long long)n * H + iy) * W + ix) * Cin + c] : 0.f;
+    }
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int co = cg * 8 + o;
+      float a = bias ? __half2float(bias[co]) : 0.f;
+      const __half* wr = sw + co * K;
+      for (int k = 0; k < K; ++k) a = fmaf(in[k], __half2float(wr[k]), a);
+      acc[o] = a;
+    }
+    const long long ob = (((long long)n * H + py) * W + px) * Cout + cg * 8;
+    if (y_fp32) {
+#pragma unroll
+      for (int o = 0; o < 8; ++o) reinterpret_cast<float*>(y)[ob + o] = acc[o];
+    } else {
+      uint4 ov;
+      __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(y) + ob) = ov;
+    }
+  }
+}
+
+// Direct 3x3 conv, small Cout (<= 8): one warp per pixel, lanes split Cin (fp16 input only).
+template <int COUT>
+__global__ void conv_small_cout_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                                       const __half* __restrict__ bias, void* __restrict__ y, int y_fp32, int N, int H,
+                                       int W, int Cin) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)N * H * W;
+  const int K = 9 * Cin;
+  for (long long pix = wid; pix < total; pix += nw) {
+    const int px = (int)(pix % W);
+    const int py = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const __half2* xr = reinterpret_cast<const __half2*>(x + (((long long)n * H + iy) * W + ix) * Cin);
+      for (int c2 = lane; c2 < Cin / 2; c2 += 32) {
+        const float2 xv = __half22float2(xr[c2]);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          const float2 wv = __half22float2(reinterpret_cast<const __half2*>(w + (size_t)o * K + tap * Cin)[c2]);
+          acc[o] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, acc[o]));
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = warp_sum(acc[o]);
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float v = acc[o] + (bias ? __half2float(bias[o]) : 0.f);
+        if (y_fp32)
+          reinterpret_cast<float*>(y)[pix * COUT + o] = v;
+        else
+          reinterpret_cast<__half*>(y)[pix * COUT + o] = __float2half_rn(v);
+      }
+    }
+  }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, __half* __restrict__ out, int n, int dim,
+                                          float max_period) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= n * half) return;
+  const int b = i / half, j = i % half;
+  const float freq = expf(-logf(max_period) * (float)j / (float)half);
+  const float a = t[b] * freq;
+  out[(size_t)b * dim + j] = __float2half_rn(cosf(a));
+  out[(size_t)b * dim + half + j] = __float2half_rn(sinf(a));
+}
+
+// One warp per output column; rows <= 16.
+__global__ void linear_small_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                                    const __half* __restrict__ bias, void* __restrict__ y, int y_fp32, int rows, int N,
+                                    int K, int silu_in) {
+  extern __shared__ float sx[];  // [rows][K]
+  for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
+    float v = __half2float(x[i]);
+    sx[i] = silu_in ? silu(v) : v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (col >= N) return;
+  float acc[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+  const __half2* wr = reinterpret_cast<const __half2*>(w + (size_t)col * K);
+  for (int k2 = lane; k2 < K / 2; k2 += 32) {
+    const float2 wv = __half22float2(wr[k2]);
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r < rows) acc[r] = fmaf(wv.x, sx[r * K + 2 * k2], fmaf(wv.y, sx[r * K + 2 * k2 + 1], acc[r]));
+  }
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    if (r >= rows) break;
+    const float v = warp_sum(acc[r]) + (bias ? __half2float(bias[col]) : 0.f);
+    if (lane == 0) {
+      if (y_fp32)
+        reinterpret_cast<float*>(y)[(size_t)r * N + col] = v;
+      else
+        reinterpret_cast<__half*>(y)[(size_t)r * N + col] = __float2half_rn(v);
+    }
+  }
+}
+
+__global__ void silu_f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2half_rn(silu(x[i]));
+}
+
+inline int ew_grid(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)kNumSMs * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int groupnorm_forward(const __half* x, const __half* gamma, const __half* beta, __half* y, float* stats, int N, int HW,
+                      int C, int groups, float eps, int act_silu, cudaStream_t s) {
+  if (C % 8 || C % groups || (C / groups) % 2) {
+    sdb_set_error("groupnorm: C=%d must be a multiple of 8 with an even group size", C);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  int P, PY, ppb, nblk;
+  gn_geometry(HW, C, N, groups, &P, &PY, &ppb, &nblk);
+  cudaMemsetAsync(stats, 0, sizeof(float) * N * groups * 2, s);
+  gn_reduce_kernel<0><<<dim3(nblk, N), P * PY, sizeof(float) * 2 * P * PY, s>>>(
+      x, nullptr, nullptr, nullptr, nullptr, stats, HW, C, groups, P, PY, ppb, eps, 0);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("gn_stats");
+  const long long total8 = (long long)N * HW * C / 8;
+  gn_apply_kernel<0><<<ew_grid(total8), 256, 0, s>>>(x, nullptr, gamma, beta, stats, nullptr, y, total8, HW, C, groups,
+                                                     eps, act_silu);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("gn_apply");
+  return SDB_OK;
+}
+
+int groupnorm_backward(const __half* x, const __half* gamma, const __half* beta, const float* stats, const __half* dy,
+                       __half* dx, float* scratch2, int N, int HW, int C, int groups, float eps, int act_silu,
+                       cudaStream_t s) {
+  int P, PY, ppb, nblk;
+  gn_geometry(HW, C, N, groups, &P, &PY, &ppb, &nblk);
+  cudaMemsetAsync(scratch2, 0, sizeof(float) * N * groups * 2, s);
+  gn_reduce_kernel<1><<<dim3(nblk, N), P * PY, sizeof(float) * 2 * P * PY, s>>>(x, dy, gamma, beta, stats, scratch2, HW,
+                                                                               C, groups, P, PY, ppb, eps, act_silu);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("gn_bwd_reduce");
+  const long long total8 = (long long)N * HW * C / 8;
+  gn_apply_kernel<1><<<ew_grid(total8), 256, 0, s>>>(x, dy, gamma, beta, stats, scratch2, dx, total8, HW, C, groups,
+                                                     eps, act_silu);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("gn_bwd_apply");
+  return SDB_OK;
+}
+
+int layernorm_forward(const __half* x, const __half* gamma, const __half* beta, __half* y, int rows, int C, float eps,
+                      cudaStream_t s) {
+  layernorm_kernel<<<(rows + 3) / 4, 128, 0, s>>>(x, gamma, beta, y, rows, C, eps);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("layernorm");
+  return SDB_OK;
+}
+
+int softmax_rows(__half* x, long long rows, int cols, long long ld, cudaStream_t s) {
+  if (cols > 4096 || ld > 4096) {
+    sdb_set_error("softmax: at most 4096 columns (got %d, ld %lld)", cols, ld);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  softmax_kernel<<<(unsigned)rows, 128, 0, s>>>(x, cols, ld);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("softmax");
+  return SDB_OK;
+}
+
+int geglu(const __half* xg, __half* y, long long rows, int inner, cudaStream_t s) {
+  geglu_kernel<<<ew_grid(rows * inner / 2), 256, 0, s>>>(xg, y, rows, inner);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("geglu");
+  return SDB_OK;
+}
+
+int silu_f32_to_f16(const float* x, __half* y, long long n, cudaStream_t s) {
+  silu_f32_to_f16_kernel<<<ew_grid(n), 256, 0, s>>>(x, y, n);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("silu");
+  return SDB_OK;
+}
+
+int upsample_nearest2x(const __half* x, __half* y, int N, int H, int W, int C, cudaStream_t s) {
+  upsample2x_kernel<<<ew_grid((long long)N * 4 * H * W * C / 8), 256, 0, s>>>(x, y, N, H, W, C / 8);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("upsample2x");
+  return SDB_OK;
+}
+
+int concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* y, long long rows, cudaStream_t s) {
+  concat_kernel<<<ew_grid(rows * (Ca + Cb) / 8), 256, 0, s>>>(a, Ca / 8, b, Cb / 8, y, rows);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("concat");
+  return SDB_OK;
+}
+
+int add_f16(const __half* a, const __half* b, __half* y, long long n, cudaStream_t s) {
+  add_kernel<<<ew_grid(n / 2), 256, 0, s>>>(a, b, y, n / 2);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("add");
+  return SDB_OK;
+}
+
+int transpose_f16(const __half* x, __half* y, int rows, int cols, cudaStream_t s) {
+  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, s>>>(x, y, rows, cols);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("transpose");
+  return SDB_OK;
+}
+
+int im2col_3x3_s2(const __half* x, __half* col, int N, int H, int W, int C, int pad_lo, cudaStream_t s) {
+  im2col_s2_kernel<<<ew_grid((long long)N * (H / 2) * (W / 2) * 9 * C / 8), 256, 0, s>>>(x, col, N, H, W, C / 8,
+                                                                                        pad_lo);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("im2col_s2");
+  return SDB_OK;
+}
+
+int col2im_3x3_s2(const __half* col, __half* dx, int N, int H, int W, int C, int pad_lo, cudaStream_t s) {
+  col2im_s2_kernel<<<ew_grid((long long)N * H * W * C / 8), 256, 0, s>>>(col, dx, N, H, W, C / 8, pad_lo);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("col2im_s2");
+  return SDB_OK;
+}
+
+int conv3x3_small(const void* x, int x_fp32, const __half* w, const __half* bias, void* y, int y_fp32, int N, int H,
+                  int W, int Cin, int Cout, cudaStream_t s) {
+  if (Cin <= 8 && Cout % 8 == 0) {
+    const size_t smem = sizeof(__half) * Cout * 9 * Cin;
+    const long long total = (long long)N * H * W * (Cout / 8);
+    if (x_fp32)
+      conv_small_cin_kernel<float><<<ew_grid(total, 128), 128, smem, s>>>(reinterpret_cast<const float*>(x), w, bias, y,
+                                                                          y_fp32, N, H, W, Cin, Cout);
+    else
+      conv_small_cin_kernel<__half><<<ew_grid(total, 128), 128, smem, s>>>(reinterpret_cast<const __half*>(x), w, bias,
+                                                                           y, y_fp32, N, H, W, Cin, Cout);
+  } else if (Cout <= 8 && !x_fp32 && Cin % 2 == 0) {
+    const long long total = (long long)N * H * W;
+    const int grid = ew_grid(total * 32);
+    const __half* xh = reinterpret_cast<const __half*>(x);
+    switch (Cout) {
+      case 3: conv_small_cout_kernel<3><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
+      case 4: conv_small_cout_kernel<4><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
+      case 8: conv_small_cout_kernel<8><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
+      default:
+        sdb_set_error("conv3x3_small: Cout=%d not instantiated", Cout);
+        return SDB_ERR_UNSUPPORTED;
+    }
+  } else {
+    sdb_set_error("conv3x3_small: unsupported Cin=%d Cout=%d", Cin, Cout);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("conv3x3_small");
+  return SDB_OK;
+}
+
+int timestep_embedding(const float* t, __half* out, int n, int dim, float max_period, cudaStream_t s) {
+  timestep_embedding_kernel<<<(n * dim / 2 + 127) / 128, 128, 0, s>>>(t, out, n, dim, max_period);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("timestep_embedding");
+  return SDB_OK;
+}
+
+int linear_small(const __half* x, const __half* w, const __half* bias, void* y, int y_fp32, int rows, int N, int K,
+                 int silu_in, cudaStream_t s) {
+  if (rows > 16 || (K & 1)) {
+    sdb_set_error("linear_small: rows=%d must be <= 16 and K even", rows);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  const size_t smem = sizeof(float) * rows * K;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr = true;
+  }
+  linear_small_kernel<<<(N + 7) / 8, 256, smem, s>>>(x, w, bias, y, y_fp32, rows, N, K, silu_in);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("linear_small");
+  return SDB_OK;
+}
+
+}  // namespace dense

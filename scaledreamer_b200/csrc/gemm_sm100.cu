@@ -1,0 +1,496 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+// One CTA computes a 128 x BN tile of D = A * B^T with fp16 operands and fp32 accumulation in tensor memory:
+//   warp 0   : TMA producer   (cp.async.bulk.tensor into a ring of 128-byte-swizzled K-major smem tiles)
+//   warp 1   : MMA issuer     (one elected thread issues tcgen05.mma 128xBNx16, commits stages back to the ring)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue       (tcgen05.ld accumulator rows -> bias / timestep-embedding / activation / residual
+//                              -> fp16 or fp32 global stores)
+// The A operand is addressed through the tensor map in one of three ways (dense.h::OperandMode): a plain
+// (batched) matrix, an NHWC activation read as shifted 4-D boxes (the 9 taps of a 3x3 convolution, zero
+// padding supplied by TMA out-of-bounds fill), or a per-head view of a [B, L, heads*64] tensor.
+//
+// Replaces on the reference path: cuDNN convolutions and cuBLAS GEMMs reached through
+// extern/mvdream/ldm/modules/diffusionmodules/openaimodel.py:255-275 (ResBlock), ldm/modules/attention.py:163-194
+// (CrossAttention), ldm/modules/diffusionmodules/model.py:129-203 (VAE ResnetBlock / AttnBlock) and their
+// diffusers equivalents (stable_diffusion_asd_guidance.py:170-178, 318-331).
+#include <cstdio>
+#include <cstring>
+
+#include "dense.h"
+#include "ptx_sm100.cuh"
+
+namespace dense {
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;               // 64 fp16 = 128 bytes = one swizzle row
+constexpr int kATileBytes = kBM * kBK * 2;
+constexpr int kThreads = 256;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBTileBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = BN <= 64 ? 6 : (BN <= 128 ? 4 : 4);
+  static constexpr int kTmemCols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void load_operand(const CUtensorMap* tm, const OperandGeom& g, void* smem, uint64_t* bar,
+                                             int kb, int r0, int z) {
+  if (g.mode == kMatrix) {
+    ptx::tma_load_3d(smem, tm, bar, kb * kBK, r0, g.batched ? z : 0);
+  } else if (g.mode == kHeads) {
+    if (g.mn_major)  // tile = [64 K-rows (sequence)][64 MN (head dim)]
+      ptx::tma_load_4d(smem, tm, bar, 0, z % g.heads, kb * kBK, z / g.heads);
+    else
+      ptx::tma_load_4d(smem, tm, bar, kb * kBK, z % g.heads, r0, z / g.heads);
+  } else {  // kConv3x3
+    const int tap = kb / g.cin_blocks, cb = kb - tap * g.cin_blocks;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int hw = g.H * g.W;
+    const int n0 = r0 / hw, rem = r0 - n0 * hw;
+    const int h0 = rem / g.W, w0 = rem - h0 * g.W;
+    ptx::tma_load_4d(smem, tm, bar, cb * kBK, w0 + dx, h0 + dy, n0);
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + C::kStages * C::kStageBytes);
+  uint64_t* empty = full + C::kStages;
+  uint64_t* accum_full = empty + C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN, z = blockIdx.z;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < C::kStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(accum_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nkb = p.num_k_blocks;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % C::kStages;
+        const uint32_t ph = (kb / C::kStages) & 1;
+        ptx::mbar_wait(&empty[s], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+        uint8_t* sa = base + s * C::kStageBytes;
+        load_operand(&tmA, p.a, sa, &full[s], kb, m0, z);
+        load_operand(&tmB, p.b, sa + kATileBytes, &full[s], kb, n0, z);
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc_f16(kBM, BN, 0, 0, p.b.mn_major);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % C::kStages;
+        const uint32_t ph = (kb / C::kStages) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(base + s * C::kStageBytes);
+        const uint32_t sb = sa + kATileBytes;
+        const uint64_t da = ptx::smem_desc_k_sw128(sa);
+        const uint64_t db = p.b.mn_major ? ptx::smem_desc_mn_sw128(sb, 8192) : ptx::smem_desc_k_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // K-major: 16 elements = 32 bytes further along the swizzled row; MN-major: 16 K-rows = 2048 bytes
+          const uint64_t a_adv = (uint64_t)((k * 32) >> 4);
+          const uint64_t b_adv = p.b.mn_major ? (uint64_t)((k * 2048) >> 4) : (uint64_t)((k * 32) >> 4);
+          ptx::umma_f16(tmem_base, da + a_adv, db + b_adv, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[s]);
+      }
+      ptx::umma_commit(accum_full);
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    ptx::mbar_wait(accum_full, 0);
+    ptx::tc_fence_after();
+    const int m = m0 + wq * 32 + lane;
+    const bool m_ok = m < p.M;
+    const long long zoff = (long long)(z / p.out_zdiv) * p.out_zs_hi + (long long)(z % p.out_zdiv) * p.out_zs_lo;
+    const float* rowb = p.rowbias ? p.rowbias + (long long)(m_ok ? m / p.rows_per_group : 0) * p.N : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, v);
+      ptx::tmem_ld_wait();
+      const int nb = n0 + c;
+      if (!m_ok || nb >= p.N) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+      const bool full_chunk = nb + 32 <= p.N;
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full_chunk || nb + j < p.N) f[j] += __half2float(__ldg(p.bias + nb + j));
+      }
+      if (rowb) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full_chunk || nb + j < p.N) f[j] += __ldg(rowb + nb + j);
+      }
+      if (p.act == kActSilu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+      } else if (p.act == kActGelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
+      }
+      if (p.residual) {
+        const __half* r = p.residual + (long long)m * p.ldr + nb;
+        if (full_chunk && (p.ldr & 7) == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r) + q);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = __half22float2(h2[e]);
+              f[q * 8 + 2 * e] += t.x;
+              f[q * 8 + 2 * e + 1] += t.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) f[j] += __half2float(__ldg(r + j));
+        }
+      }
+      if (p.out_fp32) {
+        float* o = reinterpret_cast<float*>(p.out) + zoff + (long long)m * p.ldc + nb;
+        if (full_chunk && (p.ldc & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) o[j] = f[j];
+        }
+      } else {
+        __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc + nb;
+        if (full_chunk && (p.ldc & 7) == 0 && (zoff & 7) == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 ov;
+            __half2* h2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
+            reinterpret_cast<uint4*>(o)[q] = ov;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) o[j] = __float2half_rn(f[j]);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+template <int BN>
+int launch(const GemmPlan& plan, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) {
+      sdb_set_error("gemm: smem attribute: %s", cudaGetErrorString(e));
+      return SDB_ERR_CUDA;
+    }
+    attr = true;
+  }
+  gemm_f16_kernel<BN><<<plan.grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(plan.ta, plan.tb, plan.p);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("gemm_f16");
+  return SDB_OK;
+}
+
+int pick_bn(int N) {
+  if (N % 160 == 0) return 160;
+  if (N <= 64) return 64;
+  return 128;
+}
+
+void fill_epilogue(GemmParams& p, const Epilogue& ep) {
+  p.out = ep.out;
+  p.out_fp32 = ep.out_fp32;
+  p.ldc = ep.ldc;
+  p.out_zdiv = 1;
+  p.out_zs_hi = 0;
+  p.out_zs_lo = 0;
+  p.bias = ep.bias;
+  p.rowbias = ep.rowbias;
+  p.rows_per_group = ep.rows_per_group > 0 ? ep.rows_per_group : 1;
+  p.residual = ep.residual;
+  p.ldr = ep.ldr;
+  p.alpha = ep.alpha;
+  p.act = ep.act;
+}
+
+}  // namespace
+
+int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    sdb_set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    return SDB_ERR_CUDA;
+  }
+  cuuint64_t d[5];
+  cuuint64_t st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+    if (i > 0) st[i - 1] = strides_bytes[i - 1];
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) {
+    sdb_set_error("tensor map: base pointer must be 16-byte aligned");
+    return SDB_ERR_ARG;
+  }
+  for (int i = 0; i + 1 < rank; ++i)
+    if (st[i] % 16 != 0) {
+      sdb_set_error("tensor map: stride %d (%llu bytes) must be a multiple of 16", i, (unsigned long long)st[i]);
+      return SDB_ERR_ARG;
+    }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, b, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sdb_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)", (int)r,
+                  rank, (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)(rank > 2 ? d[2] : 0),
+                  b[0], b[1], rank > 2 ? b[2] : 0);
+    return SDB_ERR_CUDA;
+  }
+  return SDB_OK;
+}
+
+int plan_gemm(GemmPlan* plan, const __half* A, long long lda, const __half* B, long long ldb, int M, int N, int K,
+              const Epilogue& ep, int batch, long long a_zs, long long b_zs, long long out_zs) {
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0 || (lda & 7) || (ldb & 7) || (a_zs & 7) || (b_zs & 7)) {
+    sdb_set_error("gemm: bad shape M=%d N=%d K=%d batch=%d lda=%lld ldb=%lld (leading dims must be multiples of 8)", M,
+                  N, K, batch, lda, ldb);
+    return SDB_ERR_ARG;
+  }
+  memset(plan, 0, sizeof(*plan));
+  plan->bn = pick_bn(N);
+  GemmParams& p = plan->p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_k_blocks = (K + kBK - 1) / kBK;
+  p.a.mode = kMatrix;
+  p.a.batched = batch > 1 && a_zs != 0;
+  p.b.mode = kMatrix;
+  p.b.batched = batch > 1 && b_zs != 0;
+  fill_epilogue(p, ep);
+  p.out_zs_hi = out_zs;
+  uint64_t da[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(p.a.batched ? batch : 1)};
+  uint64_t sa[2] = {(uint64_t)lda * 2, (uint64_t)(p.a.batched ? a_zs : (long long)M * lda) * 2};
+  uint32_t ba[3] = {kBK, kBM, 1};
+  int rc = make_tmap(&plan->ta, A, 3, da, sa, ba);
+  if (rc) return rc;
+  uint64_t db[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)(p.b.batched ? batch : 1)};
+  uint64_t sb[2] = {(uint64_t)ldb * 2, (uint64_t)(p.b.batched ? b_zs : (long long)N * ldb) * 2};
+  uint32_t bb[3] = {kBK, (uint32_t)plan->bn, 1};
+  rc = make_tmap(&plan->tb, B, 3, db, sb, bb);
+  if (rc) return rc;
+  plan->grid = dim3((M + kBM - 1) / kBM, (N + plan->bn - 1) / plan->bn, batch);
+  return SDB_OK;
+}
+
+int plan_conv3x3(GemmPlan* plan, const __half* x, int N, int H, int W, int Cin, const __half* w, int Cout,
+                 const Epilogue& ep) {
+  if (Cin % kBK != 0) {
+    sdb_set_error("conv3x3: Cin=%d must be a multiple of %d for the tensor-core path", Cin, kBK);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  int bw, bh, bn;
+  if (W >= kBM) {
+    if (W % kBM) {
+      sdb_set_error("conv3x3: W=%d must be a multiple of %d", W, kBM);
+      return SDB_ERR_UNSUPPORTED;
+    }
+    bw = kBM, bh = 1, bn = 1;
+  } else {
+    if (kBM % W) {
+      sdb_set_error("conv3x3: W=%d must divide %d", W, kBM);
+      return SDB_ERR_UNSUPPORTED;
+    }
+    bw = W;
+    if (H * W >= kBM) {
+      bh = kBM / W, bn = 1;
+      if (H % bh) {
+        sdb_set_error("conv3x3: H=%d must be a multiple of %d", H, bh);
+        return SDB_ERR_UNSUPPORTED;
+      }
+    } else {
+      if (kBM % (H * W)) {
+        sdb_set_error("conv3x3: H*W=%d must divide %d", H * W, kBM);
+        return SDB_ERR_UNSUPPORTED;
+      }
+      bh = H, bn = kBM / (H * W);
+    }
+  }
+  memset(plan, 0, sizeof(*plan));
+  plan->bn = pick_bn(Cout);
+  GemmParams& p = plan->p;
+  p.M = N * H * W;
+  p.N = Cout;
+  p.K = 9 * Cin;
+  p.num_k_blocks = 9 * (Cin / kBK);
+  p.a.mode = kConv3x3;
+  p.a.W = W;
+  p.a.H = H;
+  p.a.bw = bw;
+  p.a.bh = bh;
+  p.a.bn = bn;
+  p.a.cin_blocks = Cin / kBK;
+  p.b.mode = kMatrix;
+  fill_epilogue(p, ep);
+  uint64_t da[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t sa[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  uint32_t ba[4] = {kBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  int rc = make_tmap(&plan->ta, x, 4, da, sa, ba);
+  if (rc) return rc;
+  uint64_t db[3] = {(uint64_t)p.K, (uint64_t)Cout, 1};
+  uint64_t sb[2] = {(uint64_t)p.K * 2, (uint64_t)Cout * p.K * 2};
+  uint32_t bb[3] = {kBK, (uint32_t)plan->bn, 1};
+  rc = make_tmap(&plan->tb, w, 3, db, sb, bb);
+  if (rc) return rc;
+  plan->grid = dim3((p.M + kBM - 1) / kBM, (Cout + plan->bn - 1) / plan->bn, 1);
+  return SDB_OK;
+}
+
+int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __half* K, long long ldk, int B, int heads,
+                     int Lq, int Lk, __half* S, long long lds, float alpha) {
+  memset(plan, 0, sizeof(*plan));
+  plan->bn = Lk <= 80 ? 80 : 128;
+  GemmParams& p = plan->p;
+  p.M = Lq;
+  p.N = Lk;
+  p.K = 64;
+  p.num_k_blocks = 1;
+  p.a.mode = kHeads;
+  p.a.heads = heads;
+  p.b.mode = kHeads;
+  p.b.heads = heads;
+  Epilogue ep;
+  ep.out = S;
+  ep.ldc = lds;
+  ep.alpha = alpha;
+  fill_epilogue(p, ep);
+  p.out_zs_hi = (long long)Lq * lds;  // S is [B*heads, Lq, lds]
+  uint64_t dq[4] = {64, (uint64_t)heads, (uint64_t)Lq, (uint64_t)B};
+  uint64_t sq[3] = {128, (uint64_t)ldq * 2, (uint64_t)Lq * ldq * 2};
+  uint32_t bq[4] = {64, 1, kBM, 1};
+  int rc = make_tmap(&plan->ta, Q, 4, dq, sq, bq);
+  if (rc) return rc;
+  uint64_t dk[4] = {64, (uint64_t)heads, (uint64_t)Lk, (uint64_t)B};
+  uint64_t sk[3] = {128, (uint64_t)ldk * 2, (uint64_t)Lk * ldk * 2};
+  uint32_t bk[4] = {64, 1, (uint32_t)plan->bn, 1};
+  rc = make_tmap(&plan->tb, K, 4, dk, sk, bk);
+  if (rc) return rc;
+  plan->grid = dim3((Lq + kBM - 1) / kBM, (Lk + plan->bn - 1) / plan->bn, B * heads);
+  return SDB_OK;
+}
+
+int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half* V, long long ldv, int B, int heads,
+                    int Lq, int Lk, __half* O, long long ldo) {
+  memset(plan, 0, sizeof(*plan));
+  plan->bn = 64;
+  GemmParams& p = plan->p;
+  p.M = Lq;
+  p.N = 64;
+  p.K = Lk;
+  p.num_k_blocks = (Lk + kBK - 1) / kBK;
+  p.a.mode = kMatrix;
+  p.a.batched = 1;
+  p.b.mode = kHeads;
+  p.b.heads = heads;
+  p.b.mn_major = 1;
+  Epilogue ep;
+  ep.out = O;
+  ep.ldc = ldo;
+  fill_epilogue(p, ep);
+  p.out_zdiv = heads;
+  p.out_zs_hi = (long long)Lq * ldo;
+  p.out_zs_lo = 64;
+  uint64_t dp[3] = {(uint64_t)Lk, (uint64_t)Lq, (uint64_t)B * heads};
+  uint64_t sp[2] = {(uint64_t)ldp * 2, (uint64_t)Lq * ldp * 2};
+  uint32_t bp[3] = {kBK, kBM, 1};
+  int rc = make_tmap(&plan->ta, P, 3, dp, sp, bp);
+  if (rc) return rc;
+  uint64_t dv[4] = {64, (uint64_t)heads, (uint64_t)Lk, (uint64_t)B};
+  uint64_t sv[3] = {128, (uint64_t)ldv * 2, (uint64_t)Lk * ldv * 2};
+  uint32_t bv[4] = {64, 1, kBK, 1};
+  rc = make_tmap(&plan->tb, V, 4, dv, sv, bv);
+  if (rc) return rc;
+  plan->grid = dim3((Lq + kBM - 1) / kBM, 1, B * heads);
+  return SDB_OK;
+}
+
+int run_gemm(const GemmPlan& plan, cudaStream_t stream) {
+  switch (plan.bn) {
+    case 64: return launch<64>(plan, stream);
+    case 80: return launch<80>(plan, stream);
+    case 128: return launch<128>(plan, stream);
+    case 160: return launch<160>(plan, stream);
+  }
+  sdb_set_error("gemm: unsupported BN %d", plan.bn);
+  return SDB_ERR_UNSUPPORTED;
+}
+
+}  // namespace dense

@@ -47,6 +47,14 @@ class PackedSamplesC(C.Structure):
                 ("rgb", C.c_void_p), ("normal", C.c_void_p)]
 
 
+class GemmArgsC(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_longlong), ("B", C.c_void_p), ("ldb", C.c_longlong),
+                ("out", C.c_void_p), ("ldc", C.c_longlong), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rows_per_group", C.c_int), ("residual", C.c_void_p),
+                ("ldr", C.c_longlong), ("alpha", C.c_float), ("act", C.c_int), ("out_fp32", C.c_int),
+                ("batch", C.c_int), ("a_zs", C.c_longlong), ("b_zs", C.c_longlong), ("out_zs", C.c_longlong)]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -85,6 +93,18 @@ SIGNATURES = {
                                  _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "sdb_raygen": [_P, _P, _I, _I, _I, _P, _P, _P],
     "sdb_adamw_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
+    # ---- include/sdb200_nn.h
+    "sdb_gemm_f16": [C.POINTER(GemmArgsC), _P],
+    "sdb_conv3x3_f16": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P],
+    "sdb_conv3x3_small": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "sdb_attention_f16": [_P, _LL, _P, _LL, _P, _LL, _I, _I, _I, _I, _P, _P, _LL, _P],
+    "sdb_groupnorm_f16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
+    "sdb_groupnorm_backward_f16": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
+    "sdb_layernorm_f16": [_P, _P, _P, _P, _I, _I, _F, _P],
+    "sdb_geglu_f16": [_P, _P, _LL, _I, _P],
+    "sdb_upsample2x_f16": [_P, _P, _I, _I, _I, _I, _P],
+    "sdb_im2col3x3s2_f16": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "sdb_col2im3x3s2_f16": [_P, _P, _I, _I, _I, _I, _I, _P],
 }
 
 

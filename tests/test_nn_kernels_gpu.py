@@ -1,0 +1,156 @@
+"""GPU parity of the dense kernels (through the C ABI) against plain fp32 PyTorch on the same fp16-rounded inputs.
+
+Tolerances: operands are fp16 with fp32 accumulation, so against an fp32 reference computed from the SAME
+fp16-rounded inputs the only error is the final fp16 rounding of the output (2^-11 relative) plus accumulation
+order; relative-L2 bounds of 1e-3 are used throughout.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def rnd(*shape, dev, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).half().to(dev)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 320, 320), (300, 200, 136), (4096, 1280, 2560),
+                                   (77, 640, 1024), (5, 64, 72)])
+def test_gemm_plain(cuda_device, M, N, K):
+    from scaledreamer_b200 import nn_ops as O
+
+    a, b = rnd(M, K, dev=cuda_device, seed=1), rnd(N, K, dev=cuda_device, seed=2)
+    out = O.gemm(a, b)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().T
+    assert rel(out, ref) < 1e-3
+
+
+def test_gemm_epilogue_and_fp32_out(cuda_device):
+    from scaledreamer_b200 import nn_ops as O
+
+    M, N, K = 512, 320, 640
+    a, b = rnd(M, K, dev=cuda_device, seed=1, scale=0.5), rnd(N, K, dev=cuda_device, seed=2, scale=0.1)
+    bias, res = rnd(N, dev=cuda_device, seed=3), rnd(M, N, dev=cuda_device, seed=4)
+    rowbias = torch.randn(4, N, device=cuda_device)
+    ref = a.float() @ b.float().T * 0.7 + bias.float() + rowbias.repeat_interleave(128, 0)
+    out = O.gemm(a, b, bias=bias, rowbias=rowbias, rows_per_group=128, residual=res, alpha=0.7, act="silu", out_fp32=True)
+    assert rel(out, F.silu(ref) + res.float()) < 1e-4
+    out = O.gemm(a, b, bias=bias, act="gelu")
+    assert rel(out, F.gelu(a.float() @ b.float().T + bias.float())) < 1e-3
+
+
+def test_gemm_batched(cuda_device):
+    from scaledreamer_b200 import nn_ops as O
+
+    a, b = rnd(6, 200, 128, dev=cuda_device, seed=1), rnd(6, 96, 128, dev=cuda_device, seed=2)
+    out = O.gemm(a, b)
+    assert rel(out, torch.einsum("zmk,znk->zmn", a.float(), b.float())) < 1e-3
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(1, 16, 16, 64, 128), (2, 32, 32, 128, 320), (5, 8, 8, 320, 320),
+                                            (3, 4, 4, 128, 64), (1, 128, 128, 64, 128), (1, 256, 256, 128, 128)])
+def test_conv3x3(cuda_device, N, H, W, Cin, Cout):
+    from scaledreamer_b200 import nn_ops as O
+
+    x = rnd(N, H, W, Cin, dev=cuda_device, seed=1)
+    w = rnd(Cout, 3, 3, Cin, dev=cuda_device, seed=2, scale=1 / math.sqrt(9 * Cin))
+    bias = rnd(Cout, dev=cuda_device, seed=3)
+    rowbias = torch.randn(N, Cout, device=cuda_device)
+    res = rnd(N, H, W, Cout, dev=cuda_device, seed=5)
+    out = O.conv3x3(x, w, bias=bias, rowbias=rowbias, residual=res)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias.float(), padding=1)
+    ref = (ref + rowbias[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
+    assert rel(out, ref) < 1e-3
+
+
+@pytest.mark.parametrize("cin,cout,fp32in", [(3, 128, True), (4, 320, False), (8, 512, False), (320, 4, False),
+                                             (512, 8, False), (128, 3, False)])
+def test_conv3x3_small(cuda_device, cin, cout, fp32in):
+    from scaledreamer_b200 import nn_ops as O
+
+    x = rnd(2, 12, 20, cin, dev=cuda_device, seed=1)
+    if fp32in:
+        x = x.float()
+    w = rnd(cout, 3, 3, cin, dev=cuda_device, seed=2, scale=0.1)
+    bias = rnd(cout, dev=cuda_device, seed=3)
+    out = O.conv3x3_small(x, w, bias, out_fp32=True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias.float(), padding=1)
+    assert rel(out, ref.permute(0, 2, 3, 1)) < 1e-4
+
+
+@pytest.mark.parametrize("B,heads,Lq,Lk", [(2, 5, 256, 256), (3, 10, 64, 77), (1, 1, 128, 1024), (2, 20, 16, 77),
+                                           (1, 5, 4096, 4096)])
+def test_attention(cuda_device, B, heads, Lq, Lk):
+    from scaledreamer_b200 import nn_ops as O
+
+    q = rnd(B, Lq, heads * 64, dev=cuda_device, seed=1)
+    k = rnd(B, Lk, heads * 64, dev=cuda_device, seed=2)
+    v = rnd(B, Lk, heads * 64, dev=cuda_device, seed=3)
+    out = O.attention(q, k, v, heads)
+    sp = lambda t, L: t.float().view(B, L, heads, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(q, Lq), sp(k, Lk), sp(v, Lk)).transpose(1, 2).reshape(B, Lq, heads * 64)
+    assert rel(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("N,HW,C,silu", [(2, 64, 320, True), (1, 4096, 128, True), (3, 256, 1920, False),
+                                         (2, 16, 2560, True), (1, 1024, 512, True)])
+def test_groupnorm_forward_backward(cuda_device, N, HW, C, silu):
+    from scaledreamer_b200 import nn_ops as O
+
+    x = (rnd(N, HW, C, dev=cuda_device, seed=1) + 0.3)
+    gamma, beta = rnd(C, dev=cuda_device, seed=2) * 0.2 + 1, rnd(C, dev=cuda_device, seed=3) * 0.2
+    y, stats = O.groupnorm(x, gamma, beta, 32, 1e-5, silu)
+    xr = x.float().transpose(1, 2).requires_grad_(True)
+    ref = F.group_norm(xr, 32, gamma.float(), beta.float(), 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    assert rel(y, ref.transpose(1, 2)) < 1e-3
+    dy = rnd(N, HW, C, dev=cuda_device, seed=4)
+    ref.backward(dy.float().transpose(1, 2))
+    dx = O.groupnorm_backward(x, gamma, beta, stats, dy, 32, 1e-5, silu)
+    assert rel(dx, xr.grad.transpose(1, 2)) < 2e-3
+
+
+def test_layernorm_geglu_upsample(cuda_device):
+    from scaledreamer_b200 import nn_ops as O
+
+    x = rnd(300, 640, dev=cuda_device, seed=1)
+    g, b = rnd(640, dev=cuda_device, seed=2), rnd(640, dev=cuda_device, seed=3)
+    assert rel(O.layernorm(x, g, b), F.layer_norm(x.float(), (640,), g.float(), b.float())) < 1e-3
+    xg = rnd(100, 2 * 1280, dev=cuda_device, seed=4)
+    a, gate = xg.float().chunk(2, -1)
+    assert rel(O.geglu(xg), a * F.gelu(gate)) < 1e-3
+    im = rnd(2, 8, 8, 64, dev=cuda_device, seed=5)
+    up = F.interpolate(im.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(O.upsample2x(im).float(), up)
+
+
+@pytest.mark.parametrize("pad_lo", [0, 1])
+def test_strided_conv_via_im2col_and_its_dgrad(cuda_device, pad_lo):
+    from scaledreamer_b200 import nn_ops as O
+
+    N, H, W, Cin, Cout = 2, 16, 16, 64, 128
+    x = rnd(N, H, W, Cin, dev=cuda_device, seed=1)
+    w = rnd(Cout, 3, 3, Cin, dev=cuda_device, seed=2, scale=0.05)
+    col = O.im2col3x3s2(x, pad_lo)
+    out = O.gemm(col.view(-1, 9 * Cin), w.view(Cout, -1)).view(N, H // 2, W // 2, Cout)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    xp = xr if pad_lo else F.pad(xr, (0, 1, 0, 1))
+    ref = F.conv2d(xp, w.float().permute(0, 3, 1, 2), stride=2, padding=pad_lo)
+    assert rel(out, ref.permute(0, 2, 3, 1)) < 1e-3
+    dy = rnd(N, H // 2, W // 2, Cout, dev=cuda_device, seed=3)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    wt = w.view(Cout, 9 * Cin).t().contiguous()  # [9*Cin, Cout]
+    dcol = O.gemm(dy.view(-1, Cout), wt).view(N, H // 2, W // 2, 9 * Cin)
+    dx = O.col2im3x3s2(dcol, H, W, pad_lo)
+    assert rel(dx, xr.grad.permute(0, 2, 3, 1)) < 2e-3

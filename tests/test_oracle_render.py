@@ -25,7 +25,7 @@ def _encode_scalar(x, table, cfg):
     out = []
     for l in range(cfg.n_levels):
         s = np.float32(m["scale"][l])
-        pos = [np.float32(np.float32(v) * s + np.float32(0.5)) for v in x]
+        pos = [np.float32(np.float64(np.float32(v)) * np.float64(s) + 0.5) for v in x]
         g = [int(math.floor(p)) for p in pos]
         w = [np.float32(p - np.float32(gi)) for p, gi in zip(pos, g)]
         acc = np.zeros(2, np.float64)
