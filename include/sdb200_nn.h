@@ -79,6 +79,61 @@ int sdb_upsample2x_f16(const void* x, void* y, int n, int h, int w, int c, void*
 int sdb_im2col3x3s2_f16(const void* x, void* col, int n, int h, int w, int c, int pad_lo, void* stream);
 int sdb_col2im3x3s2_f16(const void* col, void* dx, int n, int h, int w, int c, int pad_lo, void* stream);
 
+/* ---- network executors -------------------------------------------------------------------------------------
+ * A net is created for a fixed (batch, height, width). Protocol:
+ *   create -> sdb_net_sizes -> caller allocates the two arenas -> sdb_net_bind -> for every parameter reported by
+ *   sdb_net_param: sdb_net_load_param(name, fp16 device tensor in the reported layout) -> sdb_net_finalize ->
+ *   forward / backward any number of times. Parameter names are the reference's state-dict keys
+ *   (extern/mvdream/ldm: "input_blocks.1.0.in_layers.2.weight", "encoder.down.0.block.0.conv1.weight", ...);
+ *   layouts: 3x3 conv [Cout,3,3,Cin] (the reference's [Cout,Cin,3,3] permuted 0,2,3,1), 1x1 conv / linear
+ *   [out,in], vectors [n]. */
+typedef struct sdb_net sdb_net;
+
+typedef struct {
+  int in_channels, out_channels, model_channels;
+  int num_levels;
+  int channel_mult[4];
+  int num_res_blocks;
+  int attn_levels;   /* levels [0, attn_levels) carry a SpatialTransformer */
+  int head_dim;
+  int context_dim, context_len;
+  int camera_dim;    /* 0 = single-view UNetModel; 16 = MultiViewUNetModel camera embedding */
+  int num_frames;    /* 1, or 4 for MVDream (self-attention across the views of one object) */
+} sdb_unet_cfg;
+
+typedef struct {
+  int in_channels, ch, num_levels;
+  int ch_mult[4];
+  int num_res_blocks;
+  int z_channels;
+} sdb_vae_cfg;
+
+/* UNetModel.forward / MultiViewUNetModel.forward (openaimodel.py:777-808, 1175-1213); diffusers
+ * UNet2DConditionModel as called by stable_diffusion_asd_guidance.py:318-331. */
+int sdb_unet_create(const sdb_unet_cfg* cfg, int batch, int height, int width, sdb_net** out);
+/* x fp16 [B,H,W,in_ch]; t fp32 [B]; ctx fp16 [B,context_len,context_dim]; camera fp16 [B,camera_dim] or NULL;
+ * out fp32 [B,H,W,out_ch] */
+int sdb_unet_forward(sdb_net* net, const void* x, const float* t, const void* ctx, const void* camera, float* out,
+                     void* stream);
+
+/* AutoencoderKL.encode up to (not including) quant_conv (ldm/models/autoencoder.py:81-85, model.py:518-543);
+ * diffusers vae.encode as called by stable_diffusion_asd_guidance.py:170-178. */
+int sdb_vae_encoder_create(const sdb_vae_cfg* cfg, int batch, int height, int width, sdb_net** out);
+/* x fp32 [B,H,W,3]; h fp32 [B,H/8,W/8,2*z_channels] */
+int sdb_vae_encoder_forward(sdb_net* net, const float* x, float* h, void* stream);
+/* data gradient of the last forward: d_h fp32 -> d_x fp32 [B,H,W,3] (what autograd computes through the frozen
+ * encoder in the reference's loss.backward()) */
+int sdb_vae_encoder_backward(sdb_net* net, const float* d_h, float* d_x, void* stream);
+
+void sdb_net_destroy(sdb_net* net);
+int sdb_net_sizes(sdb_net* net, long long* weight_bytes, long long* work_bytes);
+int sdb_net_bind(sdb_net* net, void* weights, void* work);
+int sdb_net_num_params(sdb_net* net);
+int sdb_net_param(sdb_net* net, int index, const char** name, int* ndim, int* shape4);
+int sdb_net_load_param(sdb_net* net, const char* name, const void* src, long long numel, void* stream);
+int sdb_net_finalize(sdb_net* net, void* stream);
+int sdb_net_num_launches(sdb_net* net, int backward);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,7 +47,9 @@ def grid_meta(cfg: GridCfg):
     a level is hashed iff res_l^3 exceeds its entries."""
     scales, ress, sizes, offsets, hashed = [], [], [], [], []
     off = 0
-    log2_pls = math.log2(cfg.per_level_scale)
+    # tcnn reads per_level_scale from JSON as a float32; the level scale is evaluated in float64 here and in the
+    # library (csrc/capi_render.cu::resolve_grid) and rounded once to float32 (tcnn itself calls exp2f on device).
+    log2_pls = math.log2(float(np.float32(cfg.per_level_scale)))
     for l in range(cfg.n_levels):
         scale = float(np.float32(2.0 ** (l * log2_pls) * cfg.base_resolution - 1.0))
         res = int(math.ceil(scale)) + 1

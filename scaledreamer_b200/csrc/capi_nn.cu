@@ -58,10 +58,10 @@ int sdb_attention_f16(const void* q, long long ldq, const void* k, long long ldk
   const long long lds = (lk + 7) / 8 * 8;
   GemmPlan ps, pa;
   int rc = plan_attn_scores(&ps, reinterpret_cast<const __half*>(q), ldq, reinterpret_cast<const __half*>(k), ldk, batch,
-                            heads, lq, lk, reinterpret_cast<__half*>(scores), lds, 0.125f);
+                            heads, 64, lq, lk, reinterpret_cast<__half*>(scores), lds, 0.125f);
   if (rc) return rc;
   rc = plan_attn_apply(&pa, reinterpret_cast<const __half*>(scores), lds, reinterpret_cast<const __half*>(v), ldv, batch,
-                       heads, lq, lk, reinterpret_cast<__half*>(out), ldo);
+                       heads, 64, lq, lk, reinterpret_cast<__half*>(out), ldo);
   if (rc) return rc;
   rc = run_gemm(ps, (cudaStream_t)stream);
   if (rc) return rc;

@@ -218,8 +218,8 @@ int sdb_hashgrid_forward(const sdb_grid_cfg* cfg, const float* table, const floa
   int rc = resolve_grid(cfg, &gm);
   if (rc) return rc;
   SDB_CHECK_ARG(gm.n_levels == 16 || gm.n_levels == 4, "hashgrid: n_levels must be 16 or 4");
-  SDB_CHECK_ARG(table && x01 && out && n >= 0, "hashgrid_forward: bad arguments");
   if (n == 0) return SDB_OK;
+  SDB_CHECK_ARG(table && x01 && out && n > 0, "hashgrid_forward: bad arguments");
   return launch_hashgrid_fwd(gm, table, x01, n, out, (cudaStream_t)stream);
 }
 
@@ -229,8 +229,8 @@ int sdb_hashgrid_backward(const sdb_grid_cfg* cfg, const float* x01, const float
   int rc = resolve_grid(cfg, &gm);
   if (rc) return rc;
   SDB_CHECK_ARG(gm.n_levels == 16 || gm.n_levels == 4, "hashgrid: n_levels must be 16 or 4");
-  SDB_CHECK_ARG(x01 && g_out && g_table && n >= 0, "hashgrid_backward: bad arguments");
   if (n == 0) return SDB_OK;
+  SDB_CHECK_ARG(x01 && g_out && g_table && n > 0, "hashgrid_backward: bad arguments");
   return launch_hashgrid_bwd(gm, x01, g_out, n, g_table, (cudaStream_t)stream);
 }
 

@@ -42,6 +42,7 @@ struct GemmParams {
   const __half* bias;
   const float* rowbias;
   int rows_per_group;
+  long long rowbias_ld;
   const __half* residual;
   long long ldr;
   float alpha;
@@ -66,6 +67,7 @@ struct Epilogue {
   const __half* bias = nullptr;
   const float* rowbias = nullptr;
   int rows_per_group = 1;
+  long long rowbias_ld = 0;  // 0 = N
   const __half* residual = nullptr;
   long long ldr = 0;
   float alpha = 1.f;
@@ -80,10 +82,10 @@ int plan_conv3x3(GemmPlan* plan, const __half* x, int N, int H, int W, int Cin, 
                  const Epilogue& ep);
 // S[b,h,Lq,Lk] = alpha * Q_h K_h^T for Q [B,Lq,heads*64] (row stride ldq), K [B,Lk,heads*64] (ldk). S row stride lds.
 int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __half* K, long long ldk, int B, int heads,
-                     int Lq, int Lk, __half* S, long long lds, float alpha);
+                     int head_dim, int Lq, int Lk, __half* S, long long lds, float alpha);
 // O[b,Lq,h*64:(h+1)*64] = P[b,h,Lq,Lk] V_h for V [B,Lk,heads*64] (ldv); O row stride ldo.
 int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half* V, long long ldv, int B, int heads,
-                    int Lq, int Lk, __half* O, long long ldo);
+                    int head_dim, int Lq, int Lk, __half* O, long long ldo, float alpha = 1.f);
 int run_gemm(const GemmPlan& plan, cudaStream_t stream);
 
 // ---- normalisation / element-wise kernels (dense_ops.cu) ------------------------------------------------
@@ -114,5 +116,10 @@ int timestep_embedding(const float* t, __half* out, int n, int dim, float max_pe
 // y[rows, N] (fp32) = act?(x[rows,K]) * w[N,K]^T + bias: tiny-M linear on CUDA cores (time / camera embeddings).
 int linear_small(const __half* x, const __half* w, const __half* bias, void* y, int y_fp32, int rows, int N, int K,
                  int silu_in, cudaStream_t s);
+
+int rotate_w3x3(const __half* w, __half* wr, int Cout, int Cin, cudaStream_t s);  // [Cout,3,3,Cin] -> [Cin,3,3,Cout] flipped
+int softmax_rows_backward(const __half* P, __half* dP, long long rows, int cols, long long ld, float scale,
+                          cudaStream_t s);
+int add_silu_f32_to_f16(const float* a, const float* b, __half* y, long long n, cudaStream_t s);  // silu(a + b?)
 
 }  // namespace dense

@@ -642,6 +642,12 @@ int conv3x3_small(const void* x, int x_fp32, const __half* w, const __half* bias
   if (Cin <= 8 && Cout % 8 == 0) {
     const size_t smem = sizeof(__half) * Cout * 9 * Cin;
     const long long total = (long long)N * H * W * (Cout / 8);
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(conv_small_cin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      cudaFuncSetAttribute(conv_small_cin_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      attr = true;
+    }
     if (x_fp32)
       conv_small_cin_kernel<float><<<ew_grid(total, 128), 128, smem, s>>>(reinterpret_cast<const float*>(x), w, bias, y,
                                                                           y_fp32, N, H, W, Cin, Cout);
@@ -691,6 +697,88 @@ int linear_small(const __half* x, const __half* w, const __half* bias, void* y, 
   linear_small_kernel<<<(N + 7) / 8, 256, smem, s>>>(x, w, bias, y, y_fp32, rows, N, K, silu_in);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("linear_small");
+  return SDB_OK;
+}
+
+}  // namespace dense
+
+// ---- additions used by the network executors -----------------------------------------------------------------
+namespace dense {
+namespace {
+
+// wr[ci, kh, kw, co] = w[co, 2-kh, 2-kw, ci]: weights of the data-gradient convolution.
+__global__ void rotate_w3x3_kernel(const __half* __restrict__ w, __half* __restrict__ wr, int Cout, int Cin) {
+  const long long total = (long long)Cout * 9 * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    long long r = i / Cout;
+    const int tap = (int)(r % 9);
+    const int ci = (int)(r / 9);
+    wr[i] = w[((long long)co * 9 + (8 - tap)) * Cin + ci];
+  }
+}
+
+// dS = P * (dP - sum_j dP_j P_j) * scale, in place on dP. One 128-thread block per row, cols <= 4096.
+__global__ void __launch_bounds__(128) softmax_bwd_kernel(const __half* __restrict__ P, __half* __restrict__ dP,
+                                                          int cols, long long ld, float scale) {
+  __shared__ float red[4];
+  const __half* pr = P + (size_t)blockIdx.x * ld;
+  __half* dr = dP + (size_t)blockIdx.x * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float p[32], d[32];
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = tid + j * 128;
+    p[j] = c < cols ? __half2float(pr[c]) : 0.f;
+    d[j] = c < cols ? __half2float(dr[c]) : 0.f;
+    dot = fmaf(p[j], d[j], dot);
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) red[warp] = dot;
+  __syncthreads();
+  dot = red[0] + red[1] + red[2] + red[3];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = tid + j * 128;
+    if (c < ld && c < 4096) dr[c] = __float2half_rn(c < cols ? p[j] * (d[j] - dot) * scale : 0.f);
+  }
+}
+
+__global__ void add_silu_kernel(const float* __restrict__ a, const float* __restrict__ b, __half* __restrict__ y,
+                                long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = a[i] + (b ? b[i] : 0.f);
+    y[i] = __float2half_rn(v / (1.f + __expf(-v)));
+  }
+}
+
+}  // namespace
+
+int rotate_w3x3(const __half* w, __half* wr, int Cout, int Cin, cudaStream_t s) {
+  rotate_w3x3_kernel<<<ew_grid((long long)Cout * 9 * Cin), 256, 0, s>>>(w, wr, Cout, Cin);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("rotate_w3x3");
+  return SDB_OK;
+}
+
+int softmax_rows_backward(const __half* P, __half* dP, long long rows, int cols, long long ld, float scale,
+                          cudaStream_t s) {
+  if (cols > 4096 || ld > 4096) {
+    sdb_set_error("softmax_backward: at most 4096 columns");
+    return SDB_ERR_UNSUPPORTED;
+  }
+  softmax_bwd_kernel<<<(unsigned)rows, 128, 0, s>>>(P, dP, cols, ld, scale);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("softmax_bwd");
+  return SDB_OK;
+}
+
+int add_silu_f32_to_f16(const float* a, const float* b, __half* y, long long n, cudaStream_t s) {
+  add_silu_kernel<<<ew_grid(n), 256, 0, s>>>(a, b, y, n);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("add_silu");
   return SDB_OK;
 }
 

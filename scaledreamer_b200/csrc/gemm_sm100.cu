@@ -43,7 +43,7 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* tm, const Operan
     ptx::tma_load_3d(smem, tm, bar, kb * kBK, r0, g.batched ? z : 0);
   } else if (g.mode == kHeads) {
     if (g.mn_major)  // tile = [64 K-rows (sequence)][64 MN (head dim)]
-      ptx::tma_load_4d(smem, tm, bar, 0, z % g.heads, kb * kBK, z / g.heads);
+      ptx::tma_load_4d(smem, tm, bar, r0, z % g.heads, kb * kBK, z / g.heads);
     else
       ptx::tma_load_4d(smem, tm, bar, kb * kBK, z % g.heads, r0, z / g.heads);
   } else {  // kConv3x3
@@ -135,7 +135,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int m = m0 + wq * 32 + lane;
     const bool m_ok = m < p.M;
     const long long zoff = (long long)(z / p.out_zdiv) * p.out_zs_hi + (long long)(z % p.out_zdiv) * p.out_zs_lo;
-    const float* rowb = p.rowbias ? p.rowbias + (long long)(m_ok ? m / p.rows_per_group : 0) * p.N : nullptr;
+    const float* rowb = p.rowbias ? p.rowbias + (long long)(m_ok ? m / p.rows_per_group : 0) * p.rowbias_ld : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t v[32];
@@ -272,6 +272,7 @@ void fill_epilogue(GemmParams& p, const Epilogue& ep) {
   p.bias = ep.bias;
   p.rowbias = ep.rowbias;
   p.rows_per_group = ep.rows_per_group > 0 ? ep.rows_per_group : 1;
+  p.rowbias_ld = ep.rowbias_ld > 0 ? ep.rowbias_ld : p.N;
   p.residual = ep.residual;
   p.ldr = ep.ldr;
   p.alpha = ep.alpha;
@@ -415,14 +416,18 @@ int plan_conv3x3(GemmPlan* plan, const __half* x, int N, int H, int W, int Cin, 
 }
 
 int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __half* K, long long ldk, int B, int heads,
-                     int Lq, int Lk, __half* S, long long lds, float alpha) {
+                     int head_dim, int Lq, int Lk, __half* S, long long lds, float alpha) {
+  if (head_dim % 64) {
+    sdb_set_error("attention: head_dim=%d must be a multiple of 64", head_dim);
+    return SDB_ERR_UNSUPPORTED;
+  }
   memset(plan, 0, sizeof(*plan));
   plan->bn = Lk <= 80 ? 80 : 128;
   GemmParams& p = plan->p;
   p.M = Lq;
   p.N = Lk;
-  p.K = 64;
-  p.num_k_blocks = 1;
+  p.K = head_dim;
+  p.num_k_blocks = head_dim / kBK;
   p.a.mode = kHeads;
   p.a.heads = heads;
   p.b.mode = kHeads;
@@ -433,13 +438,13 @@ int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __hal
   ep.alpha = alpha;
   fill_epilogue(p, ep);
   p.out_zs_hi = (long long)Lq * lds;  // S is [B*heads, Lq, lds]
-  uint64_t dq[4] = {64, (uint64_t)heads, (uint64_t)Lq, (uint64_t)B};
-  uint64_t sq[3] = {128, (uint64_t)ldq * 2, (uint64_t)Lq * ldq * 2};
+  uint64_t dq[4] = {(uint64_t)head_dim, (uint64_t)heads, (uint64_t)Lq, (uint64_t)B};
+  uint64_t sq[3] = {(uint64_t)head_dim * 2, (uint64_t)ldq * 2, (uint64_t)Lq * ldq * 2};
   uint32_t bq[4] = {64, 1, kBM, 1};
   int rc = make_tmap(&plan->ta, Q, 4, dq, sq, bq);
   if (rc) return rc;
-  uint64_t dk[4] = {64, (uint64_t)heads, (uint64_t)Lk, (uint64_t)B};
-  uint64_t sk[3] = {128, (uint64_t)ldk * 2, (uint64_t)Lk * ldk * 2};
+  uint64_t dk[4] = {(uint64_t)head_dim, (uint64_t)heads, (uint64_t)Lk, (uint64_t)B};
+  uint64_t sk[3] = {(uint64_t)head_dim * 2, (uint64_t)ldk * 2, (uint64_t)Lk * ldk * 2};
   uint32_t bk[4] = {64, 1, (uint32_t)plan->bn, 1};
   rc = make_tmap(&plan->tb, K, 4, dk, sk, bk);
   if (rc) return rc;
@@ -448,12 +453,16 @@ int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __hal
 }
 
 int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half* V, long long ldv, int B, int heads,
-                    int Lq, int Lk, __half* O, long long ldo) {
+                    int head_dim, int Lq, int Lk, __half* O, long long ldo, float alpha) {
+  if (head_dim % 64) {
+    sdb_set_error("attention: head_dim=%d must be a multiple of 64", head_dim);
+    return SDB_ERR_UNSUPPORTED;
+  }
   memset(plan, 0, sizeof(*plan));
   plan->bn = 64;
   GemmParams& p = plan->p;
   p.M = Lq;
-  p.N = 64;
+  p.N = head_dim;
   p.K = Lk;
   p.num_k_blocks = (Lk + kBK - 1) / kBK;
   p.a.mode = kMatrix;
@@ -464,21 +473,22 @@ int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half
   Epilogue ep;
   ep.out = O;
   ep.ldc = ldo;
+  ep.alpha = alpha;
   fill_epilogue(p, ep);
   p.out_zdiv = heads;
   p.out_zs_hi = (long long)Lq * ldo;
-  p.out_zs_lo = 64;
+  p.out_zs_lo = head_dim;
   uint64_t dp[3] = {(uint64_t)Lk, (uint64_t)Lq, (uint64_t)B * heads};
   uint64_t sp[2] = {(uint64_t)ldp * 2, (uint64_t)Lq * ldp * 2};
   uint32_t bp[3] = {kBK, kBM, 1};
   int rc = make_tmap(&plan->ta, P, 3, dp, sp, bp);
   if (rc) return rc;
-  uint64_t dv[4] = {64, (uint64_t)heads, (uint64_t)Lk, (uint64_t)B};
-  uint64_t sv[3] = {128, (uint64_t)ldv * 2, (uint64_t)Lk * ldv * 2};
+  uint64_t dv[4] = {(uint64_t)head_dim, (uint64_t)heads, (uint64_t)Lk, (uint64_t)B};
+  uint64_t sv[3] = {(uint64_t)head_dim * 2, (uint64_t)ldv * 2, (uint64_t)Lk * ldv * 2};
   uint32_t bv[4] = {64, 1, kBK, 1};
   rc = make_tmap(&plan->tb, V, 4, dv, sv, bv);
   if (rc) return rc;
-  plan->grid = dim3((Lq + kBM - 1) / kBM, 1, B * heads);
+  plan->grid = dim3((Lq + kBM - 1) / kBM, head_dim / 64, B * heads);
   return SDB_OK;
 }
 

@@ -55,6 +55,18 @@ class GemmArgsC(C.Structure):
                 ("batch", C.c_int), ("a_zs", C.c_longlong), ("b_zs", C.c_longlong), ("out_zs", C.c_longlong)]
 
 
+class UNetCfgC(C.Structure):
+    _fields_ = [("in_channels", C.c_int), ("out_channels", C.c_int), ("model_channels", C.c_int),
+                ("num_levels", C.c_int), ("channel_mult", C.c_int * 4), ("num_res_blocks", C.c_int),
+                ("attn_levels", C.c_int), ("head_dim", C.c_int), ("context_dim", C.c_int), ("context_len", C.c_int),
+                ("camera_dim", C.c_int), ("num_frames", C.c_int)]
+
+
+class VaeCfgC(C.Structure):
+    _fields_ = [("in_channels", C.c_int), ("ch", C.c_int), ("num_levels", C.c_int), ("ch_mult", C.c_int * 4),
+                ("num_res_blocks", C.c_int), ("z_channels", C.c_int)]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -105,6 +117,19 @@ SIGNATURES = {
     "sdb_upsample2x_f16": [_P, _P, _I, _I, _I, _I, _P],
     "sdb_im2col3x3s2_f16": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sdb_col2im3x3s2_f16": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "sdb_unet_create": [C.POINTER(UNetCfgC), _I, _I, _I, C.POINTER(C.c_void_p)],
+    "sdb_unet_forward": [_P, _P, _P, _P, _P, _P, _P],
+    "sdb_vae_encoder_create": [C.POINTER(VaeCfgC), _I, _I, _I, C.POINTER(C.c_void_p)],
+    "sdb_vae_encoder_forward": [_P, _P, _P, _P],
+    "sdb_vae_encoder_backward": [_P, _P, _P, _P],
+    "sdb_net_destroy": [_P],
+    "sdb_net_sizes": [_P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
+    "sdb_net_bind": [_P, _P, _P],
+    "sdb_net_num_params": [_P],
+    "sdb_net_param": [_P, _I, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "sdb_net_load_param": [_P, C.c_char_p, _P, _LL, _P],
+    "sdb_net_finalize": [_P, _P],
+    "sdb_net_num_launches": [_P, _I],
 }
 
 
@@ -112,7 +137,9 @@ def _declare(lib: C.CDLL) -> None:
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
         fn.argtypes = args
-        if name != "sdb_grid_num_entries":
+        if name == "sdb_net_destroy":
+            fn.restype = None
+        elif name != "sdb_grid_num_entries":
             fn.restype = C.c_int
 
 

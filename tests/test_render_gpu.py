@@ -198,8 +198,9 @@ def test_raygen_parity(cuda_device):
     sc = scene(H=20, W=28, B=3, seed=29)
     o = torch.empty(3, 20, 28, 3, device=cuda_device)
     d = torch.empty_like(o)
-    L.check(L.load().sdb_raygen(L.ptr(sc["c2w"].to(cuda_device)), L.ptr(sc["fovy"].to(cuda_device)), 3, 20, 28,
-                                L.ptr(o), L.ptr(d), L.stream_ptr()), "raygen")
+    c2w, fovy = sc["c2w"].to(cuda_device), sc["fovy"].to(cuda_device)  # keep alive: raw pointers cross the ABI
+    L.check(L.load().sdb_raygen(L.ptr(c2w), L.ptr(fovy), 3, 20, 28, L.ptr(o), L.ptr(d), L.stream_ptr()), "raygen")
+    torch.cuda.synchronize()
     torch.testing.assert_close(o.cpu().reshape(-1, 3), sc["rays_o"], atol=1e-6, rtol=0)
     torch.testing.assert_close(d.cpu().reshape(-1, 3), sc["rays_d"], atol=2e-6, rtol=0)
 
@@ -217,6 +218,8 @@ def test_adamw_matches_torch(cuda_device):
         gr = torch.randn(10007, generator=g)
         ref.grad = gr.clone()
         opt.step()
-        L.check(L.load().sdb_adamw_step(L.ptr(p), L.ptr(gr.to(cuda_device)), L.ptr(m), L.ptr(v), p.numel(), 0.01, 0.0,
+        grd = gr.to(cuda_device)
+        L.check(L.load().sdb_adamw_step(L.ptr(p), L.ptr(grd), L.ptr(m), L.ptr(v), p.numel(), 0.01, 0.0,
                                         0.99, 1e-15, 0.01, step, 1.0, L.stream_ptr()), "adamw")
+        torch.cuda.synchronize()
     torch.testing.assert_close(p.cpu(), ref.detach(), atol=1e-6, rtol=1e-5)
