@@ -1,0 +1,349 @@
+"""Field and renderer plugins of the single-prompt NeRF path (threestudio names, Config keys, attribute names and
+state-dict keys), all evaluated by the fused sm_100a render kernels:
+
+  "implicit-volume"                     threestudio/models/geometry/implicit_volume.py:19
+  "no-material"                         threestudio/models/materials/no_material.py:15
+  "neural-environment-map-background"   threestudio/models/background/neural_environment_map_background.py:15
+  "nerf-volume-renderer"                threestudio/models/renderers/nerf_volume_renderer.py:20
+
+Sub-module attribute names are part of the contract (optimizer groups and checkpoints address
+`geometry.encoding`, `geometry.density_network`, `geometry.feature_network`, `background.encoding`,
+`background.network`; configs/single-prompt_benchmark/asd_sd_nerf.yaml:115-125).
+"""
+from __future__ import annotations
+
+import math
+import random
+from dataclasses import dataclass, field
+from typing import Any, Dict, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import lib as L
+from . import render_ops as R
+from .core import BaseModule, register
+
+DEFAULT_GRID = {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 19,
+                "base_resolution": 16, "per_level_scale": 1.447269237440378}
+DEFAULT_MLP = {"otype": "VanillaMLP", "activation": "ReLU", "output_activation": "none", "n_neurons": 64,
+               "n_hidden_layers": 1}
+
+
+class _GridParams(nn.Module):
+    """Stands where tcnn.Encoding stands: one flat fp32 `params` vector in tcnn's level-major layout,
+    U(-1e-4, 1e-4) initialised (tcnn default)."""
+
+    def __init__(self, n_params: int, seed: int = 1337):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.params = nn.Parameter((torch.rand(n_params, generator=g) * 2 - 1) * 1e-4)
+
+
+class HashGridEncoding(nn.Module):
+    """networks.py:55-64 (TCNNEncoding): `.encoding.params`, n_output_dims = n_levels * n_features_per_level."""
+
+    def __init__(self, n_input_dims: int, config: dict):
+        super().__init__()
+        if config.get("otype") not in ("HashGrid", "Grid"):
+            raise NotImplementedError(f"encoding otype {config.get('otype')} is not implemented by the sm_100a kernels "
+                                      "(HashGrid only)")
+        if n_input_dims != 3:
+            raise NotImplementedError("HashGrid encodings take 3-D inputs")
+        self.grid_cfg = {k: config[k] for k in ("n_levels", "n_features_per_level", "log2_hashmap_size",
+                                                "base_resolution", "per_level_scale")}
+        self.n_input_dims = n_input_dims
+        self.n_output_dims = int(config["n_levels"]) * int(config["n_features_per_level"])
+        self.n_entries = L.grid_num_entries(self.grid_cfg)
+        self.encoding = _GridParams(self.n_entries * int(config["n_features_per_level"]))
+
+    @property
+    def table(self) -> torch.Tensor:
+        return self.encoding.params
+
+    def forward(self, x01: torch.Tensor) -> torch.Tensor:
+        return R.hashgrid_forward(x01.reshape(-1, 3), self.table.detach().view(-1, 2), self.grid_cfg)
+
+
+class VanillaMLP(nn.Module):
+    """networks.py:214-251: bias-free Linear + ReLU stack; keys layers.{0,2,...}.weight."""
+
+    def __init__(self, dim_in: int, dim_out: int, config: dict):
+        super().__init__()
+        if config.get("otype", "VanillaMLP") != "VanillaMLP":
+            raise NotImplementedError(f"network otype {config.get('otype')} is not implemented (VanillaMLP only)")
+        if config.get("output_activation", "none") not in (None, "none"):
+            raise NotImplementedError("VanillaMLP output_activation must be none")
+        self.n_neurons, self.n_hidden_layers = int(config["n_neurons"]), int(config["n_hidden_layers"])
+        layers = [nn.Linear(dim_in, self.n_neurons, bias=False), nn.ReLU(inplace=True)]
+        for _ in range(self.n_hidden_layers - 1):
+            layers += [nn.Linear(self.n_neurons, self.n_neurons, bias=False), nn.ReLU(inplace=True)]
+        layers += [nn.Linear(self.n_neurons, dim_out, bias=False)]
+        self.layers = nn.Sequential(*layers)
+
+    def weights(self):
+        return [m.weight for m in self.layers if isinstance(m, nn.Linear)]
+
+
+@register("implicit-volume")
+class ImplicitVolume(BaseModule):
+    @dataclass
+    class Config(BaseModule.Config):
+        radius: float = 1.0
+        isosurface: bool = True
+        isosurface_method: str = "mt"
+        isosurface_resolution: int = 128
+        isosurface_threshold: Union[float, str] = 25.0
+        isosurface_chunk: int = 0
+        isosurface_coarse_to_fine: bool = True
+        isosurface_deformable_grid: bool = False
+        isosurface_remove_outliers: bool = True
+        isosurface_outlier_n_faces_threshold: Union[int, float] = 0.01
+        n_input_dims: int = 3
+        n_feature_dims: int = 3
+        density_activation: Optional[str] = "softplus"
+        density_bias: Union[float, str] = "blob_magic3d"
+        density_blob_scale: float = 10.0
+        density_blob_std: float = 0.5
+        pos_encoding_config: dict = field(default_factory=lambda: dict(DEFAULT_GRID))
+        mlp_network_config: dict = field(default_factory=lambda: dict(DEFAULT_MLP))
+        normal_type: Optional[str] = "finite_difference"
+        finite_difference_normal_eps: float = 0.01
+        anneal_density_blob_std_config: Optional[dict] = None
+
+    cfg: Config
+
+    def configure(self) -> None:
+        r = self.cfg.radius
+        self.register_buffer("bbox", torch.as_tensor([[-r, -r, -r], [r, r, r]], dtype=torch.float32))
+        self.unbounded = False
+        if self.cfg.n_feature_dims != 3:
+            raise NotImplementedError("the fused renderer evaluates a 3-channel feature network")
+        if self.cfg.normal_type not in (None, "finite_difference"):
+            raise NotImplementedError(f"normal_type {self.cfg.normal_type} is not implemented (finite_difference only)")
+        mlp = self.cfg.mlp_network_config
+        if int(mlp["n_neurons"]) != 64 or int(mlp["n_hidden_layers"]) != 1:
+            raise NotImplementedError("the fused renderer is built for 32-64-{1,3} MLPs (n_neurons 64, 1 hidden layer)")
+        self.encoding = HashGridEncoding(self.cfg.n_input_dims, self.cfg.pos_encoding_config)
+        if self.encoding.n_output_dims != 32:
+            raise NotImplementedError("the fused renderer needs a 32-wide encoding (16 levels x 2 features)")
+        self.density_network = VanillaMLP(32, 1, mlp)
+        self.feature_network = VanillaMLP(32, self.cfg.n_feature_dims, mlp)
+
+    def field_params(self) -> Dict[str, torch.Tensor]:
+        w1d, w2d = self.density_network.weights()
+        w1f, w2f = self.feature_network.weights()
+        return {"table": self.encoding.table, "w1d": w1d, "w2d": w2d, "w1f": w1f, "w2f": w2f}
+
+    def field_spec_kwargs(self) -> dict:
+        return dict(grid=self.encoding.grid_cfg, radius=self.cfg.radius, density_bias=self.cfg.density_bias,
+                    density_blob_scale=self.cfg.density_blob_scale, density_blob_std=self.cfg.density_blob_std,
+                    density_activation=self.cfg.density_activation or "softplus",
+                    fd_eps=self.cfg.finite_difference_normal_eps)
+
+    def _spec(self) -> R.FieldSpec:
+        return R.FieldSpec(bg_grid=self.encoding.grid_cfg, **self.field_spec_kwargs())
+
+    def forward(self, points: torch.Tensor, output_normal: bool = False) -> Dict[str, torch.Tensor]:
+        """implicit_volume.py:109-196 on arbitrary points (no autograd: training gradients flow through the fused
+        renderer; this entry serves occupancy refresh, export and inspection)."""
+        shp = points.shape[:-1]
+        P = {k: v.detach() for k, v in self.field_params().items()}
+        d, f, n = R.field_forward(self._spec(), P, points.reshape(-1, 3), want_features=True, want_normal=output_normal)
+        out = {"density": d.view(*shp, 1), "features": f.view(*shp, 3)}
+        if output_normal:
+            out["normal"] = n.view(*shp, 3)
+            out["shading_normal"] = out["normal"]
+        return out
+
+    def forward_density(self, points: torch.Tensor) -> torch.Tensor:
+        shp = points.shape[:-1]
+        P = {k: v.detach() for k, v in self.field_params().items()}
+        d, _, _ = R.field_forward(self._spec(), P, points.reshape(-1, 3), want_features=False)
+        return d.view(*shp, 1)
+
+
+@register("no-material")
+class NoMaterial(BaseModule):
+    @dataclass
+    class Config(BaseModule.Config):
+        n_output_dims: int = 3
+        color_activation: str = "sigmoid"
+        input_feature_dims: Optional[int] = None
+        mlp_network_config: Optional[dict] = None
+        requires_normal: bool = False
+
+    cfg: Config
+    requires_tangent = False
+
+    def configure(self) -> None:
+        if self.cfg.input_feature_dims is not None and self.cfg.mlp_network_config is not None:
+            raise NotImplementedError("no-material with an MLP head is not implemented by the fused renderer")
+        if self.cfg.color_activation not in R.COLOR_ACTS:
+            raise NotImplementedError(f"color_activation {self.cfg.color_activation} is not implemented")
+        self.requires_normal = self.cfg.requires_normal
+
+    def forward(self, features: torch.Tensor, **kwargs) -> torch.Tensor:
+        x = features.view(-1, self.cfg.n_output_dims)
+        s = torch.sigmoid(x)
+        if self.cfg.color_activation == "sigmoid-mipnerf":
+            s = s * 1.002 - 0.001
+        return s.view(*features.shape[:-1], self.cfg.n_output_dims)
+
+
+@register("neural-environment-map-background")
+class NeuralEnvironmentMapBackground(BaseModule):
+    @dataclass
+    class Config(BaseModule.Config):
+        n_output_dims: int = 3
+        color_activation: str = "sigmoid"
+        dir_encoding_config: dict = field(default_factory=lambda: {"otype": "SphericalHarmonics", "degree": 3})
+        mlp_network_config: dict = field(default_factory=lambda: {"otype": "VanillaMLP", "activation": "ReLU",
+                                                                  "n_neurons": 16, "n_hidden_layers": 2})
+        random_aug: bool = False
+        random_aug_prob: float = 0.5
+        eval_color: Optional[Tuple[float, float, float]] = None
+
+    cfg: Config
+
+    def configure(self) -> None:
+        self.encoding = HashGridEncoding(3, self.cfg.dir_encoding_config)
+        mlp = self.cfg.mlp_network_config
+        if self.encoding.n_output_dims != 8 or int(mlp["n_neurons"]) != 16 or int(mlp["n_hidden_layers"]) != 2:
+            raise NotImplementedError("the fused renderer is built for a 4-level x 2 grid and an 8-16-16-3 MLP")
+        self.network = VanillaMLP(8, self.cfg.n_output_dims, mlp)
+
+    def field_params(self) -> Dict[str, torch.Tensor]:
+        w1, w2, w3 = self.network.weights()
+        return {"bg_table": self.encoding.table, "bg_w1": w1, "bg_w2": w2, "bg_w3": w3}
+
+    def sample_override(self, batch_size: int, device) -> Optional[torch.Tensor]:
+        """Random solid colour with probability random_aug_prob while training (…background.py:56-66): host coin,
+        device colours. The environment map receives no gradient on those steps (color * 0 + rand)."""
+        if self.training and self.cfg.random_aug and random.random() < self.cfg.random_aug_prob:
+            return torch.rand(batch_size, 3, device=device)
+        return None
+
+
+@register("nerf-volume-renderer")
+class NeRFVolumeRenderer(BaseModule):
+    @dataclass
+    class Config(BaseModule.Config):
+        radius: float = 1.0
+        num_samples_per_ray: int = 512
+        eval_chunk_size: int = 160000
+        randomized: bool = True
+        near_plane: float = 0.0
+        far_plane: float = 1e10
+        return_comp_normal: bool = False
+        return_normal_perturb: bool = False
+        estimator: str = "occgrid"
+        grid_prune: bool = True
+        prune_alpha_threshold: bool = True
+        proposal_network_config: Optional[dict] = None
+        prop_optimizer_config: Optional[dict] = None
+        prop_scheduler_config: Optional[dict] = None
+        num_samples_per_ray_proposal: int = 64
+        num_samples_per_ray_importance: int = 64
+
+    cfg: Config
+    OCC_RES = 32
+
+    def configure(self, geometry, material, background) -> None:
+        @dataclass
+        class SubModules:  # kept out of nn.Module registration (renderers/base.py:28-35)
+            geometry: Any
+            material: Any
+            background: Any
+
+        self.sub_modules = SubModules(geometry, material, background)
+        r = self.cfg.radius
+        self.register_buffer("bbox", torch.as_tensor([[-r, -r, -r], [r, r, r]], dtype=torch.float32))
+        if self.cfg.estimator != "occgrid":
+            raise NotImplementedError("Unknown estimator, should be in ['occgrid'] for the fused sm_100a renderer "
+                                      f"(got {self.cfg.estimator})")
+        if self.cfg.return_comp_normal or self.cfg.return_normal_perturb:
+            raise NotImplementedError("comp_normal outputs are not implemented by the fused renderer")
+        self.render_step_size = 1.732 * 2 * self.cfg.radius / self.cfg.num_samples_per_ray
+        self.randomized = self.cfg.randomized
+        self.occ: Optional[R.OccGrid] = None
+        self.packed_capacity = 0  # set > 0 by a system that consumes per-sample outputs
+
+    geometry = property(lambda self: self.sub_modules.geometry)
+    material = property(lambda self: self.sub_modules.material)
+    background = property(lambda self: self.sub_modules.background)
+
+    def _occ_grid(self, device) -> R.OccGrid:
+        if self.occ is None:
+            self.occ = R.OccGrid(self.OCC_RES, device, all_occupied=not self.cfg.grid_prune)
+        return self.occ
+
+    def _spec(self) -> R.FieldSpec:
+        return R.FieldSpec(bg_grid=self.background.encoding.grid_cfg,
+                           color_activation=self.material.cfg.color_activation,
+                           bg_color_activation=self.background.cfg.color_activation,
+                           **self.geometry.field_spec_kwargs())
+
+    def _params(self) -> Dict[str, torch.Tensor]:
+        P = dict(self.geometry.field_params())
+        P.update(self.background.field_params())
+        P["table"] = P["table"].view(-1, 2)
+        P["bg_table"] = P["bg_table"].view(-1, 2)
+        return P
+
+    def forward(self, rays_o, rays_d, light_positions=None, bg_color=None, **kwargs) -> Dict[str, torch.Tensor]:
+        B, H, W = rays_o.shape[:3]
+        dev = rays_o.device
+        n_rays = B * H * W
+        march = R.MarchSpec(render_step_size=self.render_step_size, near_plane=self.cfg.near_plane,
+                            far_plane=self.cfg.far_plane, prune=self.cfg.grid_prune and self.cfg.prune_alpha_threshold,
+                            alpha_thre=0.01, grid_res=self.OCC_RES,
+                            output_normal=bool(self.material.requires_normal and self.packed_capacity > 0))
+        jitter = torch.rand(n_rays, device=dev) if self.randomized else None
+        if bg_color is not None:
+            bg_override = bg_color.to(dev, torch.float32).reshape(-1, 3).expand(B, 3).contiguous()
+        else:
+            bg_override = self.background.sample_override(B, dev)
+        out = R.render_nerf(self._spec(), march, self._occ_grid(dev), self._params(), rays_o.reshape(-1, 3),
+                            rays_d.reshape(-1, 3), jitter, bg_override, H * W, self.packed_capacity)
+        res = {"comp_rgb": out["comp_rgb"].view(B, H, W, 3), "comp_rgb_fg": out["comp_rgb_fg"].view(B, H, W, 3),
+               "comp_rgb_bg": out["comp_rgb_bg"].view(B, H, W, 3), "opacity": out["opacity"].view(B, H, W, 1),
+               "depth": out["depth"].view(B, H, W, 1), "z_variance": out["z_variance"].view(B, H, W, 1)}
+        pk = out.get("packed")
+        if self.training and pk is not None:
+            res.update({"weights": pk["weights"], "t_starts": pk["t_starts"], "t_ends": pk["t_ends"],
+                        "ray_indices": pk["ray_indices"], "density": pk["density"], "n_samples": pk["counter"]})
+            if pk.get("normal") is not None:
+                res["normal"] = pk["normal"]
+        return res
+
+    def update_step(self, epoch: int, global_step: int, on_load_weights: bool = False) -> None:
+        """nerfacc OccGridEstimator.update_every_n_steps(step, occ_eval_fn = sigma * step_size, occ_thre=0.01,
+        ema_decay=0.95, warmup_steps=256, n=16) (nerf_volume_renderer.py:430-444)."""
+        if not (self.cfg.grid_prune and self.training and not on_load_weights) or global_step % 16 != 0:
+            return
+        dev = self.geometry.encoding.table.device
+        occ = self._occ_grid(dev)
+        n_cells = self.OCC_RES ** 3
+        if global_step < 256:
+            idx = torch.arange(n_cells, device=dev, dtype=torch.int32)
+        else:
+            n = n_cells // 4
+            uniform = torch.randint(n_cells, (n,), device=dev)
+            occupied = torch.nonzero(occ.binaries().flatten())[:, 0]
+            if occupied.numel() > n:
+                occupied = occupied[torch.randint(occupied.numel(), (n,), device=dev)]
+            idx = torch.cat([uniform, occupied]).to(torch.int32)
+        P = {k: v.detach() for k, v in self._params().items()}
+        occ.update(self._spec(), P, idx, torch.rand(idx.numel(), 3, device=dev), self.render_step_size)
+
+    def update_step_end(self, epoch: int, global_step: int) -> None:
+        pass
+
+    def train(self, mode=True):
+        self.randomized = mode and self.cfg.randomized
+        return super().train(mode=mode)
+
+    def eval(self):
+        self.randomized = False
+        return super().eval()

@@ -67,6 +67,12 @@ class VaeCfgC(C.Structure):
                 ("num_res_blocks", C.c_int), ("z_channels", C.c_int)]
 
 
+class PromptCfgC(C.Structure):
+    _fields_ = [("view_dependent", C.c_int), ("perp_neg", C.c_int), ("front_threshold", C.c_float),
+                ("back_threshold", C.c_float), ("overhead_threshold", C.c_float), ("f_sb", C.c_float * 3),
+                ("f_fsb", C.c_float * 3), ("f_fs", C.c_float * 3), ("f_sf", C.c_float * 3), ("neg_scale", C.c_float)]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -130,6 +136,13 @@ SIGNATURES = {
     "sdb_net_load_param": [_P, C.c_char_p, _P, _LL, _P],
     "sdb_net_finalize": [_P, _P],
     "sdb_net_num_launches": [_P, _I],
+    # ---- include/sdb200_asd.h
+    "sdb_resize_bilinear_forward": [_P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _P],
+    "sdb_resize_bilinear_backward": [_P, _I, _I, _I, _I, _P, _I, _I, _F, _P],
+    "sdb_asd_text_embeddings": [C.POINTER(PromptCfgC), _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "sdb_asd_prologue": [_P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P],
+    "sdb_asd_epilogue": [_P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P],
+    "sdb_asd_t_plus": [_P, _P, _I, _F, _I, _I, _P, _P],
 }
 
 

@@ -1,0 +1,277 @@
+"""Training system + fit loop for the ASD step (threestudio's "scaledreamer-system" contract without Lightning).
+
+  StableDreamer            threestudio/systems/scaledreamer.py:14-170 (training_step :48-170)
+  BaseLift3DSystem         threestudio/systems/base.py:205-303 (plugin instantiation by registry name)
+  parse_optimizer          threestudio/systems/utils.py:25-53 (per-module parameter groups by dotted path)
+  fit loop hook order      on_train_batch_start -> training_step -> backward -> optimizer step -> on_train_batch_end
+                           (pytorch-lightning 2.0.0 as used by launch.py:233-249; systems/base.py:120-202)
+Data parallelism (launch.py:233-240 -> Lightning DDP): one process per GPU, generator gradients packed in one flat
+buffer and averaged with a single NCCL all-reduce per optimizer step.
+"""
+from __future__ import annotations
+
+import os
+import time
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import core, lib as L
+from .core import C, Updateable, find, parse_structured, register
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+def getattr_recursive(m, attr: str):
+    for name in attr.split("."):
+        m = getattr(m, name)
+    return m
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW / Adam semantics (decoupled weight decay; Adam == weight_decay 0 here), one
+    sdb_adamw_step launch per parameter tensor. `grad_scale` multiplies every gradient (1/world_size after the
+    all-reduce sum)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, **unused):
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        self.grad_scale = 1.0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        lib = L.load()
+        st = L.stream_ptr()
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                state = self.state[p]
+                if not state:
+                    state["step"] = 0
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state["step"] += 1
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                L.check(lib.sdb_adamw_step(L.ptr(p.data), L.ptr(g), L.ptr(state["exp_avg"]), L.ptr(state["exp_avg_sq"]),
+                                           p.numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                           float(group["weight_decay"]), int(state["step"]), float(self.grad_scale), st),
+                        "sdb_adamw_step")
+        return None
+
+
+def parse_optimizer(config: dict, model: nn.Module) -> torch.optim.Optimizer:
+    name = config["name"]
+    args = dict(config.get("args", {}))
+    if "params" in config:
+        params = []
+        for pname, pargs in config["params"].items():
+            mod = getattr_recursive(model, pname)
+            plist = list(mod.parameters()) if isinstance(mod, nn.Module) else ([mod] if isinstance(mod, nn.Parameter) else [])
+            params.append({"params": plist, "name": pname, **pargs})
+    else:
+        params = list(model.parameters())
+    if name in ("AdamW", "Adam"):
+        if name == "Adam":
+            args.setdefault("weight_decay", 0.0)
+        return FusedAdamW(params, **args)
+    if hasattr(torch.optim, name):
+        return getattr(torch.optim, name)(params, **args)
+    raise NotImplementedError(f"optimizer {name}")
+
+
+# ------------------------------------------------------------------------------------------------ system
+def binary_cross_entropy(input, target):
+    """threestudio/utils/ops.py:365-369"""
+    return -(target * torch.log(input) + (1 - target) * torch.log(1 - input)).mean()
+
+
+class BaseSystem(nn.Module, Updateable):
+    @dataclass
+    class Config:
+        loggers: dict = field(default_factory=dict)
+        loss: dict = field(default_factory=dict)
+        optimizer: dict = field(default_factory=dict)
+        scheduler: Optional[dict] = None
+        weights: Optional[str] = None
+        weights_ignore_modules: Optional[List[str]] = None
+        cleanup_after_validation_step: bool = False
+        cleanup_after_test_step: bool = False
+
+    cfg: Config
+
+    def __init__(self, cfg, resumed=False) -> None:
+        super().__init__()
+        self.cfg = parse_structured(self.Config, cfg)
+        self._resumed = resumed
+        self.true_global_step = 0
+        self.true_current_epoch = 0
+        self.logged: Dict[str, Any] = {}
+        self.configure()
+        if self.cfg.weights is not None:
+            sd, epoch, step = core.load_module_weights(self.cfg.weights, ignore_modules=self.cfg.weights_ignore_modules)
+            self.load_state_dict(sd, strict=False)
+            self.do_update_step(epoch, step, on_load_weights=True)
+
+    def configure(self) -> None:
+        pass
+
+    def C(self, value: Any) -> float:
+        return C(value, self.true_current_epoch, self.true_global_step)
+
+    def log(self, name: str, value, **kwargs) -> None:
+        self.logged[name] = value  # device scalars stay on device; the trainer reads them back lazily
+
+    def configure_optimizers(self):
+        return parse_optimizer(self.cfg.optimizer, self)
+
+    def on_fit_start(self) -> None:
+        pass
+
+
+@register("scaledreamer-system")
+class StableDreamer(BaseSystem):
+    @dataclass
+    class Config(BaseSystem.Config):
+        geometry_type: str = ""
+        geometry: dict = field(default_factory=dict)
+        geometry_convert_from: Optional[str] = None
+        geometry_convert_inherit_texture: bool = False
+        geometry_convert_override: dict = field(default_factory=dict)
+        material_type: str = ""
+        material: dict = field(default_factory=dict)
+        background_type: str = ""
+        background: dict = field(default_factory=dict)
+        renderer_type: str = ""
+        renderer: dict = field(default_factory=dict)
+        guidance_type: str = ""
+        guidance: dict = field(default_factory=dict)
+        prompt_processor_type: str = ""
+        prompt_processor: dict = field(default_factory=dict)
+        exporter_type: str = "mesh-exporter"
+        exporter: dict = field(default_factory=dict)
+        stage: str = "coarse"
+        visualize_samples: bool = False
+        validation_via_video: bool = False
+
+    cfg: Config
+
+    def configure(self) -> None:
+        if self.cfg.geometry_convert_from:
+            raise NotImplementedError("geometry_convert_from (coarse -> refine hand-over) is outside the ASD hot path")
+        if self.cfg.stage != "coarse":
+            raise NotImplementedError(f"stage '{self.cfg.stage}' is not implemented (coarse only)")
+        dev = core.get_device()
+        self.geometry = find(self.cfg.geometry_type)(self.cfg.geometry).to(dev)
+        self.material = find(self.cfg.material_type)(self.cfg.material).to(dev)
+        self.background = find(self.cfg.background_type)(self.cfg.background).to(dev)
+        self.renderer = find(self.cfg.renderer_type)(self.cfg.renderer, geometry=self.geometry, material=self.material,
+                                                     background=self.background).to(dev)
+
+    def forward(self, batch: Dict[str, Any]) -> Dict[str, Any]:
+        return {**self.renderer(**batch)}
+
+    def on_fit_start(self) -> None:
+        self.prompt_processor = find(self.cfg.prompt_processor_type)(self.cfg.prompt_processor)
+        self.guidance = find(self.cfg.guidance_type)(self.cfg.guidance)
+        self.prompt_utils = self.prompt_processor()
+
+    def training_step(self, batch, batch_idx):
+        out = self(batch)
+        guidance_out = self.guidance(out["comp_rgb"], self.prompt_utils, **batch, rgb_as_latents=False)
+        loss = 0.0
+        lam = self.cfg.loss
+        for name, value in guidance_out.items():
+            self.log(f"train/{name}", value)
+            if name.startswith("loss_"):
+                loss = loss + value * self.C(lam[name.replace("loss_", "lambda_")])
+        if self.C(lam.get("lambda_orient", 0.0)) > 0:
+            raise NotImplementedError("lambda_orient > 0 needs gradients through finite-difference normals, which the "
+                                      "fused renderer does not provide")
+        if self.C(lam.get("lambda_sparsity", 0.0)) > 0:
+            loss_sparsity = (out["opacity"] ** 2 + 0.01).sqrt().mean()
+            self.log("train/loss_sparsity", loss_sparsity)
+            loss = loss + loss_sparsity * self.C(lam["lambda_sparsity"])
+        if self.C(lam.get("lambda_opaque", 0.0)) > 0:
+            op = out["opacity"].clamp(1.0e-3, 1.0 - 1.0e-3)
+            loss_opaque = binary_cross_entropy(op, op)
+            self.log("train/loss_opaque", loss_opaque)
+            loss = loss + loss_opaque * self.C(lam["lambda_opaque"])
+        if self.C(lam.get("lambda_z_variance", 0.0)) > 0:
+            raise NotImplementedError("lambda_z_variance > 0: z_variance is a non-differentiable output of the fused "
+                                      "renderer")
+        if self.C(lam.get("lambda_eikonal", 0.0)) > 0:
+            raise ValueError("sdf is required for eikonal loss, no sdf is found in the output.")
+        return {"loss": loss}
+
+
+# ------------------------------------------------------------------------------------------------ trainer
+class Trainer:
+    """Minimal fit loop with Lightning's hook order; optional data-parallel gradient averaging over NCCL."""
+
+    def __init__(self, max_steps: int = 1, log_every_n_steps: int = 50, accumulate_grad_batches: int = 1,
+                 distributed: Optional[bool] = None, **unused) -> None:
+        self.max_steps = int(max_steps)
+        self.log_every_n_steps = int(log_every_n_steps)
+        self.accumulate = int(accumulate_grad_batches)
+        import torch.distributed as dist
+
+        self.dist = dist if (distributed if distributed is not None else dist.is_initialized()) else None
+        self.world_size = self.dist.get_world_size() if self.dist else 1
+        self.global_step = 0
+        self.history: List[Dict[str, float]] = []
+        self._flat = None
+
+    def _allreduce_grads(self, params: List[torch.Tensor]) -> None:
+        """One collective per optimizer step on a flat fp32 buffer (replaces DDP's bucketed reducer)."""
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads:
+            return
+        n = sum(g.numel() for g in grads)
+        if self._flat is None or self._flat.numel() != n:
+            self._flat = torch.empty(n, device=grads[0].device, dtype=torch.float32)
+        off = 0
+        for g in grads:
+            self._flat[off:off + g.numel()].copy_(g.reshape(-1))
+            off += g.numel()
+        self.dist.all_reduce(self._flat, op=self.dist.ReduceOp.SUM)
+        off = 0
+        for g in grads:
+            g.copy_(self._flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    def fit(self, system: BaseSystem, datamodule) -> None:
+        device = core.get_device()
+        datamodule.setup("fit")
+        dataset = datamodule.train_dataset
+        loader = datamodule.train_dataloader()
+        system.train()
+        system.on_fit_start()
+        optimizer = system.configure_optimizers()
+        if isinstance(optimizer, FusedAdamW):
+            optimizer.grad_scale = 1.0 / (self.world_size * self.accumulate)
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        micro = 0
+        while self.global_step < self.max_steps:
+            batch = next(loader)
+            # on_train_batch_start (systems/base.py:180-184)
+            dataset.update_step(system.true_current_epoch, system.true_global_step)
+            system.do_update_step(system.true_current_epoch, system.true_global_step)
+            batch = dataset.to_device(batch, device)
+            out = system.training_step(batch, micro)
+            out["loss"].backward()
+            micro += 1
+            if micro % self.accumulate == 0:
+                if self.dist is not None:
+                    self._allreduce_grads(params)
+                optimizer.step()
+                optimizer.zero_grad(set_to_none=False)
+                self.global_step += 1
+                system.true_global_step = self.global_step
+            system.do_update_step_end(system.true_current_epoch, system.true_global_step)
+            if self.log_every_n_steps and self.global_step % self.log_every_n_steps == 0 and micro % self.accumulate == 0:
+                rec = {k: (float(v) if torch.is_tensor(v) else v) for k, v in system.logged.items()}
+                rec["step"] = self.global_step
+                self.history.append(rec)

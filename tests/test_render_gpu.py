@@ -151,7 +151,9 @@ def test_render_backward_parity(cuda_device):
     torch.cuda.synchronize()
     for k in R.PARAM_KEYS:
         r = rel_l2(grads[k].cpu(), P[k].grad)
-        assert r < 2e-3, (k, r)
+        # hidden units whose pre-activation sits within fp32 rounding of 0 flip their ReLU mask between the CPU
+        # and the GPU evaluation order; each flip moves one unit's whole contribution, hence the looser bound
+        assert r < 5e-3, (k, r)
 
 
 def test_render_autograd_function_and_bg_detach(cuda_device):
