@@ -46,6 +46,12 @@ typedef struct {
 } sdb_gemm_args;
 int sdb_gemm_f16(const sdb_gemm_args* args, void* stream);
 
+/* Measurement hooks: between begin and end every tcgen05 GEMM launch of the library is bracketed by CUDA events on
+ * its own stream; end synchronises the device and returns the summed durations, algorithmic FLOPs (2*M*N*K per
+ * launch) and launch count. */
+int sdb_gemm_profile_begin(void);
+int sdb_gemm_profile_end(double* total_ms, double* total_flops, int* launches);
+
 /* 3x3 stride-1 pad-1 convolution as implicit GEMM: x [N,H,W,Cin], w [Cout, 3,3,Cin] (= [Cout, 9*Cin]),
  * out [N,H,W,Cout]; epilogue as sdb_gemm_f16 with rows_per_group = H*W (the per-image timestep-embedding add
  * of ResBlock, openaimodel.py:262-272). Cin % 64 == 0. Replaces conv_nd(...) of openaimodel.py:203,230 and
@@ -64,7 +70,9 @@ int sdb_attention_f16(const void* q, long long ldq, const void* k, long long ldk
                       int batch, int heads, int lq, int lk, void* scores, void* out, long long ldo, void* stream);
 
 /* GroupNorm over [N, HW, C] with optional fused SiLU (GroupNorm32 + SiLU, openaimodel.py:200-203; Normalize +
- * nonlinearity, model.py:129-141). stats: [N, groups, 2] fp32 (sum, sum of squares) written by the forward. */
+ * nonlinearity, model.py:129-141). stats / scratch: fp32 buffers of sdb_groupnorm_workspace_floats() elements; the
+ * first [N, groups, 2] hold (sum, sum of squares), the rest per-block partials of the order-fixed reduction. */
+long long sdb_groupnorm_workspace_floats(int n, int hw, int c, int groups);
 int sdb_groupnorm_f16(const void* x, const void* gamma, const void* beta, void* y, float* stats, int n, int hw,
                       int c, int groups, float eps, int silu, void* stream);
 /* dx of the above given dy; scratch: [N, groups, 2] fp32. */

@@ -70,6 +70,10 @@ int sdb_attention_f16(const void* q, long long ldq, const void* k, long long ldk
   return run_gemm(pa, (cudaStream_t)stream);
 }
 
+long long sdb_groupnorm_workspace_floats(int n, int hw, int c, int groups) {
+  return groupnorm_workspace_floats(n, hw, c, groups);
+}
+
 int sdb_groupnorm_f16(const void* x, const void* gamma, const void* beta, void* y, float* stats, int n, int hw,
                       int c, int groups, float eps, int silu, void* stream) {
   SDB_CHECK_ARG(x && gamma && beta && y && stats, "groupnorm: NULL argument");
@@ -116,6 +120,16 @@ int sdb_col2im3x3s2_f16(const void* col, void* dx, int n, int h, int w, int c, i
   SDB_CHECK_ARG(col && dx, "col2im: NULL argument");
   return col2im_3x3_s2(reinterpret_cast<const __half*>(col), reinterpret_cast<__half*>(dx), n, h, w, c, pad_lo,
                        (cudaStream_t)stream);
+}
+
+int sdb_gemm_profile_begin(void) {
+  profile_begin();
+  return SDB_OK;
+}
+
+int sdb_gemm_profile_end(double* total_ms, double* total_flops, int* launches) {
+  SDB_CHECK_ARG(total_ms && total_flops && launches, "gemm_profile_end: NULL argument");
+  return profile_end(total_ms, total_flops, launches);
 }
 
 }  // extern "C"

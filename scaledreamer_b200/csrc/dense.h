@@ -87,9 +87,15 @@ int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __hal
 int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half* V, long long ldv, int B, int heads,
                     int head_dim, int Lq, int Lk, __half* O, long long ldo, float alpha = 1.f);
 int run_gemm(const GemmPlan& plan, cudaStream_t stream);
+// per-launch CUDA-event timing of every tcgen05 GEMM launched between begin and end (bench.py roofline)
+void profile_begin();
+int profile_end(double* ms, double* flops, int* launches);
 
 // ---- normalisation / element-wise kernels (dense_ops.cu) ------------------------------------------------
-// GroupNorm(32 groups) over NHWC fp16 with optional fused SiLU. stats: [N,32,2] fp32 scratch (sum, sumsq).
+// Size (floats) of the `stats` / `scratch2` buffers below: [N,groups,2] results followed by per-block partials
+// (the reduction is two-stage and order-fixed, so statistics are bitwise reproducible).
+long long groupnorm_workspace_floats(int N, int HW, int C, int groups);
+// GroupNorm(32 groups) over NHWC fp16 with optional fused SiLU. stats: fp32 (sum, sumsq) per (n, group).
 int groupnorm_forward(const __half* x, const __half* gamma, const __half* beta, __half* y, float* stats, int N, int HW,
                       int C, int groups, float eps, int silu, cudaStream_t s);
 // dx for y = silu?(GN(x)): needs x, gamma, beta and the forward stats; scratch2: [N,groups,2] fp32.

@@ -81,8 +81,10 @@ __global__ void gn_reduce_kernel(const __half* __restrict__ x, const __half* __r
           t0 += sm[yy * P + q];
           t1 += sm[blockDim.x + yy * P + q];
         }
-      atomicAdd(&out[(n * groups + g) * 2], t0);
-      atomicAdd(&out[(n * groups + g) * 2 + 1], t1);
+      // per-block partial; summed in fixed order by gn_finalize_kernel (bitwise reproducible statistics)
+      float* po = out + (((size_t)n * gridDim.x + blockIdx.x) * groups + g) * 2;
+      po[0] = t0;
+      po[1] = t1;
     }
     __syncthreads();
     a0 += s0;
@@ -90,6 +92,16 @@ __global__ void gn_reduce_kernel(const __half* __restrict__ x, const __half* __r
   }
   (void)a0;
   (void)a1;
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblk, int groups,
+                                   int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g, k)
+  if (i >= total) return;
+  const int k = i & 1, g = (i >> 1) % groups, n = (i >> 1) / groups;
+  float acc = 0.f;
+  for (int b = 0; b < nblk; ++b) acc += partial[(((size_t)n * nblk + b) * groups + g) * 2 + k];
+  out[i] = acc;
 }
 
 // y = act(GN(x)) (MODE 0) or dx of it (MODE 1); 8 channels (16 bytes) per thread.
@@ -522,6 +534,12 @@ inline int ew_grid(long long total, int block = 256) {
 
 }  // namespace
 
+long long groupnorm_workspace_floats(int N, int HW, int C, int groups) {
+  int P, PY, ppb, nblk;
+  gn_geometry(HW, C, N, groups, &P, &PY, &ppb, &nblk);
+  return (long long)N * groups * 2 * (1 + nblk);
+}
+
 int groupnorm_forward(const __half* x, const __half* gamma, const __half* beta, __half* y, float* stats, int N, int HW,
                       int C, int groups, float eps, int act_silu, cudaStream_t s) {
   if (C % 8 || C % groups || (C / groups) % 2) {
@@ -530,11 +548,13 @@ int groupnorm_forward(const __half* x, const __half* gamma, const __half* beta, 
   }
   int P, PY, ppb, nblk;
   gn_geometry(HW, C, N, groups, &P, &PY, &ppb, &nblk);
-  cudaMemsetAsync(stats, 0, sizeof(float) * N * groups * 2, s);
+  float* partial = stats + (size_t)N * groups * 2;
   gn_reduce_kernel<0><<<dim3(nblk, N), P * PY, sizeof(float) * 2 * P * PY, s>>>(
-      x, nullptr, nullptr, nullptr, nullptr, stats, HW, C, groups, P, PY, ppb, eps, 0);
+      x, nullptr, nullptr, nullptr, nullptr, partial, HW, C, groups, P, PY, ppb, eps, 0);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_stats");
+  gn_finalize_kernel<<<(N * groups * 2 + 127) / 128, 128, 0, s>>>(partial, stats, nblk, groups, N * groups * 2);
+  SDB_COUNT_LAUNCH();
   const long long total8 = (long long)N * HW * C / 8;
   gn_apply_kernel<0><<<ew_grid(total8), 256, 0, s>>>(x, nullptr, gamma, beta, stats, nullptr, y, total8, HW, C, groups,
                                                      eps, act_silu);
@@ -548,11 +568,13 @@ int groupnorm_backward(const __half* x, const __half* gamma, const __half* beta,
                        cudaStream_t s) {
   int P, PY, ppb, nblk;
   gn_geometry(HW, C, N, groups, &P, &PY, &ppb, &nblk);
-  cudaMemsetAsync(scratch2, 0, sizeof(float) * N * groups * 2, s);
-  gn_reduce_kernel<1><<<dim3(nblk, N), P * PY, sizeof(float) * 2 * P * PY, s>>>(x, dy, gamma, beta, stats, scratch2, HW,
+  float* partial = scratch2 + (size_t)N * groups * 2;
+  gn_reduce_kernel<1><<<dim3(nblk, N), P * PY, sizeof(float) * 2 * P * PY, s>>>(x, dy, gamma, beta, stats, partial, HW,
                                                                                C, groups, P, PY, ppb, eps, act_silu);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_bwd_reduce");
+  gn_finalize_kernel<<<(N * groups * 2 + 127) / 128, 128, 0, s>>>(partial, scratch2, nblk, groups, N * groups * 2);
+  SDB_COUNT_LAUNCH();
   const long long total8 = (long long)N * HW * C / 8;
   gn_apply_kernel<1><<<ew_grid(total8), 256, 0, s>>>(x, dy, gamma, beta, stats, scratch2, dx, total8, HW, C, groups,
                                                      eps, act_silu);

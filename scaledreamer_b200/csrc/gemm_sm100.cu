@@ -16,6 +16,7 @@
 // diffusers equivalents (stable_diffusion_asd_guidance.py:170-178, 318-331).
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "dense.h"
 #include "ptx_sm100.cuh"
@@ -238,6 +239,14 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Optional per-launch timing (bench.py roofline): CUDA events on the launching stream around every GEMM launch.
+struct ProfRec {
+  cudaEvent_t a, b;
+  double flops;
+};
+bool g_prof = false;
+std::vector<ProfRec> g_recs;
+
 template <int BN>
 int launch(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr = false;
@@ -250,7 +259,18 @@ int launch(const GemmPlan& plan, cudaStream_t stream) {
     }
     attr = true;
   }
+  ProfRec rec;
+  if (g_prof) {
+    cudaEventCreate(&rec.a);
+    cudaEventCreate(&rec.b);
+    rec.flops = 2.0 * plan.p.M * plan.p.N * plan.p.K * plan.grid.z;
+    cudaEventRecord(rec.a, stream);
+  }
   gemm_f16_kernel<BN><<<plan.grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(plan.ta, plan.tb, plan.p);
+  if (g_prof) {
+    cudaEventRecord(rec.b, stream);
+    g_recs.push_back(rec);
+  }
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gemm_f16");
   return SDB_OK;
@@ -489,6 +509,34 @@ int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half
   rc = make_tmap(&plan->tb, V, 4, dv, sv, bv);
   if (rc) return rc;
   plan->grid = dim3((Lq + kBM - 1) / kBM, head_dim / 64, B * heads);
+  return SDB_OK;
+}
+
+void profile_begin() {
+  g_recs.clear();
+  g_prof = true;
+}
+
+int profile_end(double* ms, double* flops, int* launches) {
+  g_prof = false;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    sdb_set_error("profile_end: %s", cudaGetErrorString(e));
+    return SDB_ERR_CUDA;
+  }
+  double t = 0.0, f = 0.0;
+  for (ProfRec& r : g_recs) {
+    float m = 0.f;
+    cudaEventElapsedTime(&m, r.a, r.b);
+    t += m;
+    f += r.flops;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  *ms = t;
+  *flops = f;
+  *launches = (int)g_recs.size();
+  g_recs.clear();
   return SDB_OK;
 }
 

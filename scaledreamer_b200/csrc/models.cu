@@ -137,7 +137,7 @@ int Net::run(const std::vector<Op>& ops, cudaStream_t s) {
 T Net::gn(std::vector<Op>* ops, const T& x, const std::string& name, float eps, bool silu, float** stats_out) {
   const __half* g = param(name + ".weight", 1, x.c);
   const __half* b = param(name + ".bias", 1, x.c);
-  float* stats = reinterpret_cast<float*>(work((long long)x.n * 32 * 2 * 4));
+  float* stats = reinterpret_cast<float*>(work(groupnorm_workspace_floats(x.n, x.h * x.w, x.c, 32) * 4));
   T y = act(x.n, x.h, x.w, x.c);
   if (stats_out) *stats_out = stats;
   if (!dry_) {
@@ -524,7 +524,7 @@ int VaeEncoder::build() {
     const __half* b = dry_ ? nullptr : params_[index_.at(name + ".bias")].ptr;
     tape.push_back([=](const T& dy) {
       T dx = act(x.n, x.h, x.w, x.c);
-      float* sc = reinterpret_cast<float*>(work((long long)x.n * 32 * 2 * 4));
+      float* sc = reinterpret_cast<float*>(work(groupnorm_workspace_floats(x.n, x.h * x.w, x.c, 32) * 4));
       bwd([=](cudaStream_t s) {
         return groupnorm_backward(x.p, g, b, stats, dy.p, dx.p, sc, x.n, x.h * x.w, x.c, 32, 1e-6f, silu ? 1 : 0, s);
       });

@@ -69,7 +69,7 @@ class _ASDGuidanceBase(BaseObject):
         self.grad_clip_val: Optional[float] = None
         self.set_min_max_steps(C(self.cfg.min_step_percent, 0, 0), C(self.cfg.max_step_percent, 0, 0))
         self._nets_for = None
-        self.loss_scale = float(os.environ.get("SDB_VAE_LOSS_SCALE", "1024"))
+        self.loss_scale = float(os.environ.get("SDB_VAE_LOSS_SCALE", "1"))
         self.weights_seed = int(os.environ.get("SDB_WEIGHTS_SEED", "0"))
 
     def set_min_max_steps(self, min_step_percent=0.02, max_step_percent=0.98):

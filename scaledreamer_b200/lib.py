@@ -113,9 +113,12 @@ SIGNATURES = {
     "sdb_adamw_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
     # ---- include/sdb200_nn.h
     "sdb_gemm_f16": [C.POINTER(GemmArgsC), _P],
+    "sdb_gemm_profile_begin": [],
+    "sdb_gemm_profile_end": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)],
     "sdb_conv3x3_f16": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P],
     "sdb_conv3x3_small": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "sdb_attention_f16": [_P, _LL, _P, _LL, _P, _LL, _I, _I, _I, _I, _P, _P, _LL, _P],
+    "sdb_groupnorm_workspace_floats": [_I, _I, _I, _I],
     "sdb_groupnorm_f16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
     "sdb_groupnorm_backward_f16": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
     "sdb_layernorm_f16": [_P, _P, _P, _P, _I, _I, _F, _P],
@@ -152,6 +155,8 @@ def _declare(lib: C.CDLL) -> None:
         fn.argtypes = args
         if name == "sdb_net_destroy":
             fn.restype = None
+        elif name == "sdb_groupnorm_workspace_floats":
+            fn.restype = C.c_longlong
         elif name != "sdb_grid_num_entries":
             fn.restype = C.c_int
 

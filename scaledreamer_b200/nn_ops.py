@@ -96,7 +96,7 @@ def groupnorm(x: torch.Tensor, gamma, beta, groups=32, eps=1e-5, silu=False):
     n, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (n * c)
     y = torch.empty_like(x)
-    stats = torch.empty(n, groups, 2, device=x.device, dtype=torch.float32)
+    stats = torch.empty(lib.sdb_groupnorm_workspace_floats(n, hw, c, groups), device=x.device, dtype=torch.float32)
     L.check(lib.sdb_groupnorm_f16(_h(x), _h(gamma), _h(beta), L.ptr(y), L.ptr(stats), n, hw, c, groups, eps, int(silu),
                                   L.stream_ptr()), "sdb_groupnorm_f16")
     return y, stats
@@ -107,7 +107,7 @@ def groupnorm_backward(x, gamma, beta, stats, dy, groups=32, eps=1e-5, silu=Fals
     n, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (n * c)
     dx = torch.empty_like(x)
-    scratch = torch.empty(n, groups, 2, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(lib.sdb_groupnorm_workspace_floats(n, hw, c, groups), device=x.device, dtype=torch.float32)
     L.check(lib.sdb_groupnorm_backward_f16(_h(x), _h(gamma), _h(beta), L.ptr(stats), _h(dy), L.ptr(dx), L.ptr(scratch),
                                            n, hw, c, groups, eps, int(silu), L.stream_ptr()),
             "sdb_groupnorm_backward_f16")
