@@ -17,9 +17,9 @@ def step(i):
     b = ds.to_device(ds.collate({}), dev)
     out = system.training_step(b, i); out["loss"].backward(); opt.step(); opt.zero_grad(set_to_none=False)
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-for i in range(W): step(i + 1)
+for i in range(W): step(i)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-step(W + 1)
+step(W)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
