@@ -298,6 +298,7 @@ def main() -> None:
         n_prof = 3
         lib.sdb_gemm_profile_begin()
         samples_kept = 0
+        fwd_each = []
         for _ in range(n_prof):
             b = ds.to_device(host_batch(), dev)
             a0, a1, a2, a3, a4 = ev(), ev(), ev(), ev(), ev()
@@ -313,6 +314,7 @@ def main() -> None:
             opt.zero_grad(set_to_none=False)
             a4.record()
             torch.cuda.synchronize()
+            fwd_each.append(a0.elapsed_time(a1))
             for k, (x, y) in zip(acc, ((a0, a1), (a1, a2), (a2, a3), (a3, a4))):
                 acc[k] += x.elapsed_time(y) / n_prof
         gm, gf, gl = C.c_double(), C.c_double(), C.c_int()
@@ -325,23 +327,25 @@ def main() -> None:
         P = {k: v.detach() for k, v in rr._params().items()}
         march = R.MarchSpec(render_step_size=rr.render_step_size, prune=True, grid_res=32)
         jit = torch.rand(H * W, device=dev)
-        o = R.render_forward_raw(rr._spec(), march, P, rr._occ_grid(dev), b["rays_o"].reshape(-1, 3),
-                                 b["rays_d"].reshape(-1, 3), jit, None, H * W, 1 << 25)
-        samples_kept = int(o["packed"]["counter"].item())
-        del o
-        f0, f1, f2 = ev(), ev(), ev()
+        ro_, rd_ = b["rays_o"].reshape(-1, 3).contiguous(), b["rays_d"].reshape(-1, 3).contiguous()
+        tape = R.RenderTape.acquire(march, rr._spec().radius, H * W, dev)
+        o = R.render_forward_v2_raw(rr._spec(), march, P, rr._occ_grid(dev), ro_, rd_, jit, None, H * W, tape)
+        samples_kept = int(tape.counter[0].item())
+        tape.check_overflow()
         grads = {k: torch.zeros_like(v) for k, v in P.items()}
+        g_rgb = torch.randn_like(o["comp_rgb"])
+        f0, f1, f2 = ev(), ev(), ev()
         f0.record()
-        o = R.render_forward_raw(rr._spec(), march, P, rr._occ_grid(dev), b["rays_o"].reshape(-1, 3),
-                                 b["rays_d"].reshape(-1, 3), jit, None, H * W, 0)
+        o = R.render_forward_v2_raw(rr._spec(), march, P, rr._occ_grid(dev), ro_, rd_, jit, None, H * W, tape)
         f1.record()
-        R.render_backward_raw(rr._spec(), march, P, grads, rr._occ_grid(dev), b["rays_o"].reshape(-1, 3),
-                              b["rays_d"].reshape(-1, 3), jit, None, H * W, o, torch.randn_like(o["comp_rgb"]))
+        R.render_backward_tape_raw(rr._spec(), march, P, grads, rd_, None, H * W, o, tape, g_rgb)
         f2.record()
+        tape.release()
         torch.cuda.synchronize()
         prof = dict(phase_ms=acc, gemm_ms_per_step=gm.value / n_prof, gemm_tflop_per_step=gf.value / n_prof / 1e12,
                     gemm_launches_per_step=gl.value // n_prof, render_fwd_kernel_ms=f0.elapsed_time(f1),
-                    render_bwd_kernel_ms=f1.elapsed_time(f2), render_samples_kept=samples_kept)
+                    render_bwd_kernel_ms=f1.elapsed_time(f2), render_samples_kept=samples_kept,
+                    render_tapes_allocated=R.RenderTape.n_allocated, render_fwd_phase_ms_each=fwd_each)
 
     if rank != 0:
         if world > 1:
@@ -356,11 +360,11 @@ def main() -> None:
                  "achieved": gemm_tfs, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tfs / pk["tf_sustained"],
                  "traffic": None, "ms_per_step": prof["gemm_ms_per_step"], "peak_source": pk["src"] + " sustained bf16"}
     rb = rbytes_b / 1e9 / (prof["render_bwd_kernel_ms"] / 1e3)
-    roof_rbwd = {"kernel": "render_nerf_bwd_kernel", "bound": "hbm", "achieved": rb, "peak": pk["hbm"], "unit": "GB/s",
+    roof_rbwd = {"kernel": "render_composite_bwd_kernel + render_field_bwd_kernel (tape backward)", "bound": "hbm", "achieved": rb, "peak": pk["hbm"], "unit": "GB/s",
                  "frac": rb / pk["hbm"], "traffic": None, "ms_per_step": prof["render_bwd_kernel_ms"],
                  "peak_source": pk["src"] + " copy bandwidth"}
     rf = rbytes_f / 1e9 / (prof["render_fwd_kernel_ms"] / 1e3)
-    roof_rfwd = {"kernel": "render_nerf_fwd_kernel", "bound": "hbm", "achieved": rf, "peak": pk["hbm"], "unit": "GB/s",
+    roof_rfwd = {"kernel": "render_nerf_fwd2_kernel", "bound": "hbm", "achieved": rf, "peak": pk["hbm"], "unit": "GB/s",
                  "frac": rf / pk["hbm"], "traffic": None, "ms_per_step": prof["render_fwd_kernel_ms"],
                  "peak_source": pk["src"] + " copy bandwidth"}
     roofs = sorted([roof_gemm, roof_rbwd, roof_rfwd], key=lambda r: -r["ms_per_step"])

@@ -142,6 +142,39 @@ int sdb_render_nerf_backward(const sdb_field* field, const sdb_field_grads* grad
                              const float* opacity, const float* depth, const float* g_comp_rgb,
                              const float* g_opacity, const float* g_depth, int* work, void* stream);
 
+/* ---- tape-based renderer (v2): same maths, the forward records every kept sample so the backward neither
+ * re-marches nor re-gathers the hash grid. ------------------------------------------------------------- */
+typedef struct {
+  int capacity;             /* sample slots, multiple of 128 (worst case: sdb_render_tape_geometry) */
+  int max_chunks;           /* stride of ray_chunks */
+  int* counter;             /* [2] out: kept samples, overflow flag (non-zero: enlarge the tape and re-run) */
+  float* enc;               /* [capacity*32] tile-transposed encodings: [capacity/32][32 features][32 slots] */
+  float* pos;               /* [3*capacity] x01,y01,z01 planes */
+  float* sample;            /* [8*capacity] raw, o0, o1, o2, w, T*exp(-sigma*delta), t_mid, delta planes;
+                               the backward overwrites planes 0..3 with d raw, d o0..2 */
+  uint32_t* ray_chunks;     /* [n_rays*max_chunks] (slot0 << 5) | (count-1), front to back */
+  int* ray_nchunks;         /* [n_rays] */
+} sdb_render_tape;
+
+/* Host-only: worst-case tape geometry for n_rays rays through the [-radius, radius]^3 box. */
+int sdb_render_tape_geometry(const sdb_march_cfg* march, float radius, int n_rays, long long* capacity,
+                             int* max_chunks);
+
+/* Same contract as sdb_render_nerf_forward (no packed extras); tape may be NULL (no gradient wanted). */
+int sdb_render_nerf_forward_v2(const sdb_field* field, const sdb_march_cfg* march, const uint32_t* occ_bits,
+                               const float* occ_mean, const float* rays_o, const float* rays_d, const float* jitter,
+                               const float* bg_override, int n_rays, int rays_per_image, float* comp_rgb,
+                               float* comp_rgb_fg, float* comp_rgb_bg, float* opacity, float* depth,
+                               float* z_variance, const sdb_render_tape* tape, int* work, void* stream);
+
+/* Backward of sdb_render_nerf_forward_v2 from its tape (two launches: per-ray compositing gradient +
+ * environment map, then per-sample MLP backward + hash-grid scatter). Gradients accumulate (+=). */
+int sdb_render_nerf_backward_tape(const sdb_field* field, const sdb_field_grads* grads, const sdb_march_cfg* march,
+                                  const float* rays_d, const float* bg_override, int n_rays, int rays_per_image,
+                                  const float* comp_rgb_fg, const float* comp_rgb_bg, const float* opacity,
+                                  const float* depth, const float* g_comp_rgb, const float* g_opacity,
+                                  const float* g_depth, const sdb_render_tape* tape, void* stream);
+
 /* rays from cameras (threestudio/utils/ops.py:183-269 get_ray_directions + get_rays):
  * c2w [B,4,4], fovy [B] (radians) -> rays_o, rays_d [B,H,W,3] (normalised). */
 int sdb_raygen(const float* c2w, const float* fovy, int n_images, int height, int width, float* rays_o,

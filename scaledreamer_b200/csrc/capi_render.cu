@@ -6,7 +6,7 @@
 #include <cstring>
 
 #include "../../include/sdb200.h"
-#include "render_types.cuh"
+#include "render_tape.cuh"
 
 unsigned long long g_sdb_launch_count = 0ull;
 static thread_local char g_err[512] = "";
@@ -188,7 +188,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 extern "C" {
 
 const char* sdb_last_error(void) { return g_err; }
-int sdb_abi_version(void) { return 1; }
+int sdb_abi_version(void) { return 2; }
 unsigned long long sdb_launch_count(void) { return g_sdb_launch_count; }
 
 long long sdb_grid_num_entries(const sdb_grid_cfg* cfg) {
@@ -361,6 +361,131 @@ int sdb_render_nerf_backward(const sdb_field* field, const sdb_field_grads* grad
   fg.bg_w2 = grads->bg_w2;
   fg.bg_w3 = grads->bg_w3;
   return launch_render_bwd(fm, fp, fg, mm, io, (cudaStream_t)stream);
+}
+
+static int resolve_tape(const sdb_render_tape* t, int n_rays, RenderTape* out) {
+  SDB_CHECK_ARG(t->capacity > 0 && t->capacity % 128 == 0, "tape: capacity must be a positive multiple of 128");
+  SDB_CHECK_ARG(t->capacity <= (1 << 27), "tape: capacity must be <= 2^27 slots");
+  SDB_CHECK_ARG(t->max_chunks > 0, "tape: max_chunks must be > 0");
+  SDB_CHECK_ARG(t->counter && t->enc && t->pos && t->sample && t->ray_chunks && t->ray_nchunks,
+                "tape: NULL buffer");
+  (void)n_rays;
+  out->capacity = t->capacity;
+  out->max_chunks = t->max_chunks;
+  out->counter = t->counter;
+  out->enc = t->enc;
+  out->pos = t->pos;
+  out->sample = t->sample;
+  out->ray_chunks = t->ray_chunks;
+  out->ray_nchunks = t->ray_nchunks;
+  return SDB_OK;
+}
+
+int sdb_render_tape_geometry(const sdb_march_cfg* march, float radius, int n_rays, long long* capacity,
+                             int* max_chunks) {
+  SDB_CHECK_ARG(march && march->render_step_size > 0.f && radius > 0.f && n_rays >= 0 && capacity && max_chunks,
+                "tape_geometry: bad arguments");
+  // longest chord of the box, clipped by the near / far planes, on the fixed-step lattice (+ the marcher's slack)
+  double chord = 2.0 * std::sqrt(3.0) * (double)radius;
+  const double span = (double)march->far_plane - (double)march->near_plane;
+  if (span < chord) chord = span > 0.0 ? span : 0.0;
+  const long long per_ray = (long long)std::ceil(chord / (double)march->render_step_size) + 4;
+  long long cap = per_ray * (long long)n_rays;
+  cap = (cap + 127) / 128 * 128;
+  if (cap < 128) cap = 128;
+  *capacity = cap;
+  *max_chunks = (int)((per_ray + 31) / 32) + 1;
+  return SDB_OK;
+}
+
+int sdb_render_nerf_forward_v2(const sdb_field* field, const sdb_march_cfg* march, const uint32_t* occ_bits,
+                               const float* occ_mean, const float* rays_o, const float* rays_d, const float* jitter,
+                               const float* bg_override, int n_rays, int rays_per_image, float* comp_rgb,
+                               float* comp_rgb_fg, float* comp_rgb_bg, float* opacity, float* depth,
+                               float* z_variance, const sdb_render_tape* tape, int* work, void* stream) {
+  FieldMeta fm;
+  FieldPtrs fp;
+  MarchMeta mm;
+  int rc = resolve_field(field, &fm, &fp, true);
+  if (rc) return rc;
+  rc = resolve_march(march, &mm);
+  if (rc) return rc;
+  SDB_CHECK_ARG(occ_bits && rays_o && rays_d && work, "render_forward_v2: NULL input");
+  SDB_CHECK_ARG(comp_rgb && comp_rgb_fg && comp_rgb_bg && opacity && depth && z_variance,
+                "render_forward_v2: NULL output");
+  SDB_CHECK_ARG(n_rays >= 0 && rays_per_image > 0, "render_forward_v2: bad ray counts");
+  if (n_rays == 0) return SDB_OK;
+  RayIO io;
+  memset(&io, 0, sizeof(io));
+  io.rays_o = rays_o;
+  io.rays_d = rays_d;
+  io.jitter = jitter;
+  io.bg_override = bg_override;
+  io.occ_bits = occ_bits;
+  io.occ_mean = occ_mean;
+  io.n_rays = n_rays;
+  io.rays_per_image = rays_per_image;
+  io.comp_rgb = comp_rgb;
+  io.comp_rgb_fg = comp_rgb_fg;
+  io.comp_rgb_bg = comp_rgb_bg;
+  io.opacity = opacity;
+  io.depth = depth;
+  io.z_variance = z_variance;
+  io.work_counter = work;
+  RenderTape t;
+  if (tape) {
+    rc = resolve_tape(tape, n_rays, &t);
+    if (rc) return rc;
+  }
+  return launch_render_fwd2(fm, fp, mm, io, tape ? &t : nullptr, (cudaStream_t)stream);
+}
+
+int sdb_render_nerf_backward_tape(const sdb_field* field, const sdb_field_grads* grads, const sdb_march_cfg* march,
+                                  const float* rays_d, const float* bg_override, int n_rays, int rays_per_image,
+                                  const float* comp_rgb_fg, const float* comp_rgb_bg, const float* opacity,
+                                  const float* depth, const float* g_comp_rgb, const float* g_opacity,
+                                  const float* g_depth, const sdb_render_tape* tape, void* stream) {
+  FieldMeta fm;
+  FieldPtrs fp;
+  MarchMeta mm;
+  int rc = resolve_field(field, &fm, &fp, true);
+  if (rc) return rc;
+  rc = resolve_march(march, &mm);
+  if (rc) return rc;
+  SDB_CHECK_ARG(grads && grads->table && grads->w1_density && grads->w2_density && grads->w1_feature &&
+                    grads->w2_feature && grads->bg_table && grads->bg_w1 && grads->bg_w2 && grads->bg_w3,
+                "render_backward_tape: NULL gradient buffer");
+  SDB_CHECK_ARG(rays_d && comp_rgb_fg && comp_rgb_bg && opacity && depth && g_comp_rgb && tape,
+                "render_backward_tape: NULL input");
+  SDB_CHECK_ARG(n_rays >= 0 && rays_per_image > 0, "render_backward_tape: bad ray counts");
+  if (n_rays == 0) return SDB_OK;
+  RenderTape t;
+  rc = resolve_tape(tape, n_rays, &t);
+  if (rc) return rc;
+  RayIO io;
+  memset(&io, 0, sizeof(io));
+  io.rays_d = rays_d;
+  io.bg_override = bg_override;
+  io.n_rays = n_rays;
+  io.rays_per_image = rays_per_image;
+  io.comp_rgb_fg = const_cast<float*>(comp_rgb_fg);
+  io.comp_rgb_bg = const_cast<float*>(comp_rgb_bg);
+  io.opacity = const_cast<float*>(opacity);
+  io.depth = const_cast<float*>(depth);
+  io.g_comp_rgb = g_comp_rgb;
+  io.g_opacity = g_opacity;
+  io.g_depth = g_depth;
+  FieldGrads fg;
+  fg.table = grads->table;
+  fg.w1d = grads->w1_density;
+  fg.w2d = grads->w2_density;
+  fg.w1f = grads->w1_feature;
+  fg.w2f = grads->w2_feature;
+  fg.bg_table = grads->bg_table;
+  fg.bg_w1 = grads->bg_w1;
+  fg.bg_w2 = grads->bg_w2;
+  fg.bg_w3 = grads->bg_w3;
+  return launch_render_bwd2(fm, fp, fg, mm, io, t, (cudaStream_t)stream);
 }
 
 int sdb_raygen(const float* c2w, const float* fovy, int n_images, int height, int width, float* rays_o,

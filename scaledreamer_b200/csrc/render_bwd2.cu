@@ -1,0 +1,472 @@
+// Tape-based NeRF volume-render backward for sm_100a: no re-march, no re-gather.
+//
+//   render_composite_bwd_kernel  (per ray)    image gradient -> d raw-density, d feature pre-activations of every
+//                                             kept sample (written over tape.sample rows 0..3), plus the whole
+//                                             environment-map backward (thread per ray).
+//   render_field_bwd_kernel      (per sample) both MLP backward passes as register-tiled fp32 contractions on
+//                                             128-sample tiles (hidden recompute, dE = dH W1, dW1 += dH^T E,
+//                                             dW2 += H^T d out) and the trilinear scatter into the table gradient.
+//
+// Replaces the autograd chain behind threestudio/models/renderers/nerf_volume_renderer.py:118-428 (nerfacc
+// accumulate_along_rays / render_weight_from_density backward, VanillaMLP backward through cuBLAS,
+// tcnn kernel_grid_backward) and neural_environment_map_background.py:46-67.
+//
+// Compositing gradient with the per-ray forward outputs saved: dL/dsigma_i = delta_i (g_i (T_i - w_i) - (R - P_i)),
+//   g_i = dL/dw_i = <gC, c_i> + gD t_i + gO,  R = <gC, C_fg> + gO op + gD depth,  P_i = sum_{j<=i} g_j w_j.
+#include "render_tape.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ composite backward
+constexpr int kCbWarps = 8;
+
+struct CbSmem {
+  float b1[kBgHidden * kBgEncDim];
+  float b2[kBgHidden * kBgHidden];
+  float b3[3 * kBgHidden];
+  float gB1[kBgHidden * kBgEncDim];
+  float gB2[kBgHidden * kBgHidden];
+  float gB3[3 * kBgHidden];
+};
+
+__global__ void __launch_bounds__(kCbWarps * 32)
+render_composite_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, const FieldGrads g, const RayIO io,
+                            const RenderTape tape) {
+  __shared__ CbSmem s;
+  for (int i = threadIdx.x; i < kBgHidden * kBgEncDim; i += blockDim.x) s.b1[i] = p.bg_w1[i], s.gB1[i] = 0.f;
+  for (int i = threadIdx.x; i < kBgHidden * kBgHidden; i += blockDim.x) s.b2[i] = p.bg_w2[i], s.gB2[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * kBgHidden; i += blockDim.x) s.b3[i] = p.bg_w3[i], s.gB3[i] = 0.f;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int n_items = (io.n_rays + 31) / 32;
+  const float2* bg_table = reinterpret_cast<const float2*>(p.bg_table);
+  float2* g_bg_table = reinterpret_cast<float2*>(g.bg_table);
+  const size_t cap = (size_t)tape.capacity;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+
+  for (int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items; item += warps_total) {
+    // ---- per-lane ray gradients + background backward (thread per ray) ----
+    const int my_ray = lane * n_items + item;
+    const bool my_valid = my_ray < io.n_rays;
+    float md[3] = {0.f, 0.f, 1.f};
+    float gC[3] = {0.f, 0.f, 0.f}, gO = 0.f, gD = 0.f, Rtot = 0.f;
+    float dbg[3] = {0.f, 0.f, 0.f};
+    if (my_valid) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        md[c] = __ldg(io.rays_d + 3 * my_ray + c);
+        gC[c] = __ldg(io.g_comp_rgb + 3 * my_ray + c);
+      }
+      const float op = __ldg(io.opacity + my_ray);
+      const float dp = __ldg(io.depth + my_ray);
+      gO = io.g_opacity ? __ldg(io.g_opacity + my_ray) : 0.f;
+      gD = io.g_depth ? __ldg(io.g_depth + my_ray) : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float b = __ldg(io.comp_rgb_bg + 3 * my_ray + c);
+        gO = fmaf(-gC[c], b, gO);  // comp_rgb = fg + bg (1 - op)
+        Rtot = fmaf(gC[c], __ldg(io.comp_rgb_fg + 3 * my_ray + c), Rtot);
+        dbg[c] = gC[c] * (1.f - op);
+      }
+      Rtot = fmaf(gO, op, Rtot);
+      Rtot = fmaf(gD, dp, Rtot);
+    }
+    if (!io.bg_override) {  // random-colour augmentation detaches the environment map (color * 0 + rand)
+      BgActs a;
+      float bgc[3];
+      float dpre[3] = {0.f, 0.f, 0.f}, dh2[kBgHidden], dh1[kBgHidden], denc[kBgEncDim];
+      if (my_valid) {
+        bg_forward(f, bg_table, s.b1, s.b2, s.b3, md[0], md[1], md[2], a, bgc);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dpre[c] = dbg[c] * color_activation_grad(f.bg_color_act, a.pre[c]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kBgEncDim; ++i) a.enc[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < kBgHidden; ++i) a.h1[i] = a.h2[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kBgHidden; ++i) {
+        float v = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v = fmaf(s.b3[c * kBgHidden + i], dpre[c], v);
+        dh2[i] = a.h2[i] > 0.f ? v : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kBgHidden; ++i) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < kBgHidden; ++j) v = fmaf(s.b2[j * kBgHidden + i], dh2[j], v);
+        dh1[i] = a.h1[i] > 0.f ? v : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kBgEncDim; ++i) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < kBgHidden; ++j) v = fmaf(s.b1[j * kBgEncDim + i], dh1[j], v);
+        denc[i] = v;
+      }
+      if (my_valid)
+        grid_scatter<4>(g_bg_table, f.bg_grid, (md[0] + 1.f) * 0.5f, (md[1] + 1.f) * 0.5f, (md[2] + 1.f) * 0.5f, denc);
+      // weight grads: reduce over the 32 rays of the bundle, one shared-memory atomic per weight
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < kBgHidden; ++i) {
+          const float v = warp_sum(a.h2[i] * dpre[c]);
+          if (lane == 0) atomicAdd(&s.gB3[c * kBgHidden + i], v);
+        }
+#pragma unroll
+      for (int j = 0; j < kBgHidden; ++j)
+#pragma unroll
+        for (int i = 0; i < kBgHidden; ++i) {
+          const float v = warp_sum(a.h1[i] * dh2[j]);
+          if (lane == 0) atomicAdd(&s.gB2[j * kBgHidden + i], v);
+        }
+#pragma unroll
+      for (int j = 0; j < kBgHidden; ++j)
+#pragma unroll
+        for (int i = 0; i < kBgEncDim; ++i) {
+          const float v = warp_sum(a.enc[i] * dh1[j]);
+          if (lane == 0) atomicAdd(&s.gB1[j * kBgEncDim + i], v);
+        }
+    }
+
+    // ---- per-ray prefix over the taped samples (warp per ray, lanes over the samples of a chunk) ----
+    for (int r = 0; r < 32; ++r) {
+      const int ray = r * n_items + item;
+      if (ray >= io.n_rays) break;
+      const int nch = __ldg(tape.ray_nchunks + ray);
+      if (nch == 0) continue;
+      const float rgC0 = __shfl_sync(kFullMask, gC[0], r), rgC1 = __shfl_sync(kFullMask, gC[1], r),
+                  rgC2 = __shfl_sync(kFullMask, gC[2], r);
+      const float rgO = __shfl_sync(kFullMask, gO, r), rgD = __shfl_sync(kFullMask, gD, r);
+      const float rR = __shfl_sync(kFullMask, Rtot, r);
+      const uint32_t* chunks = tape.ray_chunks + (size_t)ray * tape.max_chunks;
+      float P = 0.f;
+      for (int c0 = 0; c0 < nch; c0 += 32) {
+        const uint32_t mine = (c0 + lane < nch) ? __ldg(chunks + c0 + lane) : 0u;
+        const int nc = min(32, nch - c0);
+        for (int c = 0; c < nc; ++c) {
+          const uint32_t ch = __shfl_sync(kFullMask, mine, c);
+          const int slot0 = (int)(ch >> 5), cnt = (int)(ch & 31u) + 1;
+          float draw = 0.f, df0 = 0.f, df1 = 0.f, df2 = 0.f, gw_w = 0.f, g_w = 0.f, Te = 0.f, delta = 0.f, raw = 0.f;
+          float* sp = tape.sample + slot0 + lane;
+          const bool act = lane < cnt;
+          if (act) {
+            raw = sp[0];
+            const float o0 = sp[cap], o1 = sp[2 * cap], o2 = sp[3 * cap];
+            const float w = sp[4 * cap];
+            Te = sp[5 * cap];
+            const float tm = sp[6 * cap];
+            delta = sp[7 * cap];
+            const float k0 = color_activation(f.color_act, o0), k1 = color_activation(f.color_act, o1),
+                        k2 = color_activation(f.color_act, o2);
+            g_w = fmaf(rgC0, k0, fmaf(rgC1, k1, fmaf(rgC2, k2, fmaf(rgD, tm, rgO))));
+            gw_w = g_w * w;
+            df0 = w * rgC0 * color_activation_grad(f.color_act, o0);
+            df1 = w * rgC1 * color_activation_grad(f.color_act, o1);
+            df2 = w * rgC2 * color_activation_grad(f.color_act, o2);
+          }
+          const float inclP = warp_scan_incl(gw_w, lane);
+          if (act) {
+            const float dsigma = delta * (g_w * Te - (rR - (P + inclP)));
+            draw = dsigma * density_activation_grad(f.density_act, raw);
+            sp[0] = draw;
+            sp[cap] = df0;
+            sp[2 * cap] = df1;
+            sp[3 * cap] = df2;
+          }
+          P += __shfl_sync(kFullMask, inclP, 31);
+        }
+      }
+    }
+  }
+
+  if (!io.bg_override) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBgHidden * kBgEncDim; i += blockDim.x) atomicAdd(g.bg_w1 + i, s.gB1[i]);
+    for (int i = threadIdx.x; i < kBgHidden * kBgHidden; i += blockDim.x) atomicAdd(g.bg_w2 + i, s.gB2[i]);
+    for (int i = threadIdx.x; i < 3 * kBgHidden; i += blockDim.x) atomicAdd(g.bg_w3 + i, s.gB3[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ field backward
+constexpr int kFbThreads = 128;          // 4 warps, one 32-sample sub-tile each
+constexpr int kFbTile = 128;             // samples per CTA tile
+constexpr int kEtStride = 36;            // floats per feature row of a sub-tile (32 samples + pad)
+constexpr int kDhStride = kFbTile + 4;   // floats per hidden row of the dH^T tile
+
+struct FbSmem {
+  float wp[2][kWpSize];                  // W1 permuted for the hidden recompute (density, feature)
+  float w1[2][kHidden * kEncDim];        // W1 row-major [hidden][enc] for dE = dH W1
+  float w2d[kHidden];
+  float w2f[3 * kHidden];
+  float et[4][kEncDim * kEtStride];      // encodings, feature-major per sub-tile
+  float dht[kHidden * kDhStride];        // dH^T of the current net: [hidden][sample]
+  float pos[3][kFbTile];
+  float dout[4][kFbTile];                // d raw, d o0..2
+  float g2d[kHidden];
+  float g2f[3 * kHidden];
+};
+
+__global__ void __launch_bounds__(kFbThreads, 2)
+render_field_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, const FieldGrads g,
+                        const RenderTape tape) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FbSmem& s = *reinterpret_cast<FbSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int li = lane >> 3, lj = lane & 7;
+  stage_w1_perm(s.wp[0], p.w1d, tid, kFbThreads);
+  stage_w1_perm(s.wp[1], p.w1f, tid, kFbThreads);
+  for (int i = tid; i < kHidden * kEncDim; i += kFbThreads) {
+    s.w1[0][i] = p.w1d[i];
+    s.w1[1][i] = p.w1f[i];
+  }
+  for (int i = tid; i < kHidden; i += kFbThreads) s.w2d[i] = p.w2d[i], s.g2d[i] = 0.f;
+  for (int i = tid; i < 3 * kHidden; i += kFbThreads) s.w2f[i] = p.w2f[i], s.g2f[i] = 0.f;
+  __syncthreads();
+
+  const int n = min(__ldg(tape.counter), tape.capacity);
+  const int n_tiles = (n + kFbTile - 1) / kFbTile;
+  const size_t cap = (size_t)tape.capacity;
+  float2* g_table = reinterpret_cast<float2*>(g.table);
+
+  // persistent accumulators
+  float accw[2][4][4];  // dW1[net][hidden hg + 16 a][enc eg + 8 b]
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) accw[q][a][b] = 0.f;
+  float g2d[8], g2f[3][8];  // dW2 partials for hidden_of(lj, b)
+#pragma unroll
+  for (int b = 0; b < 8; ++b) g2d[b] = g2f[0][b] = g2f[1][b] = g2f[2][b] = 0.f;
+  const int hg = tid >> 3, eg = tid & 7;
+  // this lane scatters levels 2*lj and 2*lj+1
+  float lv_scale[2];
+  uint32_t lv_res[2], lv_size[2], lv_off[2], lv_hashed[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int l = 2 * lj + q;
+    lv_scale[q] = f.grid.scale[l];
+    lv_res[q] = f.grid.res[l];
+    lv_size[q] = f.grid.size[l];
+    lv_off[q] = f.grid.offset[l];
+    lv_hashed[q] = f.grid.hashed[l];
+  }
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int base = tile * kFbTile;
+    // ---- load: encodings (zero for slots past the end), positions, output grads ----
+    {
+      const float4* src = reinterpret_cast<const float4*>(tape.enc + (size_t)base * kEncDim);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int q = tid + kFbThreads * r;        // float4 index within the 4 x 32 x 32 block
+        const int sub = q >> 8, k = (q & 255) >> 3, s4 = q & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int slot = base + sub * 32 + s4 * 4;
+        if (slot + 3 < n) {
+          v = __ldg(src + q);
+        } else if (slot < n) {
+          const float* sc = reinterpret_cast<const float*>(src + q);
+          v.x = sc[0];
+          if (slot + 1 < n) v.y = sc[1];
+          if (slot + 2 < n) v.z = sc[2];
+        }
+        *reinterpret_cast<float4*>(&s.et[sub][k * kEtStride + s4 * 4]) = v;
+      }
+      const int slot = base + tid;
+      const bool ok = slot < n;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s.pos[c][tid] = ok ? tape.pos[c * cap + slot] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s.dout[c][tid] = ok ? tape.sample[c * cap + slot] : 0.f;
+    }
+    __syncthreads();
+
+    float dE[8][4];  // d enc for samples 8 li + a, features 4 lj + c
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dE[a][c] = 0.f;
+
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      // (a) hidden recompute for this warp's 32 samples, (b) dH and dW2 partials
+      {
+        float acc[8][8];
+        hidden_tile(s.et[warp], kEtStride, s.wp[net], li, lj, acc);
+        const int s0 = warp * 32 + 8 * li;
+        if (net == 0) {
+          float w2[8];
+#pragma unroll
+          for (int b = 0; b < 8; ++b) w2[b] = s.w2d[hidden_of(lj, b)];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            const float dr = s.dout[0][s0 + a];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+              const float h = fmaxf(acc[a][b], 0.f);
+              g2d[b] = fmaf(h, dr, g2d[b]);
+              acc[a][b] = acc[a][b] > 0.f ? w2[b] * dr : 0.f;
+            }
+          }
+        } else {
+          float w20[8], w21[8], w22[8];
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            w20[b] = s.w2f[hidden_of(lj, b)];
+            w21[b] = s.w2f[kHidden + hidden_of(lj, b)];
+            w22[b] = s.w2f[2 * kHidden + hidden_of(lj, b)];
+          }
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            const float d0 = s.dout[1][s0 + a], d1 = s.dout[2][s0 + a], d2 = s.dout[3][s0 + a];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+              const float h = fmaxf(acc[a][b], 0.f);
+              g2f[0][b] = fmaf(h, d0, g2f[0][b]);
+              g2f[1][b] = fmaf(h, d1, g2f[1][b]);
+              g2f[2][b] = fmaf(h, d2, g2f[2][b]);
+              acc[a][b] = acc[a][b] > 0.f ? fmaf(w20[b], d0, fmaf(w21[b], d1, w22[b] * d2)) : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          float* row = s.dht + hidden_of(lj, b) * kDhStride + s0;
+          *reinterpret_cast<float4*>(row) = make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
+          *reinterpret_cast<float4*>(row + 4) = make_float4(acc[4][b], acc[5][b], acc[6][b], acc[7][b]);
+        }
+      }
+      __syncwarp();
+      // (c) dE += dH W1 for this warp's samples
+      {
+        const float* dcol = s.dht + warp * 32 + 8 * li;
+        const float* wrow = s.w1[net] + 4 * lj;
+#pragma unroll 4
+        for (int h = 0; h < kHidden; ++h) {
+          const float4 d0 = *reinterpret_cast<const float4*>(dcol + h * kDhStride);
+          const float4 d1 = *reinterpret_cast<const float4*>(dcol + h * kDhStride + 4);
+          const float4 wv = *reinterpret_cast<const float4*>(wrow + h * kEncDim);
+          const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            dE[a][0] = fmaf(d[a], wv.x, dE[a][0]);
+            dE[a][1] = fmaf(d[a], wv.y, dE[a][1]);
+            dE[a][2] = fmaf(d[a], wv.z, dE[a][2]);
+            dE[a][3] = fmaf(d[a], wv.w, dE[a][3]);
+          }
+        }
+      }
+      __syncthreads();
+      // (d) dW1[net] += dH^T E over the 128 samples of the tile: thread owns hidden {hg + 16 a} x enc {eg + 8 b}
+#pragma unroll 1
+      for (int sub = 0; sub < 4; ++sub) {
+#pragma unroll 2
+        for (int s4 = 0; s4 < 8; ++s4) {
+          float4 dv[4], ev[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            dv[a] = *reinterpret_cast<const float4*>(s.dht + (hg + 16 * a) * kDhStride + sub * 32 + s4 * 4);
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            ev[b] = *reinterpret_cast<const float4*>(&s.et[sub][(eg + 8 * b) * kEtStride + s4 * 4]);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              float v = accw[net][a][b];
+              v = fmaf(dv[a].x, ev[b].x, v);
+              v = fmaf(dv[a].y, ev[b].y, v);
+              v = fmaf(dv[a].z, ev[b].z, v);
+              v = fmaf(dv[a].w, ev[b].w, v);
+              accw[net][a][b] = v;
+            }
+        }
+      }
+      __syncthreads();  // dht is rewritten by the next net / et by the next tile
+    }
+
+    // ---- scatter: this lane owns levels 2 lj, 2 lj + 1 of samples 8 li + a ----
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int sl = warp * 32 + 8 * li + a;
+      if (base + sl >= n) continue;
+      const float x = s.pos[0][sl], y = s.pos[1][sl], z = s.pos[2][sl];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float gx = dE[a][2 * q], gy = dE[a][2 * q + 1];
+        if (gx == 0.f && gy == 0.f) continue;
+        const LevelCell c = level_cell(lv_scale[q], x, y, z);
+        float2* tl = g_table + lv_off[q];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t idx = grid_index(lv_hashed[q], lv_res[q], lv_size[q], c.ix + (k & 1), c.iy + ((k >> 1) & 1),
+                                          c.iz + ((k >> 2) & 1));
+          const float w = corner_weight(c, k);
+          atomicAdd(tl + idx, make_float2(w * gx, w * gy));  // red.global.add.v2.f32
+        }
+      }
+    }
+  }
+
+  // ---- flush weight gradients ----
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int idx = (hg + 16 * a) * kEncDim + eg + 8 * b;
+      atomicAdd(g.w1d + idx, accw[0][a][b]);
+      atomicAdd(g.w1f + idx, accw[1][a][b]);
+    }
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    float v = g2d[b];
+    v += __shfl_xor_sync(kFullMask, v, 8);
+    v += __shfl_xor_sync(kFullMask, v, 16);
+    if (li == 0) atomicAdd(&s.g2d[hidden_of(lj, b)], v);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float u = g2f[c][b];
+      u += __shfl_xor_sync(kFullMask, u, 8);
+      u += __shfl_xor_sync(kFullMask, u, 16);
+      if (li == 0) atomicAdd(&s.g2f[c * kHidden + hidden_of(lj, b)], u);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kHidden; i += kFbThreads) atomicAdd(g.w2d + i, s.g2d[i]);
+  for (int i = tid; i < 3 * kHidden; i += kFbThreads) atomicAdd(g.w2f + i, s.g2f[i]);
+}
+
+}  // namespace
+
+int launch_render_bwd2(const FieldMeta& f, const FieldPtrs& p, const FieldGrads& g, const MarchMeta& m, const RayIO& io,
+                       const RenderTape& tape, cudaStream_t stream) {
+  (void)m;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(render_field_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(FbSmem));
+    if (e != cudaSuccess) {
+      sdb_set_error("render_field_bwd: smem attribute: %s", cudaGetErrorString(e));
+      return SDB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int n_items = (io.n_rays + 31) / 32;
+  const int grid_a = min(kNumSMs * 4, (n_items + kCbWarps - 1) / kCbWarps);
+  render_composite_bwd_kernel<<<grid_a, kCbWarps * 32, 0, stream>>>(f, p, g, io, tape);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("render_composite_bwd");
+  const int max_tiles = (tape.capacity + kFbTile - 1) / kFbTile;
+  const int grid_b = max(1, min(kNumSMs * 2, max_tiles));
+  render_field_bwd_kernel<<<grid_b, kFbThreads, sizeof(FbSmem), stream>>>(f, p, g, tape);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("render_field_bwd");
+  return SDB_OK;
+}

@@ -1,0 +1,112 @@
+// Sample tape + warp-cooperative tiny-MLP tiles shared by the v2 render kernels (render_fwd2.cu, render_bwd2.cu).
+//
+// v1 (render_fwd.cu / render_bwd.cu) evaluates the 32-64-{1,3} MLPs thread-per-sample with the weights broadcast
+// from shared memory: one LDS.128 per four FFMA and a fully unrolled 16-level encode -- ncu showed it stalled on
+// instruction fetch and the LSU at 12-15 % occupancy. v2 keeps the warp-per-ray march but
+//   * evaluates the hidden layers as 32-sample x 64-unit register tiles (lane (i,j) = 8 samples x 8 units, operands
+//     read as LDS.128 with 16 FFMA per load),
+//   * records every kept sample on a TAPE (encoding, position, pre-activations, weight, transmittance) so the
+//     backward never re-marches or re-gathers: a light per-ray pass turns the image gradient into per-sample
+//     d(raw density) / d(features), and a sample-parallel pass does the MLP backward + hash-grid scatter.
+// Reference maths: see field.cuh / render_fwd.cu headers (nerf_volume_renderer.py:118-428, networks.py:214-251).
+#pragma once
+#include "field.cuh"
+
+// Kept samples of one forward launch. All buffers are caller-owned device memory.
+struct RenderTape {
+  int capacity;          // sample slots (multiple of 128)
+  int max_chunks;        // stride of ray_chunks (>= ceil(max candidates per ray / 32) + 1)
+  int* counter;          // [2]: kept samples written, overflow flag
+  float* enc;            // [capacity/32][32 (feature k)][32 (slot)]  tile-transposed encodings
+  float* pos;            // [3][capacity]  x01, y01, z01
+  float* sample;         // [8][capacity]  raw, o0, o1, o2, w, T*exp(-sigma*delta), t_mid, delta
+                         //                (the backward overwrites rows 0..3 with d raw, d o0..2)
+  uint32_t* ray_chunks;  // [n_rays][max_chunks]  (slot0 << 5) | (count - 1), front to back
+  int* ray_nchunks;      // [n_rays]
+};
+
+static constexpr int kWpSize = kEncDim * kHidden;  // 2048 floats per net
+
+// Hidden unit owned by lane column j, register b.
+__device__ __forceinline__ int hidden_of(int j, int b) { return j + 8 * b; }
+
+// Stages W1 [64][32] (nn.Linear layout) as Wp[k][half][j][c] = W1[hidden_of(j, 4*half + c)][k] so that lane column j
+// reads its eight units of input feature k as two conflict-free LDS.128.
+__device__ __forceinline__ void stage_w1_perm(float* __restrict__ Wp, const float* __restrict__ W1, int tid, int nthr) {
+  for (int idx = tid; idx < kWpSize; idx += nthr) {
+    const int k = idx >> 6, rem = idx & 63, half = rem >> 5, j = (rem & 31) >> 2, c = rem & 3;
+    Wp[idx] = W1[hidden_of(j, 4 * half + c) * kEncDim + k];
+  }
+}
+
+// acc[a][b] = sum_k ET[k][8i + a] * W1[hidden_of(j, b)][k]   (ET: [32][es] floats, feature-major)
+__device__ __forceinline__ void hidden_tile(const float* __restrict__ ET, int es, const float* __restrict__ Wp, int i,
+                                            int j, float (&acc)[8][8]) {
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+#pragma unroll 2
+  for (int k = 0; k < kEncDim; ++k) {
+    const float4 e0 = *reinterpret_cast<const float4*>(ET + k * es + 8 * i);
+    const float4 e1 = *reinterpret_cast<const float4*>(ET + k * es + 8 * i + 4);
+    const float4 w0 = *reinterpret_cast<const float4*>(Wp + (k * 16 + j) * 4);
+    const float4 w1 = *reinterpret_cast<const float4*>(Wp + (k * 16 + 8 + j) * 4);
+    const float e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(e[a], w[b], acc[a][b]);
+  }
+}
+
+// v[a] holds this lane's partial sum for sample 8i + a; returns the total of sample 8i + j (= this lane's own
+// sample) over the eight lanes of the i-group: a reduce-scatter in 7 shuffles.
+__device__ __forceinline__ float reduce_scatter8(const float (&v)[8], int j) {
+  float u[4], t[2];
+  const bool h4 = (j & 4) != 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float send = h4 ? v[q] : v[q + 4];
+    const float keep = h4 ? v[q + 4] : v[q];
+    u[q] = keep + __shfl_xor_sync(kFullMask, send, 4);
+  }
+  const bool h2 = (j & 2) != 0;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float send = h2 ? u[q] : u[q + 2];
+    const float keep = h2 ? u[q + 2] : u[q];
+    t[q] = keep + __shfl_xor_sync(kFullMask, send, 2);
+  }
+  const bool h1 = (j & 1) != 0;
+  const float send = h1 ? t[0] : t[1];
+  const float keep = h1 ? t[1] : t[0];
+  return keep + __shfl_xor_sync(kFullMask, send, 1);
+}
+
+// One level of the hash grid for point (x,y,z) in [0,1]^3: cell corner + trilinear fractions.
+struct LevelCell {
+  uint32_t ix, iy, iz;
+  float wx, wy, wz;
+};
+__device__ __forceinline__ LevelCell level_cell(float s, float x, float y, float z) {
+  LevelCell c;
+  const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
+  const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+  c.ix = (uint32_t)(int)fx;
+  c.iy = (uint32_t)(int)fy;
+  c.iz = (uint32_t)(int)fz;
+  c.wx = px - fx;
+  c.wy = py - fy;
+  c.wz = pz - fz;
+  return c;
+}
+__device__ __forceinline__ float corner_weight(const LevelCell& c, int k) {
+  return ((k & 1) ? c.wx : 1.f - c.wx) * (((k >> 1) & 1) ? c.wy : 1.f - c.wy) * (((k >> 2) & 1) ? c.wz : 1.f - c.wz);
+}
+
+int launch_render_fwd2(const FieldMeta& f, const FieldPtrs& p, const MarchMeta& m, const RayIO& io,
+                       const RenderTape* tape, cudaStream_t stream);
+int launch_render_bwd2(const FieldMeta& f, const FieldPtrs& p, const FieldGrads& g, const MarchMeta& m, const RayIO& io,
+                       const RenderTape& tape, cudaStream_t stream);

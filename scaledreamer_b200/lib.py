@@ -47,6 +47,11 @@ class PackedSamplesC(C.Structure):
                 ("rgb", C.c_void_p), ("normal", C.c_void_p)]
 
 
+class RenderTapeC(C.Structure):
+    _fields_ = [("capacity", C.c_int), ("max_chunks", C.c_int), ("counter", C.c_void_p), ("enc", C.c_void_p),
+                ("pos", C.c_void_p), ("sample", C.c_void_p), ("ray_chunks", C.c_void_p), ("ray_nchunks", C.c_void_p)]
+
+
 class GemmArgsC(C.Structure):
     _fields_ = [("A", C.c_void_p), ("lda", C.c_longlong), ("B", C.c_void_p), ("ldb", C.c_longlong),
                 ("out", C.c_void_p), ("ldc", C.c_longlong), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
@@ -109,6 +114,11 @@ SIGNATURES = {
                                 _P, _P, _P, _P, _P, _P, C.POINTER(PackedSamplesC), _P, _P],
     "sdb_render_nerf_backward": [C.POINTER(FieldC), C.POINTER(FieldGradsC), C.POINTER(MarchCfgC), _P, _P, _P, _P,
                                  _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "sdb_render_tape_geometry": [C.POINTER(MarchCfgC), _F, _I, C.POINTER(C.c_longlong), C.POINTER(C.c_int)],
+    "sdb_render_nerf_forward_v2": [C.POINTER(FieldC), C.POINTER(MarchCfgC), _P, _P, _P, _P, _P, _P, _I, _I,
+                                   _P, _P, _P, _P, _P, _P, C.POINTER(RenderTapeC), _P, _P],
+    "sdb_render_nerf_backward_tape": [C.POINTER(FieldC), C.POINTER(FieldGradsC), C.POINTER(MarchCfgC), _P, _P, _I, _I,
+                                      _P, _P, _P, _P, _P, _P, _P, C.POINTER(RenderTapeC), _P],
     "sdb_raygen": [_P, _P, _I, _I, _I, _P, _P, _P],
     "sdb_adamw_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
     # ---- include/sdb200_nn.h

@@ -220,24 +220,124 @@ def render_backward_raw(spec: FieldSpec, march: MarchSpec, params, grads, occ: O
         L.ptr(g_opacity), L.ptr(g_depth), L.ptr(work), L.stream_ptr()), "sdb_render_nerf_backward")
 
 
+class RenderTape:
+    """Device buffers of the v2 renderer's sample tape (include/sdb200.h sdb_render_tape), sized for the worst case
+    (every lattice sample of every ray kept) so the forward can never overflow it. Tapes are pooled: a forward takes
+    a free one, its backward hands it back (two forwards before a backward simply use two tapes)."""
+
+    _pool: Dict[tuple, list] = {}
+    n_allocated = 0  # tapes ever created (diagnostics: should stay at the number of concurrently live forwards)
+
+    def __init__(self, capacity: int, max_chunks: int, n_rays: int, device):
+        RenderTape.n_allocated += 1
+        self.capacity, self.max_chunks, self.n_rays = capacity, max_chunks, n_rays
+        self.counter = torch.zeros(2, dtype=torch.int32, device=device)
+        self.enc = torch.empty(capacity * 32, device=device)
+        self.pos = torch.empty(3 * capacity, device=device)
+        self.sample = torch.empty(8 * capacity, device=device)
+        self.ray_chunks = torch.empty(n_rays * max_chunks, dtype=torch.int32, device=device)
+        self.ray_nchunks = torch.zeros(n_rays, dtype=torch.int32, device=device)
+        self.key = None
+
+    def to_c(self) -> L.RenderTapeC:
+        return L.RenderTapeC(self.capacity, self.max_chunks, L.ptr(self.counter), L.ptr(self.enc), L.ptr(self.pos),
+                             L.ptr(self.sample), L.ptr(self.ray_chunks), L.ptr(self.ray_nchunks))
+
+    @classmethod
+    def acquire(cls, march: "MarchSpec", radius: float, n_rays: int, device) -> "RenderTape":
+        lib = L.load()
+        m = march.to_c()
+        cap, mc = C.c_longlong(), C.c_int()
+        L.check(lib.sdb_render_tape_geometry(C.byref(m), float(radius), int(n_rays), C.byref(cap), C.byref(mc)),
+                "sdb_render_tape_geometry")
+        if cap.value > (1 << 27):
+            raise RuntimeError(f"render tape of {cap.value} samples exceeds 2^27 slots; split the ray batch")
+        key = (int(cap.value), int(mc.value), int(n_rays), str(device))
+        free = cls._pool.setdefault(key, [])
+        tape = free.pop() if free else cls(int(cap.value), int(mc.value), int(n_rays), device)
+        tape.key = key
+        return tape
+
+    def release(self) -> None:
+        if self.key is not None:
+            self._pool.setdefault(self.key, []).append(self)
+            self.key = None
+
+    def check_overflow(self) -> None:
+        if int(self.counter[1].item()) != 0:
+            raise RuntimeError("render tape overflow: kept samples exceeded the worst-case capacity")
+
+
+def render_forward_v2_raw(spec: FieldSpec, march: MarchSpec, params, occ: OccGrid, rays_o, rays_d, jitter, bg_override,
+                          rays_per_image: int, tape: Optional[RenderTape]):
+    """Runs sdb_render_nerf_forward_v2 (tape may be None: no gradient wanted)."""
+    lib = L.load()
+    f = make_field_c(spec, params)
+    m = march.to_c()
+    dev = rays_o.device
+    n = rays_o.shape[0]
+    out = {k: torch.empty(n, 3, device=dev) for k in ("comp_rgb", "comp_rgb_fg", "comp_rgb_bg")}
+    out.update({k: torch.empty(n, device=dev) for k in ("opacity", "depth", "z_variance")})
+    work = torch.zeros(1, dtype=torch.int32, device=dev)
+    tc = tape.to_c() if tape is not None else None
+    L.check(lib.sdb_render_nerf_forward_v2(
+        C.byref(f), C.byref(m), L.ptr(occ.bits), L.ptr(occ.mean), L.ptr(rays_o), L.ptr(rays_d), L.ptr(jitter),
+        L.ptr(bg_override), n, int(rays_per_image), L.ptr(out["comp_rgb"]), L.ptr(out["comp_rgb_fg"]),
+        L.ptr(out["comp_rgb_bg"]), L.ptr(out["opacity"]), L.ptr(out["depth"]), L.ptr(out["z_variance"]),
+        C.byref(tc) if tc is not None else None, L.ptr(work), L.stream_ptr()), "sdb_render_nerf_forward_v2")
+    out["packed"] = None
+    return out
+
+
+def render_backward_tape_raw(spec: FieldSpec, march: MarchSpec, params, grads, rays_d, bg_override,
+                             rays_per_image: int, saved, tape: RenderTape, g_comp_rgb, g_opacity=None,
+                             g_depth=None) -> None:
+    """Runs sdb_render_nerf_backward_tape; accumulates into `grads` (dict keyed like params)."""
+    lib = L.load()
+    f = make_field_c(spec, params)
+    m = march.to_c()
+    g = L.FieldGradsC()
+    for name, key in (("table", "table"), ("w1_density", "w1d"), ("w2_density", "w2d"), ("w1_feature", "w1f"),
+                      ("w2_feature", "w2f"), ("bg_table", "bg_table"), ("bg_w1", "bg_w1"), ("bg_w2", "bg_w2"),
+                      ("bg_w3", "bg_w3")):
+        setattr(g, name, L.ptr(grads[key]))
+    tc = tape.to_c()
+    L.check(lib.sdb_render_nerf_backward_tape(
+        C.byref(f), C.byref(g), C.byref(m), L.ptr(rays_d), L.ptr(bg_override), rays_d.shape[0], int(rays_per_image),
+        L.ptr(saved["comp_rgb_fg"]), L.ptr(saved["comp_rgb_bg"]), L.ptr(saved["opacity"]), L.ptr(saved["depth"]),
+        L.ptr(g_comp_rgb), L.ptr(g_opacity), L.ptr(g_depth), C.byref(tc), L.stream_ptr()),
+        "sdb_render_nerf_backward_tape")
+
+
 class _RenderNeRF(torch.autograd.Function):
     """comp_rgb, opacity, depth = render(params...) with the fused backward. Gradient flows to the nine field
-    parameter tensors only (rays are data)."""
+    parameter tensors only (rays are data). Default path: v2 forward + sample tape + tape backward. When per-sample
+    extras are requested (packed_capacity > 0) the v1 kernels run instead (forward with packed outputs, backward by
+    re-marching)."""
 
     @staticmethod
     def forward(ctx, spec, march, occ, rays_o, rays_d, jitter, bg_override, rays_per_image, packed_capacity,
                 holder, *param_tensors):
         params = dict(zip(PARAM_KEYS, param_tensors))
-        out = render_forward_raw(spec, march, params, occ, rays_o, rays_d, jitter, bg_override, rays_per_image,
-                                 packed_capacity)
         ctx.spec, ctx.march, ctx.occ, ctx.rpi = spec, march, occ, rays_per_image
-        ctx.bits_snapshot = occ.bits.clone()  # the grid may be refreshed before backward runs
-        ctx.mean_snapshot = occ.mean.clone()
+        ctx.has_jitter, ctx.has_bg = jitter is not None, bg_override is not None
+        ctx.tape = None
+        need_grad = any(ctx.needs_input_grad[10:])
+        if packed_capacity > 0:
+            out = render_forward_raw(spec, march, params, occ, rays_o, rays_d, jitter, bg_override, rays_per_image,
+                                     packed_capacity)
+            ctx.bits_snapshot = occ.bits.clone()  # the grid may be refreshed before backward runs
+            ctx.mean_snapshot = occ.mean.clone()
+        else:
+            if need_grad:
+                ctx.tape = RenderTape.acquire(march, spec.radius, rays_o.shape[0], rays_o.device)
+            out = render_forward_v2_raw(spec, march, params, occ, rays_o, rays_d, jitter, bg_override,
+                                        rays_per_image, ctx.tape)
         ctx.save_for_backward(rays_o, rays_d, jitter if jitter is not None else rays_o.new_zeros(0),
                               bg_override if bg_override is not None else rays_o.new_zeros(0),
                               out["comp_rgb_fg"], out["comp_rgb_bg"], out["opacity"], out["depth"], *param_tensors)
-        ctx.has_jitter, ctx.has_bg = jitter is not None, bg_override is not None
         holder.update(out)  # non-differentiable extras (fg/bg/z_variance/packed) for the caller
+        holder["tape"] = ctx.tape
         ctx.mark_non_differentiable(out["comp_rgb_fg"], out["comp_rgb_bg"], out["z_variance"])
         return out["comp_rgb"], out["opacity"], out["depth"]
 
@@ -246,15 +346,22 @@ class _RenderNeRF(torch.autograd.Function):
         rays_o, rays_d, jitter, bg_override, fg, bg, op, depth, *param_tensors = ctx.saved_tensors
         params = dict(zip(PARAM_KEYS, param_tensors))
         grads = {k: torch.zeros_like(v) for k, v in params.items()}
-        occ = ctx.occ
-        snap = OccGrid.__new__(OccGrid)
-        snap.res, snap.bits, snap.mean, snap.occs = occ.res, ctx.bits_snapshot, ctx.mean_snapshot, occ.occs
         g_rgb = g_rgb.contiguous() if g_rgb is not None else torch.zeros_like(fg)
-        render_backward_raw(ctx.spec, ctx.march, params, grads, snap, rays_o, rays_d,
-                            jitter if ctx.has_jitter else None, bg_override if ctx.has_bg else None, ctx.rpi,
-                            {"comp_rgb_fg": fg, "comp_rgb_bg": bg, "opacity": op, "depth": depth}, g_rgb,
-                            g_op.contiguous() if g_op is not None else None,
-                            g_depth.contiguous() if g_depth is not None else None)
+        g_op = g_op.contiguous() if g_op is not None else None
+        g_depth = g_depth.contiguous() if g_depth is not None else None
+        saved = {"comp_rgb_fg": fg, "comp_rgb_bg": bg, "opacity": op, "depth": depth}
+        if ctx.tape is not None:
+            render_backward_tape_raw(ctx.spec, ctx.march, params, grads, rays_d, bg_override if ctx.has_bg else None,
+                                     ctx.rpi, saved, ctx.tape, g_rgb, g_op, g_depth)
+            ctx.tape.release()
+            ctx.tape = None
+        else:
+            occ = ctx.occ
+            snap = OccGrid.__new__(OccGrid)
+            snap.res, snap.bits, snap.mean, snap.occs = occ.res, ctx.bits_snapshot, ctx.mean_snapshot, occ.occs
+            render_backward_raw(ctx.spec, ctx.march, params, grads, snap, rays_o, rays_d,
+                                jitter if ctx.has_jitter else None, bg_override if ctx.has_bg else None, ctx.rpi,
+                                saved, g_rgb, g_op, g_depth)
         return (None,) * 10 + tuple(grads[k] for k in PARAM_KEYS)
 
 

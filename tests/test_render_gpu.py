@@ -63,7 +63,8 @@ def test_field_forward_parity(cuda_device):
     assert cos.median() > 0.999 and (cos > 0.99).float().mean() > 0.97
 
 
-def _run_gpu(sc, dev, bg_override=None, jitter=True, packed=0, output_normal=False):
+def _run_gpu(sc, dev, bg_override=None, jitter=True, packed=0, output_normal=False, version=1, tape=False):
+    """version 1: recompute-based kernels (render_fwd.cu); version 2: tiled MLP + sample tape (render_fwd2.cu)."""
     from scaledreamer_b200 import render_ops as R
 
     spec = field_spec_from_oracle(sc["fcfg"])
@@ -71,9 +72,15 @@ def _run_gpu(sc, dev, bg_override=None, jitter=True, packed=0, output_normal=Fal
     occ = R.OccGrid(sc["mcfg"].grid_res, dev)
     occ.set_binaries(sc["binary"], sc["occs"])
     P = _to(dev, sc["P"])
-    out = R.render_forward_raw(spec, march, P, occ, sc["rays_o"].to(dev).contiguous(), sc["rays_d"].to(dev).contiguous(),
-                               sc["jitter"].to(dev) if jitter else None,
-                               bg_override.to(dev) if bg_override is not None else None, sc["H"] * sc["W"], packed)
+    ro_, rd_ = sc["rays_o"].to(dev).contiguous(), sc["rays_d"].to(dev).contiguous()
+    jit = sc["jitter"].to(dev) if jitter else None
+    bgo = bg_override.to(dev) if bg_override is not None else None
+    if version == 1:
+        out = R.render_forward_raw(spec, march, P, occ, ro_, rd_, jit, bgo, sc["H"] * sc["W"], packed)
+    else:
+        tp = R.RenderTape.acquire(march, spec.radius, ro_.shape[0], dev) if tape else None
+        out = R.render_forward_v2_raw(spec, march, P, occ, ro_, rd_, jit, bgo, sc["H"] * sc["W"], tp)
+        out["tape"] = tp
     torch.cuda.synchronize()
     return out, (spec, march, occ, P)
 
@@ -86,25 +93,61 @@ def _check_rays(out, ref, max_abs=2e-2):
         assert ((a - b).abs() > 1e-3).float().mean() < 2e-3, k
 
 
+@pytest.mark.parametrize("version", [1, 2])
 @pytest.mark.parametrize("H,W,B,prune", [(32, 32, 1, True), (24, 40, 2, True), (16, 16, 1, False)])
-def test_render_forward_parity(cuda_device, H, W, B, prune):
+def test_render_forward_parity(cuda_device, H, W, B, prune, version):
     sc = scene(H=H, W=W, B=B, seed=7 + H, prune=prune, n_samples=512 if prune else 96)
     occ_mean = float(sc["occs"].mean())
     ref = ro.render(sc["rays_o"], sc["rays_d"], sc["jitter"], None, sc["binary"].numpy(), occ_mean, sc["P"],
                     sc["fcfg"], sc["mcfg"], H * W)
-    out, _ = _run_gpu(sc, cuda_device)
+    out, _ = _run_gpu(sc, cuda_device, version=version, tape=(version == 2))
+    if version == 2:
+        out["tape"].check_overflow()
     _check_rays(out, ref)
     zv = out["z_variance"].cpu()
     assert rel_l2(zv, ref["z_variance"]) < 5e-3
 
 
-def test_render_forward_bg_override_and_no_jitter(cuda_device):
+@pytest.mark.parametrize("version", [1, 2])
+def test_render_forward_bg_override_and_no_jitter(cuda_device, version):
     sc = scene(H=16, W=16, B=2, seed=11)
     bgc = torch.tensor([[0.1, 0.5, 0.9], [0.7, 0.2, 0.3]])
     ref = ro.render(sc["rays_o"], sc["rays_d"], None, bgc, sc["binary"].numpy(), float(sc["occs"].mean()), sc["P"],
                     sc["fcfg"], sc["mcfg"], 256)
-    out, _ = _run_gpu(sc, cuda_device, bg_override=bgc, jitter=False)
+    out, _ = _run_gpu(sc, cuda_device, bg_override=bgc, jitter=False, version=version)
     _check_rays(out, ref)
+
+
+def test_render_tape_contents(cuda_device):
+    """The tape holds exactly the oracle's kept samples: count, weights re-accumulating to the opacity image, and the
+    stored encodings equal to a stand-alone hash-grid encode of the stored positions."""
+    from scaledreamer_b200 import render_ops as R
+
+    sc = scene(H=16, W=16, seed=13)
+    ref = ro.render(sc["rays_o"], sc["rays_d"], sc["jitter"], None, sc["binary"].numpy(), float(sc["occs"].mean()),
+                    sc["P"], sc["fcfg"], sc["mcfg"], 256)
+    out, (spec, march, occ, P) = _run_gpu(sc, cuda_device, version=2, tape=True)
+    tp = out["tape"]
+    tp.check_overflow()
+    n = int(tp.counter[0].item())
+    n_ref = ref["ray_indices"].numel()
+    assert abs(n - n_ref) <= max(2, n_ref // 2000), (n, n_ref)
+    cap = tp.capacity
+    w = tp.sample.view(8, cap)[4, :n]
+    assert abs(float(w.sum()) - float(out["opacity"].sum())) < 1e-3 * float(out["opacity"].sum())
+    pos = tp.pos.view(3, cap)[:, :n].t().contiguous()
+    enc = R.hashgrid_forward(pos, P["table"], spec.grid)
+    taped = tp.enc.view(cap // 32, 32, 32).permute(0, 2, 1).reshape(cap, 32)[:n]
+    torch.testing.assert_close(taped, enc, atol=1e-6, rtol=1e-5)
+    # chunk lists cover every slot exactly once
+    nch = tp.ray_nchunks.cpu()
+    chunks = tp.ray_chunks.view(-1, tp.max_chunks).cpu().to(torch.int64) & 0xFFFFFFFF
+    covered = torch.zeros(n, dtype=torch.int32)
+    for r in torch.nonzero(nch)[:, 0].tolist():
+        for c in range(int(nch[r])):
+            v = int(chunks[r, c])
+            covered[(v >> 5):(v >> 5) + (v & 31) + 1] += 1
+    assert bool((covered == 1).all())
 
 
 def test_render_packed_samples_parity(cuda_device):
@@ -154,6 +197,41 @@ def test_render_backward_parity(cuda_device):
         # hidden units whose pre-activation sits within fp32 rounding of 0 flip their ReLU mask between the CPU
         # and the GPU evaluation order; each flip moves one unit's whole contribution, hence the looser bound
         assert r < 5e-3, (k, r)
+
+    # v2: tape-based backward, same oracle, plus agreement with the recompute-based kernel
+    out2, (spec, march, occ, Pd) = _run_gpu(sc, cuda_device, version=2, tape=True)
+    grads2 = {k: torch.zeros_like(v) for k, v in Pd.items()}
+    R.render_backward_tape_raw(spec, march, Pd, grads2, sc["rays_d"].to(cuda_device).contiguous(), None, 576, out2,
+                               out2["tape"], g_rgb.to(cuda_device), g_op.to(cuda_device), g_dp.to(cuda_device))
+    torch.cuda.synchronize()
+    out2["tape"].check_overflow()
+    for k in R.PARAM_KEYS:
+        r = rel_l2(grads2[k].cpu(), P[k].grad)
+        assert r < 5e-3, ("v2", k, r)
+        assert rel_l2(grads2[k], grads[k]) < 5e-3, ("v2 vs v1", k)
+
+
+def test_render_backward_tape_ragged_tail(cuda_device):
+    """Sample count not a multiple of the 128-sample tile and rays without any sample (camera looking away)."""
+    from scaledreamer_b200 import render_ops as R
+
+    sc = scene(H=9, W=7, B=1, seed=31)
+    sc["rays_d"][:20] = -sc["rays_d"][:20]  # these rays miss the box
+    P = {k: v.clone().requires_grad_(True) for k, v in sc["P"].items()}
+    ref = ro.render(sc["rays_o"], sc["rays_d"], sc["jitter"], None, sc["binary"].numpy(), float(sc["occs"].mean()),
+                    P, sc["fcfg"], sc["mcfg"], 63)
+    g = torch.Generator().manual_seed(2)
+    g_rgb = torch.randn(63, 3, generator=g)
+    (ref["comp_rgb"] * g_rgb).sum().backward()
+    out, (spec, march, occ, Pd) = _run_gpu(sc, cuda_device, version=2, tape=True)
+    _check_rays(out, ref)
+    grads = {k: torch.zeros_like(v) for k, v in Pd.items()}
+    R.render_backward_tape_raw(spec, march, Pd, grads, sc["rays_d"].to(cuda_device).contiguous(), None, 63, out,
+                               out["tape"], g_rgb.to(cuda_device))
+    torch.cuda.synchronize()
+    assert int(out["tape"].counter[0].item()) % 128 != 0
+    for k in R.PARAM_KEYS:
+        assert rel_l2(grads[k].cpu(), P[k].grad) < 5e-3, k
 
 
 def test_render_autograd_function_and_bg_detach(cuda_device):
