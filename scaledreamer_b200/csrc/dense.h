@@ -47,6 +47,9 @@ struct GemmParams {
   long long ldr;
   float alpha;
   int act;
+  int splits;          // > 1: split-K over blockIdx.z, fp32 partial planes in ws, epilogue by splitk_finalize_kernel
+  float* ws;           // [splits][M][N] fp32
+  int row_softmax;     // BN == 80 only: the epilogue applies softmax over the (single-tile) row of N <= 80 scores
 };
 
 struct GemmPlan {
@@ -72,6 +75,7 @@ struct Epilogue {
   long long ldr = 0;
   float alpha = 1.f;
   int act = kActNone;
+  float* splitk_ws = nullptr;  // gemm_splits(M,N,K) * M * N floats: lets the planner split K when M*N is small
 };
 
 // out[M,N] = A[M,K] * B[N,K]^T. lda/ldb in elements (multiples of 8). Optional batching over z with element strides.
@@ -81,11 +85,14 @@ int plan_gemm(GemmPlan* plan, const __half* A, long long lda, const __half* B, l
 int plan_conv3x3(GemmPlan* plan, const __half* x, int N, int H, int W, int Cin, const __half* w, int Cout,
                  const Epilogue& ep);
 // S[b,h,Lq,Lk] = alpha * Q_h K_h^T for Q [B,Lq,heads*64] (row stride ldq), K [B,Lk,heads*64] (ldk). S row stride lds.
+// fuse_softmax (Lk <= 80 only): S holds softmax(alpha Q K^T) and columns [Lk, lds) are zeroed.
 int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __half* K, long long ldk, int B, int heads,
-                     int head_dim, int Lq, int Lk, __half* S, long long lds, float alpha);
+                     int head_dim, int Lq, int Lk, __half* S, long long lds, float alpha, int fuse_softmax = 0);
 // O[b,Lq,h*64:(h+1)*64] = P[b,h,Lq,Lk] V_h for V [B,Lk,heads*64] (ldv); O row stride ldo.
 int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half* V, long long ldv, int B, int heads,
                     int head_dim, int Lq, int Lk, __half* O, long long ldo, float alpha = 1.f);
+// K splits plan_gemm / plan_conv3x3 use for this shape when the epilogue carries a workspace (1 = no split).
+int gemm_splits(int M, int N, int K);
 int run_gemm(const GemmPlan& plan, cudaStream_t stream);
 // per-launch CUDA-event timing of every tcgen05 GEMM launched between begin and end (bench.py roofline)
 void profile_begin();

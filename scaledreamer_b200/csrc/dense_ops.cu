@@ -94,14 +94,18 @@ __global__ void gn_reduce_kernel(const __half* __restrict__ x, const __half* __r
   (void)a1;
 }
 
+// One warp per (n, group, k): lanes stride over the per-block partials, then a butterfly sum -- a fixed order, so the
+// statistics stay bitwise reproducible run to run.
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblk, int groups,
                                    int total) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g, k)
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // (n, g, k)
+  const int lane = threadIdx.x & 31;
   if (i >= total) return;
   const int k = i & 1, g = (i >> 1) % groups, n = (i >> 1) / groups;
   float acc = 0.f;
-  for (int b = 0; b < nblk; ++b) acc += partial[(((size_t)n * nblk + b) * groups + g) * 2 + k];
-  out[i] = acc;
+  for (int b = lane; b < nblk; b += 32) acc += partial[(((size_t)n * nblk + b) * groups + g) * 2 + k];
+  acc = warp_sum(acc);
+  if (lane == 0) out[i] = acc;
 }
 
 // y = act(GN(x)) (MODE 0) or dx of it (MODE 1); 8 channels (16 bytes) per thread.
@@ -214,39 +218,65 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __r
 }
 
 // ---------------------------------------------------------------------------------------------- softmax
-// One 128-thread block per row; up to 4096 columns cached in registers.
-__global__ void __launch_bounds__(128) softmax_kernel(__half* __restrict__ x, int cols, long long ld) {
-  __shared__ float red[4];
+// One block of 32*WARPS threads per row; each thread owns ITEMS groups of 8 consecutive columns (16-byte accesses),
+// the row stays in registers between the max / sum / normalise passes. cols <= 256 * WARPS * ITEMS.
+template <int WARPS, int ITEMS>
+__global__ void __launch_bounds__(32 * WARPS) softmax_kernel(__half* __restrict__ x, int cols, long long ld) {
+  __shared__ float red[WARPS];
   __half* row = x + (size_t)blockIdx.x * ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float v[32];
+  float v[ITEMS][8];
   float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int c = tid + j * 128;
-    v[j] = c < cols ? __half2float(row[c]) : -INFINITY;
-    mx = fmaxf(mx, v[j]);
+  for (int it = 0; it < ITEMS; ++it) {
+    const int c0 = (tid + it * 32 * WARPS) * 8;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (c0 < ld) raw = *reinterpret_cast<const uint4*>(row + c0);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      v[it][2 * e] = c0 + 2 * e < cols ? f.x : -INFINITY;
+      v[it][2 * e + 1] = c0 + 2 * e + 1 < cols ? f.y : -INFINITY;
+      mx = fmaxf(mx, fmaxf(v[it][2 * e], v[it][2 * e + 1]));
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  __syncthreads();
+  if (WARPS > 1) {
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+  }
   float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    v[j] = tid + j * 128 < cols ? __expf(v[j] - mx) : 0.f;
-    sum += v[j];
-  }
-  sum = warp_sum(sum);
-  if (lane == 0) red[warp] = sum;
-  __syncthreads();
-  const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+  for (int it = 0; it < ITEMS; ++it)
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int c = tid + j * 128;
-    if (c < ld && c < 4096) row[c] = __float2half_rn(v[j] * inv);
+    for (int e = 0; e < 8; ++e) {
+      v[it][e] = __expf(v[it][e] - mx);  // exp(-inf) = 0 for the masked tail
+      sum += v[it][e];
+    }
+  sum = warp_sum(sum);
+  if (WARPS > 1) {
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = red[0];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) sum += red[w];
+  }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int c0 = (tid + it * 32 * WARPS) * 8;
+    if (c0 >= ld) continue;
+    uint4 ov;
+    __half2* h2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[it][2 * e] * inv, v[it][2 * e + 1] * inv);
+    *reinterpret_cast<uint4*>(row + c0) = ov;
   }
 }
 
@@ -553,7 +583,7 @@ int groupnorm_forward(const __half* x, const __half* gamma, const __half* beta, 
       x, nullptr, nullptr, nullptr, nullptr, partial, HW, C, groups, P, PY, ppb, eps, 0);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_stats");
-  gn_finalize_kernel<<<(N * groups * 2 + 127) / 128, 128, 0, s>>>(partial, stats, nblk, groups, N * groups * 2);
+  gn_finalize_kernel<<<(N * groups * 2 + 3) / 4, 128, 0, s>>>(partial, stats, nblk, groups, N * groups * 2);
   SDB_COUNT_LAUNCH();
   const long long total8 = (long long)N * HW * C / 8;
   gn_apply_kernel<0><<<ew_grid(total8), 256, 0, s>>>(x, nullptr, gamma, beta, stats, nullptr, y, total8, HW, C, groups,
@@ -573,7 +603,7 @@ int groupnorm_backward(const __half* x, const __half* gamma, const __half* beta,
                                                                                C, groups, P, PY, ppb, eps, act_silu);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_bwd_reduce");
-  gn_finalize_kernel<<<(N * groups * 2 + 127) / 128, 128, 0, s>>>(partial, scratch2, nblk, groups, N * groups * 2);
+  gn_finalize_kernel<<<(N * groups * 2 + 3) / 4, 128, 0, s>>>(partial, scratch2, nblk, groups, N * groups * 2);
   SDB_COUNT_LAUNCH();
   const long long total8 = (long long)N * HW * C / 8;
   gn_apply_kernel<1><<<ew_grid(total8), 256, 0, s>>>(x, dy, gamma, beta, stats, scratch2, dx, total8, HW, C, groups,
@@ -592,11 +622,16 @@ int layernorm_forward(const __half* x, const __half* gamma, const __half* beta, 
 }
 
 int softmax_rows(__half* x, long long rows, int cols, long long ld, cudaStream_t s) {
-  if (cols > 4096 || ld > 4096) {
-    sdb_set_error("softmax: at most 4096 columns (got %d, ld %lld)", cols, ld);
+  if (cols > 4096 || ld > 4096 || (ld & 7) || (reinterpret_cast<uintptr_t>(x) & 15)) {
+    sdb_set_error("softmax: at most 4096 columns, row stride a multiple of 8, 16-byte aligned base (got %d, ld %lld)",
+                  cols, ld);
     return SDB_ERR_UNSUPPORTED;
   }
-  softmax_kernel<<<(unsigned)rows, 128, 0, s>>>(x, cols, ld);
+  const unsigned g = (unsigned)rows;
+  if (ld <= 256) softmax_kernel<1, 1><<<g, 32, 0, s>>>(x, cols, ld);
+  else if (ld <= 1024) softmax_kernel<4, 1><<<g, 128, 0, s>>>(x, cols, ld);
+  else if (ld <= 2048) softmax_kernel<4, 2><<<g, 128, 0, s>>>(x, cols, ld);
+  else softmax_kernel<4, 4><<<g, 128, 0, s>>>(x, cols, ld);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("softmax");
   return SDB_OK;

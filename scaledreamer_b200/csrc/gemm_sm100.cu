@@ -14,6 +14,7 @@
 // extern/mvdream/ldm/modules/diffusionmodules/openaimodel.py:255-275 (ResBlock), ldm/modules/attention.py:163-194
 // (CrossAttention), ldm/modules/diffusionmodules/model.py:129-203 (VAE ResnetBlock / AttnBlock) and their
 // diffusers equivalents (stable_diffusion_asd_guidance.py:170-178, 318-331).
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -33,7 +34,8 @@ template <int BN>
 struct Cfg {
   static constexpr int kBTileBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = BN <= 64 ? 6 : (BN <= 128 ? 4 : 4);
+  // two CTAs share an SM (one CTA's epilogue overlaps the other's main loop): <= ~110 KB of ring per CTA
+  static constexpr int kStages = BN <= 80 ? 4 : 3;
   static constexpr int kTmemCols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -58,7 +60,7 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* tm, const Operan
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
@@ -70,7 +72,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN, z = blockIdx.z;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
@@ -92,7 +94,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int nkb = p.num_k_blocks;
+  // split-K: blockIdx.z selects a contiguous range of K blocks and a fp32 partial plane of the workspace
+  int kb0 = 0, nkb = p.num_k_blocks;
+  if (p.splits > 1) {
+    const int per = (p.num_k_blocks + p.splits - 1) / p.splits;
+    kb0 = blockIdx.z * per;
+    nkb = min(per, p.num_k_blocks - kb0);
+  }
+  const int z = p.splits > 1 ? 0 : (int)blockIdx.z;
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -102,8 +111,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ptx::mbar_wait(&empty[s], ph ^ 1u);
         ptx::mbar_arrive_expect_tx(&full[s], C::kStageBytes);
         uint8_t* sa = base + s * C::kStageBytes;
-        load_operand(&tmA, p.a, sa, &full[s], kb, m0, z);
-        load_operand(&tmB, p.b, sa + kATileBytes, &full[s], kb, n0, z);
+        load_operand(&tmA, p.a, sa, &full[s], kb0 + kb, m0, z);
+        load_operand(&tmB, p.b, sa + kATileBytes, &full[s], kb0 + kb, n0, z);
       }
     }
   } else if (warp == 1) {
@@ -137,6 +146,47 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool m_ok = m < p.M;
     const long long zoff = (long long)(z / p.out_zdiv) * p.out_zs_hi + (long long)(z % p.out_zdiv) * p.out_zs_lo;
     const float* rowb = p.rowbias ? p.rowbias + (long long)(m_ok ? m / p.rows_per_group : 0) * p.rowbias_ld : nullptr;
+    if constexpr (BN == 80) {
+      if (p.row_softmax) {
+        // whole score row in this tile (N <= 80): softmax(alpha * acc) in registers, padding columns zeroed
+        uint32_t v[96];
+        uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+        uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+        uint32_t(&v2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[64]);
+        const uint32_t tb = tmem_base + ((uint32_t)(wq * 32) << 16);
+        ptx::tmem_ld_32x32(tb, v0);
+        ptx::tmem_ld_32x32(tb + 32u, v1);
+        ptx::tmem_ld_32x32(tb + 64u, v2);  // columns 80..95 are unallocated-by-MMA garbage and are masked below
+        ptx::tmem_ld_wait();
+        if (m_ok) {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 80; ++j)
+            if (j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]) * p.alpha);
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 80; ++j) {
+            const float e = j < p.N ? __expf(__uint_as_float(v[j]) * p.alpha - mx) : 0.f;
+            v[j] = __float_as_uint(e);
+            sum += e;
+          }
+          const float inv = 1.f / sum;
+          __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc;
+#pragma unroll
+          for (int q = 0; q < 10; ++q) {
+            if (q * 8 >= p.ldc) break;
+            uint4 ov;
+            __half2* h2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              h2[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]) * inv, __uint_as_float(v[q * 8 + 2 * e + 1]) * inv);
+            reinterpret_cast<uint4*>(o)[q] = ov;
+          }
+        }
+        ptx::tc_fence_before();
+        goto epilogue_done;
+      }
+    }
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t v[32];
@@ -144,6 +194,19 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       ptx::tmem_ld_wait();
       const int nb = n0 + c;
       if (!m_ok || nb >= p.N) continue;
+      if (p.splits > 1) {  // raw fp32 partial sums; splitk_finalize_kernel applies the epilogue
+        float* o = p.ws + ((long long)blockIdx.z * p.M + m) * p.N + nb;
+        if (nb + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<uint4*>(o)[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) o[j] = __uint_as_float(v[j]);
+        }
+        continue;
+      }
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
@@ -215,6 +278,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     ptx::tc_fence_before();
+  epilogue_done:;
   }
   __syncthreads();
   if (warp == 2) {
@@ -238,6 +302,8 @@ EncodeTiledFn get_encode() {
   }
   return fn;
 }
+
+__global__ void splitk_finalize_kernel(const GemmParams p);
 
 // Optional per-launch timing (bench.py roofline): CUDA events on the launching stream around every GEMM launch.
 struct ProfRec {
@@ -263,10 +329,16 @@ int launch(const GemmPlan& plan, cudaStream_t stream) {
   if (g_prof) {
     cudaEventCreate(&rec.a);
     cudaEventCreate(&rec.b);
-    rec.flops = 2.0 * plan.p.M * plan.p.N * plan.p.K * plan.grid.z;
+    rec.flops = 2.0 * plan.p.M * plan.p.N * plan.p.K * (plan.p.splits > 1 ? 1 : plan.grid.z);
     cudaEventRecord(rec.a, stream);
   }
   gemm_f16_kernel<BN><<<plan.grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(plan.ta, plan.tb, plan.p);
+  if (plan.p.splits > 1) {
+    const long long total = (long long)plan.p.M * ((plan.p.N + 3) / 4);
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 8);
+    splitk_finalize_kernel<<<grid, 256, 0, stream>>>(plan.p);
+    SDB_COUNT_LAUNCH();
+  }
   if (g_prof) {
     cudaEventRecord(rec.b, stream);
     g_recs.push_back(rec);
@@ -275,6 +347,21 @@ int launch(const GemmPlan& plan, cudaStream_t stream) {
   SDB_CHECK_LAUNCH("gemm_f16");
   return SDB_OK;
 }
+
+}  // namespace
+
+int gemm_splits(int M, int N, int K) {
+  const int bn = N % 160 == 0 ? 160 : (N <= 64 ? 64 : 128);
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
+  const int nkb = (K + kBK - 1) / kBK;
+  if (tiles >= 64 || nkb < 8) return 1;
+  int sp = std::min(std::min(2 * kNumSMs / tiles, nkb / 4), 16);
+  if (sp <= 1) return 1;
+  const int per = (nkb + sp - 1) / sp;
+  return (nkb + per - 1) / per;  // every split owns at least one K block
+}
+
+namespace {
 
 int pick_bn(int N) {
   if (N % 160 == 0) return 160;
@@ -297,6 +384,47 @@ void fill_epilogue(GemmParams& p, const Epilogue& ep) {
   p.ldr = ep.ldr;
   p.alpha = ep.alpha;
   p.act = ep.act;
+  p.splits = 1;
+  p.ws = nullptr;
+  p.row_softmax = 0;
+}
+
+// thread per 4 output columns: sums the split planes in fixed order (bitwise reproducible), then the GEMM epilogue
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const GemmParams p) {
+  const int n4 = (p.N + 3) / 4;
+  const long long total = (long long)p.M * n4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / n4), nb = (int)(i % n4) * 4;
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < p.splits; ++s) {
+      const float* w = p.ws + ((long long)s * p.M + m) * p.N + nb;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (nb + j < p.N) f[j] += w[j];
+    }
+    const float* rowb = p.rowbias ? p.rowbias + (long long)(m / p.rows_per_group) * p.rowbias_ld : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (nb + j >= p.N) continue;
+      float v = f[j] * p.alpha;
+      if (p.bias) v += __half2float(p.bias[nb + j]);
+      if (rowb) v += rowb[nb + j];
+      if (p.act == kActSilu) v = v / (1.f + __expf(-v));
+      else if (p.act == kActGelu) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+      if (p.residual) v += __half2float(p.residual[(long long)m * p.ldr + nb + j]);
+      if (p.out_fp32) reinterpret_cast<float*>(p.out)[(long long)m * p.ldc + nb + j] = v;
+      else reinterpret_cast<__half*>(p.out)[(long long)m * p.ldc + nb + j] = __float2half_rn(v);
+    }
+  }
+}
+
+void apply_splitk(GemmPlan* plan, const Epilogue& ep) {
+  if (!ep.splitk_ws || plan->grid.z != 1) return;
+  const int sp = gemm_splits(plan->p.M, plan->p.N, plan->p.K);
+  if (sp <= 1) return;
+  plan->p.splits = sp;
+  plan->p.ws = ep.splitk_ws;
+  plan->grid.z = sp;
 }
 
 }  // namespace
@@ -369,6 +497,7 @@ int plan_gemm(GemmPlan* plan, const __half* A, long long lda, const __half* B, l
   rc = make_tmap(&plan->tb, B, 3, db, sb, bb);
   if (rc) return rc;
   plan->grid = dim3((M + kBM - 1) / kBM, (N + plan->bn - 1) / plan->bn, batch);
+  apply_splitk(plan, ep);
   return SDB_OK;
 }
 
@@ -432,11 +561,16 @@ int plan_conv3x3(GemmPlan* plan, const __half* x, int N, int H, int W, int Cin, 
   rc = make_tmap(&plan->tb, w, 3, db, sb, bb);
   if (rc) return rc;
   plan->grid = dim3((p.M + kBM - 1) / kBM, (Cout + plan->bn - 1) / plan->bn, 1);
+  apply_splitk(plan, ep);
   return SDB_OK;
 }
 
 int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __half* K, long long ldk, int B, int heads,
-                     int head_dim, int Lq, int Lk, __half* S, long long lds, float alpha) {
+                     int head_dim, int Lq, int Lk, __half* S, long long lds, float alpha, int fuse_softmax) {
+  if (fuse_softmax && (Lk > 80 || lds > 80 || (lds & 7))) {
+    sdb_set_error("attention: fused softmax needs Lk <= 80 and lds <= 80 (multiple of 8); got %d / %lld", Lk, lds);
+    return SDB_ERR_UNSUPPORTED;
+  }
   if (head_dim % 64) {
     sdb_set_error("attention: head_dim=%d must be a multiple of 64", head_dim);
     return SDB_ERR_UNSUPPORTED;
@@ -458,6 +592,7 @@ int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __hal
   ep.alpha = alpha;
   fill_epilogue(p, ep);
   p.out_zs_hi = (long long)Lq * lds;  // S is [B*heads, Lq, lds]
+  p.row_softmax = fuse_softmax ? 1 : 0;
   uint64_t dq[4] = {(uint64_t)head_dim, (uint64_t)heads, (uint64_t)Lq, (uint64_t)B};
   uint64_t sq[3] = {(uint64_t)head_dim * 2, (uint64_t)ldq * 2, (uint64_t)Lq * ldq * 2};
   uint32_t bq[4] = {64, 1, kBM, 1};

@@ -152,6 +152,8 @@ T Net::gn(std::vector<Op>* ops, const T& x, const std::string& name, float eps, 
 T Net::conv3(std::vector<Op>* ops, const T& x, const __half* w, const __half* bias, int cout, const float* rowbias,
              long long rowbias_ld, const T* residual) {
   T y = act(x.n, x.h, x.w, cout);
+  const int sp = gemm_splits((int)x.rows(), cout, 9 * x.c);  // few output tiles, long K: split K over more SMs
+  float* ws = sp > 1 ? reinterpret_cast<float*>(work((long long)sp * x.rows() * cout * 4)) : nullptr;
   if (!dry_) {
     Epilogue ep;
     ep.out = y.p;
@@ -160,6 +162,7 @@ T Net::conv3(std::vector<Op>* ops, const T& x, const __half* w, const __half* bi
     ep.rowbias = rowbias;
     ep.rows_per_group = x.h * x.w;
     ep.rowbias_ld = rowbias_ld;
+    ep.splitk_ws = ws;
     if (residual) {
       ep.residual = residual->p;
       ep.ldr = cout;
@@ -174,12 +177,15 @@ T Net::conv3(std::vector<Op>* ops, const T& x, const __half* w, const __half* bi
 T Net::linear(std::vector<Op>* ops, const T& x, const __half* w, const __half* bias, int cout, const T* residual,
               int act_kind) {
   T y = act(x.n, x.h, x.w, cout);
+  const int sp = gemm_splits((int)x.rows(), cout, x.c);
+  float* ws = sp > 1 ? reinterpret_cast<float*>(work((long long)sp * x.rows() * cout * 4)) : nullptr;
   if (!dry_) {
     Epilogue ep;
     ep.out = y.p;
     ep.ldc = cout;
     ep.bias = bias;
     ep.act = act_kind;
+    ep.splitk_ws = ws;
     if (residual) {
       ep.residual = residual->p;
       ep.ldr = cout;
@@ -195,6 +201,8 @@ T Net::conv3_s2(std::vector<Op>* ops, const T& x, const __half* w, const __half*
   T y = act(x.n, x.h / 2, x.w / 2, cout);
   reset_scratch();
   __half* col = reinterpret_cast<__half*>(scratch(y.rows() * 9 * x.c * 2));
+  const int sp = gemm_splits((int)y.rows(), cout, 9 * x.c);
+  float* ws = sp > 1 ? reinterpret_cast<float*>(work((long long)sp * y.rows() * cout * 4)) : nullptr;
   if (!dry_) {
     const T xx = x;
     ops->push_back([=](cudaStream_t s) { return im2col_3x3_s2(xx.p, col, xx.n, xx.h, xx.w, xx.c, pad_lo, s); });
@@ -202,6 +210,7 @@ T Net::conv3_s2(std::vector<Op>* ops, const T& x, const __half* w, const __half*
     ep.out = y.p;
     ep.ldc = cout;
     ep.bias = bias;
+    ep.splitk_ws = ws;
     GemmPlan plan;
     if (fail(plan_gemm(&plan, col, 9 * x.c, w, 9 * x.c, (int)y.rows(), cout, 9 * x.c, ep))) return y;
     ops->push_back([plan](cudaStream_t s) { return run_gemm(plan, s); });
@@ -219,12 +228,14 @@ T Net::attention(std::vector<Op>* ops, const __half* q, long long ldq, const __h
   T o = act(B, 1, Lq, inner);
   if (!dry_) {
     GemmPlan ps, pa;
-    if (fail(plan_attn_scores(&ps, q, ldq, k, ldk, B, heads, head_dim, Lq, Lk, S, lds, 1.f / sqrtf((float)head_dim))))
+    const int fuse = Lk <= 80 ? 1 : 0;  // cross-attention: the whole score row sits in one tile, softmax in the epilogue
+    if (fail(plan_attn_scores(&ps, q, ldq, k, ldk, B, heads, head_dim, Lq, Lk, S, lds, 1.f / sqrtf((float)head_dim),
+                              fuse)))
       return o;
     if (fail(plan_attn_apply(&pa, S, lds, v, ldv, B, heads, head_dim, Lq, Lk, o.p, inner))) return o;
     const long long rows = (long long)B * heads * Lq;
     ops->push_back([ps](cudaStream_t s) { return run_gemm(ps, s); });
-    ops->push_back([=](cudaStream_t s) { return softmax_rows(S, rows, Lk, lds, s); });
+    if (!fuse) ops->push_back([=](cudaStream_t s) { return softmax_rows(S, rows, Lk, lds, s); });
     ops->push_back([pa](cudaStream_t s) { return run_gemm(pa, s); });
   }
   return o;

@@ -205,8 +205,8 @@ struct FbSmem {
   float w2f[3 * kHidden];
   float et[4][kEncDim * kEtStride];      // encodings, feature-major per sub-tile
   float dht[kHidden * kDhStride];        // dH^T of the current net: [hidden][sample]
-  float pos[3][kFbTile];
-  float dout[4][kFbTile];                // d raw, d o0..2
+  float pos[2][3][kFbTile];              // double-buffered: the next tile streams in during the scatter
+  float dout[2][4][kFbTile];             // d raw, d o0..2
   float g2d[kHidden];
   float g2f[3 * kHidden];
 };
@@ -258,34 +258,44 @@ render_field_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, 
     lv_hashed[q] = f.grid.hashed[l];
   }
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // cp.async staging of one tile: encodings (16-byte copies, zero-filled past the end), positions, output grads
+  auto issue_tile = [&](int tile, int buf) {
     const int base = tile * kFbTile;
-    // ---- load: encodings (zero for slots past the end), positions, output grads ----
-    {
-      const float4* src = reinterpret_cast<const float4*>(tape.enc + (size_t)base * kEncDim);
+    const float* src = tape.enc + (size_t)base * kEncDim;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int q = tid + kFbThreads * r;        // float4 index within the 4 x 32 x 32 block
-        const int sub = q >> 8, k = (q & 255) >> 3, s4 = q & 7;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int slot = base + sub * 32 + s4 * 4;
-        if (slot + 3 < n) {
-          v = __ldg(src + q);
-        } else if (slot < n) {
-          const float* sc = reinterpret_cast<const float*>(src + q);
-          v.x = sc[0];
-          if (slot + 1 < n) v.y = sc[1];
-          if (slot + 2 < n) v.z = sc[2];
-        }
-        *reinterpret_cast<float4*>(&s.et[sub][k * kEtStride + s4 * 4]) = v;
-      }
-      const int slot = base + tid;
-      const bool ok = slot < n;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) s.pos[c][tid] = ok ? tape.pos[c * cap + slot] : 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) s.dout[c][tid] = ok ? tape.sample[c * cap + slot] : 0.f;
+    for (int r = 0; r < 8; ++r) {
+      const int q = tid + kFbThreads * r;  // float4 index within the 4 x 32 x 32 block
+      const int sub = q >> 8, k = (q & 255) >> 3, s4 = q & 7;
+      const int slot = base + sub * 32 + s4 * 4;
+      const int valid = min(max(n - slot, 0), 4) * 4;  // bytes
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s.et[sub][k * kEtStride + s4 * 4]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + (size_t)q * 4), "r"(valid)
+                   : "memory");
     }
+    const int slot = base + tid;
+    const int valid = slot < n ? 4 : 0;
+    const size_t off = slot < n ? (size_t)slot : 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s.pos[buf][c][tid]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(tape.pos + c * cap + off), "r"(valid)
+                   : "memory");
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s.dout[buf][c][tid]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(tape.sample + c * cap + off),
+                   "r"(valid)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  if ((int)blockIdx.x < n_tiles) issue_tile(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    const int base = tile * kFbTile;
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
     float dE[8][4];  // d enc for samples 8 li + a, features 4 lj + c
@@ -307,7 +317,7 @@ render_field_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, 
           for (int b = 0; b < 8; ++b) w2[b] = s.w2d[hidden_of(lj, b)];
 #pragma unroll
           for (int a = 0; a < 8; ++a) {
-            const float dr = s.dout[0][s0 + a];
+            const float dr = s.dout[buf][0][s0 + a];
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
               const float h = fmaxf(acc[a][b], 0.f);
@@ -325,7 +335,7 @@ render_field_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, 
           }
 #pragma unroll
           for (int a = 0; a < 8; ++a) {
-            const float d0 = s.dout[1][s0 + a], d1 = s.dout[2][s0 + a], d2 = s.dout[3][s0 + a];
+            const float d0 = s.dout[buf][1][s0 + a], d1 = s.dout[buf][2][s0 + a], d2 = s.dout[buf][3][s0 + a];
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
               const float h = fmaxf(acc[a][b], 0.f);
@@ -392,12 +402,15 @@ render_field_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, 
       __syncthreads();  // dht is rewritten by the next net / et by the next tile
     }
 
+    // the tile buffers are free (every thread passed the barrier above): stream the next tile in behind the scatter
+    if (tile + (int)gridDim.x < n_tiles) issue_tile(tile + gridDim.x, buf ^ 1);
+
     // ---- scatter: this lane owns levels 2 lj, 2 lj + 1 of samples 8 li + a ----
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
       const int sl = warp * 32 + 8 * li + a;
       if (base + sl >= n) continue;
-      const float x = s.pos[0][sl], y = s.pos[1][sl], z = s.pos[2][sl];
+      const float x = s.pos[buf][0][sl], y = s.pos[buf][1][sl], z = s.pos[buf][2][sl];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const float gx = dE[a][2 * q], gy = dE[a][2 * q + 1];

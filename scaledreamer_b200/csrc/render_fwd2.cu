@@ -1,6 +1,7 @@
 // Fused NeRF volume-render forward, v2 (sm_100a): warp-per-ray lattice march, rolled 16-level hash-grid encode staged
 // through a per-warp shared-memory tile, density / colour MLPs as 32-sample x 64-unit register tiles, warp-shuffle
-// transmittance scans, front-to-back compositing, background blend -- ONE launch -- and, when a tape is supplied,
+// transmittance scans, front-to-back compositing and background blend in one march launch (the environment map is a
+// thread-per-ray pre-pass) and, when a tape is supplied,
 // a record of every kept sample for the tape-based backward (render_bwd2.cu).
 //
 // Replaces the same reference lines as render_fwd.cu (threestudio/models/renderers/nerf_volume_renderer.py:118-428:
@@ -17,9 +18,6 @@ struct Fwd2Smem {
   float wpf[kWpSize];  // feature W1, permuted
   float w2d[kHidden];
   float w2f[3 * kHidden];
-  float b1[kBgHidden * kBgEncDim];
-  float b2[kBgHidden * kBgHidden];
-  float b3[3 * kBgHidden];
   uint32_t occ[1024];
   float et[kF2Warps][kEncDim * 32];  // per-warp encoding tile, feature-major: et[k][sample]
 };
@@ -50,6 +48,32 @@ __device__ __forceinline__ void encode_to_tile(const float2* __restrict__ table,
   }
 }
 
+// Environment map (or the random-colour override) for every ray, thread per ray -> comp_rgb_bg.
+__global__ void __launch_bounds__(128)
+render_bg_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, const RayIO io) {
+  __shared__ float b1[kBgHidden * kBgEncDim], b2[kBgHidden * kBgHidden], b3[3 * kBgHidden];
+  for (int i = threadIdx.x; i < kBgHidden * kBgEncDim; i += blockDim.x) b1[i] = p.bg_w1[i];
+  for (int i = threadIdx.x; i < kBgHidden * kBgHidden; i += blockDim.x) b2[i] = p.bg_w2[i];
+  for (int i = threadIdx.x; i < 3 * kBgHidden; i += blockDim.x) b3[i] = p.bg_w3[i];
+  __syncthreads();
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= io.n_rays) return;
+  float bg[3];
+  if (io.bg_override) {
+    const int img = ray / io.rays_per_image;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) bg[c] = __ldg(io.bg_override + 3 * img + c);
+  } else {
+    BgActs a;
+    bg_forward(f, reinterpret_cast<const float2*>(p.bg_table), b1, b2, b3, __ldg(io.rays_d + 3 * ray),
+               __ldg(io.rays_d + 3 * ray + 1), __ldg(io.rays_d + 3 * ray + 2), a, bg);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) io.comp_rgb_bg[3 * ray + c] = bg[c];
+}
+
+constexpr int kRaysPerItem = 4;  // work-stealing granularity: consecutive rays of one image row
+
 __global__ void __launch_bounds__(kF2Warps * 32, 4)
 render_nerf_fwd2_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, const __grid_constant__ MarchMeta m,
                         const RayIO io, const RenderTape tape, const int has_tape) {
@@ -60,18 +84,14 @@ render_nerf_fwd2_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, 
   stage_w1_perm(s.wpf, p.w1f, threadIdx.x, blockDim.x);
   for (int i = threadIdx.x; i < kHidden; i += blockDim.x) s.w2d[i] = p.w2d[i];
   for (int i = threadIdx.x; i < 3 * kHidden; i += blockDim.x) s.w2f[i] = p.w2f[i];
-  for (int i = threadIdx.x; i < kBgHidden * kBgEncDim; i += blockDim.x) s.b1[i] = p.bg_w1[i];
-  for (int i = threadIdx.x; i < kBgHidden * kBgHidden; i += blockDim.x) s.b2[i] = p.bg_w2[i];
-  for (int i = threadIdx.x; i < 3 * kBgHidden; i += blockDim.x) s.b3[i] = p.bg_w3[i];
   for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s.occ[i] = io.occ_bits[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int li = lane >> 3, lj = lane & 7;
   float* et = s.et[warp];
-  const int n_items = (io.n_rays + 31) / 32;
+  const int n_items = (io.n_rays + kRaysPerItem - 1) / kRaysPerItem;
   const float2* table = reinterpret_cast<const float2*>(p.table);
-  const float2* bg_table = reinterpret_cast<const float2*>(p.bg_table);
   const float inv2r = 0.5f / f.radius;
   float thre = 0.f, eps_T = 0.f;
   if (m.prune) {
@@ -86,36 +106,13 @@ render_nerf_fwd2_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, 
     item = __shfl_sync(kFullMask, item, 0);
     if (item >= n_items) break;
 
-    // ---- phase 1: per-lane ray setup + background (thread per ray) ----
-    const int my_ray = lane * n_items + item;
-    const bool my_valid = my_ray < io.n_rays;
-    float mo[3] = {0.f, 0.f, 0.f}, md[3] = {0.f, 0.f, 1.f}, mjit = 0.f, mbg[3] = {0.f, 0.f, 0.f};
-    if (my_valid) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        mo[c] = __ldg(io.rays_o + 3 * my_ray + c);
-        md[c] = __ldg(io.rays_d + 3 * my_ray + c);
-      }
-      if (io.jitter) mjit = __ldg(io.jitter + my_ray);
-      if (io.bg_override) {
-        const int img = my_ray / io.rays_per_image;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) mbg[c] = __ldg(io.bg_override + 3 * img + c);
-      } else {
-        BgActs a;
-        bg_forward(f, bg_table, s.b1, s.b2, s.b3, md[0], md[1], md[2], a, mbg);
-      }
-    }
-    float r_op = 0.f, r_depth = 0.f, r_tt = 0.f, r_fg[3] = {0.f, 0.f, 0.f};
-
-    // ---- phase 2: warp-per-ray march over the bundle ----
-    for (int r = 0; r < 32; ++r) {
-      const int ray = r * n_items + item;
+    for (int r = 0; r < kRaysPerItem; ++r) {
+      const int ray = item * kRaysPerItem + r;
       if (ray >= io.n_rays) break;
       Marcher mc;
-      mc.init(__shfl_sync(kFullMask, mo[0], r), __shfl_sync(kFullMask, mo[1], r), __shfl_sync(kFullMask, mo[2], r),
-              __shfl_sync(kFullMask, md[0], r), __shfl_sync(kFullMask, md[1], r), __shfl_sync(kFullMask, md[2], r),
-              __shfl_sync(kFullMask, mjit, r), m, f.radius);
+      mc.init(__ldg(io.rays_o + 3 * ray), __ldg(io.rays_o + 3 * ray + 1), __ldg(io.rays_o + 3 * ray + 2),
+              __ldg(io.rays_d + 3 * ray), __ldg(io.rays_d + 3 * ray + 1), __ldg(io.rays_d + 3 * ray + 2),
+              io.jitter ? __ldg(io.jitter + ray) : 0.f, m, f.radius);
       float S_all = 0.f, S_kept = 0.f;
       float a_w = 0.f, a_wt = 0.f, a_wtt = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f;
       int nchunk = 0;
@@ -243,32 +240,22 @@ render_nerf_fwd2_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, 
       a_r = warp_sum(a_r);
       a_g = warp_sum(a_g);
       a_b = warp_sum(a_b);
-      if (lane == r) {
-        r_op = a_w;
-        r_depth = a_wt;
-        r_tt = a_wtt;
-        r_fg[0] = a_r;
-        r_fg[1] = a_g;
-        r_fg[2] = a_b;
-      }
-    }
-
-    // ---- phase 3: per-lane outputs ----
-    if (my_valid) {
-      const float one_m = 1.f - r_op;
+      if (lane == 0) {
+        const float fg[3] = {a_r, a_g, a_b};
+        const float one_m = 1.f - a_w;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        io.comp_rgb_fg[3 * my_ray + c] = r_fg[c];
-        io.comp_rgb_bg[3 * my_ray + c] = mbg[c];
-        io.comp_rgb[3 * my_ray + c] = fmaf(mbg[c], one_m, r_fg[c]);
+        for (int c = 0; c < 3; ++c) {
+          io.comp_rgb_fg[3 * ray + c] = fg[c];
+          io.comp_rgb[3 * ray + c] = fmaf(io.comp_rgb_bg[3 * ray + c], one_m, fg[c]);  // bg: render_bg_kernel
+        }
+        io.opacity[ray] = a_w;
+        io.depth[ray] = a_wt;
+        // z-variance (nerf_volume_renderer.py:335-349) in one pass: sum w~ (t - zbar)^2 with w~ = w / clamp(op, 1e-5)
+        const float cl = fmaxf(a_w, 1e-5f);
+        const float zbar = a_wt / cl;
+        const float zv = a_wtt / cl - 2.f * zbar * (a_wt / cl) + zbar * zbar * (a_w / cl);
+        io.z_variance[ray] = a_w > 0.5f ? fmaxf(zv, 0.f) : 0.f;
       }
-      io.opacity[my_ray] = r_op;
-      io.depth[my_ray] = r_depth;
-      // z-variance (nerf_volume_renderer.py:335-349) in one pass: sum w~ (t - zbar)^2 with w~ = w / clamp(op, 1e-5)
-      const float cl = fmaxf(r_op, 1e-5f);
-      const float zbar = r_depth / cl;
-      const float zv = r_tt / cl - 2.f * zbar * (r_depth / cl) + zbar * zbar * (r_op / cl);
-      io.z_variance[my_ray] = r_op > 0.5f ? fmaxf(zv, 0.f) : 0.f;
     }
   }
 }
@@ -294,7 +281,10 @@ int launch_render_fwd2(const FieldMeta& f, const FieldPtrs& p, const MarchMeta& 
     t = *tape;
     cudaMemsetAsync(t.counter, 0, 2 * sizeof(int), stream);
   }
-  const int n_items = (io.n_rays + 31) / 32;
+  render_bg_kernel<<<(io.n_rays + 127) / 128, 128, 0, stream>>>(f, p, io);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("render_bg");
+  const int n_items = (io.n_rays + kRaysPerItem - 1) / kRaysPerItem;
   const int grid = min(kNumSMs * 4, (n_items + kF2Warps - 1) / kF2Warps);
   render_nerf_fwd2_kernel<<<grid, kF2Warps * 32, sizeof(Fwd2Smem), stream>>>(f, p, m, io, t, tape ? 1 : 0);
   SDB_COUNT_LAUNCH();
