@@ -297,6 +297,8 @@ def main() -> None:
         acc = {"render_fwd": 0.0, "guidance_fwd": 0.0, "backward": 0.0, "optimizer": 0.0}
         n_prof = 3
         lib.sdb_gemm_profile_begin()
+        if os.environ.get("SDB_GEMM_CSV"):
+            lib.sdb_gemm_profile_dump(os.environ["SDB_GEMM_CSV"].encode())
         samples_kept = 0
         fwd_each = []
         for _ in range(n_prof):

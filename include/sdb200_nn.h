@@ -51,6 +51,8 @@ int sdb_gemm_f16(const sdb_gemm_args* args, void* stream);
  * launch) and launch count. */
 int sdb_gemm_profile_begin(void);
 int sdb_gemm_profile_end(double* total_ms, double* total_flops, int* launches);
+/* HOST path: the next sdb_gemm_profile_end() also writes one CSV row per launch (M,N,K,batch,splits,bn,mode,ms). */
+int sdb_gemm_profile_dump(const char* csv_path);
 
 /* 3x3 stride-1 pad-1 convolution as implicit GEMM: x [N,H,W,Cin], w [Cout, 3,3,Cin] (= [Cout, 9*Cin]),
  * out [N,H,W,Cout]; epilogue as sdb_gemm_f16 with rows_per_group = H*W (the per-image timestep-embedding add
@@ -68,6 +70,10 @@ int sdb_conv3x3_small(const void* x, int x_fp32, const void* weight, const void*
  * Replaces CrossAttention.forward (attention.py:163-194) / diffusers AttnProcessor2_0. */
 int sdb_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                       int batch, int heads, int lq, int lk, void* scores, void* out, long long ldo, void* stream);
+/* Same result without the scores buffer: one fused tcgen05 kernel (QK^T into tensor memory, online softmax,
+ * PV from a shared-memory P tile). head_dim 64. Used for every self-attention of the UNet. */
+int sdb_flash_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                            int batch, int heads, int lq, int lk, void* out, long long ldo, void* stream);
 
 /* GroupNorm over [N, HW, C] with optional fused SiLU (GroupNorm32 + SiLU, openaimodel.py:200-203; Normalize +
  * nonlinearity, model.py:129-141). stats / scratch: fp32 buffers of sdb_groupnorm_workspace_floats() elements; the

@@ -70,6 +70,17 @@ int sdb_attention_f16(const void* q, long long ldq, const void* k, long long ldk
   return run_gemm(pa, (cudaStream_t)stream);
 }
 
+int sdb_flash_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                            int batch, int heads, int lq, int lk, void* out, long long ldo, void* stream) {
+  SDB_CHECK_ARG(q && k && v && out && batch > 0 && heads > 0 && lq > 0 && lk > 0, "flash_attention: bad arguments");
+  FlashPlan fp;
+  int rc = plan_flash_attn(&fp, reinterpret_cast<const __half*>(q), ldq, reinterpret_cast<const __half*>(k), ldk,
+                           reinterpret_cast<const __half*>(v), ldv, batch, heads, 64, lq, lk,
+                           reinterpret_cast<__half*>(out), ldo, 0.125f);
+  if (rc) return rc;
+  return run_flash_attn(fp, (cudaStream_t)stream);
+}
+
 long long sdb_groupnorm_workspace_floats(int n, int hw, int c, int groups) {
   return groupnorm_workspace_floats(n, hw, c, groups);
 }
@@ -124,6 +135,11 @@ int sdb_col2im3x3s2_f16(const void* col, void* dx, int n, int h, int w, int c, i
 
 int sdb_gemm_profile_begin(void) {
   profile_begin();
+  return SDB_OK;
+}
+
+int sdb_gemm_profile_dump(const char* csv_path) {
+  profile_dump_to(csv_path);
   return SDB_OK;
 }
 

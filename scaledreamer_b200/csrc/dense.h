@@ -94,8 +94,24 @@ int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half
 // K splits plan_gemm / plan_conv3x3 use for this shape when the epilogue carries a workspace (1 = no split).
 int gemm_splits(int M, int N, int K);
 int run_gemm(const GemmPlan& plan, cudaStream_t stream);
+
+// Fused attention (flash_attn_sm100.cu): O[b,Lq,h*64:(h+1)*64] = softmax(alpha Q_h K_h^T) V_h, head_dim 64, no score
+// matrix in HBM. Q [B,Lq,heads*64] (row stride ldq), K/V [B,Lk,heads*64] (ldk/ldv), O row stride ldo.
+struct FlashPlan {
+  CUtensorMap tq, tk, tv;
+  int Lq, Lk, heads;
+  float scale_log2;
+  __half* out;
+  long long ldo;
+  dim3 grid;
+  double flops;
+};
+int plan_flash_attn(FlashPlan* plan, const __half* Q, long long ldq, const __half* K, long long ldk, const __half* V,
+                    long long ldv, int B, int heads, int head_dim, int Lq, int Lk, __half* O, long long ldo, float alpha);
+int run_flash_attn(const FlashPlan& plan, cudaStream_t stream);
 // per-launch CUDA-event timing of every tcgen05 GEMM launched between begin and end (bench.py roofline)
 void profile_begin();
+void profile_dump_to(const char* path);  // the next profile_end() also writes one CSV row per launch
 int profile_end(double* ms, double* flops, int* launches);
 
 // ---- normalisation / element-wise kernels (dense_ops.cu) ------------------------------------------------

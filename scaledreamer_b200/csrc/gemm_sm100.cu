@@ -309,7 +309,9 @@ __global__ void splitk_finalize_kernel(const GemmParams p);
 struct ProfRec {
   cudaEvent_t a, b;
   double flops;
+  int M, N, K, z, splits, bn, mode;
 };
+char g_prof_dump[512] = "";
 bool g_prof = false;
 std::vector<ProfRec> g_recs;
 
@@ -330,6 +332,8 @@ int launch(const GemmPlan& plan, cudaStream_t stream) {
     cudaEventCreate(&rec.a);
     cudaEventCreate(&rec.b);
     rec.flops = 2.0 * plan.p.M * plan.p.N * plan.p.K * (plan.p.splits > 1 ? 1 : plan.grid.z);
+    rec.M = plan.p.M, rec.N = plan.p.N, rec.K = plan.p.K, rec.z = plan.p.splits > 1 ? 1 : (int)plan.grid.z;
+    rec.splits = plan.p.splits, rec.bn = BN, rec.mode = plan.p.a.mode;
     cudaEventRecord(rec.a, stream);
   }
   gemm_f16_kernel<BN><<<plan.grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(plan.ta, plan.tb, plan.p);
@@ -354,7 +358,8 @@ int gemm_splits(int M, int N, int K) {
   const int bn = N % 160 == 0 ? 160 : (N <= 64 ? 64 : 128);
   const int tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
   const int nkb = (K + kBK - 1) / kBK;
-  if (tiles >= 64 || nkb < 8) return 1;
+  // below one CTA per SM the TMA ring of a lone CTA is latency-bound: split K until ~2 CTAs per SM are in flight
+  if (tiles >= kNumSMs || nkb < 8) return 1;
   int sp = std::min(std::min(2 * kNumSMs / tiles, nkb / 4), 16);
   if (sp <= 1) return 1;
   const int per = (nkb + sp - 1) / sp;
@@ -647,6 +652,10 @@ int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half
   return SDB_OK;
 }
 
+void profile_dump_to(const char* path) {
+  snprintf(g_prof_dump, sizeof(g_prof_dump), "%s", path ? path : "");
+}
+
 void profile_begin() {
   g_recs.clear();
   g_prof = true;
@@ -660,14 +669,21 @@ int profile_end(double* ms, double* flops, int* launches) {
     return SDB_ERR_CUDA;
   }
   double t = 0.0, f = 0.0;
+  FILE* fp = g_prof_dump[0] ? fopen(g_prof_dump, "w") : nullptr;
+  if (fp) fprintf(fp, "M,N,K,batch,splits,bn,a_mode,ms,tflops\n");
   for (ProfRec& r : g_recs) {
     float m = 0.f;
     cudaEventElapsedTime(&m, r.a, r.b);
+    if (fp)
+      fprintf(fp, "%d,%d,%d,%d,%d,%d,%d,%.5f,%.1f\n", r.M, r.N, r.K, r.z, r.splits, r.bn, r.mode, m,
+              r.flops / (m * 1e-3) / 1e12);
     t += m;
     f += r.flops;
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
+  if (fp) fclose(fp);
+  g_prof_dump[0] = 0;
   *ms = t;
   *flops = f;
   *launches = (int)g_recs.size();

@@ -221,6 +221,17 @@ T Net::conv3_s2(std::vector<Op>* ops, const T& x, const __half* w, const __half*
 T Net::attention(std::vector<Op>* ops, const __half* q, long long ldq, const __half* k, long long ldk, const __half* v,
                  long long ldv, int B, int heads, int head_dim, int Lq, int Lk, __half** probs_out) {
   const int inner = heads * head_dim;
+  if (head_dim == 64 && Lk > 80 && !probs_out) {  // self-attention: fused, the score matrix never reaches HBM
+    T o = act(B, 1, Lq, inner);
+    if (!dry_) {
+      FlashPlan fp;
+      if (fail(plan_flash_attn(&fp, q, ldq, k, ldk, v, ldv, B, heads, head_dim, Lq, Lk, o.p, inner,
+                               1.f / sqrtf((float)head_dim))))
+        return o;
+      ops->push_back([fp](cudaStream_t s) { return run_flash_attn(fp, s); });
+    }
+    return o;
+  }
   const long long lds = align_up(Lk, 8);
   const long long sbytes = (long long)B * heads * Lq * lds * 2;
   __half* S = reinterpret_cast<__half*>(probs_out ? work(sbytes) : scratch(sbytes));

@@ -124,10 +124,12 @@ SIGNATURES = {
     # ---- include/sdb200_nn.h
     "sdb_gemm_f16": [C.POINTER(GemmArgsC), _P],
     "sdb_gemm_profile_begin": [],
+    "sdb_gemm_profile_dump": [C.c_char_p],
     "sdb_gemm_profile_end": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)],
     "sdb_conv3x3_f16": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P],
     "sdb_conv3x3_small": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "sdb_attention_f16": [_P, _LL, _P, _LL, _P, _LL, _I, _I, _I, _I, _P, _P, _LL, _P],
+    "sdb_flash_attention_f16": [_P, _LL, _P, _LL, _P, _LL, _I, _I, _I, _I, _P, _LL, _P],
     "sdb_groupnorm_workspace_floats": [_I, _I, _I, _I],
     "sdb_groupnorm_f16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
     "sdb_groupnorm_backward_f16": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],

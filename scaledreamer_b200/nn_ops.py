@@ -90,6 +90,22 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> 
     return out
 
 
+def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """Same contract as attention(), one fused kernel (no score matrix). q/k/v may be column slices of a fused
+    [B, L, 3*heads*64] projection (row stride = stride(1))."""
+    lib = L.load()
+    B, Lq, inner = q.shape
+    Lk = k.shape[1]
+    out = torch.empty(B, Lq, inner, device=q.device, dtype=torch.float16)
+    for t in (q, k, v):
+        if t.dtype != torch.float16 or t.stride(2) != 1 or t.stride(0) != t.shape[1] * t.stride(1):
+            raise RuntimeError("flash_attention: fp16 tensors with unit channel stride and packed batches expected")
+    L.check(lib.sdb_flash_attention_f16(q.data_ptr(), q.stride(1), k.data_ptr(), k.stride(1), v.data_ptr(), v.stride(1),
+                                        B, heads, Lq, Lk, L.ptr(out), out.stride(1), L.stream_ptr()),
+            "sdb_flash_attention_f16")
+    return out
+
+
 def groupnorm(x: torch.Tensor, gamma, beta, groups=32, eps=1e-5, silu=False):
     """x [N, ..., C] channels-last. Returns (y, stats)."""
     lib = L.load()

@@ -102,6 +102,28 @@ def test_attention(cuda_device, B, heads, Lq, Lk):
     assert rel(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,heads,Lq,Lk", [(2, 5, 256, 256), (1, 5, 4096, 4096), (2, 20, 64, 64), (3, 10, 64, 77),
+                                           (1, 3, 200, 333), (1, 10, 1024, 1024)])
+def test_flash_attention(cuda_device, B, heads, Lq, Lk):
+    """Fused attention against SDPA, with q/k/v taken as column slices of one fused projection (as the UNet does),
+    ragged lengths (not multiples of the 128-row tiles) and the single-block case."""
+    from scaledreamer_b200 import nn_ops as O
+
+    L = max(Lq, Lk)
+    qkv = rnd(B, L, 3 * heads * 64, dev=cuda_device, seed=7)
+    if Lq == Lk:
+        q, k, v = qkv[..., :heads * 64], qkv[..., heads * 64:2 * heads * 64], qkv[..., 2 * heads * 64:]
+    else:
+        q = rnd(B, Lq, heads * 64, dev=cuda_device, seed=1)
+        k = rnd(B, Lk, heads * 64, dev=cuda_device, seed=2)
+        v = rnd(B, Lk, heads * 64, dev=cuda_device, seed=3)
+    out = O.flash_attention(q, k, v, heads)
+    sp = lambda t, Ln: t.float().reshape(B, Ln, heads, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(q, Lq), sp(k, Lk), sp(v, Lk)).transpose(1, 2).reshape(B, Lq, heads * 64)
+    assert rel(out, ref) < 2e-3
+    assert torch.isfinite(out.float()).all()
+
+
 @pytest.mark.parametrize("N,HW,C,silu", [(2, 64, 320, True), (1, 4096, 128, True), (3, 256, 1920, False),
                                          (2, 16, 2560, True), (1, 1024, 512, True)])
 def test_groupnorm_forward_backward(cuda_device, N, HW, C, silu):
