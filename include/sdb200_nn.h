@@ -53,6 +53,9 @@ int sdb_gemm_profile_begin(void);
 int sdb_gemm_profile_end(double* total_ms, double* total_flops, int* launches);
 /* HOST path: the next sdb_gemm_profile_end() also writes one CSV row per launch (M,N,K,batch,splits,bn,mode,ms). */
 int sdb_gemm_profile_dump(const char* csv_path);
+/* Diagnostics: non-NULL device buffer of >= 296*4 uint64 -> every GEMM CTA stamps %globaltimer at entry / after
+ * set-up / first accumulator ready / exit. NULL switches it off. */
+int sdb_gemm_debug_timeline(unsigned long long* device_buf);
 
 /* 3x3 stride-1 pad-1 convolution as implicit GEMM: x [N,H,W,Cin], w [Cout, 3,3,Cin] (= [Cout, 9*Cin]),
  * out [N,H,W,Cout]; epilogue as sdb_gemm_f16 with rows_per_group = H*W (the per-image timestep-embedding add

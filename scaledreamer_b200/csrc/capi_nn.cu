@@ -138,6 +138,11 @@ int sdb_gemm_profile_begin(void) {
   return SDB_OK;
 }
 
+int sdb_gemm_debug_timeline(unsigned long long* device_buf) {
+  debug_timeline(device_buf);
+  return SDB_OK;
+}
+
 int sdb_gemm_profile_dump(const char* csv_path) {
   profile_dump_to(csv_path);
   return SDB_OK;

@@ -49,6 +49,8 @@ struct GemmParams {
   int act;
   int splits;          // > 1: split-K over blockIdx.z, fp32 partial planes in ws, epilogue by splitk_finalize_kernel
   float* ws;           // [splits][M][N] fp32
+  int tiles_m, tiles_n, tiles_z;  // tile grid walked by the persistent CTAs (filled at launch)
+  unsigned long long* dbg;  // optional [gridDim.x][4] globaltimer stamps: entry, setup done, first accumulator, exit
   int row_softmax;     // BN == 80 only: the epilogue applies softmax over the (single-tile) row of N <= 80 scores
 };
 
@@ -110,6 +112,9 @@ int plan_flash_attn(FlashPlan* plan, const __half* Q, long long ldq, const __hal
                     long long ldv, int B, int heads, int head_dim, int Lq, int Lk, __half* O, long long ldo, float alpha);
 int run_flash_attn(const FlashPlan& plan, cudaStream_t stream);
 // per-launch CUDA-event timing of every tcgen05 GEMM launched between begin and end (bench.py roofline)
+int profile_mark_begin(double flops, int M, int N, int K, int z, cudaStream_t stream);  // -1 when not profiling
+void profile_mark_end(int idx, cudaStream_t stream);
+void debug_timeline(unsigned long long* device_buf);  // non-null: every GEMM launch stamps its CTAs into device_buf
 void profile_begin();
 void profile_dump_to(const char* path);  // the next profile_end() also writes one CSV row per launch
 int profile_end(double* ms, double* flops, int* launches);

@@ -303,7 +303,9 @@ int run_flash_attn(const FlashPlan& plan, cudaStream_t stream) {
   }
   FlashParams p;
   p.Lq = plan.Lq, p.Lk = plan.Lk, p.heads = plan.heads, p.scale_log2 = plan.scale_log2, p.out = plan.out, p.ldo = plan.ldo;
+  const int rec = profile_mark_begin(plan.flops, plan.Lq, plan.Lk, kD, (int)plan.grid.y, stream);
   flash_attn_f16_kernel<<<plan.grid, kFaThreads, kFaSmem, stream>>>(plan.tq, plan.tk, plan.tv, p);
+  profile_mark_end(rec, stream);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("flash_attn_f16");
   return SDB_OK;

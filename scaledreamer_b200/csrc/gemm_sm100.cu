@@ -30,12 +30,13 @@ constexpr int kBK = 64;               // 64 fp16 = 128 bytes = one swizzle row
 constexpr int kATileBytes = kBM * kBK * 2;
 constexpr int kThreads = 256;
 
-template <int BN>
+// DEEP: at most one CTA per SM is in flight (<= 148 tiles), so the ring takes the whole shared memory instead.
+template <int BN, bool DEEP = false>
 struct Cfg {
   static constexpr int kBTileBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   // two CTAs share an SM (one CTA's epilogue overlaps the other's main loop): <= ~110 KB of ring per CTA
-  static constexpr int kStages = BN <= 80 ? 4 : 3;
+  static constexpr int kStages = DEEP ? (BN <= 80 ? 8 : 6) : (BN <= 80 ? 4 : 3);
   static constexpr int kTmemCols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -59,20 +60,212 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* tm, const Operan
   }
 }
 
+// Epilogue of one 128 x BN tile for the 32 rows of TMEM lane quadrant wq (one row per thread).
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 2)
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int wq, int lane, int m0, int n0,
+                                              int z, int zsplit) {
+  const int m = m0 + wq * 32 + lane;
+  const bool m_ok = m < p.M;
+  const long long zoff = (long long)(z / p.out_zdiv) * p.out_zs_hi + (long long)(z % p.out_zdiv) * p.out_zs_lo;
+  const float* rowb = p.rowbias ? p.rowbias + (long long)(m_ok ? m / p.rows_per_group : 0) * p.rowbias_ld : nullptr;
+  if constexpr (BN == 80) {
+    if (p.row_softmax) {
+      // whole score row in this tile (N <= 80): softmax(alpha * acc) in registers, padding columns zeroed
+      uint32_t v[96];
+      uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+      uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+      uint32_t(&v2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[64]);
+      const uint32_t tb = tmem_base + ((uint32_t)(wq * 32) << 16);
+      ptx::tmem_ld_32x32(tb, v0);
+      ptx::tmem_ld_32x32(tb + 32u, v1);
+      ptx::tmem_ld_32x32(tb + 64u, v2);  // columns 80..95 are unallocated-by-MMA garbage and are masked below
+      ptx::tmem_ld_wait();
+      if (m_ok) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 80; ++j)
+          if (j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]) * p.alpha);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 80; ++j) {
+          const float e = j < p.N ? __expf(__uint_as_float(v[j]) * p.alpha - mx) : 0.f;
+          v[j] = __float_as_uint(e);
+          sum += e;
+        }
+        const float inv = 1.f / sum;
+        __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc;
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+          if (q * 8 >= p.ldc) break;
+          uint4 ov;
+          __half2* h2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            h2[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]) * inv, __uint_as_float(v[q * 8 + 2 * e + 1]) * inv);
+          reinterpret_cast<uint4*>(o)[q] = ov;
+        }
+      }
+      return;
+    }
+  }
+  // Latency matters more than bandwidth here (4 warps, one row per thread): every global load of a chunk is issued
+  // BEFORE the wait on the tensor-memory read, and the residual of the next chunk is prefetched a chunk ahead.
+  const bool res_vec = p.residual && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
+  const bool bias_vec = p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+  const bool rowb_vec = rowb && (reinterpret_cast<uintptr_t>(rowb) & 15) == 0;
+  const __half* rrow = p.residual ? p.residual + (long long)m * p.ldr : nullptr;
+  uint4 rcur[4], rnext[4];
+  auto load_res = [&](int c, uint4(&rv)[4]) {
+    const bool on = res_vec && m_ok && n0 + c + 32 <= p.N;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      rv[q] = on ? __ldg(reinterpret_cast<const uint4*>(rrow + n0 + c) + q) : make_uint4(0, 0, 0, 0);
+  };
+  if (p.splits == 1) load_res(0, rcur);
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, v);
+    const int nb = n0 + c;
+    const bool full_chunk = nb + 32 <= p.N;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = 0.f;
+    if (p.splits == 1 && nb < p.N) {
+      if (p.bias) {
+        if (bias_vec && full_chunk) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + nb) + q);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = __half22float2(h2[e]);
+              f[q * 8 + 2 * e] = t.x;
+              f[q * 8 + 2 * e + 1] = t.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) f[j] = __half2float(__ldg(p.bias + nb + j));
+        }
+      }
+      if (rowb) {
+        if (rowb_vec && full_chunk && (p.rowbias_ld & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(rowb + nb) + q);
+            f[4 * q] += t.x, f[4 * q + 1] += t.y, f[4 * q + 2] += t.z, f[4 * q + 3] += t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) f[j] += __ldg(rowb + nb + j);
+        }
+      }
+      if (c + 32 < BN) load_res(c + 32, rnext);
+    }
+    ptx::tmem_ld_wait();
+    if (!m_ok || nb >= p.N) continue;
+    if (p.splits > 1) {  // raw fp32 partial sums; splitk_finalize_kernel applies the epilogue
+      float* o = p.ws + ((long long)zsplit * p.M + m) * p.N + nb;
+      if (nb + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          reinterpret_cast<uint4*>(o)[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < p.N) o[j] = __uint_as_float(v[j]);
+      }
+      continue;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), p.alpha, f[j]);
+    if (p.act == kActSilu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+    } else if (p.act == kActGelu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
+    }
+    if (p.residual) {
+      if (res_vec && full_chunk) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&rcur[q]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 t = __half22float2(h2[e]);
+            f[q * 8 + 2 * e] += t.x;
+            f[q * 8 + 2 * e + 1] += t.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < p.N) f[j] += __half2float(__ldg(rrow + nb + j));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+    if (p.out_fp32) {
+      float* o = reinterpret_cast<float*>(p.out) + zoff + (long long)m * p.ldc + nb;
+      if (full_chunk && (p.ldc & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < p.N) o[j] = f[j];
+      }
+    } else {
+      __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc + nb;
+      if (full_chunk && (p.ldc & 7) == 0 && (zoff & 7) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 ov;
+          __half2* h2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
+          reinterpret_cast<uint4*>(o)[q] = ov;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < p.N) o[j] = __float2half_rn(f[j]);
+      }
+    }
+  }
+}
+
+// Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, then n, then z / K split).
+// The TMA ring keeps running across tile boundaries, so the next tile's operands stream in while the epilogue
+// warps drain the accumulator; two CTAs share an SM, so one CTA's epilogue also overlaps the other's main loop.
+template <int BN, bool DEEP>
+__global__ void __launch_bounds__(kThreads, DEEP ? 1 : 2)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, DEEP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(base + C::kStages * C::kStageBytes);
   uint64_t* empty = full + C::kStages;
   uint64_t* accum_full = empty + C::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint64_t* accum_empty = accum_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+  auto stamp = [&](int slot) {
+    if (p.dbg && threadIdx.x == 128) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[(size_t)blockIdx.x * 4 + slot] = t;
+    }
+  };
+  stamp(0);
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
@@ -84,6 +277,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       ptx::mbar_init(&empty[s], 1);
     }
     ptx::mbar_init(accum_full, 1);
+    ptx::mbar_init(accum_empty, 128);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -94,192 +288,82 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // split-K: blockIdx.z selects a contiguous range of K blocks and a fp32 partial plane of the workspace
-  int kb0 = 0, nkb = p.num_k_blocks;
-  if (p.splits > 1) {
-    const int per = (p.num_k_blocks + p.splits - 1) / p.splits;
-    kb0 = blockIdx.z * per;
-    nkb = min(per, p.num_k_blocks - kb0);
-  }
-  const int z = p.splits > 1 ? 0 : (int)blockIdx.z;
+  stamp(1);
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total = tiles_mn * p.tiles_z;
+  const int per_split = (p.num_k_blocks + p.splits - 1) / p.splits;
+
+  // tile -> (m0, n0, batch index z, split index zs, K-block range)
+#define SDB_DECODE_TILE(tile)                                                        \
+  const int t_mn = (tile) % tiles_mn, t_z = (tile) / tiles_mn;                       \
+  const int m0 = (t_mn % p.tiles_m) * kBM, n0 = (t_mn / p.tiles_m) * BN;             \
+  const int z = p.splits > 1 ? 0 : t_z, zs = p.splits > 1 ? t_z : 0;                 \
+  const int kb0 = zs * per_split;                                                    \
+  const int nkb = p.splits > 1 ? min(per_split, p.num_k_blocks - kb0) : p.num_k_blocks;
 
   if (warp == 0) {
     if (ptx::elect_one()) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % C::kStages;
-        const uint32_t ph = (kb / C::kStages) & 1;
-        ptx::mbar_wait(&empty[s], ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(&full[s], C::kStageBytes);
-        uint8_t* sa = base + s * C::kStageBytes;
-        load_operand(&tmA, p.a, sa, &full[s], kb0 + kb, m0, z);
-        load_operand(&tmB, p.b, sa + kATileBytes, &full[s], kb0 + kb, n0, z);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        SDB_DECODE_TILE(tile)
+        (void)zs;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+          uint8_t* sa = base + s * C::kStageBytes;
+          load_operand(&tmA, p.a, sa, &full[s], kb0 + kb, m0, z);
+          load_operand(&tmB, p.b, sa + kATileBytes, &full[s], kb0 + kb, n0, z);
+        }
       }
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_f16(kBM, BN, 0, 0, p.b.mn_major);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % C::kStages;
-        const uint32_t ph = (kb / C::kStages) & 1;
-        ptx::mbar_wait(&full[s], ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
+        SDB_DECODE_TILE(tile)
+        (void)m0; (void)n0; (void)z; (void)zs; (void)kb0;
+        ptx::mbar_wait(accum_empty, (tcount & 1) ^ 1u);  // the epilogue warps drained the previous tile
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(base + s * C::kStageBytes);
-        const uint32_t sb = sa + kATileBytes;
-        const uint64_t da = ptx::smem_desc_k_sw128(sa);
-        const uint64_t db = p.b.mn_major ? ptx::smem_desc_mn_sw128(sb, 8192) : ptx::smem_desc_k_sw128(sb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(base + s * C::kStageBytes);
+          const uint32_t sb = sa + kATileBytes;
+          const uint64_t da = ptx::smem_desc_k_sw128(sa);
+          const uint64_t db = p.b.mn_major ? ptx::smem_desc_mn_sw128(sb, 8192) : ptx::smem_desc_k_sw128(sb);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // K-major: 16 elements = 32 bytes further along the swizzled row; MN-major: 16 K-rows = 2048 bytes
-          const uint64_t a_adv = (uint64_t)((k * 32) >> 4);
-          const uint64_t b_adv = p.b.mn_major ? (uint64_t)((k * 2048) >> 4) : (uint64_t)((k * 32) >> 4);
-          ptx::umma_f16(tmem_base, da + a_adv, db + b_adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            // K-major: 16 elements = 32 bytes further along the swizzled row; MN-major: 16 K-rows = 2048 bytes
+            const uint64_t a_adv = (uint64_t)((k * 32) >> 4);
+            const uint64_t b_adv = p.b.mn_major ? (uint64_t)((k * 2048) >> 4) : (uint64_t)((k * 32) >> 4);
+            ptx::umma_f16(tmem_base, da + a_adv, db + b_adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[s]);
         }
-        ptx::umma_commit(&empty[s]);
+        ptx::umma_commit(accum_full);
       }
-      ptx::umma_commit(accum_full);
     }
   } else if (warp >= 4) {
     const int wq = warp & 3;
-    ptx::mbar_wait(accum_full, 0);
-    ptx::tc_fence_after();
-    const int m = m0 + wq * 32 + lane;
-    const bool m_ok = m < p.M;
-    const long long zoff = (long long)(z / p.out_zdiv) * p.out_zs_hi + (long long)(z % p.out_zdiv) * p.out_zs_lo;
-    const float* rowb = p.rowbias ? p.rowbias + (long long)(m_ok ? m / p.rows_per_group : 0) * p.rowbias_ld : nullptr;
-    if constexpr (BN == 80) {
-      if (p.row_softmax) {
-        // whole score row in this tile (N <= 80): softmax(alpha * acc) in registers, padding columns zeroed
-        uint32_t v[96];
-        uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-        uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-        uint32_t(&v2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[64]);
-        const uint32_t tb = tmem_base + ((uint32_t)(wq * 32) << 16);
-        ptx::tmem_ld_32x32(tb, v0);
-        ptx::tmem_ld_32x32(tb + 32u, v1);
-        ptx::tmem_ld_32x32(tb + 64u, v2);  // columns 80..95 are unallocated-by-MMA garbage and are masked below
-        ptx::tmem_ld_wait();
-        if (m_ok) {
-          float mx = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 80; ++j)
-            if (j < p.N) mx = fmaxf(mx, __uint_as_float(v[j]) * p.alpha);
-          float sum = 0.f;
-#pragma unroll
-          for (int j = 0; j < 80; ++j) {
-            const float e = j < p.N ? __expf(__uint_as_float(v[j]) * p.alpha - mx) : 0.f;
-            v[j] = __float_as_uint(e);
-            sum += e;
-          }
-          const float inv = 1.f / sum;
-          __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc;
-#pragma unroll
-          for (int q = 0; q < 10; ++q) {
-            if (q * 8 >= p.ldc) break;
-            uint4 ov;
-            __half2* h2 = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              h2[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]) * inv, __uint_as_float(v[q * 8 + 2 * e + 1]) * inv);
-            reinterpret_cast<uint4*>(o)[q] = ov;
-          }
-        }
-        ptx::tc_fence_before();
-        goto epilogue_done;
-      }
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
+      SDB_DECODE_TILE(tile)
+      (void)kb0; (void)nkb;
+      ptx::mbar_wait(accum_full, tcount & 1);
+      ptx::tc_fence_after();
+      if (tcount == 0) stamp(2);
+      epilogue_tile<BN>(p, tmem_base, wq, lane, m0, n0, z, zs);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(accum_empty);
     }
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, v);
-      ptx::tmem_ld_wait();
-      const int nb = n0 + c;
-      if (!m_ok || nb >= p.N) continue;
-      if (p.splits > 1) {  // raw fp32 partial sums; splitk_finalize_kernel applies the epilogue
-        float* o = p.ws + ((long long)blockIdx.z * p.M + m) * p.N + nb;
-        if (nb + 32 <= p.N && (p.N & 3) == 0) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            reinterpret_cast<uint4*>(o)[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) o[j] = __uint_as_float(v[j]);
-        }
-        continue;
-      }
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-      const bool full_chunk = nb + 32 <= p.N;
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full_chunk || nb + j < p.N) f[j] += __half2float(__ldg(p.bias + nb + j));
-      }
-      if (rowb) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full_chunk || nb + j < p.N) f[j] += __ldg(rowb + nb + j);
-      }
-      if (p.act == kActSilu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
-      } else if (p.act == kActGelu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
-      }
-      if (p.residual) {
-        const __half* r = p.residual + (long long)m * p.ldr + nb;
-        if (full_chunk && (p.ldr & 7) == 0) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r) + q);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 t = __half22float2(h2[e]);
-              f[q * 8 + 2 * e] += t.x;
-              f[q * 8 + 2 * e + 1] += t.y;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) f[j] += __half2float(__ldg(r + j));
-        }
-      }
-      if (p.out_fp32) {
-        float* o = reinterpret_cast<float*>(p.out) + zoff + (long long)m * p.ldc + nb;
-        if (full_chunk && (p.ldc & 3) == 0) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) o[j] = f[j];
-        }
-      } else {
-        __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc + nb;
-        if (full_chunk && (p.ldc & 7) == 0 && (zoff & 7) == 0) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 ov;
-            __half2* h2 = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
-            reinterpret_cast<uint4*>(o)[q] = ov;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) o[j] = __float2half_rn(f[j]);
-        }
-      }
-    }
-    ptx::tc_fence_before();
-  epilogue_done:;
   }
+#undef SDB_DECODE_TILE
+  stamp(3);
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
@@ -313,14 +397,15 @@ struct ProfRec {
 };
 char g_prof_dump[512] = "";
 bool g_prof = false;
+unsigned long long* g_dbg = nullptr;
 std::vector<ProfRec> g_recs;
 
-template <int BN>
-int launch(const GemmPlan& plan, cudaStream_t stream) {
+template <int BN, bool DEEP>
+int launch_v(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BN>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<BN, DEEP>::kSmemBytes);
     if (e != cudaSuccess) {
       sdb_set_error("gemm: smem attribute: %s", cudaGetErrorString(e));
       return SDB_ERR_CUDA;
@@ -336,11 +421,16 @@ int launch(const GemmPlan& plan, cudaStream_t stream) {
     rec.splits = plan.p.splits, rec.bn = BN, rec.mode = plan.p.a.mode;
     cudaEventRecord(rec.a, stream);
   }
-  gemm_f16_kernel<BN><<<plan.grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(plan.ta, plan.tb, plan.p);
+  GemmParams prm = plan.p;
+  prm.dbg = g_dbg;
+  prm.tiles_m = (int)plan.grid.x, prm.tiles_n = (int)plan.grid.y, prm.tiles_z = (int)plan.grid.z;
+  const long long total_tiles = (long long)plan.grid.x * plan.grid.y * plan.grid.z;
+  const int ctas = (int)std::min<long long>(total_tiles, DEEP ? (long long)kNumSMs : 2LL * kNumSMs);
+  gemm_f16_kernel<BN, DEEP><<<ctas, kThreads, Cfg<BN, DEEP>::kSmemBytes, stream>>>(plan.ta, plan.tb, prm);
   if (plan.p.splits > 1) {
     const long long total = (long long)plan.p.M * ((plan.p.N + 3) / 4);
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 8);
-    splitk_finalize_kernel<<<grid, 256, 0, stream>>>(plan.p);
+    splitk_finalize_kernel<<<grid, 256, 0, stream>>>(prm);
     SDB_COUNT_LAUNCH();
   }
   if (g_prof) {
@@ -352,6 +442,12 @@ int launch(const GemmPlan& plan, cudaStream_t stream) {
   return SDB_OK;
 }
 
+template <int BN>
+int launch(const GemmPlan& plan, cudaStream_t stream) {
+  const long long total_tiles = (long long)plan.grid.x * plan.grid.y * plan.grid.z;
+  return total_tiles <= kNumSMs ? launch_v<BN, true>(plan, stream) : launch_v<BN, false>(plan, stream);
+}
+
 }  // namespace
 
 int gemm_splits(int M, int N, int K) {
@@ -359,7 +455,7 @@ int gemm_splits(int M, int N, int K) {
   const int tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
   const int nkb = (K + kBK - 1) / kBK;
   // below one CTA per SM the TMA ring of a lone CTA is latency-bound: split K until ~2 CTAs per SM are in flight
-  if (tiles >= kNumSMs || nkb < 8) return 1;
+  if (tiles >= kNumSMs || nkb < 48) return 1;
   int sp = std::min(std::min(2 * kNumSMs / tiles, nkb / 4), 16);
   if (sp <= 1) return 1;
   const int per = (nkb + sp - 1) / sp;
@@ -390,6 +486,7 @@ void fill_epilogue(GemmParams& p, const Epilogue& ep) {
   p.alpha = ep.alpha;
   p.act = ep.act;
   p.splits = 1;
+  p.dbg = nullptr;
   p.ws = nullptr;
   p.row_softmax = 0;
 }
@@ -651,6 +748,24 @@ int plan_attn_apply(GemmPlan* plan, const __half* P, long long ldp, const __half
   plan->grid = dim3((Lq + kBM - 1) / kBM, head_dim / 64, B * heads);
   return SDB_OK;
 }
+
+// Brackets a non-GEMM tensor-core launch (flash attention) with the same event records.
+int profile_mark_begin(double flops, int M, int N, int K, int z, cudaStream_t stream) {
+  if (!g_prof) return -1;
+  ProfRec rec;
+  cudaEventCreate(&rec.a);
+  cudaEventCreate(&rec.b);
+  rec.flops = flops;
+  rec.M = M, rec.N = N, rec.K = K, rec.z = z, rec.splits = 1, rec.bn = 0, rec.mode = 9;
+  cudaEventRecord(rec.a, stream);
+  g_recs.push_back(rec);
+  return (int)g_recs.size() - 1;
+}
+void profile_mark_end(int idx, cudaStream_t stream) {
+  if (idx >= 0 && idx < (int)g_recs.size()) cudaEventRecord(g_recs[idx].b, stream);
+}
+
+void debug_timeline(unsigned long long* device_buf) { g_dbg = device_buf; }
 
 void profile_dump_to(const char* path) {
   snprintf(g_prof_dump, sizeof(g_prof_dump), "%s", path ? path : "");

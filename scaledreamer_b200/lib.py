@@ -125,6 +125,7 @@ SIGNATURES = {
     "sdb_gemm_f16": [C.POINTER(GemmArgsC), _P],
     "sdb_gemm_profile_begin": [],
     "sdb_gemm_profile_dump": [C.c_char_p],
+    "sdb_gemm_debug_timeline": [_P],
     "sdb_gemm_profile_end": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)],
     "sdb_conv3x3_f16": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P],
     "sdb_conv3x3_small": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
