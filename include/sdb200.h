@@ -175,6 +175,49 @@ int sdb_render_nerf_backward_tape(const sdb_field* field, const sdb_field_grads*
                                   const float* depth, const float* g_comp_rgb, const float* g_opacity,
                                   const float* g_depth, const sdb_render_tape* tape, void* stream);
 
+/* ---- prompt-conditioned hash-grid field (amortized generators) -------------------------------------------
+ * out = relu(enc(x) W1[b]) W2[b], weights per prompt b from a hypernetwork, two optional heads on one encoding:
+ *   head a 32->64->1: SDF of "Hyper-iNGP" (custom/amortized/models/geometry/hyper_iNGP.py:261-349, torch.bmm);
+ *   head b 32->64->3: its features, or the colour of "multiprompt-neural-hashgrid-environment-map-background"
+ *                     (custom/amortized/models/background/multiprompt_..._background.py:83-101).
+ * points01 [n_prompts, n_points, 3] already contracted to [0,1]; w1 [n_prompts,32,64], w2 [n_prompts,64,{1,3}]
+ * (the `enc @ W` layout the reference hypernetwork emits). A head is skipped when its w1 is NULL.
+ * tape (optional, sdb_hyper_field_tape_floats floats) keeps the encodings for the backward. */
+long long sdb_hyper_field_tape_floats(int n_prompts, int n_points);
+int sdb_hyper_field_forward(const sdb_grid_cfg* grid, const float* table, const float* points01, int n_prompts,
+                            int n_points, const float* w1_a, const float* w2_a, const float* w1_b, const float* w2_b,
+                            float* out_a, float* out_b, float* tape, void* stream);
+/* Gradients accumulate (+=) into g_table [entries,2], g_w1_* [n_prompts,32,64], g_w2_* [n_prompts,64,{1,3}].
+ * d_out_a [n_prompts,n_points] / d_out_b [n_prompts,n_points,3] may be NULL (head without gradient). */
+int sdb_hyper_field_backward(const sdb_grid_cfg* grid, const float* points01, int n_prompts, int n_points,
+                             const float* w1_a, const float* w2_a, const float* w1_b, const float* w2_b,
+                             const float* tape, const float* d_out_a, const float* d_out_b, float* g_table,
+                             float* g_w1_a, float* g_w2_a, float* g_w1_b, float* g_w2_b, void* stream);
+
+/* ---- VolSDF importance renderer (dense [n_rays, S] samples; amortized path) -------------------------------
+ * Replaces ImportanceEstimator.sampling (threestudio/models/estimators.py:23-101), volsdf_density / get_alpha
+ * (renderers/neus_volume_renderer.py:19-23,93-96) and the nerfacc compositing calls of
+ * custom/amortized/models/renderers/generative_space_volsdf_volume_renderer.py:356-424. */
+/* points[n_rays, n_coarse, 3]: mid-points of the proposal intervals with edges near + (far-near) (j + u)/(n_coarse+1). */
+int sdb_volsdf_coarse_points(const float* rays_o, const float* rays_d, const float* u_coarse, int n_rays,
+                             int n_coarse, float near_plane, float far_plane, float* points, void* stream);
+/* sdf[n_rays, n_coarse] at those points -> t_all[n_rays, n_coarse + n_fine + 2]: proposal edges merged with the
+ * n_fine + 1 inverse-CDF edges drawn at (j + u_fine)/(n_fine+1), sorted. */
+int sdb_volsdf_resample(const float* sdf, const float* u_coarse, const float* u_fine, int n_rays, int n_coarse,
+                        int n_fine, float near_plane, float far_plane, float inv_std, float* t_all, void* stream);
+/* alpha = |delta| sigma_volsdf(sdf), w = alpha prod_{j<i}(1-alpha_j); rgb = sigmoid(features).
+ * Outputs weights [n_rays,S], opacity / depth / z_variance [n_rays], comp_rgb_fg / comp_normal [n_rays,3]. */
+int sdb_volsdf_composite_forward(const float* sdf, const float* features, const float* normal, const float* t_mid,
+                                 const float* delta, int n_rays, int n_samples, float inv_std, float* weights,
+                                 float* opacity, float* depth, float* comp_rgb_fg, float* z_variance,
+                                 float* comp_normal, void* stream);
+/* d_sdf [n_rays,S], d_features [n_rays,S,3] from the gradients of comp_rgb_fg / opacity / depth. */
+int sdb_volsdf_composite_backward(const float* sdf, const float* features, const float* t_mid, const float* delta,
+                                  const float* weights, const float* opacity, const float* depth,
+                                  const float* comp_rgb_fg, const float* g_comp_rgb_fg, const float* g_opacity,
+                                  const float* g_depth, int n_rays, int n_samples, float inv_std, float* d_sdf,
+                                  float* d_features, void* stream);
+
 /* rays from cameras (threestudio/utils/ops.py:183-269 get_ray_directions + get_rays):
  * c2w [B,4,4], fovy [B] (radians) -> rays_o, rays_d [B,H,W,3] (normalised). */
 int sdb_raygen(const float* c2w, const float* fovy, int n_images, int height, int width, float* rays_o,

@@ -38,6 +38,12 @@ typedef struct {
 int sdb_asd_text_embeddings(const sdb_prompt_cfg* cfg, const void* emb_vd, const void* uncond_vd,
                             const float* elevation, const float* azimuth, int batch, int tokens, int dim, void* ctx,
                             float* neg_weights, void* stream);
+/* Multi-prompt batches (custom/amortized/models/prompt_processors/base.py:434-568): emb_tables is the stacked
+ * [n_prompts, 4 (or 1 when not view dependent), tokens, dim] table of this rank's prompt library and prompt_idx [B]
+ * (device, int32) names the prompt of every sample; everything else as above. */
+int sdb_asd_text_embeddings_multi(const sdb_prompt_cfg* cfg, const void* emb_tables, const void* uncond_vd,
+                                  const int* prompt_idx, int n_prompts, const float* elevation, const float* azimuth,
+                                  int batch, int tokens, int dim, void* ctx, float* neg_weights, void* stream);
 
 /* moments = quant_conv(h) ; z = (mean + exp(0.5*clamp(logvar,-30,20)) * eps_post) * scaling_factor
  * (autoencoder.py:81-85, distributions.py:24-37, interface.py:108-111 / vae.config.scaling_factor);

@@ -1,0 +1,188 @@
+"""CPU oracle of the amortized (multi-prompt) generator path -- TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench.py's CPU
+legs may import it; the product path never does).
+
+Restates, in plain fp32 PyTorch on the CPU, the reference's
+  LinearHyperNetwork / Hypernet_Sdf      custom/amortized/models/geometry/hyper_iNGP.py:18-111, 206-349
+  multi-prompt environment map           custom/amortized/models/background/multiprompt_neural_environment_hashgrid_map_background.py:83-116
+  ImportanceEstimator.sampling           threestudio/models/estimators.py:23-101
+  volsdf_density / get_alpha             threestudio/models/renderers/neus_volume_renderer.py:19-23, 93-96
+  GenerativeSpaceVolSDFVolumeRenderer    custom/amortized/models/renderers/generative_space_volsdf_volume_renderer.py:89-446
+  eikonal / sparsity / opaque losses     custom/amortized/systems/multiprompt_radience_field_generator.py:127-216
+
+PARITY UNPINNED for the nerfacc pieces (nerfacc v0.5.2 is an un-vendored dependency, not installable here):
+`importance_sampling` is restated as inverse-CDF sampling at u_j = (j + b) / (n + 1), j = 0..n, with one offset b per
+ray (U[0,1) when stratified, 0.5 otherwise) and linear interpolation inside a CDF bin; `render_weight_from_alpha` as
+T_i = prod_{j<i} (1 - alpha_j); `render_transmittance_from_density` as T_i = exp(-sum_{j<i} sigma_j dt_j). The random
+offsets are explicit inputs so that oracle and kernels consume identical draws. The hash grid follows
+oracle/render_oracle.py (tiny-cuda-nn semantics, also unpinned).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from oracle import render_oracle as ro
+
+
+@dataclass
+class HyperCfg:
+    grid: ro.GridCfg = field(default_factory=ro.GridCfg)
+    radius: float = 2.0
+    sdf_bias_radius: float = 0.5     # sdf_bias: sphere, sdf_bias_params: 0.5
+    fd_eps: float = 0.01
+    c_dim: int = 1024
+    n_neurons: int = 64
+
+
+@dataclass
+class VolSDFCfg:
+    near: float = 0.1
+    far: float = 4.0
+    n_coarse: int = 128              # num_samples_per_ray_importance (proposal intervals)
+    n_fine: int = 64                 # num_samples_per_ray
+    inv_std: float = math.exp(0.340119 * 10.0)
+
+
+def make_hypernet(c_dim: int, n_neurons: int, n_out: int, seed: int) -> Dict[str, torch.Tensor]:
+    """LinearHyperNetwork parameters (hyper_iNGP.py:58-77, 101-108): xavier-normal weights, zero biases."""
+    g = torch.Generator().manual_seed(seed)
+    xavier = lambda o, i: torch.randn(o, i, generator=g) * math.sqrt(2.0 / (i + o))
+    return {"layers.0.weight": xavier(n_neurons, c_dim), "layers.1.weight": torch.ones(n_neurons),
+            "layers.1.bias": torch.zeros(n_neurons), "layers.3.weight": xavier(n_out, n_neurons),
+            "layers.3.bias": torch.zeros(n_out)}
+
+
+def hypernet_forward(P: Dict[str, torch.Tensor], text_embed: torch.Tensor, out_dims: Dict[str, list]):
+    """-> {name: [W_in_hidden [B,32,64], W_hidden_out [B,64,k]]} (hyper_iNGP.py:79-99)."""
+    h = text_embed @ P["layers.0.weight"].t()
+    h = F.layer_norm(h, (h.shape[-1],), P["layers.1.weight"], P["layers.1.bias"], 1e-5)
+    h = F.silu(h)
+    out = h @ P["layers.3.weight"].t() + P["layers.3.bias"]
+    res, start = {}, 0
+    for name, ch in out_dims.items():
+        mats = []
+        for i, o in zip(ch[:-1], ch[1:]):
+            mats.append(out[:, start:start + i * o].reshape(-1, i, o))
+            start += i * o
+        res[name] = mats
+    return res
+
+
+def hyper_mlp(enc: torch.Tensor, mats) -> torch.Tensor:
+    """hypernet_forward (hyper_iNGP.py:238-259): bmm chain with ReLU between, no bias."""
+    x = enc
+    for i, w in enumerate(mats):
+        x = torch.bmm(x, w)
+        if i < len(mats) - 1:
+            x = torch.relu(x)
+    return x
+
+
+def hyper_sdf(points: torch.Tensor, table: torch.Tensor, cache, cfg: HyperCfg) -> torch.Tensor:
+    """forward_sdf (hyper_iNGP.py:324-349). points [B, N, 3] -> [B, N]."""
+    B, N, _ = points.shape
+    x01 = (points + cfg.radius) / (2 * cfg.radius)
+    enc = ro.hashgrid_encode(x01.reshape(-1, 3), table, cfg.grid).view(B, N, -1)
+    sdf = hyper_mlp(enc, cache["sdf_weights"])[..., 0]
+    return sdf + (points.norm(dim=-1) - cfg.sdf_bias_radius)
+
+
+def hyper_field(points: torch.Tensor, table: torch.Tensor, cache, cfg: HyperCfg, output_normal: bool = False):
+    """Hypernet_Sdf.forward (hyper_iNGP.py:261-322)."""
+    B, N, _ = points.shape
+    x01 = (points + cfg.radius) / (2 * cfg.radius)
+    enc = ro.hashgrid_encode(x01.reshape(-1, 3), table, cfg.grid).view(B, N, -1)
+    sdf = hyper_mlp(enc, cache["sdf_weights"])[..., 0] + (points.norm(dim=-1) - cfg.sdf_bias_radius)
+    out = {"sdf": sdf.reshape(B * N, 1), "features": hyper_mlp(enc, cache["feature_weights"]).reshape(B * N, 3)}
+    if output_normal:
+        eps = cfg.fd_eps
+        offs = (points[..., None, :] + eps * torch.eye(3)).clamp(-cfg.radius, cfg.radius)   # [B,N,3,3]
+        sdf_off = hyper_sdf(offs.reshape(B, N * 3, 3), table, cache, cfg).view(B, N, 3)
+        sdf_grad = (sdf_off - sdf[..., None]) / eps
+        normal = F.normalize(sdf_grad, dim=-1)
+        out.update(normal=normal.reshape(B * N, 3), shading_normal=normal.reshape(B * N, 3),
+                   sdf_grad=sdf_grad.reshape(B * N, 3))
+    return out
+
+
+def hyper_background(dirs: torch.Tensor, table: torch.Tensor, mats, grid: ro.GridCfg) -> torch.Tensor:
+    """dirs [B, HW, 3] (unit) -> sigmoid colour [B, HW, 3]."""
+    B, N, _ = dirs.shape
+    enc = ro.hashgrid_encode(((dirs + 1.0) / 2.0).reshape(-1, 3), table, grid).view(B, N, -1)
+    return torch.sigmoid(hyper_mlp(enc, mats))
+
+
+def volsdf_density(sdf: torch.Tensor, inv_std: float) -> torch.Tensor:
+    a = min(max(inv_std, 0.0), 80.0)
+    return a * (0.5 + 0.5 * torch.sign(sdf) * torch.expm1(-sdf.abs() * a))
+
+
+def importance_sampling(edges: torch.Tensor, cdfs: torch.Tensor, n: int, offset: torch.Tensor) -> torch.Tensor:
+    """Inverse-CDF resampling to n intervals (n + 1 sorted edges). edges/cdfs [Nr, m]; offset [Nr] in [0,1)."""
+    u = (torch.arange(n + 1, dtype=edges.dtype)[None, :] + offset[:, None]) / (n + 1)
+    idx = torch.searchsorted(cdfs.contiguous(), u.contiguous(), right=True).clamp(1, cdfs.shape[1] - 1)
+    c_lo, c_hi = torch.gather(cdfs, 1, idx - 1), torch.gather(cdfs, 1, idx)
+    e_lo, e_hi = torch.gather(edges, 1, idx - 1), torch.gather(edges, 1, idx)
+    w = ((u - c_lo) / (c_hi - c_lo).clamp_min(1e-10)).clamp(0.0, 1.0)
+    return e_lo + (e_hi - e_lo) * w
+
+
+def sample_intervals(rays_o, rays_d, n_rays_per_prompt, table, cache, hcfg: HyperCfg, vcfg: VolSDFCfg,
+                     u_coarse: torch.Tensor, u_fine: torch.Tensor) -> torch.Tensor:
+    """ImportanceEstimator.sampling with one VolSDF proposal (estimators.py:60-101) -> sorted t [Nr, n_c + n_f + 2]."""
+    Nr = rays_o.shape[0]
+    B = Nr // n_rays_per_prompt
+    with torch.no_grad():
+        unit = torch.tensor([[0.0, 1.0]]).expand(Nr, 2)
+        s_c = importance_sampling(unit, unit, vcfg.n_coarse, u_coarse)
+        t_c = vcfg.near + s_c * (vcfg.far - vcfg.near)
+        mid = 0.5 * (t_c[:, :-1] + t_c[:, 1:])
+        pts = rays_o[:, None, :] + rays_d[:, None, :] * mid[..., None]
+        sdf = hyper_sdf(pts.reshape(B, -1, 3), table, cache, hcfg).reshape(Nr, -1)
+        sigma = volsdf_density(sdf, vcfg.inv_std)
+        sd = sigma * (t_c[:, 1:] - t_c[:, :-1])
+        trans = torch.exp(-(torch.cumsum(sd, -1) - sd))
+        cdfs = 1.0 - torch.cat([trans, torch.zeros_like(trans[:, :1])], -1)
+        s_f = importance_sampling(s_c, cdfs, vcfg.n_fine, u_fine)
+        t_f = vcfg.near + s_f * (vcfg.far - vcfg.near)
+        t_all, _ = torch.sort(torch.cat([t_c, t_f], -1), -1)
+    return t_all
+
+
+def composite(sdf, rgb, normal, t_mid, delta, inv_std):
+    """get_alpha (VolSDF) + render_weight_from_alpha + accumulate_along_rays on dense [Nr, S] samples."""
+    alpha = delta.abs() * volsdf_density(sdf, inv_std)
+    T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha[:, :-1]], -1), -1)
+    w = T * alpha
+    opacity = w.sum(-1)
+    depth = (w * t_mid).sum(-1)
+    fg = (w[..., None] * rgb).sum(-2)
+    z_var = (w * (t_mid - depth[:, None]) ** 2).sum(-1)
+    cn = F.normalize((w[..., None] * normal).sum(-2), dim=-1)
+    cn = torch.lerp(torch.zeros_like(cn), (cn.detach() + 1.0) / 2.0, opacity[:, None])
+    return dict(weights=w, opacity=opacity, depth=depth, comp_rgb_fg=fg, z_variance=z_var, comp_normal=cn)
+
+
+def render(rays_o, rays_d, n_rays_per_prompt, table, cache, bg_rgb, hcfg: HyperCfg, vcfg: VolSDFCfg, u_coarse, u_fine):
+    """GenerativeSpaceVolSDFVolumeRenderer._forward. rays [Nr,3]; bg_rgb [Nr,3] -> dict of per-ray / per-sample outputs."""
+    Nr = rays_o.shape[0]
+    B = Nr // n_rays_per_prompt
+    t = sample_intervals(rays_o, rays_d, n_rays_per_prompt, table, cache, hcfg, vcfg, u_coarse, u_fine)
+    t_mid, delta = 0.5 * (t[:, :-1] + t[:, 1:]), t[:, 1:] - t[:, :-1]
+    S = t_mid.shape[1]
+    pts = rays_o[:, None, :] + rays_d[:, None, :] * t_mid[..., None]
+    geo = hyper_field(pts.reshape(B, -1, 3), table, cache, hcfg, output_normal=True)
+    rgb = torch.sigmoid(geo["features"]).view(Nr, S, 3)
+    out = composite(geo["sdf"].view(Nr, S), rgb, geo["normal"].view(Nr, S, 3), t_mid, delta, vcfg.inv_std)
+    out["comp_rgb_bg"] = bg_rgb
+    out["comp_rgb"] = out["comp_rgb_fg"] + bg_rgb * (1.0 - out["opacity"][:, None])
+    out.update(t=t, t_points=t_mid, t_intervals=delta, sdf=geo["sdf"], sdf_grad=geo["sdf_grad"], normal=geo["normal"])
+    return out
+
+
+def eikonal_loss(sdf_grad: torch.Tensor) -> torch.Tensor:
+    return ((torch.linalg.norm(sdf_grad, ord=2, dim=-1) - 1.0) ** 2).mean()

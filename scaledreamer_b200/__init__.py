@@ -6,4 +6,4 @@ lives in libsdb200.so (csrc/, C ABI in include/*.h). There is no CPU or PyTorch 
 __version__ = "0.1.0"
 
 from .core import C, find, load_config, parse_structured, register  # noqa: F401
-from . import data, fields, guidance, prompts, systems  # noqa: F401  (registration side effects)
+from . import data, fields, guidance, prompts, systems, amortized  # noqa: F401  (registration side effects)

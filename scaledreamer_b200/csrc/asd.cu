@@ -124,14 +124,16 @@ __device__ PromptPlan make_plan(const sdb_prompt_cfg& c, float ele, float azi_ra
 __global__ void text_embeddings_kernel(const __grid_constant__ sdb_prompt_cfg c, const __half* __restrict__ emb,
                                        const __half* __restrict__ unc, const float* __restrict__ elevation,
                                        const float* __restrict__ azimuth, int B, long long row8,
-                                       __half* __restrict__ ctx, float* __restrict__ neg_w) {
+                                       __half* __restrict__ ctx, float* __restrict__ neg_w,
+                                       const int* __restrict__ prompt_idx, long long table_stride8) {
   const int b = blockIdx.y;
   const PromptPlan p = make_plan(c, elevation[b], azimuth[b]);
   if (neg_w && blockIdx.x == 0 && threadIdx.x == 0) {
     neg_w[2 * b] = p.w0 * c.neg_scale;
     neg_w[2 * b + 1] = p.w1 * c.neg_scale;
   }
-  const uint4* E = reinterpret_cast<const uint4*>(emb);
+  // multi-prompt: every sample reads the table of its own prompt out of a stacked [P, n_dir, tokens, dim] tensor
+  const uint4* E = reinterpret_cast<const uint4*>(emb) + (prompt_idx ? (long long)prompt_idx[b] * table_stride8 : 0LL);
   const uint4* U = reinterpret_cast<const uint4*>(unc);
   uint4* O = reinterpret_cast<uint4*>(ctx);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < row8;
@@ -359,9 +361,27 @@ int sdb_asd_text_embeddings(const sdb_prompt_cfg* cfg, const void* emb_vd, const
   dim3 grid((unsigned)((row8 + 255) / 256), batch);
   text_embeddings_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       *cfg, reinterpret_cast<const __half*>(emb_vd), reinterpret_cast<const __half*>(uncond_vd), elevation, azimuth,
-      batch, row8, reinterpret_cast<__half*>(ctx), cfg->perp_neg ? neg_weights : nullptr);
+      batch, row8, reinterpret_cast<__half*>(ctx), cfg->perp_neg ? neg_weights : nullptr, nullptr, 0);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("asd_text_embeddings");
+  return SDB_OK;
+}
+
+int sdb_asd_text_embeddings_multi(const sdb_prompt_cfg* cfg, const void* emb_tables, const void* uncond_vd,
+                                  const int* prompt_idx, int n_prompts, const float* elevation, const float* azimuth,
+                                  int batch, int tokens, int dim, void* ctx, float* neg_weights, void* stream) {
+  SDB_CHECK_ARG(cfg && emb_tables && uncond_vd && prompt_idx && elevation && azimuth && ctx && batch > 0 && n_prompts > 0,
+                "text_embeddings_multi: bad arguments");
+  SDB_CHECK_ARG(((long long)tokens * dim) % 8 == 0, "text_embeddings: tokens*dim must be a multiple of 8");
+  SDB_CHECK_ARG(!cfg->perp_neg || cfg->view_dependent, "Perp-Neg only works with view-dependent prompting");
+  const long long row8 = (long long)tokens * dim / 8;
+  const long long stride8 = (cfg->view_dependent ? 4 : 1) * row8;
+  dim3 grid((unsigned)((row8 + 255) / 256), batch);
+  text_embeddings_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      *cfg, reinterpret_cast<const __half*>(emb_tables), reinterpret_cast<const __half*>(uncond_vd), elevation, azimuth,
+      batch, row8, reinterpret_cast<__half*>(ctx), cfg->perp_neg ? neg_weights : nullptr, prompt_idx, stride8);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("asd_text_embeddings_multi");
   return SDB_OK;
 }
 

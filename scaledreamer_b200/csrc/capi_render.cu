@@ -143,6 +143,12 @@ static int resolve_march(const sdb_march_cfg* c, MarchMeta* m) {
   return SDB_OK;
 }
 
+int launch_hyper_field_fwd(const GridMeta&, const float*, const float*, int, int, const float*, const float*, const float*,
+                           const float*, float*, float*, float*, cudaStream_t);
+int launch_hyper_field_bwd(const GridMeta&, const float*, int, int, const float*, const float*, const float*,
+                           const float*, const float*, const float*, const float*, float*, float*, float*, float*,
+                           float*, cudaStream_t);
+
 namespace {
 
 __global__ void raygen_kernel(const float* __restrict__ c2w, const float* __restrict__ fovy, int B, int H, int W,
@@ -486,6 +492,42 @@ int sdb_render_nerf_backward_tape(const sdb_field* field, const sdb_field_grads*
   fg.bg_w2 = grads->bg_w2;
   fg.bg_w3 = grads->bg_w3;
   return launch_render_bwd2(fm, fp, fg, mm, io, t, (cudaStream_t)stream);
+}
+
+long long sdb_hyper_field_tape_floats(int n_prompts, int n_points) {
+  const long long n_pad = ((long long)n_points + 127) / 128 * 128;
+  return (long long)n_prompts * n_pad * kEncDim;
+}
+
+int sdb_hyper_field_forward(const sdb_grid_cfg* grid, const float* table, const float* points01, int n_prompts,
+                            int n_points, const float* w1_a, const float* w2_a, const float* w1_b, const float* w2_b,
+                            float* out_a, float* out_b, float* tape, void* stream) {
+  GridMeta gm;
+  int rc = resolve_grid(grid, &gm);
+  if (rc) return rc;
+  SDB_CHECK_ARG(gm.n_levels * 2 == kEncDim, "hyper_field: the encoding must be 16 levels x 2 features");
+  SDB_CHECK_ARG(table && points01 && n_prompts > 0 && n_points >= 0, "hyper_field_forward: bad arguments");
+  SDB_CHECK_ARG((w1_a && w2_a && out_a) || (w1_b && w2_b && out_b), "hyper_field_forward: no head requested");
+  SDB_CHECK_ARG((!w1_a || (w2_a && out_a)) && (!w1_b || (w2_b && out_b)), "hyper_field_forward: incomplete head");
+  if (n_points == 0) return SDB_OK;
+  return launch_hyper_field_fwd(gm, table, points01, n_prompts, n_points, w1_a, w2_a, w1_b, w2_b, out_a, out_b, tape,
+                                (cudaStream_t)stream);
+}
+
+int sdb_hyper_field_backward(const sdb_grid_cfg* grid, const float* points01, int n_prompts, int n_points,
+                             const float* w1_a, const float* w2_a, const float* w1_b, const float* w2_b,
+                             const float* tape, const float* d_out_a, const float* d_out_b, float* g_table,
+                             float* g_w1_a, float* g_w2_a, float* g_w1_b, float* g_w2_b, void* stream) {
+  GridMeta gm;
+  int rc = resolve_grid(grid, &gm);
+  if (rc) return rc;
+  SDB_CHECK_ARG(gm.n_levels * 2 == kEncDim, "hyper_field: the encoding must be 16 levels x 2 features");
+  SDB_CHECK_ARG(points01 && tape && g_table && n_prompts > 0 && n_points >= 0, "hyper_field_backward: bad arguments");
+  SDB_CHECK_ARG(!d_out_a || (w1_a && w2_a && g_w1_a && g_w2_a), "hyper_field_backward: head a is incomplete");
+  SDB_CHECK_ARG(!d_out_b || (w1_b && w2_b && g_w1_b && g_w2_b), "hyper_field_backward: head b is incomplete");
+  if (n_points == 0 || (!d_out_a && !d_out_b)) return SDB_OK;
+  return launch_hyper_field_bwd(gm, points01, n_prompts, n_points, w1_a, w2_a, w1_b, w2_b, tape, d_out_a, d_out_b,
+                                g_table, g_w1_a, g_w2_a, g_w1_b, g_w2_b, (cudaStream_t)stream);
 }
 
 int sdb_raygen(const float* c2w, const float* fovy, int n_images, int height, int width, float* rays_o,

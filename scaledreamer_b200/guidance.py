@@ -178,9 +178,7 @@ class _ASDGuidanceBase(BaseObject):
         pc = self._prompt_cfg(prompt_utils)
         elevation = elevation.to(dev, torch.float32).contiguous()
         azimuth = azimuth.to(dev, torch.float32).contiguous()
-        emb, unc = prompt_utils.tables(bool(self.cfg.view_dependent_prompting))
-        L.check(lib.sdb_asd_text_embeddings(C_.byref(pc), L.ptr(emb), L.ptr(unc), L.ptr(elevation), L.ptr(azimuth), B, 77,
-                                            1024, L.ptr(b["ctx"]), L.ptr(b["neg_w"]), st), "text_embeddings")
+        prompt_utils.fill_context(pc, elevation, azimuth, b["ctx"], b["neg_w"])
         # (6) frozen UNet on the concatenated batch
         cam = self._camera_cond(c2w)
         self.unet.forward(b["unet_x"], b["unet_t"], b["ctx"], cam, out=b["eps"])

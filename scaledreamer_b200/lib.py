@@ -119,6 +119,13 @@ SIGNATURES = {
                                    _P, _P, _P, _P, _P, _P, C.POINTER(RenderTapeC), _P, _P],
     "sdb_render_nerf_backward_tape": [C.POINTER(FieldC), C.POINTER(FieldGradsC), C.POINTER(MarchCfgC), _P, _P, _I, _I,
                                       _P, _P, _P, _P, _P, _P, _P, C.POINTER(RenderTapeC), _P],
+    "sdb_hyper_field_tape_floats": [_I, _I],
+    "sdb_hyper_field_forward": [C.POINTER(GridCfgC), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "sdb_hyper_field_backward": [C.POINTER(GridCfgC), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "sdb_volsdf_coarse_points": [_P, _P, _P, _I, _I, _F, _F, _P, _P],
+    "sdb_volsdf_resample": [_P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P],
+    "sdb_volsdf_composite_forward": [_P, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P],
+    "sdb_volsdf_composite_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P],
     "sdb_raygen": [_P, _P, _I, _I, _I, _P, _P, _P],
     "sdb_adamw_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
     # ---- include/sdb200_nn.h
@@ -156,6 +163,7 @@ SIGNATURES = {
     "sdb_resize_bilinear_forward": [_P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _P],
     "sdb_resize_bilinear_backward": [_P, _I, _I, _I, _I, _P, _I, _I, _F, _P],
     "sdb_asd_text_embeddings": [C.POINTER(PromptCfgC), _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "sdb_asd_text_embeddings_multi": [C.POINTER(PromptCfgC), _P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _P],
     "sdb_asd_prologue": [_P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P],
     "sdb_asd_epilogue": [_P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _F, _F, _F, _I, _I, _I, _P, _P, _P, _P, _P],
     "sdb_asd_t_plus": [_P, _P, _I, _F, _I, _I, _P, _P],
@@ -168,7 +176,7 @@ def _declare(lib: C.CDLL) -> None:
         fn.argtypes = args
         if name == "sdb_net_destroy":
             fn.restype = None
-        elif name == "sdb_groupnorm_workspace_floats":
+        elif name in ("sdb_groupnorm_workspace_floats", "sdb_hyper_field_tape_floats"):
             fn.restype = C.c_longlong
         elif name != "sdb_grid_num_entries":
             fn.restype = C.c_int

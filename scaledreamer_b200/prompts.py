@@ -66,6 +66,14 @@ class PromptProcessorOutput:
             return self.text_embeddings_vd, self.uncond_text_embeddings_vd
         return self.text_embeddings, self.uncond_text_embeddings
 
+    def fill_context(self, pc: L.PromptCfgC, elevation, azimuth, ctx, neg_w) -> None:
+        """Writes the UNet context batch of the ASD step ([vd, uncond, (neg x2,) vd] blocks) and the Perp-Neg weights
+        into the guidance's persistent buffers: one launch, no host sync."""
+        emb, unc = self.tables(bool(pc.view_dependent))
+        L.check(L.load().sdb_asd_text_embeddings(C_.byref(pc), L.ptr(emb), L.ptr(unc), L.ptr(elevation), L.ptr(azimuth),
+                                                 elevation.shape[0], 77, emb.shape[-1], L.ptr(ctx), L.ptr(neg_w),
+                                                 L.stream_ptr()), "sdb_asd_text_embeddings")
+
     def _run(self, elevation, azimuth, view_dependent, perp_neg):
         B = elevation.shape[0]
         dev = self.text_embeddings_vd.device

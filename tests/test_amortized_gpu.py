@@ -1,0 +1,249 @@
+"""GPU parity of the amortized (multi-prompt) path against oracle/amortized_oracle.py, through the C ABI / plugins.
+Tolerances: 1e-3 relative on forward quantities (north_star); gradients 5e-3 (ReLU-mask flips at fp32 rounding, as
+for the single-prompt field)."""
+import json
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import amortized_oracle as ao, render_oracle as ro
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(B, seed=0, table_scale=0.05):
+    hcfg, vcfg = ao.HyperCfg(), ao.VolSDFCfg()
+    g = torch.Generator().manual_seed(seed)
+    n = ro.grid_meta(hcfg.grid)["n_entries"]
+    table = (torch.rand(n, 2, generator=g) * 2 - 1) * table_scale
+    out_dims = {"sdf_weights": [32, 64, 1], "feature_weights": [32, 64, 3]}
+    hp = ao.make_hypernet(hcfg.c_dim, hcfg.n_neurons, 32 * 64 * 2 + 64 + 192, seed + 1)
+    emb = torch.randn(B, hcfg.c_dim, generator=g)
+    cache = ao.hypernet_forward(hp, emb, out_dims)
+    return hcfg, vcfg, table, cache, g
+
+
+@pytest.mark.parametrize("B,N", [(1, 1000), (3, 333), (2, 128)])
+def test_hyper_field_forward_backward(cuda_device, B, N):
+    """Both heads, per-prompt weights, N not a multiple of the 128-point tile; gradients to table and weights."""
+    from scaledreamer_b200 import amortized as A
+
+    hcfg, _, table, cache, g = _setup(B, seed=B)
+    x01 = torch.rand(B, N, 3, generator=g)
+    tbl = table.clone().requires_grad_(True)
+    mats = {k: [m.clone().requires_grad_(True) for m in v] for k, v in cache.items()}
+    enc = ro.hashgrid_encode(x01.reshape(-1, 3), tbl, hcfg.grid).view(B, N, -1)
+    ra = ao.hyper_mlp(enc, mats["sdf_weights"])[..., 0]
+    rb = ao.hyper_mlp(enc, mats["feature_weights"])
+    ga, gb = torch.randn(B, N, generator=g), torch.randn(B, N, 3, generator=g)
+    ((ra * ga).sum() + (rb * gb).sum()).backward()
+
+    dev = cuda_device
+    tbl_d = table.to(dev).requires_grad_(True)
+    md = {k: [m.detach().to(dev).requires_grad_(True) for m in v] for k, v in cache.items()}
+    a, b = A.hyper_field(vars(hcfg.grid), x01.to(dev), tbl_d, head_a=tuple(md["sdf_weights"]),
+                         head_b=tuple(md["feature_weights"]))
+    assert rel_l2(a.cpu(), ra.detach()) < 1e-3 and rel_l2(b.cpu(), rb.detach()) < 1e-3
+    ((a * ga.to(dev)).sum() + (b * gb.to(dev)).sum()).backward()
+    assert rel_l2(tbl_d.grad.cpu(), tbl.grad) < 5e-3
+    for k in mats:
+        for i in range(2):
+            assert rel_l2(md[k][i].grad.cpu(), mats[k][i].grad) < 5e-3, (k, i)
+    # single-head calls (offset points: SDF only; environment map: colour only)
+    a2, none = A.hyper_field(vars(hcfg.grid), x01.to(dev), tbl_d.detach(), head_a=tuple(m.detach() for m in md["sdf_weights"]))
+    assert none is None and rel_l2(a2.cpu(), ra.detach()) < 1e-3
+
+
+def test_volsdf_resample_and_composite(cuda_device):
+    """Importance resampling and compositing kernels on their own, against the oracle pieces."""
+    import ctypes as C
+
+    from scaledreamer_b200 import amortized as A, lib as L
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    Nr, nc, nf, near, far, inv_std = 257, 128, 64, 0.1, 4.0, 30.0
+    o = torch.randn(Nr, 3, generator=g) * 0.1 + torch.tensor([0.0, -1.6, 0.2])
+    d = torch.nn.functional.normalize(torch.tensor([[0.0, 1.0, -0.1]]) + 0.2 * torch.randn(Nr, 3, generator=g), dim=-1)
+    uc, uf = torch.rand(Nr, generator=g), torch.rand(Nr, generator=g)
+    unit = torch.tensor([[0.0, 1.0]]).expand(Nr, 2)
+    s_c = ao.importance_sampling(unit, unit, nc, uc)
+    t_c = near + s_c * (far - near)
+    mid = 0.5 * (t_c[:, :-1] + t_c[:, 1:])
+    pts_ref = o[:, None] + d[:, None] * mid[..., None]
+    lib = L.load()
+    od, dd, ucd, ufd = o.to(dev), d.to(dev), uc.to(dev), uf.to(dev)
+    pts = torch.empty(Nr, nc, 3, device=dev)
+    L.check(lib.sdb_volsdf_coarse_points(L.ptr(od), L.ptr(dd), L.ptr(ucd), Nr, nc, near, far, L.ptr(pts), L.stream_ptr()), "pts")
+    torch.testing.assert_close(pts.cpu(), pts_ref, atol=2e-6, rtol=1e-5)
+    sdf = pts_ref.norm(dim=-1) - 0.5 + 0.02 * torch.randn(Nr, nc, generator=g)
+    sigma = ao.volsdf_density(sdf, inv_std)
+    sd = sigma * (t_c[:, 1:] - t_c[:, :-1])
+    trans = torch.exp(-(torch.cumsum(sd, -1) - sd))
+    cdfs = 1.0 - torch.cat([trans, torch.zeros_like(trans[:, :1])], -1)
+    t_f = near + ao.importance_sampling(s_c, cdfs, nf, uf) * (far - near)
+    t_ref, _ = torch.sort(torch.cat([t_c, t_f], -1), -1)
+    sdf_d = sdf.to(dev).contiguous()
+    t_all = torch.empty(Nr, nc + nf + 2, device=dev)
+    L.check(lib.sdb_volsdf_resample(L.ptr(sdf_d), L.ptr(ucd), L.ptr(ufd), Nr, nc, nf, near, far, inv_std, L.ptr(t_all),
+                                    L.stream_ptr()), "resample")
+    t_gpu = t_all.cpu()
+    assert (t_gpu[:, 1:] >= t_gpu[:, :-1]).all()
+    # a CDF bin hit within float rounding of its edge may move one fine edge by a bin: compare robustly
+    assert (t_gpu - t_ref).abs().max() < 1e-3 and rel_l2(t_gpu, t_ref) < 1e-5
+
+    S = nc + nf + 1
+    t_mid, delta = 0.5 * (t_ref[:, :-1] + t_ref[:, 1:]), t_ref[:, 1:] - t_ref[:, :-1]
+    p2 = o[:, None] + d[:, None] * t_mid[..., None]
+    sdf2 = (p2.norm(dim=-1) - 0.5 + 0.01 * torch.randn(Nr, S, generator=g)).requires_grad_(True)
+    feat = torch.randn(Nr, S, 3, generator=g).requires_grad_(True)
+    nrm = torch.nn.functional.normalize(torch.randn(Nr, S, 3, generator=g), dim=-1)
+    ref = ao.composite(sdf2, torch.sigmoid(feat), nrm, t_mid, delta, inv_std)
+    gfg, gop, gdp = torch.randn(Nr, 3, generator=g), torch.randn(Nr, generator=g), torch.randn(Nr, generator=g)
+    ((ref["comp_rgb_fg"] * gfg).sum() + (ref["opacity"] * gop).sum() + (ref["depth"] * gdp).sum()).backward()
+    sd2, fd2 = sdf2.detach().to(dev).requires_grad_(True), feat.detach().to(dev).requires_grad_(True)
+    fg, op, dp, zv, w, cn = A._VolSDFComposite.apply(sd2, fd2, nrm.to(dev), t_mid.to(dev), delta.to(dev), inv_std)
+    for got, key in ((fg, "comp_rgb_fg"), (op, "opacity"), (dp, "depth"), (w, "weights"), (cn, "comp_normal")):
+        assert rel_l2(got.cpu(), ref[key].detach()) < 1e-3, key
+    assert (zv.cpu() - ref["z_variance"].detach()).abs().max() < 1e-4
+    ((fg * gfg.to(dev)).sum() + (op * gop.to(dev)).sum() + (dp * gdp.to(dev)).sum()).backward()
+    assert rel_l2(sd2.grad.cpu(), sdf2.grad) < 2e-3
+    assert rel_l2(fd2.grad.cpu(), feat.grad) < 1e-3
+
+
+def test_hyper_geometry_eikonal_gradients(cuda_device):
+    """"Hyper-iNGP" plugin forward(output_normal=True) on fixed points: sdf / features / sdf_grad and the gradient of the
+    eikonal loss (through the four SDF evaluations per point) w.r.t. the hash table and the hypernetwork."""
+    import scaledreamer_b200 as sd
+
+    dev = cuda_device
+    hcfg, _, table, _, g = _setup(2, seed=11)
+    geo = sd.find("Hyper-iNGP")({"radius": 2.0, "sdf_bias": "sphere", "sdf_bias_params": 0.5,
+                                 "hypernet_config": {"c_dim": 1024, "out_dims": {"sdf_weights": [64, 1], "feature_weights": [64, 3]},
+                                                     "spectral_norm": False, "n_neurons": 64, "n_hidden_layers": 1}}).to(dev)
+    geo.update_step(0, 0)
+    with torch.no_grad():
+        geo.encoding.encoding.params.copy_(table.reshape(-1).to(dev))
+    emb = torch.randn(2, 1024, generator=g)
+    pts = (torch.rand(2, 1500, 3, generator=g) * 2 - 1) * 1.2
+    pts[0, :4] = torch.tensor([[2.0, 2.0, 2.0], [1.999, -2.0, 0.0], [0.0, 0.0, 0.0], [-2.0, 1.995, 1.0]])  # offset clamp at the box
+    t = table.clone().requires_grad_(True)
+    hp = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in geo.hypernet.state_dict().items()}
+    cache = ao.hypernet_forward(hp, emb, {"sdf_weights": [32, 64, 1], "feature_weights": [32, 64, 3]})
+    ref = ao.hyper_field(pts, t, cache, hcfg, output_normal=True)
+    (ao.eikonal_loss(ref["sdf_grad"]) + ref["features"].square().mean()).backward()
+    out = geo(pts.to(dev), geo.generate_space_cache(None, emb.to(dev)), output_normal=True)
+    assert set(out) == {"sdf", "features", "normal", "shading_normal", "sdf_grad"}
+    assert rel_l2(out["sdf"].cpu(), ref["sdf"].detach()) < 1e-4 and rel_l2(out["features"].cpu(), ref["features"].detach()) < 1e-3
+    assert rel_l2(out["sdf_grad"].cpu(), ref["sdf_grad"].detach()) < 1e-3
+    (((torch.linalg.norm(out["sdf_grad"], ord=2, dim=-1) - 1.0) ** 2).mean() + out["features"].square().mean()).backward()
+    assert rel_l2(geo.encoding.table.grad.cpu().view(-1, 2), t.grad) < 5e-3
+    for k, v in geo.hypernet.named_parameters():
+        assert rel_l2(v.grad.cpu(), hp[k].grad) < 5e-3, k
+
+
+def _write_library(tmp_path, prompts):
+    (tmp_path / "load").mkdir(exist_ok=True)
+    json.dump({"train": prompts, "val": prompts[:1], "test": prompts[:1]}, open(tmp_path / "load" / "lib.json", "w"))
+
+
+def test_volsdf_renderer_plugin_matches_oracle(cuda_device):
+    """Geometry + background + renderer plugins (reference names / Config keys) against the oracle render on the same
+    random draws, including the gradients of an image + eikonal loss w.r.t. hash table and hypernetwork output."""
+    import scaledreamer_b200 as sd
+
+    dev = cuda_device
+    torch.manual_seed(0)
+    geo = sd.find("Hyper-iNGP")({"radius": 2.0, "sdf_bias": "sphere", "sdf_bias_params": 0.5,
+                                 "hypernet_config": {"c_dim": 1024, "out_dims": {"sdf_weights": [64, 1], "feature_weights": [64, 3]},
+                                                     "spectral_norm": False, "n_neurons": 64, "n_hidden_layers": 1}}).to(dev)
+    mat = sd.find("no-material")({"n_output_dims": 3, "color_activation": "sigmoid", "requires_normal": True}).to(dev)
+    bgm = sd.find("multiprompt-neural-hashgrid-environment-map-background")(
+        {"color_activation": "sigmoid", "random_aug": False,
+         "pos_encoding_config": {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 19,
+                                 "base_resolution": 16, "per_level_scale": 1.0}}).to(dev)
+    ren = sd.find("generative-space-volsdf-volume-renderer")(
+        {"radius": 2.0, "use_volsdf": True, "trainable_variance": False, "learned_variance_init": 0.340119,
+         "estimator": "importance", "num_samples_per_ray": 64, "num_samples_per_ray_importance": 128, "near_plane": 0.1,
+         "far_plane": 4.0}, geometry=geo, material=mat, background=bgm).to(dev)
+    ren.train()
+    geo.update_step(0, 0)
+    with torch.no_grad():
+        geo.encoding.encoding.params.mul_(500.0)  # 1e-4 init -> 0.05: the MLP output matters
+    B, H, W = 2, 6, 5
+    g = torch.Generator().manual_seed(3)
+    o = (torch.tensor([0.0, -1.6, 0.3]) + 0.05 * torch.randn(B, 1, 1, 3, generator=g)).expand(B, H, W, 3).contiguous()
+    d = torch.nn.functional.normalize(torch.tensor([0.0, 1.0, -0.15]) + 0.2 * torch.randn(B, H, W, 3, generator=g), dim=-1)
+    emb = torch.randn(B, 1024, generator=g)
+    uc, uf = torch.rand(B * H * W, generator=g), torch.rand(B * H * W, generator=g)
+    out = ren(o.to(dev), d.to(dev), None, text_embed=emb.to(dev), u_coarse=uc.to(dev), u_fine=uf.to(dev))
+
+    # oracle on the plugin's own parameters
+    hcfg, vcfg = ao.HyperCfg(), ao.VolSDFCfg()
+    table = geo.encoding.table.detach().cpu().view(-1, 2).clone().requires_grad_(True)
+    hp = {k: v.detach().cpu() for k, v in geo.hypernet.state_dict().items()}
+    cache = ao.hypernet_forward(hp, emb, {"sdf_weights": [32, 64, 1], "feature_weights": [32, 64, 3]})
+    for v in cache.values():
+        for m in v:
+            m.retain_grad() if m.requires_grad else m.requires_grad_(True)
+    bg_hp = {k: v.detach().cpu() for k, v in bgm.hypernet.state_dict().items()}
+    bg_cache = ao.hypernet_forward(bg_hp, emb, {"bg_weights": [32, 64, 3]})
+    bg_grid = ro.GridCfg(16, 2, 19, 16, 1.0)
+    bg_ref = ao.hyper_background(d.view(B, H * W, 3), bgm.encoding.table.detach().cpu().view(-1, 2), bg_cache["bg_weights"],
+                                 bg_grid).view(-1, 3)
+    ref = ao.render(o.view(-1, 3), d.view(-1, 3), H * W, table, cache, bg_ref, hcfg, vcfg, uc, uf)
+    for k in ("comp_rgb", "comp_rgb_fg", "comp_rgb_bg", "opacity", "depth", "comp_normal"):
+        assert rel_l2(out[k].reshape(-1).cpu(), ref[k].detach().reshape(-1)) < 1e-3, k
+    # (sdf(x + eps e_k) - sdf(x)) / 0.01 amplifies fp32 rounding of the two SDF values a hundredfold
+    assert rel_l2(out["sdf_grad"].cpu(), ref["sdf_grad"].detach()) < 1e-2
+    assert float(out["opacity"].max()) > 0.5
+
+    # image losses only: the eikonal gradient is checked on identical points in test_hyper_geometry_eikonal_gradients
+    # (here the two sides place their fine samples ~1e-5 apart, which a rough field turns into a different FD gradient)
+    gimg = torch.randn(B * H * W, 3, generator=g)
+    loss_ref = (ref["comp_rgb"] * gimg).sum() + ref["opacity"].sum() + 0.3 * ref["depth"].sum()
+    loss_ref.backward()
+    loss = (out["comp_rgb"].view(-1, 3) * gimg.to(dev)).sum() + out["opacity"].sum() + 0.3 * out["depth"].sum()
+    loss.backward()
+    assert rel_l2(geo.encoding.table.grad.cpu().view(-1, 2), table.grad) < 5e-3
+    # hypernetwork: compare the gradient that reaches its last layer's bias (= d loss / d flat weight vector)
+    flat_ref = torch.cat([cache["sdf_weights"][0].grad.reshape(B, -1), cache["sdf_weights"][1].grad.reshape(B, -1),
+                          cache["feature_weights"][0].grad.reshape(B, -1), cache["feature_weights"][1].grad.reshape(B, -1)], 1)
+    assert rel_l2(geo.hypernet.layers[3].bias.grad.cpu(), flat_ref.sum(0)) < 5e-3
+
+
+def test_multiprompt_system_training_step(cuda_device, tmp_path, monkeypatch):
+    """C4-shaped yaml (reference schema) -> data module, multi-prompt processor, system, one optimizer step."""
+    import scaledreamer_b200 as sd
+
+    monkeypatch.chdir(tmp_path)
+    _write_library(tmp_path, ["a red apple", "a wooden chair", "a blue car"])
+    cfg_path = os.path.join(os.path.dirname(__file__), "configs", "asd_sd_hyper_iNGP.yaml")
+    cfg = sd.load_config(cfg_path, cli_args=["system.prompt_processor.prompt_library=lib", "data.batch_size=2",
+                                             "data.width=32", "data.height=32"])
+    dm = sd.find(cfg.data_type)(cfg.data)
+    dm.setup("fit")
+    ds = dm.train_dataset
+    system = sd.find(cfg.system_type)(cfg.system)
+    system.train()
+    system.on_fit_start()
+    opt = system.configure_optimizers()
+    before = system.geometry.hypernet.layers[3].weight.detach().clone()
+    tb = system.geometry.encoding.table.detach().clone()
+    for step in range(2):
+        ds.update_step(0, step)
+        system.true_global_step = step
+        system.do_update_step(0, step)
+        batch = ds.to_device(ds.collate({}), cuda_device)
+        assert len(batch["prompt"]) == 2 and batch["noise"].shape == (2, 0)
+        out = system.training_step(batch, step)
+        assert torch.isfinite(out["loss"])
+        out["loss"].backward()
+        opt.step()
+        opt.zero_grad(set_to_none=False)
+    assert (system.geometry.hypernet.layers[3].weight.detach() - before).abs().max() > 0
+    assert (system.geometry.encoding.table.detach() - tb).abs().max() > 0
+    assert "train/loss_eikonal" in system.logged and "train/loss_asd" in system.logged
