@@ -352,6 +352,7 @@ def main() -> None:
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
     pk = peaks()
     gemm_tfs = prof["gemm_tflop_per_step"] / (prof["gemm_ms_per_step"] / 1e3)
@@ -391,6 +392,7 @@ def main() -> None:
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -206,17 +206,29 @@ int sdb_volsdf_coarse_points(const float* rays_o, const float* rays_d, const flo
 int sdb_volsdf_resample(const float* sdf, const float* u_coarse, const float* u_fine, int n_rays, int n_coarse,
                         int n_fine, float near_plane, float far_plane, float inv_std, float* t_all, void* stream);
 /* alpha = |delta| sigma_volsdf(sdf), w = alpha prod_{j<i}(1-alpha_j); rgb = sigmoid(features).
+ * color_activation: 0 sigmoid, 1 sigmoid-mipnerf (sigmoid * 1.002 - 0.001; materials/no_material.py:41-54).
  * Outputs weights [n_rays,S], opacity / depth / z_variance [n_rays], comp_rgb_fg / comp_normal [n_rays,3]. */
 int sdb_volsdf_composite_forward(const float* sdf, const float* features, const float* normal, const float* t_mid,
-                                 const float* delta, int n_rays, int n_samples, float inv_std, float* weights,
+                                 const float* delta, int n_rays, int n_samples, float inv_std, int color_activation,
+                                 float* weights,
                                  float* opacity, float* depth, float* comp_rgb_fg, float* z_variance,
                                  float* comp_normal, void* stream);
 /* d_sdf [n_rays,S], d_features [n_rays,S,3] from the gradients of comp_rgb_fg / opacity / depth. */
 int sdb_volsdf_composite_backward(const float* sdf, const float* features, const float* t_mid, const float* delta,
                                   const float* weights, const float* opacity, const float* depth,
                                   const float* comp_rgb_fg, const float* g_comp_rgb_fg, const float* g_opacity,
-                                  const float* g_depth, int n_rays, int n_samples, float inv_std, float* d_sdf,
-                                  float* d_features, void* stream);
+                                  const float* g_depth, int n_rays, int n_samples, float inv_std, int color_activation,
+                                  float* d_sdf, float* d_features, void* stream);
+
+/* ---- triplane feature lookup ("Triplane-transformer-sdf", custom/amortized/models/geometry/utils.py:67-97) ---------
+ * planes_cl [n_prompts, 3, H, W, C] fp32 CHANNELS-LAST; points [n_prompts, n_points, 3] in [-1,1];
+ * enc [n_prompts, n_points, 3*C] plane-major: plane 0 samples (x,y), plane 1 (x,z), plane 2 (z,y) with
+ * F.grid_sample(bilinear, zeros padding, align_corners=False) semantics. */
+int sdb_triplane_sample_forward(const float* planes_cl, const float* points, int n_prompts, int n_points, int height,
+                                int width, int channels, float* enc, void* stream);
+/* d_planes_cl += scatter(d_enc) (caller zeroes). */
+int sdb_triplane_sample_backward(const float* d_enc, const float* points, int n_prompts, int n_points, int height,
+                                 int width, int channels, float* d_planes_cl, void* stream);
 
 /* rays from cameras (threestudio/utils/ops.py:183-269 get_ray_directions + get_rays):
  * c2w [B,4,4], fovy [B] (radians) -> rays_o, rays_d [B,H,W,3] (normalised). */
@@ -229,6 +241,12 @@ int sdb_raygen(const float* c2w, const float* fovy, int n_images, int height, in
 int sdb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                    void* stream);
+
+/* Adan (threestudio/systems/optimizers.py:23-315; C5's optimizer), one fused pass. prev_grad keeps the previous
+ * gradient (= -neg_pre_grad of the reference); step is 1-based. */
+int sdb_adan_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* exp_avg_diff,
+                  float* prev_grad, long long n, float lr, float beta1, float beta2, float beta3, float eps,
+                  float weight_decay, int step, float grad_scale, int no_prox, void* stream);
 
 #ifdef __cplusplus
 }

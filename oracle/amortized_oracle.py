@@ -186,3 +186,73 @@ def render(rays_o, rays_d, n_rays_per_prompt, table, cache, bg_rgb, hcfg: HyperC
 
 def eikonal_loss(sdf_grad: torch.Tensor) -> torch.Tensor:
     return ((torch.linalg.norm(sdf_grad, ord=2, dim=-1) - 1.0) ** 2).mean()
+
+
+# ------------------------------------------------------------------------------------------------ triplane / Adan
+_PLANE_AXES = torch.tensor([[[1, 0, 0], [0, 1, 0], [0, 0, 1]], [[1, 0, 0], [0, 0, 1], [0, 1, 0]],
+                            [[0, 0, 1], [0, 1, 0], [1, 0, 0]]], dtype=torch.float32)
+
+
+def sample_from_planes(plane_features: torch.Tensor, coordinates: torch.Tensor, box_warp: float = 2.0) -> torch.Tensor:
+    """custom/amortized/models/geometry/utils.py:67-97 restated with the same torch primitives (inverse plane matrices,
+    bmm, F.grid_sample bilinear / zeros / align_corners=False). plane_features [N,3,C,H,W], coordinates [N,M,3]."""
+    N, n_planes, C, H, W = plane_features.shape
+    M = coordinates.shape[1]
+    pf = plane_features.reshape(N * n_planes, C, H, W)
+    coords = (2.0 / box_warp) * coordinates
+    c = coords.unsqueeze(1).expand(-1, n_planes, -1, -1).reshape(N * n_planes, M, 3)
+    inv = torch.linalg.inv(_PLANE_AXES).unsqueeze(0).expand(N, -1, -1, -1).reshape(N * n_planes, 3, 3)
+    proj = torch.bmm(c, inv)[..., :2].unsqueeze(1)
+    out = F.grid_sample(pf, proj.float(), mode="bilinear", padding_mode="zeros", align_corners=False)
+    out = out.permute(0, 3, 2, 1).reshape(N, n_planes, M, C)
+    return out.permute(0, 2, 1, 3).reshape(N, M, n_planes * C).contiguous()
+
+
+def vanilla_mlp(x: torch.Tensor, weights) -> torch.Tensor:
+    """threestudio/models/networks.py:214-251: bias-free Linear + ReLU stack."""
+    for i, w in enumerate(weights):
+        x = x @ w.t()
+        if i < len(weights) - 1:
+            x = torch.relu(x)
+    return x
+
+
+def triplane_field(points, planes, w_sdf, w_feat, radius, sdf_bias_radius, fd_eps, output_normal=False):
+    """TriplaneTransformerSDF.forward (triplane_transformer.py:153-239). points [B,N,3] world, planes [B,3,C,H,W]."""
+    B, N, _ = points.shape
+    contract = lambda p: (p + radius) / (2 * radius) * 2.0 - 1.0
+    sdf_of = lambda p: vanilla_mlp(sample_from_planes(planes, contract(p)), w_sdf)[..., 0] + (p.norm(dim=-1) - sdf_bias_radius)
+    enc = sample_from_planes(planes, contract(points))
+    sdf = vanilla_mlp(enc, w_sdf)[..., 0] + (points.norm(dim=-1) - sdf_bias_radius)
+    out = {"sdf": sdf.reshape(B * N, 1), "features": vanilla_mlp(enc, w_feat).reshape(B * N, -1)}
+    if output_normal:
+        offs = (points[..., None, :] + fd_eps * torch.eye(3)).clamp(-radius, radius)
+        sdf_grad = (sdf_of(offs.reshape(B, N * 3, 3)).view(B, N, 3) - sdf[..., None]) / fd_eps
+        out.update(sdf_grad=sdf_grad.reshape(B * N, 3), normal=F.normalize(sdf_grad, dim=-1).reshape(B * N, 3))
+    return out
+
+
+def adan_step(p, g, state, step, lr, betas, eps, weight_decay=0.0, no_prox=False):
+    """threestudio/systems/optimizers.py:141-250 (_single_tensor_adan with the step-1 neg_pre_grad initialisation of
+    :171-172), max_grad_norm = 0. state: dict of exp_avg / exp_avg_sq / exp_avg_diff / neg_pre_grad (created on step 1)."""
+    b1, b2, b3 = betas
+    if step == 1:
+        for k in ("exp_avg", "exp_avg_sq", "exp_avg_diff"):
+            state[k] = torch.zeros_like(p)
+        state["neg_pre_grad"] = g.clone().mul_(-1.0)
+    bc1, bc2, bc3 = 1 - b1 ** step, 1 - b2 ** step, 1 - b3 ** step
+    npg = state["neg_pre_grad"]
+    npg.add_(g)
+    state["exp_avg"].mul_(b1).add_(g, alpha=1 - b1)
+    state["exp_avg_diff"].mul_(b2).add_(npg, alpha=1 - b2)
+    npg.mul_(b2).add_(g)
+    state["exp_avg_sq"].mul_(b3).addcmul_(npg, npg, value=1 - b3)
+    denom = (state["exp_avg_sq"].sqrt() / math.sqrt(bc3)).add_(eps)
+    if no_prox:
+        p.mul_(1 - lr * weight_decay)
+    p.addcdiv_(state["exp_avg"], denom, value=-lr / bc1)
+    p.addcdiv_(state["exp_avg_diff"], denom, value=-lr * b2 / bc2)
+    if not no_prox:
+        p.div_(1 + lr * weight_decay)
+    npg.zero_().add_(g, alpha=-1.0)
+    return p

@@ -3,7 +3,9 @@
   "Hyper-iNGP"                                   custom/amortized/models/geometry/hyper_iNGP.py:114
   "multiprompt-neural-hashgrid-environment-map-background"   custom/amortized/models/background/…background.py:17
   "generative-space-volsdf-volume-renderer"      custom/amortized/models/renderers/generative_space_volsdf_volume_renderer.py:37
+  "Triplane-transformer-sdf"                     custom/amortized/models/geometry/triplane_transformer.py:20
   "multiprompt-camera-datamodule"                custom/amortized/data/multiprompt.py:166
+  "multiprompt-multiview-camera-datamodule"      custom/amortized/data/multiview_multiprompt.py:78
   "stable-diffusion-multi-prompt-processor"      custom/amortized/models/prompt_processors/stable_diffusion_multi_prompt_processor.py
   "multiprompt-radience-field-generator-system"  custom/amortized/systems/multiprompt_radience_field_generator.py:18
 
@@ -30,7 +32,7 @@ import torch.nn.functional as F
 from . import lib as L
 from . import core
 from .core import BaseModule, BaseObject, find, get_rank, parse_structured, register
-from .data import RandomCameraDataModuleConfig, RandomCameraIterableDataset
+from .data import RandomCameraDataModuleConfig, RandomCameraIterableDataset, RandomMultiviewCameraIterableDataset
 from .fields import DEFAULT_GRID, HashGridEncoding
 from .prompts import DIRECTIONS, PromptProcessorOutput, hash_prompt
 from .systems import BaseSystem, binary_cross_entropy
@@ -252,6 +254,215 @@ class HypernetSdf(BaseModule):
         return super().train(mode)
 
 
+# ------------------------------------------------------------------------------------------------ triplane
+class _TriplaneSample(torch.autograd.Function):
+    """enc [B, N, 3C] = bilinear samples of planes_cl [B, 3, H, W, C] (channels-last) at points [B, N, 3] in [-1, 1]."""
+
+    @staticmethod
+    def forward(ctx, planes_cl, points):
+        lib = L.load()
+        B, _, H, W, Cc = planes_cl.shape
+        N = points.shape[1]
+        planes_cl, points = planes_cl.contiguous().float(), points.detach().contiguous().float()
+        enc = torch.empty(B, N, 3 * Cc, device=points.device)
+        L.check(lib.sdb_triplane_sample_forward(L.ptr(planes_cl.detach()), L.ptr(points), B, N, H, W, Cc, L.ptr(enc),
+                                                L.stream_ptr()), "sdb_triplane_sample_forward")
+        ctx.save_for_backward(points)
+        ctx.shape = (B, H, W, Cc, N)
+        return enc
+
+    @staticmethod
+    def backward(ctx, d_enc):
+        (points,) = ctx.saved_tensors
+        B, H, W, Cc, N = ctx.shape
+        d_planes = torch.zeros(B, 3, H, W, Cc, device=points.device)
+        L.check(L.load().sdb_triplane_sample_backward(L.ptr(d_enc.contiguous().float()), L.ptr(points), B, N, H, W, Cc,
+                                                      L.ptr(d_planes), L.stream_ptr()), "sdb_triplane_sample_backward")
+        return d_planes, None
+
+
+class _Attention(nn.Module):
+    """diffusers.models.attention_processor.Attention as the reference instantiates it (bias-free q/k/v, biased
+    to_out[0], no dropout; triplane_transformer_modules.py:45-53) on torch SDPA."""
+
+    def __init__(self, query_dim: int, heads: int, dim_head: int, cross_attention_dim: int):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads = heads
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(cross_attention_dim, inner, bias=False)
+        self.to_v = nn.Linear(cross_attention_dim, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+
+    def forward(self, x, context=None):
+        ctx = x if context is None else context
+        B, Lq, _ = x.shape
+        sp = lambda t: t.view(B, t.shape[1], self.heads, -1).transpose(1, 2)
+        o = F.scaled_dot_product_attention(sp(self.to_q(x)), sp(self.to_k(ctx)), sp(self.to_v(ctx)))
+        return self.to_out[0](o.transpose(1, 2).reshape(B, Lq, -1))
+
+
+class _BlockCross(nn.Module):  # ConditionModulationBlock (local text: cross-attention to the 77 token embeddings)
+    def __init__(self, inner_dim, cond_dim, num_heads, eps, mlp_ratio):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(inner_dim, eps)
+        self.cross_attn = _Attention(inner_dim, num_heads, inner_dim // num_heads, cond_dim)
+        self.norm2 = nn.LayerNorm(inner_dim, eps)
+        self.self_attn = _Attention(inner_dim, num_heads, inner_dim // num_heads, inner_dim)
+        self.norm3 = nn.LayerNorm(inner_dim, eps)
+        hid = int(inner_dim * mlp_ratio)
+        self.mlp = nn.Sequential(nn.Linear(inner_dim, hid), nn.GELU(), nn.Dropout(0.0), nn.Linear(hid, inner_dim),
+                                 nn.Dropout(0.0))
+
+    def forward(self, x, cond):
+        x = x + self.cross_attn(self.norm1(x), cond)
+        x = x + self.self_attn(self.norm2(x))
+        return x + self.mlp(self.norm3(x))
+
+
+class _BlockConcat(nn.Module):  # ConditionModulationBlockwoCrossAttn (global text: condition token prepended)
+    def __init__(self, inner_dim, cond_dim, num_heads, eps, mlp_ratio):
+        super().__init__()
+        self.norm2 = nn.LayerNorm(inner_dim, eps)
+        self.self_attn = _Attention(inner_dim, num_heads, inner_dim // num_heads, inner_dim)
+        self.norm3 = nn.LayerNorm(inner_dim, eps)
+        hid = int(inner_dim * mlp_ratio)
+        self.mlp = nn.Sequential(nn.GELU(), nn.Linear(inner_dim, hid), nn.GELU(), nn.Linear(hid, inner_dim),
+                                 nn.Dropout(0.0))
+
+    def forward(self, x, cond):
+        x = torch.cat([cond, x], dim=1)
+        x = x + self.self_attn(self.norm2(x))
+        x = x + self.mlp(self.norm3(x))
+        return x[:, 1:, :]
+
+
+class TriplaneTransformer(nn.Module):
+    """custom/amortized/extern/triplane_transformer_modules.py:115-187 (state-dict compatible). A TRAINED dense network
+    ("next"): it runs on torch / cuBLAS / SDPA for now; everything downstream of its output
+    planes is this repo's CUDA."""
+
+    def __init__(self, inner_dim: int, condition_dim: int, triplane_low_res: int, triplane_high_res: int,
+                 triplane_dim: int, num_layers: int, num_heads: int, local_text: bool, mlp_ratio: float = 4.0,
+                 eps: float = 1e-6, flash_attention: bool = False):
+        super().__init__()
+        self.triplane_low_res, self.triplane_high_res, self.triplane_dim = triplane_low_res, triplane_high_res, triplane_dim
+        self.pos_embed = nn.Parameter(torch.randn(1, 3 * triplane_low_res ** 2, inner_dim) * (1.0 / inner_dim) ** 0.5)
+        self.needs_local_text = local_text
+        blk = _BlockCross if local_text else _BlockConcat
+        self.layers = nn.ModuleList([blk(inner_dim, condition_dim, num_heads, eps, mlp_ratio) for _ in range(num_layers)])
+        self.norm = nn.LayerNorm(inner_dim, eps=eps)
+        self.deconv = nn.ConvTranspose2d(inner_dim, triplane_dim, kernel_size=2, stride=2, padding=0, bias=False)
+        if not local_text:
+            self.proj = nn.Linear(condition_dim, inner_dim)
+
+    def forward(self, text_embed: torch.Tensor) -> torch.Tensor:
+        N, H = text_embed.shape[0], self.triplane_low_res
+        if not self.needs_local_text:
+            text_embed = self.proj(text_embed).unsqueeze(1)
+        x = self.pos_embed.repeat(N, 1, 1)
+        for layer in self.layers:
+            x = layer(x, text_embed)
+        x = self.norm(x).view(N, 3, H, H, -1)
+        x = torch.einsum("nihwd->indhw", x).contiguous().view(3 * N, -1, H, H)
+        x = self.deconv(x)
+        x = x.view(3, N, *x.shape[-3:])
+        return torch.einsum("indhw->nidhw", x).contiguous()  # [N, 3, C, 2H, 2H]
+
+
+@register("Triplane-transformer-sdf")
+class TriplaneTransformerSDF(BaseModule):
+    @dataclass
+    class Config(BaseModule.Config):
+        radius: float = 1.0
+        isosurface: bool = True
+        isosurface_method: str = "mt"
+        isosurface_resolution: int = 128
+        isosurface_threshold: Union[float, str] = 0.0
+        isosurface_chunk: int = 0
+        isosurface_coarse_to_fine: bool = True
+        isosurface_deformable_grid: bool = False
+        isosurface_remove_outliers: bool = False
+        isosurface_outlier_n_faces_threshold: Union[int, float] = 0.01
+        n_feature_dims: int = 3
+        space_generator_config: dict = field(default_factory=lambda: {
+            "inner_dim": 768, "condition_dim": 1024, "triplane_low_res": 32, "triplane_high_res": 64, "triplane_dim": 32,
+            "num_layers": 12, "num_heads": 16, "flash_attention": False, "local_text": False})
+        mlp_network_config: dict = field(default_factory=lambda: {
+            "otype": "VanillaMLP", "activation": "ReLU", "output_activation": "none", "n_neurons": 64,
+            "n_hidden_layers": 2})
+        backbone: str = "triplane_transformer"
+        normal_type: Optional[str] = "finite_difference"
+        finite_difference_normal_eps: Union[float, str] = 0.01
+        sdf_bias: Union[float, str] = 0.0
+        sdf_bias_params: Optional[Any] = None
+
+    cfg: Config
+
+    def configure(self) -> None:
+        from .fields import VanillaMLP
+
+        r = self.cfg.radius
+        self.register_buffer("bbox", torch.as_tensor([[-r, -r, -r], [r, r, r]], dtype=torch.float32))
+        self.unbounded = False
+        if self.cfg.backbone != "triplane_transformer":
+            raise ValueError(f"Unknown backbone {self.cfg.backbone}")
+        if self.cfg.normal_type != "finite_difference":
+            raise NotImplementedError(f"normal_type == {self.cfg.normal_type} is not implemented yet.")
+        if self.cfg.isosurface_deformable_grid:
+            raise NotImplementedError("isosurface_deformable_grid is outside the ASD hot path")
+        self.space_generator = TriplaneTransformer(**self.cfg.space_generator_config)
+        input_dim = int(self.cfg.space_generator_config["triplane_dim"]) * 3
+        self.sdf_network = VanillaMLP(input_dim, 1, self.cfg.mlp_network_config)
+        self.feature_network = VanillaMLP(input_dim, self.cfg.n_feature_dims, self.cfg.mlp_network_config)
+        self.finite_difference_normal_eps: Optional[float] = None
+
+    def initialize_shape(self) -> None:
+        pass
+
+    def update_step(self, epoch: int, global_step: int, on_load_weights: bool = False):
+        if not isinstance(self.cfg.finite_difference_normal_eps, float):
+            raise NotImplementedError("progressive finite_difference_normal_eps is not implemented yet.")
+        self.finite_difference_normal_eps = self.cfg.finite_difference_normal_eps
+
+    def generate_space_cache(self, styles=None, text_embed: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.space_generator(text_embed=text_embed)
+
+    _sdf_bias = HypernetSdf._sdf_bias
+
+    def interpolate_encodings(self, points: torch.Tensor, space_cache: torch.Tensor) -> torch.Tensor:
+        """points [B, N, 3] in [-1, 1], space_cache [B, 3, C, H, W] -> [B, N, 3C] (utils.py:80-97; box_warp = 2)."""
+        planes_cl = space_cache.permute(0, 1, 3, 4, 2).contiguous()
+        return _TriplaneSample.apply(planes_cl, points)
+
+    def _contract(self, points: torch.Tensor) -> torch.Tensor:  # scale_tensor(x, bbox, (-1, 1))
+        return (points - self.bbox[0]) / (self.bbox[1] - self.bbox[0]) * 2.0 - 1.0
+
+    def forward_sdf(self, points: torch.Tensor, space_cache: torch.Tensor) -> torch.Tensor:
+        B = points.shape[0]
+        flat = points.reshape(B, -1, 3)
+        enc = self.interpolate_encodings(self._contract(flat), space_cache)
+        sdf = self.sdf_network.layers(enc)[..., 0] + self._sdf_bias(flat)
+        return sdf.view(*points.shape[:-1], 1)
+
+    def forward(self, points: torch.Tensor, space_cache: torch.Tensor, output_normal: bool = False):
+        B, N, _ = points.shape
+        enc = self.interpolate_encodings(self._contract(points), space_cache)
+        sdf = self.sdf_network.layers(enc)[..., 0] + self._sdf_bias(points)
+        out = {"sdf": sdf.reshape(B * N, 1), "features": self.feature_network.layers(enc).reshape(B * N, -1)}
+        if output_normal:
+            assert self.finite_difference_normal_eps is not None
+            eps = self.finite_difference_normal_eps
+            offs = (points[..., None, :] + eps * torch.eye(3, device=points.device)).clamp(-self.cfg.radius,
+                                                                                           self.cfg.radius)
+            sdf_off = self.forward_sdf(offs.reshape(B, N * 3, 3), space_cache).view(B, N, 3)
+            sdf_grad = (sdf_off - sdf[..., None]) / eps
+            normal = F.normalize(sdf_grad, dim=-1)
+            out.update(normal=normal.reshape(B * N, 3), shading_normal=normal.reshape(B * N, 3),
+                       sdf_grad=sdf_grad.reshape(B * N, 3))
+        return out
+
+
 # ------------------------------------------------------------------------------------------------ background
 @register("multiprompt-neural-hashgrid-environment-map-background")
 class MultipromptNeuralHashgridEnvironmentMapBackground(BaseModule):
@@ -318,7 +529,7 @@ class _VolSDFComposite(torch.autograd.Function):
     generative_space_volsdf_volume_renderer.py:356-397) in one launch each way (csrc/volsdf.cu)."""
 
     @staticmethod
-    def forward(ctx, sdf, feat, normal, t_mid, delta, inv_std: float):
+    def forward(ctx, sdf, feat, normal, t_mid, delta, inv_std: float, color_act: int = 0):
         lib = L.load()
         Nr, S = sdf.shape
         dev = sdf.device
@@ -328,11 +539,11 @@ class _VolSDFComposite(torch.autograd.Function):
         opacity, depth, zvar = (torch.empty(Nr, device=dev) for _ in range(3))
         fg, cn = torch.empty(Nr, 3, device=dev), torch.empty(Nr, 3, device=dev)
         L.check(lib.sdb_volsdf_composite_forward(L.ptr(sdf), L.ptr(feat), L.ptr(normal), L.ptr(t_mid), L.ptr(delta), Nr,
-                                                 S, float(inv_std), L.ptr(weights), L.ptr(opacity), L.ptr(depth),
+                                                 S, float(inv_std), int(color_act), L.ptr(weights), L.ptr(opacity), L.ptr(depth),
                                                  L.ptr(fg), L.ptr(zvar), L.ptr(cn), L.stream_ptr()),
                 "sdb_volsdf_composite_forward")
         ctx.save_for_backward(sdf, feat, t_mid, delta, weights, opacity, depth, fg)
-        ctx.inv_std = float(inv_std)
+        ctx.inv_std, ctx.color_act = float(inv_std), int(color_act)
         ctx.mark_non_differentiable(weights, zvar, cn)
         return fg, opacity, depth, zvar, weights, cn
 
@@ -346,9 +557,9 @@ class _VolSDFComposite(torch.autograd.Function):
         d_sdf, d_feat = torch.empty_like(sdf), torch.empty_like(feat)
         L.check(lib.sdb_volsdf_composite_backward(L.ptr(sdf), L.ptr(feat), L.ptr(t_mid), L.ptr(delta), L.ptr(weights),
                                                   L.ptr(opacity), L.ptr(depth), L.ptr(fg), L.ptr(g_fg), L.ptr(g_op),
-                                                  L.ptr(g_depth), Nr, S, ctx.inv_std, L.ptr(d_sdf), L.ptr(d_feat),
-                                                  L.stream_ptr()), "sdb_volsdf_composite_backward")
-        return d_sdf, d_feat, None, None, None, None
+                                                  L.ptr(g_depth), Nr, S, ctx.inv_std, ctx.color_act, L.ptr(d_sdf),
+                                                  L.ptr(d_feat), L.stream_ptr()), "sdb_volsdf_composite_backward")
+        return d_sdf, d_feat, None, None, None, None, None
 
 
 @register("generative-space-volsdf-volume-renderer")
@@ -434,7 +645,10 @@ class GenerativeSpaceVolSDFVolumeRenderer(BaseModule):
             if not self.training:
                 assert Bc == 1, "batch_size of space_cache must be 1 or equal to batch_size of rays_o"
             assert B % Bc == 0
-            space_cache = {k: [m.repeat_interleave(B // Bc, dim=0) for m in v] for k, v in space_cache.items()}
+            if torch.is_tensor(space_cache):
+                space_cache = space_cache.repeat_interleave(B // Bc, dim=0)
+            else:
+                space_cache = {k: [m.repeat_interleave(B // Bc, dim=0) for m in v] for k, v in space_cache.items()}
             if text_embed is not None:
                 text_embed = text_embed.repeat_interleave(B // Bc, dim=0)
         Nr, HW = B * H * W, H * W
@@ -445,10 +659,13 @@ class GenerativeSpaceVolSDFVolumeRenderer(BaseModule):
         positions = o[:, None, :] + d[:, None, :] * t_mid[..., None]
         geo = self.geometry(positions.view(B, HW * S, 3), space_cache=space_cache, output_normal=True)
         inv_std = float(self.variance.inv_std.clamp(1.0e-6, 1.0e6))
-        if getattr(self.material, "cfg", None) is not None and self.material.cfg.color_activation != "sigmoid":
-            raise NotImplementedError("the VolSDF compositing kernel applies the sigmoid colour activation of no-material")
+        color_act = {"sigmoid": 0, "sigmoid-mipnerf": 1}.get(self.material.cfg.color_activation)
+        if color_act is None or type(self.material).__name__ != "NoMaterial":
+            raise NotImplementedError("the VolSDF compositing kernel fuses no-material with a sigmoid / sigmoid-mipnerf "
+                                      "colour activation")
         fg, opacity, depth, z_var, weights, comp_normal = _VolSDFComposite.apply(
-            geo["sdf"].view(Nr, S), geo["features"].view(Nr, S, 3), geo["normal"].view(Nr, S, 3), t_mid, delta, inv_std)
+            geo["sdf"].view(Nr, S), geo["features"].view(Nr, S, 3), geo["normal"].view(Nr, S, 3), t_mid, delta, inv_std,
+            color_act)
         if getattr(self.background, "enabling_hypernet", False):
             comp_rgb_bg = self.background(dirs=rays_d, text_embed=text_embed)
         else:
@@ -546,6 +763,52 @@ class MultipromptCameraDataModule:
             yield self.train_dataset.collate({})
 
 
+@dataclass
+class MultiviewMultipromptRandomCameraDataModuleConfig(MultipromptRandomCameraDataModuleConfig):
+    relative_radius: bool = True
+    n_view: int = 1
+    zoom_range: Tuple[float, float] = (1.0, 1.0)
+
+
+class MultiviewMultipromptRandomCameraIterableDataset(RandomMultiviewCameraIterableDataset):
+    config_cls = MultiviewMultipromptRandomCameraDataModuleConfig
+
+    def __init__(self, cfg: Any, prompt_library: Dict) -> None:
+        super().__init__(cfg)
+        assert "train" in prompt_library, "prompt library must contain train split"
+        self.prompt_library = prompt_library["train"]
+        self.n_view = self.cfg.n_view
+
+    def collate(self, batch=None) -> Dict[str, Any]:
+        n_prompts = self.batch_size // self.n_view
+        out = super().collate(batch)
+        out["noise"] = torch.randn(n_prompts, self.cfg.dim_gaussian)
+        if len(self.prompt_library) < n_prompts:
+            out["prompt"] = random.choices(self.prompt_library, k=n_prompts)
+        else:
+            out["prompt"] = random.sample(self.prompt_library, k=n_prompts)
+        return out
+
+
+@register("multiprompt-multiview-camera-datamodule")
+class MultiviewMultipromptCameraDataModule:
+    def __init__(self, cfg=None) -> None:
+        self.cfg = parse_structured(MultiviewMultipromptRandomCameraDataModuleConfig, cfg)
+        rank, world = _world()
+        self.prompt_library = load_prompt_library(self.cfg, rank, world)
+        self.train_dataset = None
+
+    def setup(self, stage=None) -> None:
+        if stage in (None, "fit"):
+            self.train_dataset = MultiviewMultipromptRandomCameraIterableDataset(self.cfg, self.prompt_library)
+
+    def train_dataloader(self):
+        if self.train_dataset is None:
+            self.setup("fit")
+        while True:
+            yield self.train_dataset.collate({})
+
+
 # ------------------------------------------------------------------------------------------------ prompts
 class MultiPromptProcessorOutput:
     """custom/amortized/models/prompt_processors/base.py:410-568. The processor keeps one stacked device table
@@ -559,6 +822,9 @@ class MultiPromptProcessorOutput:
         self.use_perp_neg = bool(proc.cfg.use_perp_neg)
 
     def get_global_text_embeddings(self) -> torch.Tensor:
+        """[B, 1024] pooled embeddings, or the [B, 77, 1024] token embeddings when use_local_text_embeddings (:426-432)."""
+        if self.proc.cfg.use_local_text_embeddings:
+            return self.proc.local_table[self.prompt_idx.long(), 0].float()
         return self.proc.global_table[self.prompt_idx.long()]
 
     def prompt_cfg_c(self, view_dependent: bool, perp_neg: bool) -> L.PromptCfgC:
@@ -643,8 +909,6 @@ class StableDiffusionMultiPromptProcessor(BaseObject):
     def configure(self) -> None:
         if self.cfg.use_prompt_debiasing:
             raise NotImplementedError("Prompt debiasing is not implemented yet")
-        if self.cfg.use_local_text_embeddings:
-            raise NotImplementedError("use_local_text_embeddings: the hypernetworks take the pooled [1024] embedding")
         if self.cfg.eval_prompt is None:
             rank, world = _world()
             lib = load_prompt_library(self.cfg, rank, world)

@@ -189,6 +189,29 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// Adan (threestudio/systems/optimizers.py:200-250, _single_tensor_adan) fused into one pass; prev_g holds the previous
+// (clipped) gradient, i.e. minus the reference's neg_pre_grad.
+__global__ void adan_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ n, float* __restrict__ d, float* __restrict__ prev_g, long long count,
+                            float lr, float b1, float b2, float b3, float eps, float wd, float bc1, float bc2,
+                            float bc3_sqrt, float gscale, int first, int no_prox) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float diff = first ? 0.f : gi - prev_g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float di = b2 * d[i] + (1.f - b2) * diff;
+    const float u = b2 * diff + gi;
+    const float ni = b3 * n[i] + (1.f - b3) * u * u;
+    m[i] = mi, d[i] = di, n[i] = ni, prev_g[i] = gi;
+    const float denom = sqrtf(ni) / bc3_sqrt + eps;
+    float pi = p[i];
+    if (no_prox) pi *= 1.f - lr * wd;
+    pi -= (lr / bc1) * (mi / denom) + (lr * b2 / bc2) * (di / denom);
+    if (!no_prox) pi /= 1.f + lr * wd;
+    p[i] = pi;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -553,6 +576,24 @@ int sdb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
                                                        weight_decay, bc1, std::sqrt(bc2), grad_scale);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("adamw_step");
+  return SDB_OK;
+}
+
+int sdb_adan_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* exp_avg_diff,
+                  float* prev_grad, long long n, float lr, float beta1, float beta2, float beta3, float eps,
+                  float weight_decay, int step, float grad_scale, int no_prox, void* stream) {
+  SDB_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && exp_avg_diff && prev_grad && n >= 0 && step >= 1,
+                "adan_step: bad arguments");
+  if (n == 0) return SDB_OK;
+  const float bc1 = 1.f - (float)std::pow((double)beta1, (double)step);
+  const float bc2 = 1.f - (float)std::pow((double)beta2, (double)step);
+  const float bc3 = 1.f - (float)std::pow((double)beta3, (double)step);
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)kNumSMs * 8);
+  adan_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, exp_avg_diff, prev_grad, n, lr,
+                                                      beta1, beta2, beta3, eps, weight_decay, bc1, bc2, std::sqrt(bc3),
+                                                      grad_scale, step == 1 ? 1 : 0, no_prox);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("adan_step");
   return SDB_OK;
 }
 

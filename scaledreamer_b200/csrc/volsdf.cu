@@ -111,7 +111,7 @@ constexpr int kCpWarps = 8;
 __global__ void __launch_bounds__(kCpWarps * 32)
 volsdf_composite_fwd_kernel(const float* __restrict__ sdf, const float* __restrict__ feat,
                             const float* __restrict__ normal, const float* __restrict__ t_mid,
-                            const float* __restrict__ delta, int n_rays, int S, float inv_std,
+                            const float* __restrict__ delta, int n_rays, int S, float inv_std, int color_act,
                             float* __restrict__ weights, float* __restrict__ opacity, float* __restrict__ depth,
                             float* __restrict__ fg, float* __restrict__ zvar, float* __restrict__ cn) {
   const int lane = threadIdx.x & 31;
@@ -140,7 +140,9 @@ volsdf_composite_fwd_kernel(const float* __restrict__ sdf, const float* __restri
       a_wtt = fmaf(w * t, t, a_wtt);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        a_c[c] = fmaf(w, 1.f / (1.f + expf(-feat[(base + j) * 3 + c])), a_c[c]);
+        float col = 1.f / (1.f + expf(-feat[(base + j) * 3 + c]));
+        if (color_act == 1) col = col * 1.002f - 0.001f;
+        a_c[c] = fmaf(w, col, a_c[c]);
         a_n[c] = fmaf(w, normal[(base + j) * 3 + c], a_n[c]);
       }
     }
@@ -172,7 +174,7 @@ volsdf_composite_bwd_kernel(const float* __restrict__ sdf, const float* __restri
                             const float* __restrict__ weights, const float* __restrict__ opacity,
                             const float* __restrict__ depth, const float* __restrict__ fg,
                             const float* __restrict__ g_fg, const float* __restrict__ g_op,
-                            const float* __restrict__ g_depth, int n_rays, int S, float inv_std,
+                            const float* __restrict__ g_depth, int n_rays, int S, float inv_std, int color_act,
                             float* __restrict__ d_sdf, float* __restrict__ d_feat) {
   const int lane = threadIdx.x & 31;
   const int ray = blockIdx.x * kCpWarps + (threadIdx.x >> 5);
@@ -188,13 +190,17 @@ volsdf_composite_bwd_kernel(const float* __restrict__ sdf, const float* __restri
   (void)weights;
   for (int j0 = 0; j0 < S; j0 += 32) {
     const int j = j0 + lane;
-    float gw = 0.f, g = 0.f, s = 0.f, dl = 0.f, alpha = 0.f, c[3] = {0.f, 0.f, 0.f};
+    float gw = 0.f, g = 0.f, s = 0.f, dl = 0.f, alpha = 0.f, c[3] = {0.f, 0.f, 0.f}, sg[3] = {0.f, 0.f, 0.f};
+    const float cs = color_act == 1 ? 1.002f : 1.f, co = color_act == 1 ? -0.001f : 0.f;
     if (j < S) {
       s = sdf[base + j];
       dl = fabsf(delta[base + j]);
       alpha = dl * volsdf_sigma(s, a);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) c[k] = 1.f / (1.f + expf(-feat[(base + j) * 3 + k]));
+      for (int k = 0; k < 3; ++k) {
+        sg[k] = 1.f / (1.f + expf(-feat[(base + j) * 3 + k]));
+        c[k] = fmaf(sg[k], cs, co);
+      }
       g = fmaf(gC0, c[0], fmaf(gC1, c[1], fmaf(gC2, c[2], fmaf(gD, t_mid[base + j], gO))));
     }
     // transmittance re-derived with the forward's multiplicative scan
@@ -213,9 +219,9 @@ volsdf_composite_bwd_kernel(const float* __restrict__ sdf, const float* __restri
       const float dalpha = g * T - suffix / one_m;
       const float dsigma_ds = s == 0.f ? 0.f : -0.5f * a * a * expf(-fabsf(s) * a);
       d_sdf[base + j] = dalpha * dl * dsigma_ds;
-      d_feat[(base + j) * 3 + 0] = w * gC0 * c[0] * (1.f - c[0]);
-      d_feat[(base + j) * 3 + 1] = w * gC1 * c[1] * (1.f - c[1]);
-      d_feat[(base + j) * 3 + 2] = w * gC2 * c[2] * (1.f - c[2]);
+      d_feat[(base + j) * 3 + 0] = w * gC0 * cs * sg[0] * (1.f - sg[0]);
+      d_feat[(base + j) * 3 + 1] = w * gC1 * cs * sg[1] * (1.f - sg[1]);
+      d_feat[(base + j) * 3 + 2] = w * gC2 * cs * sg[2] * (1.f - sg[2]);
     }
     P += __shfl_sync(kFullMask, incl, 31);
   }
@@ -255,14 +261,14 @@ int sdb_volsdf_resample(const float* sdf, const float* u_coarse, const float* u_
 }
 
 int sdb_volsdf_composite_forward(const float* sdf, const float* features, const float* normal, const float* t_mid,
-                                 const float* delta, int n_rays, int n_samples, float inv_std, float* weights,
-                                 float* opacity, float* depth, float* comp_rgb_fg, float* z_variance,
+                                 const float* delta, int n_rays, int n_samples, float inv_std, int color_activation,
+                                 float* weights, float* opacity, float* depth, float* comp_rgb_fg, float* z_variance,
                                  float* comp_normal, void* stream) {
   SDB_CHECK_ARG(sdf && features && normal && t_mid && delta && weights && opacity && depth && comp_rgb_fg &&
                     z_variance && comp_normal && n_rays >= 0 && n_samples > 0, "volsdf_composite_forward: bad arguments");
   if (n_rays == 0) return SDB_OK;
   volsdf_composite_fwd_kernel<<<(n_rays + kCpWarps - 1) / kCpWarps, kCpWarps * 32, 0, (cudaStream_t)stream>>>(
-      sdf, features, normal, t_mid, delta, n_rays, n_samples, inv_std, weights, opacity, depth, comp_rgb_fg,
+      sdf, features, normal, t_mid, delta, n_rays, n_samples, inv_std, color_activation, weights, opacity, depth, comp_rgb_fg,
       z_variance, comp_normal);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("volsdf_composite_forward");
@@ -272,15 +278,15 @@ int sdb_volsdf_composite_forward(const float* sdf, const float* features, const 
 int sdb_volsdf_composite_backward(const float* sdf, const float* features, const float* t_mid, const float* delta,
                                   const float* weights, const float* opacity, const float* depth,
                                   const float* comp_rgb_fg, const float* g_comp_rgb_fg, const float* g_opacity,
-                                  const float* g_depth, int n_rays, int n_samples, float inv_std, float* d_sdf,
-                                  float* d_features, void* stream) {
+                                  const float* g_depth, int n_rays, int n_samples, float inv_std, int color_activation,
+                                  float* d_sdf, float* d_features, void* stream) {
   SDB_CHECK_ARG(sdf && features && t_mid && delta && weights && opacity && depth && comp_rgb_fg && g_comp_rgb_fg &&
                     g_opacity && g_depth && d_sdf && d_features && n_rays >= 0 && n_samples > 0,
                 "volsdf_composite_backward: bad arguments");
   if (n_rays == 0) return SDB_OK;
   volsdf_composite_bwd_kernel<<<(n_rays + kCpWarps - 1) / kCpWarps, kCpWarps * 32, 0, (cudaStream_t)stream>>>(
       sdf, features, t_mid, delta, weights, opacity, depth, comp_rgb_fg, g_comp_rgb_fg, g_opacity, g_depth, n_rays,
-      n_samples, inv_std, d_sdf, d_features);
+      n_samples, inv_std, color_activation, d_sdf, d_features);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("volsdf_composite_backward");
   return SDB_OK;

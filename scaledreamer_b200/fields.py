@@ -65,6 +65,44 @@ class HashGridEncoding(nn.Module):
         return R.hashgrid_forward(x01.reshape(-1, 3), self.table.detach().view(-1, 2), self.grid_cfg)
 
 
+class SphericalHarmonicsEncoding(nn.Module):
+    """tiny-cuda-nn "SphericalHarmonics" (un-vendored; real SH basis on the direction 2 x01 - 1), degrees 1..3. It has no
+    parameters and runs once per RAY, so it stays a few element-wise torch ops."""
+
+    def __init__(self, degree: int):
+        super().__init__()
+        if not 1 <= degree <= 3:
+            raise NotImplementedError("SphericalHarmonics encodings of degree 1..3 are implemented")
+        self.degree, self.n_input_dims, self.n_output_dims = degree, 3, degree * degree
+
+    def forward(self, x01: torch.Tensor) -> torch.Tensor:
+        d = x01 * 2.0 - 1.0
+        x, y, z = d[..., 0], d[..., 1], d[..., 2]
+        out = [torch.full_like(x, 0.28209479177387814)]
+        if self.degree > 1:
+            out += [-0.48860251190291987 * y, 0.48860251190291987 * z, -0.48860251190291987 * x]
+        if self.degree > 2:
+            out += [1.0925484305920792 * x * y, -1.0925484305920792 * y * z,
+                    0.94617469575755997 * z * z - 0.31539156525251999, -1.0925484305920792 * x * z,
+                    0.54627421529603959 * (x * x - y * y)]
+        return torch.stack(out, dim=-1)
+
+
+class _HashGridFn(torch.autograd.Function):
+    """tcnn.Encoding forward / backward (sdb_hashgrid_forward / sdb_hashgrid_backward) with a gradient to the table."""
+
+    @staticmethod
+    def forward(ctx, x01, table, grid_cfg):
+        ctx.save_for_backward(x01.detach())
+        ctx.grid_cfg, ctx.n_entries = grid_cfg, table.shape[0]
+        return R.hashgrid_forward(x01.detach(), table.detach(), grid_cfg)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (x01,) = ctx.saved_tensors
+        return None, R.hashgrid_backward(x01, g_out, ctx.n_entries, ctx.grid_cfg), None
+
+
 class VanillaMLP(nn.Module):
     """networks.py:214-251: bias-free Linear + ReLU stack; keys layers.{0,2,...}.weight."""
 
@@ -207,15 +245,39 @@ class NeuralEnvironmentMapBackground(BaseModule):
     cfg: Config
 
     def configure(self) -> None:
-        self.encoding = HashGridEncoding(3, self.cfg.dir_encoding_config)
-        mlp = self.cfg.mlp_network_config
-        if self.encoding.n_output_dims != 8 or int(mlp["n_neurons"]) != 16 or int(mlp["n_hidden_layers"]) != 2:
-            raise NotImplementedError("the fused renderer is built for a 4-level x 2 grid and an 8-16-16-3 MLP")
-        self.network = VanillaMLP(8, self.cfg.n_output_dims, mlp)
+        enc_cfg, mlp = self.cfg.dir_encoding_config, self.cfg.mlp_network_config
+        if enc_cfg.get("otype") == "SphericalHarmonics":  # the class default; used by the Triplane configs
+            self.encoding = SphericalHarmonicsEncoding(int(enc_cfg.get("degree", 3)))
+        else:
+            self.encoding = HashGridEncoding(3, enc_cfg)
+        self.fusable = (isinstance(self.encoding, HashGridEncoding) and self.encoding.n_output_dims == 8
+                        and int(mlp["n_neurons"]) == 16 and int(mlp["n_hidden_layers"]) == 2)
+        self.network = VanillaMLP(self.encoding.n_output_dims, self.cfg.n_output_dims, mlp)
 
     def field_params(self) -> Dict[str, torch.Tensor]:
+        if not self.fusable:
+            raise NotImplementedError("the fused NeRF renderer is built for a 4-level x 2 hash grid and an 8-16-16-3 MLP "
+                                      "environment map")
         w1, w2, w3 = self.network.weights()
         return {"bg_table": self.encoding.table, "bg_w1": w1, "bg_w2": w2, "bg_w3": w3}
+
+    def forward(self, dirs: torch.Tensor) -> torch.Tensor:
+        """Stand-alone differentiable evaluation (neural_environment_map_background.py:46-67) for renderers that call
+        the background as a module (the VolSDF renderer of the amortized path). The NeRF renderer fuses it instead."""
+        shp = dirs.shape[:-1]
+        x01 = ((dirs + 1.0) / 2.0).reshape(-1, 3)
+        if isinstance(self.encoding, SphericalHarmonicsEncoding):
+            enc = self.encoding(x01)
+        else:
+            enc = _HashGridFn.apply(x01, self.encoding.table.view(-1, 2), self.encoding.grid_cfg)
+        color = torch.sigmoid(self.network.layers(enc))
+        if self.cfg.color_activation == "sigmoid-mipnerf":
+            color = color * 1.002 - 0.001
+        color = color.view(*shp, self.cfg.n_output_dims)
+        if self.training and self.cfg.random_aug and random.random() < self.cfg.random_aug_prob:
+            color = color * 0 + torch.rand(dirs.shape[0], 1, 1, self.cfg.n_output_dims, device=dirs.device).expand(
+                *shp, -1)
+        return color
 
     def sample_override(self, batch_size: int, device) -> Optional[torch.Tensor]:
         """Random solid colour with probability random_aug_prob while training (…background.py:56-66): host coin,

@@ -124,10 +124,13 @@ SIGNATURES = {
     "sdb_hyper_field_backward": [C.POINTER(GridCfgC), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "sdb_volsdf_coarse_points": [_P, _P, _P, _I, _I, _F, _F, _P, _P],
     "sdb_volsdf_resample": [_P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P],
-    "sdb_volsdf_composite_forward": [_P, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P],
-    "sdb_volsdf_composite_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P],
+    "sdb_volsdf_composite_forward": [_P, _P, _P, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P],
+    "sdb_volsdf_composite_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P, _P, _P],
+    "sdb_triplane_sample_forward": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "sdb_triplane_sample_backward": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "sdb_raygen": [_P, _P, _I, _I, _I, _P, _P, _P],
     "sdb_adamw_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
+    "sdb_adan_step": [_P, _P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _I, _F, _I, _P],
     # ---- include/sdb200_nn.h
     "sdb_gemm_f16": [C.POINTER(GemmArgsC), _P],
     "sdb_gemm_profile_begin": [],

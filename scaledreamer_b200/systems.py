@@ -62,6 +62,40 @@ class FusedAdamW(torch.optim.Optimizer):
         return None
 
 
+class FusedAdan(torch.optim.Optimizer):
+    """Adan (threestudio/systems/optimizers.py:23-315; the Triplane-Transformer configs), one sdb_adan_step launch per
+    parameter tensor. max_grad_norm > 0 (global-norm clipping with a host sync) is not implemented."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.98, 0.92, 0.99), eps=1e-8, weight_decay=0.0, max_grad_norm=0.0,
+                 no_prox=False, foreach=True, **unused):
+        if max_grad_norm > 0:
+            raise NotImplementedError("Adan max_grad_norm > 0 is not implemented")
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, no_prox=no_prox))
+        self.grad_scale = 1.0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        lib = L.load()
+        st = L.stream_ptr()
+        for group in self.param_groups:
+            b1, b2, b3 = group["betas"]
+            group["step"] = group.get("step", 0) + 1
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                state = self.state[p]
+                if not state:
+                    for k in ("exp_avg", "exp_avg_sq", "exp_avg_diff", "prev_grad"):
+                        state[k] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                L.check(lib.sdb_adan_step(L.ptr(p.data), L.ptr(g), L.ptr(state["exp_avg"]), L.ptr(state["exp_avg_sq"]),
+                                          L.ptr(state["exp_avg_diff"]), L.ptr(state["prev_grad"]), p.numel(),
+                                          float(group["lr"]), float(b1), float(b2), float(b3), float(group["eps"]),
+                                          float(group["weight_decay"]), int(group["step"]), float(self.grad_scale),
+                                          int(bool(group["no_prox"])), st), "sdb_adan_step")
+        return None
+
+
 def parse_optimizer(config: dict, model: nn.Module) -> torch.optim.Optimizer:
     name = config["name"]
     args = dict(config.get("args", {}))
@@ -77,6 +111,8 @@ def parse_optimizer(config: dict, model: nn.Module) -> torch.optim.Optimizer:
         if name == "Adam":
             args.setdefault("weight_decay", 0.0)
         return FusedAdamW(params, **args)
+    if name == "Adan":
+        return FusedAdan(params, **args)
     if hasattr(torch.optim, name):
         return getattr(torch.optim, name)(params, **args)
     raise NotImplementedError(f"optimizer {name}")
@@ -225,22 +261,24 @@ class Trainer:
         self._flat = None
 
     def _allreduce_grads(self, params: List[torch.Tensor]) -> None:
-        """One collective per optimizer step on a flat fp32 buffer (replaces DDP's bucketed reducer)."""
-        grads = [p.grad for p in params if p.grad is not None]
-        if not grads:
+        """One collective per optimizer step on a flat fp32 buffer (replaces DDP's bucketed reducer). After the first
+        step every `.grad` IS a view of that buffer (autograd accumulates into it in place, zero_grad(set_to_none=False)
+        clears it in place), so no gather / scatter copies remain around the all-reduce."""
+        with_grad = [p for p in params if p.grad is not None]
+        if not with_grad:
             return
-        n = sum(g.numel() for g in grads)
+        n = sum(p.grad.numel() for p in with_grad)
         if self._flat is None or self._flat.numel() != n:
-            self._flat = torch.empty(n, device=grads[0].device, dtype=torch.float32)
+            self._flat = torch.empty(n, device=with_grad[0].grad.device, dtype=torch.float32)
         off = 0
-        for g in grads:
-            self._flat[off:off + g.numel()].copy_(g.reshape(-1))
-            off += g.numel()
+        for p in with_grad:
+            g, k = p.grad, p.grad.numel()
+            view = self._flat[off:off + k].view_as(g)
+            if g.data_ptr() != view.data_ptr():
+                view.copy_(g)
+                p.grad = view
+            off += k
         self.dist.all_reduce(self._flat, op=self.dist.ReduceOp.SUM)
-        off = 0
-        for g in grads:
-            g.copy_(self._flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
 
     def fit(self, system: BaseSystem, datamodule) -> None:
         device = core.get_device()
@@ -250,7 +288,7 @@ class Trainer:
         system.train()
         system.on_fit_start()
         optimizer = system.configure_optimizers()
-        if isinstance(optimizer, FusedAdamW):
+        if isinstance(optimizer, (FusedAdamW, FusedAdan)):
             optimizer.grad_scale = 1.0 / (self.world_size * self.accumulate)
         params = [p for g in optimizer.param_groups for p in g["params"]]
         micro = 0

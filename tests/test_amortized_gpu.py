@@ -247,3 +247,106 @@ def test_multiprompt_system_training_step(cuda_device, tmp_path, monkeypatch):
     assert (system.geometry.hypernet.layers[3].weight.detach() - before).abs().max() > 0
     assert (system.geometry.encoding.table.detach() - tb).abs().max() > 0
     assert "train/loss_eikonal" in system.logged and "train/loss_asd" in system.logged
+
+
+@pytest.mark.parametrize("B,N,H", [(1, 1000, 64), (2, 257, 16)])
+def test_triplane_sample_forward_backward(cuda_device, B, N, H):
+    """Triplane lookup against F.grid_sample (the reference's sample_from_planes restated), incl. points outside the
+    box (zeros padding) and exactly on texel centres / borders."""
+    from scaledreamer_b200.amortized import _TriplaneSample
+
+    g = torch.Generator().manual_seed(B)
+    planes = torch.randn(B, 3, 32, H, H, generator=g).requires_grad_(True)
+    pts = torch.rand(B, N, 3, generator=g) * 2.4 - 1.2
+    pts[0, :3] = torch.tensor([[1.0, -1.0, 0.0], [-1.0, 1.0, 1.0], [(2 * 3 + 1) / H - 1, 0.5, -0.25]])
+    ref = ao.sample_from_planes(planes, pts)
+    go = torch.randn(ref.shape, generator=g)
+    (ref * go).sum().backward()
+    pl = planes.detach().permute(0, 1, 3, 4, 2).contiguous().to(cuda_device).requires_grad_(True)
+    enc = _TriplaneSample.apply(pl, pts.to(cuda_device))
+    assert rel_l2(enc.detach().cpu(), ref.detach()) < 1e-5
+    (enc * go.to(cuda_device)).sum().backward()
+    assert rel_l2(pl.grad.permute(0, 1, 4, 2, 3).cpu(), planes.grad) < 1e-5
+
+
+def test_adan_matches_reference_update(cuda_device):
+    from scaledreamer_b200.systems import FusedAdan
+
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(4099, generator=g)
+    ref, st = p0.clone(), {}
+    p = torch.nn.Parameter(p0.clone().to(cuda_device))
+    opt = FusedAdan([p], lr=2e-4, betas=(0.98, 0.92, 0.99), eps=1e-15, weight_decay=0.01)
+    for step in range(1, 5):
+        gr = torch.randn(4099, generator=g)
+        ao.adan_step(ref, gr, st, step, 2e-4, (0.98, 0.92, 0.99), 1e-15, weight_decay=0.01)
+        p.grad = gr.to(cuda_device)
+        opt.step()
+    torch.testing.assert_close(p.detach().cpu(), ref, atol=1e-6, rtol=1e-5)
+
+
+def test_triplane_geometry_matches_oracle(cuda_device):
+    """"Triplane-transformer-sdf" forward(output_normal=True) on given planes: sdf / features / sdf_grad and the
+    gradients that reach the planes (-> generator) and the two MLPs."""
+    import scaledreamer_b200 as sd
+
+    dev = cuda_device
+    torch.manual_seed(0)
+    geo = sd.find("Triplane-transformer-sdf")({
+        "radius": 2.0, "sdf_bias": "sphere", "sdf_bias_params": 0.8,
+        "space_generator_config": {"inner_dim": 64, "condition_dim": 1024, "triplane_low_res": 8, "triplane_high_res": 16,
+                                   "triplane_dim": 32, "num_layers": 1, "num_heads": 4, "mlp_ratio": 4, "local_text": True}}).to(dev)
+    geo.update_step(0, 0)
+    g = torch.Generator().manual_seed(1)
+    planes = (torch.randn(2, 3, 32, 16, 16, generator=g) * 0.3).requires_grad_(True)
+    pts = (torch.rand(2, 700, 3, generator=g) * 2 - 1) * 1.9
+    ws = [w.detach().cpu().clone().requires_grad_(True) for w in geo.sdf_network.weights()]
+    wf = [w.detach().cpu().clone().requires_grad_(True) for w in geo.feature_network.weights()]
+    ref = ao.triplane_field(pts, planes, ws, wf, 2.0, 0.8, 0.01, output_normal=True)
+    (ao.eikonal_loss(ref["sdf_grad"]) + ref["features"].square().mean() + ref["sdf"].mean()).backward()
+    pl = planes.detach().to(dev).requires_grad_(True)
+    out = geo(pts.to(dev), pl, output_normal=True)
+    assert rel_l2(out["sdf"].cpu(), ref["sdf"].detach()) < 1e-4 and rel_l2(out["features"].cpu(), ref["features"].detach()) < 1e-3
+    assert rel_l2(out["sdf_grad"].cpu(), ref["sdf_grad"].detach()) < 2e-3
+    (((torch.linalg.norm(out["sdf_grad"], ord=2, dim=-1) - 1.0) ** 2).mean() + out["features"].square().mean()
+     + out["sdf"].mean()).backward()
+    assert rel_l2(pl.grad.cpu(), planes.grad) < 5e-3
+    for a, b in zip(list(geo.sdf_network.weights()) + list(geo.feature_network.weights()), ws + wf):
+        assert rel_l2(a.grad.cpu(), b.grad) < 5e-3
+    cache = geo.generate_space_cache(None, torch.randn(2, 77, 1024, generator=g).to(dev))
+    assert cache.shape == (2, 3, 32, 16, 16)
+
+
+def test_triplane_multiview_system_training_step(cuda_device, tmp_path, monkeypatch):
+    """C5-shaped yaml (reference schema; a 2-layer generator to keep the test short): multi-view multi-prompt data ->
+    Triplane-Transformer -> VolSDF renderer (4 views share one prompt's planes) -> MVDream guidance -> Adan."""
+    import scaledreamer_b200 as sd
+    from scaledreamer_b200.systems import FusedAdan
+
+    monkeypatch.chdir(tmp_path)
+    _write_library(tmp_path, ["a red apple", "a wooden chair"])
+    cfg_path = os.path.join(os.path.dirname(__file__), "configs", "asd_mv_triplane_transformer.yaml")
+    cfg = sd.load_config(cfg_path, cli_args=["system.prompt_processor.prompt_library=lib", "data.width=32",
+                                             "data.height=32", "system.geometry.space_generator_config.num_layers=2"])
+    dm = sd.find(cfg.data_type)(cfg.data)
+    dm.setup("fit")
+    ds = dm.train_dataset
+    system = sd.find(cfg.system_type)(cfg.system)
+    system.train()
+    system.on_fit_start()
+    opt = system.configure_optimizers()
+    assert isinstance(opt, FusedAdan)
+    w0 = system.geometry.space_generator.deconv.weight.detach().clone()
+    for step in range(2):
+        ds.update_step(0, step)
+        system.true_global_step = step
+        system.do_update_step(0, step)
+        batch = ds.to_device(ds.collate({}), cuda_device)
+        assert len(batch["prompt"]) == 1 and batch["rays_o"].shape[0] == 4
+        out = system.training_step(batch, step)
+        assert torch.isfinite(out["loss"])
+        out["loss"].backward()
+        opt.step()
+        opt.zero_grad(set_to_none=False)
+    assert (system.geometry.space_generator.deconv.weight.detach() - w0).abs().max() > 0
+    assert "train/loss_eikonal" in system.logged and "train/loss_asd" in system.logged

@@ -79,3 +79,29 @@ def test_render_invariants_and_fd_normals():
     fd = ao.hyper_field(p.detach(), table, c1, hcfg, output_normal=True)["sdf_grad"].view(1, 50, 3)
     assert torch.nn.functional.cosine_similarity(fd, ga, dim=-1).min() > 0.95
     assert abs(float(ao.eikonal_loss(fd.view(-1, 3)))) < 0.5
+
+
+def test_sample_from_planes_axes_and_borders():
+    """Plane 0 reads (x, y), plane 1 (x, z), plane 2 (z, y); texel centres reproduce the texel; outside is zero."""
+    C, H, W = 4, 8, 8
+    planes = torch.zeros(1, 3, C, H, W)
+    planes[0, 0, 0] = torch.arange(W)[None, :].float().expand(H, W)   # varies along grid-x (W)
+    planes[0, 1, 0] = torch.arange(H)[:, None].float().expand(H, W)   # varies along grid-y (H)
+    planes[0, 2, 0] = torch.arange(W)[None, :].float().expand(H, W)
+    centre = lambda i, n: (2 * i + 1) / n - 1
+    p = torch.tensor([[[centre(2, W), centre(5, H), centre(6, W)]]])
+    enc = ao.sample_from_planes(planes, p)
+    assert enc.shape == (1, 1, 12)
+    assert abs(float(enc[0, 0, 0]) - 2.0) < 1e-5      # plane 0: u = x -> column 2
+    assert abs(float(enc[0, 0, 4]) - 6.0) < 1e-5      # plane 1: v = z -> row 6
+    assert abs(float(enc[0, 0, 8]) - 6.0) < 1e-5      # plane 2: u = z -> column 6
+    assert float(ao.sample_from_planes(planes + 1.0, torch.tensor([[[3.0, 3.0, 3.0]]])).abs().max()) == 0.0
+
+
+def test_adan_matches_closed_form_first_step():
+    g = torch.tensor([0.5, -2.0])
+    p = torch.tensor([1.0, 1.0])
+    st = {}
+    ao.adan_step(p, g, st, 1, 0.1, (0.98, 0.92, 0.99), 1e-15)
+    # step 1: diff = 0, m = (1-b1) g, n = (1-b3) g^2 -> update = lr * sign(g) (bias corrections cancel)
+    torch.testing.assert_close(p, torch.tensor([0.9, 1.1]), atol=1e-6, rtol=0)
