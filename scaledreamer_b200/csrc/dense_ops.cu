@@ -409,16 +409,22 @@ __global__ void col2im_s2_kernel(const __half* __restrict__ col, __half* __restr
   }
 }
 
-// Direct 3x3 conv, small Cin (<= 8): thread = (pixel, 8 consecutive output channels).
-template <typename TIn>
-__global__ void conv_small_cin_kernel(const TIn* __restrict__ x, const __half* __restrict__ w,
-                                      const __half* __restrict__ bias, void* __restrict__ y, int y_fp32, int N, int H,
-                                      int W, int Cin, int Cout) {
-  extern __shared__ __half sw[];  // [Cout][9*Cin]
-  const int K = 9 * Cin;
-  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) sw[i] = w[i];
+// Direct 3x3 conv, small Cin (3 or 4): thread = (pixel, 8 consecutive output channels). CIN is a template parameter
+// so the 9*CIN input taps stay in registers and the 8 x 9*CIN FMAs unroll; weights sit in shared memory as fp32,
+// transposed to [k][Cout] so the eight channels of a thread are two float4 reads shared by the whole warp column.
+template <typename TIn, int CIN>
+__global__ void __launch_bounds__(128)
+conv_small_cin_kernel(const TIn* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+                      void* __restrict__ y, int y_fp32, int N, int H, int W, int Cout, int CT) {
+  extern __shared__ float swf[];  // [9*CIN][CT]: the CT output channels of slice blockIdx.y
+  constexpr int K = 9 * CIN;
+  const int co0 = blockIdx.y * CT;
+  for (int i = threadIdx.x; i < CT * K; i += blockDim.x) {
+    const int co = i / K, k = i - co * K;
+    swf[k * CT + co] = __half2float(w[(size_t)(co0 + co) * K + k]);
+  }
   __syncthreads();
-  const int co8n = Cout / 8;
+  const int co8n = CT / 8;
   const long long total = (long long)N * H * W * co8n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -428,26 +434,35 @@ __global__ void conv_small_cin_kernel(const TIn* __restrict__ x, const __half* _
     r /= W;
     const int py = (int)(r % H);
     const int n = (int)(r / H);
-    float in[72];
+    float in[K];
+#pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
       const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-      for (int c = 0; c < Cin; ++c)
-        in[tap * Cin + c] = ok ? (float)x[(((long long)n * H + iy) * W + ix) * Cin + c] : 0.f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+        in[tap * CIN + c] = ok ? (float)x[(((long long)n * H + iy) * W + ix) * CIN + c] : 0.f;
     }
     float acc[8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const int co = cg * 8 + o;
-      float a = bias ? __half2float(bias[co]) : 0.f;
-      const __half* wr = sw + co * K;
-      for (int k = 0; k < K; ++k) a = fmaf(in[k], __half2float(wr[k]), a);
-      acc[o] = a;
-    }
-    const long long ob = (((long long)n * H + py) * W + px) * Cout + cg * 8;
-    if (y_fp32) {
+    for (int o = 0; o < 8; ++o) acc[o] = bias ? __half2float(bias[co0 + cg * 8 + o]) : 0.f;
 #pragma unroll
-      for (int o = 0; o < 8; ++o) reinterpret_cast<float*>(y)[ob + o] = acc[o];
+    for (int k = 0; k < K; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4*>(swf + k * CT + cg * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(swf + k * CT + cg * 8 + 4);
+      acc[0] = fmaf(in[k], w0.x, acc[0]);
+      acc[1] = fmaf(in[k], w0.y, acc[1]);
+      acc[2] = fmaf(in[k], w0.z, acc[2]);
+      acc[3] = fmaf(in[k], w0.w, acc[3]);
+      acc[4] = fmaf(in[k], w1.x, acc[4]);
+      acc[5] = fmaf(in[k], w1.y, acc[5]);
+      acc[6] = fmaf(in[k], w1.z, acc[6]);
+      acc[7] = fmaf(in[k], w1.w, acc[7]);
+    }
+    const long long ob = (((long long)n * H + py) * W + px) * Cout + co0 + cg * 8;
+    if (y_fp32) {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + ob)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + ob)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     } else {
       uint4 ov;
       __half2* oh = reinterpret_cast<__half2*>(&ov);
@@ -696,21 +711,24 @@ int col2im_3x3_s2(const __half* col, __half* dx, int N, int H, int W, int C, int
 
 int conv3x3_small(const void* x, int x_fp32, const __half* w, const __half* bias, void* y, int y_fp32, int N, int H,
                   int W, int Cin, int Cout, cudaStream_t s) {
-  if (Cin <= 8 && Cout % 8 == 0) {
-    const size_t smem = sizeof(__half) * Cout * 9 * Cin;
-    const long long total = (long long)N * H * W * (Cout / 8);
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(conv_small_cin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      cudaFuncSetAttribute(conv_small_cin_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      attr = true;
+  if ((Cin == 3 || Cin == 4 || Cin == 8) && Cout % 8 == 0) {
+    int CT = 128;  // output-channel slice per block: the largest multiple of 8 <= 128 dividing Cout
+    while (Cout % CT) CT -= 8;
+    const size_t smem = sizeof(float) * CT * 9 * Cin;  // <= 36 KB
+    const long long total = (long long)N * H * W * (CT / 8);
+    const dim3 grid(ew_grid(total, 128), Cout / CT);
+#define SDB_SMALL_CIN(T, CI) \
+  conv_small_cin_kernel<T, CI><<<grid, 128, smem, s>>>(reinterpret_cast<const T*>(x), w, bias, y, y_fp32, N, H, W, Cout, CT)
+    if (x_fp32) {
+      if (Cin == 3) SDB_SMALL_CIN(float, 3);
+      else if (Cin == 4) SDB_SMALL_CIN(float, 4);
+      else SDB_SMALL_CIN(float, 8);
+    } else {
+      if (Cin == 3) SDB_SMALL_CIN(__half, 3);
+      else if (Cin == 4) SDB_SMALL_CIN(__half, 4);
+      else SDB_SMALL_CIN(__half, 8);
     }
-    if (x_fp32)
-      conv_small_cin_kernel<float><<<ew_grid(total, 128), 128, smem, s>>>(reinterpret_cast<const float*>(x), w, bias, y,
-                                                                          y_fp32, N, H, W, Cin, Cout);
-    else
-      conv_small_cin_kernel<__half><<<ew_grid(total, 128), 128, smem, s>>>(reinterpret_cast<const __half*>(x), w, bias,
-                                                                           y, y_fp32, N, H, W, Cin, Cout);
+#undef SDB_SMALL_CIN
   } else if (Cout <= 8 && !x_fp32 && Cin % 2 == 0) {
     const long long total = (long long)N * H * W;
     const int grid = ew_grid(total * 32);
