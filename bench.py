@@ -271,12 +271,25 @@ def main() -> None:
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
+    # The loss of step i is copied to pinned host memory asynchronously and read on the host one step later (after
+    # step i+1 has been enqueued), the way a logging trainer consumes it: every step still pays its H2D inputs and a
+    # D2H result, but the host never drains the GPU queue between steps.
+    loss_pinned = torch.empty(2, dtype=torch.float32).pin_memory()
+    loss_events = [torch.cuda.Event(), torch.cuda.Event()]
+    losses_host = []
+    for i in range(args.steps):
         hb = host_batch()
         h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
         loss = step(ds.to_device(hb, dev))
-        loss_host = float(loss)  # device -> host read of the step's result
+        loss_pinned[i & 1].copy_(loss.detach(), non_blocking=True)
+        loss_events[i & 1].record()
+        if i > 0:
+            loss_events[(i - 1) & 1].synchronize()
+            losses_host.append(float(loss_pinned[(i - 1) & 1]))
         d2h = 4
+    loss_events[(args.steps - 1) & 1].synchronize()
+    losses_host.append(float(loss_pinned[(args.steps - 1) & 1]))
+    assert len(losses_host) == args.steps and all(v == v for v in losses_host)
     e3.record()
     sync_all()
     ms_e2e = e2.elapsed_time(e3)

@@ -17,7 +17,9 @@ enum OperandMode : int {
   kHeads = 2,   // 4D map {d, heads, L, B}: per-head view of a [B, L, heads*d] tensor, z = b*heads + h
 };
 
-enum Act : int { kActNone = 0, kActSilu = 1, kActGelu = 2 };
+// kActGeglu: the weight rows are interleaved (interleave_geglu_rows) so every 32-column chunk holds 16 value columns
+// followed by their 16 gate columns; the epilogue writes value * gelu(gate) into N/2 output columns.
+enum Act : int { kActNone = 0, kActSilu = 1, kActGelu = 2, kActGeglu = 3 };
 
 struct OperandGeom {
   int mode;
@@ -151,6 +153,8 @@ int timestep_embedding(const float* t, __half* out, int n, int dim, float max_pe
 int linear_small(const __half* x, const __half* w, const __half* bias, void* y, int y_fp32, int rows, int N, int K,
                  int silu_in, cudaStream_t s);
 
+// dst[chunk*32 + j] = src[chunk*16 + j] (j < 16) | src[half_rows + chunk*16 + j - 16]: rows of `cols` halfs.
+int interleave_geglu_rows(const __half* src, __half* dst, int half_rows, int cols, cudaStream_t s);
 int rotate_w3x3(const __half* w, __half* wr, int Cout, int Cin, cudaStream_t s);  // [Cout,3,3,Cin] -> [Cin,3,3,Cout] flipped
 int softmax_rows_backward(const __half* P, __half* dP, long long rows, int cols, long long ld, float scale,
                           cudaStream_t s);

@@ -190,6 +190,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
     }
+    if (p.act == kActGeglu) {  // chunk = 16 values | 16 gates (interleaved weight rows): value * gelu(gate)
+      __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc + (nb >> 1);
+      uint4 ov[2];
+      __half2* h2 = reinterpret_cast<__half2*>(ov);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float g0 = f[16 + 2 * e], g1 = f[17 + 2 * e];
+        h2[e] = __floats2half2_rn(f[2 * e] * (0.5f * g0 * (1.f + erff(g0 * 0.70710678118654752f))),
+                                  f[2 * e + 1] * (0.5f * g1 * (1.f + erff(g1 * 0.70710678118654752f))));
+      }
+      reinterpret_cast<uint4*>(o)[0] = ov[0];
+      reinterpret_cast<uint4*>(o)[1] = ov[1];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+      continue;
+    }
     if (p.residual) {
       if (res_vec && full_chunk) {
 #pragma unroll

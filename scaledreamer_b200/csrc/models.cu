@@ -356,9 +356,22 @@ T UNet::transformer(const T& x, const std::string& name) {
   T n3 = ln(h, blk + ".norm3");
   const __half* wf1 = param(blk + ".ff.net.0.proj.weight", 2, 8 * C, C);
   const __half* bf1 = param(blk + ".ff.net.0.proj.bias", 1, 8 * C);
-  T g = linear(&fwd_, n3, wf1, bf1, 8 * C);
+  // GEGLU fused into the projection's epilogue: value / gate weight rows interleaved per 32-column chunk (derived copy)
+  __half* wf1i = derived((long long)8 * C * C);
+  __half* bf1i = derived(8 * C);
+  post([=](cudaStream_t s) { return interleave_geglu_rows(wf1, wf1i, 4 * C, C, s); });
+  post([=](cudaStream_t s) { return interleave_geglu_rows(bf1, bf1i, 4 * C, 1, s); });
   T gg = act(x.n, x.h, x.w, 4 * C);
-  if (!dry_) fwd_.push_back([=](cudaStream_t s) { return geglu(g.p, gg.p, g.rows(), 4 * C, s); });
+  if (!dry_) {
+    Epilogue ep;
+    ep.out = gg.p;
+    ep.ldc = 4 * C;
+    ep.bias = bf1i;
+    ep.act = kActGeglu;
+    GemmPlan plan;
+    if (fail(plan_gemm(&plan, n3.p, C, wf1i, C, (int)n3.rows(), 8 * C, C, ep))) return gg;
+    fwd_.push_back([plan](cudaStream_t s) { return run_gemm(plan, s); });
+  }
   const __half* wf2 = param(blk + ".ff.net.2.weight", 2, C, 4 * C);
   const __half* bf2 = param(blk + ".ff.net.2.bias", 1, C);
   h = linear(&fwd_, gg, wf2, bf2, C, &h);
