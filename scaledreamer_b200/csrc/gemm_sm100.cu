@@ -16,6 +16,7 @@
 // diffusers equivalents (stable_diffusion_asd_guidance.py:170-178, 318-331).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -28,7 +29,6 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kBK = 64;               // 64 fp16 = 128 bytes = one swizzle row
 constexpr int kATileBytes = kBM * kBK * 2;
-constexpr int kThreads = 256;
 
 // DEEP: at most one CTA per SM is in flight (<= 148 tiles), so the ring takes the whole shared memory instead.
 template <int BN, bool DEEP = false>
@@ -37,7 +37,13 @@ struct Cfg {
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   // two CTAs share an SM (one CTA's epilogue overlaps the other's main loop): <= ~110 KB of ring per CTA
   static constexpr int kStages = DEEP ? (BN <= 80 ? 8 : 6) : (BN <= 80 ? 4 : 3);
-  static constexpr int kTmemCols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  // DEEP: two accumulators in tensor memory (the MMA warp fills one while the epilogue drains the other) and two sets
+  // of four epilogue warps that take alternate 32-column chunks of a tile.
+  static constexpr int kAccBufs = DEEP ? 2 : 1;
+  static constexpr int kEpiSets = DEEP ? 2 : 1;
+  static constexpr int kThreads = 128 + 128 * kEpiSets;
+  static constexpr int kAccStride = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr int kTmemCols = kAccStride * kAccBufs;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -63,12 +69,13 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* tm, const Operan
 // Epilogue of one 128 x BN tile for the 32 rows of TMEM lane quadrant wq (one row per thread).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int wq, int lane, int m0, int n0,
-                                              int z, int zsplit) {
+                                              int z, int zsplit, int set, int nsets) {
   const int m = m0 + wq * 32 + lane;
   const bool m_ok = m < p.M;
   const long long zoff = (long long)(z / p.out_zdiv) * p.out_zs_hi + (long long)(z % p.out_zdiv) * p.out_zs_lo;
   const float* rowb = p.rowbias ? p.rowbias + (long long)(m_ok ? m / p.rows_per_group : 0) * p.rowbias_ld : nullptr;
   if constexpr (BN == 80) {
+    if (p.row_softmax && set != 0) return;  // the whole row belongs to one thread: the first warp set does it
     if (p.row_softmax) {
       // whole score row in this tile (N <= 80): softmax(alpha * acc) in registers, padding columns zeroed
       uint32_t v[96];
@@ -121,9 +128,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     for (int q = 0; q < 4; ++q)
       rv[q] = on ? __ldg(reinterpret_cast<const uint4*>(rrow + n0 + c) + q) : make_uint4(0, 0, 0, 0);
   };
-  if (p.splits == 1) load_res(0, rcur);
+  const int cstep = 32 * nsets;
+  if (p.splits == 1) load_res(32 * set, rcur);
 #pragma unroll 1
-  for (int c = 0; c < BN; c += 32) {
+  for (int c = 32 * set; c < BN; c += cstep) {
     uint32_t v[32];
     ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, v);
     const int nb = n0 + c;
@@ -164,7 +172,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
             if (nb + j < p.N) f[j] += __ldg(rowb + nb + j);
         }
       }
-      if (c + 32 < BN) load_res(c + 32, rnext);
+      if (c + cstep < BN) load_res(c + cstep, rnext);
     }
     ptx::tmem_ld_wait();
     if (!m_ok || nb >= p.N) continue;
@@ -261,7 +269,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 // The TMA ring keeps running across tile boundaries, so the next tile's operands stream in while the epilogue
 // warps drain the accumulator; two CTAs share an SM, so one CTA's epilogue also overlaps the other's main loop.
 template <int BN, bool DEEP>
-__global__ void __launch_bounds__(kThreads, DEEP ? 1 : 2)
+__global__ void __launch_bounds__(Cfg<BN, DEEP>::kThreads, DEEP ? 1 : 2)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, DEEP>;
@@ -269,9 +277,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(base + C::kStages * C::kStageBytes);
   uint64_t* empty = full + C::kStages;
-  uint64_t* accum_full = empty + C::kStages;
-  uint64_t* accum_empty = accum_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + 1);
+  uint64_t* accum_full = empty + C::kStages;        // [kAccBufs]
+  uint64_t* accum_empty = accum_full + C::kAccBufs;  // [kAccBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + C::kAccBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto stamp = [&](int slot) {
@@ -292,8 +300,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
-    ptx::mbar_init(accum_full, 1);
-    ptx::mbar_init(accum_empty, 128);
+    for (int b = 0; b < C::kAccBufs; ++b) {
+      ptx::mbar_init(&accum_full[b], 1);
+      ptx::mbar_init(&accum_empty[b], 128 * C::kEpiSets);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -341,7 +351,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
         SDB_DECODE_TILE(tile)
         (void)m0; (void)n0; (void)z; (void)zs; (void)kb0;
-        ptx::mbar_wait(accum_empty, (tcount & 1) ^ 1u);  // the epilogue warps drained the previous tile
+        const uint32_t buf = tcount % C::kAccBufs, use = tcount / C::kAccBufs;
+        const uint32_t tmem_acc = tmem_base + buf * C::kAccStride;
+        ptx::mbar_wait(&accum_empty[buf], (use & 1) ^ 1u);  // the epilogue warps drained this accumulator
         ptx::tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % C::kStages;
@@ -357,25 +369,26 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // K-major: 16 elements = 32 bytes further along the swizzled row; MN-major: 16 K-rows = 2048 bytes
             const uint64_t a_adv = (uint64_t)((k * 32) >> 4);
             const uint64_t b_adv = p.b.mn_major ? (uint64_t)((k * 2048) >> 4) : (uint64_t)((k * 32) >> 4);
-            ptx::umma_f16(tmem_base, da + a_adv, db + b_adv, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_f16(tmem_acc, da + a_adv, db + b_adv, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(&empty[s]);
         }
-        ptx::umma_commit(accum_full);
+        ptx::umma_commit(&accum_full[buf]);
       }
     }
   } else if (warp >= 4) {
-    const int wq = warp & 3;
+    const int wq = warp & 3, set = (warp - 4) >> 2;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
       SDB_DECODE_TILE(tile)
       (void)kb0; (void)nkb;
-      ptx::mbar_wait(accum_full, tcount & 1);
+      const uint32_t buf = tcount % C::kAccBufs, use = tcount / C::kAccBufs;
+      ptx::mbar_wait(&accum_full[buf], use & 1);
       ptx::tc_fence_after();
       if (tcount == 0) stamp(2);
-      epilogue_tile<BN>(p, tmem_base, wq, lane, m0, n0, z, zs);
+      epilogue_tile<BN>(p, tmem_base + buf * C::kAccStride, wq, lane, m0, n0, z, zs, set, C::kEpiSets);
       ptx::tc_fence_before();
-      ptx::mbar_arrive(accum_empty);
+      ptx::mbar_arrive(&accum_empty[buf]);
     }
   }
 #undef SDB_DECODE_TILE
@@ -442,7 +455,7 @@ int launch_v(const GemmPlan& plan, cudaStream_t stream) {
   prm.tiles_m = (int)plan.grid.x, prm.tiles_n = (int)plan.grid.y, prm.tiles_z = (int)plan.grid.z;
   const long long total_tiles = (long long)plan.grid.x * plan.grid.y * plan.grid.z;
   const int ctas = (int)std::min<long long>(total_tiles, DEEP ? (long long)kNumSMs : 2LL * kNumSMs);
-  gemm_f16_kernel<BN, DEEP><<<ctas, kThreads, Cfg<BN, DEEP>::kSmemBytes, stream>>>(plan.ta, plan.tb, prm);
+  gemm_f16_kernel<BN, DEEP><<<ctas, Cfg<BN, DEEP>::kThreads, Cfg<BN, DEEP>::kSmemBytes, stream>>>(plan.ta, plan.tb, prm);
   if (plan.p.splits > 1) {
     const long long total = (long long)plan.p.M * ((plan.p.N + 3) / 4);
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 8);
@@ -460,8 +473,14 @@ int launch_v(const GemmPlan& plan, cudaStream_t stream) {
 
 template <int BN>
 int launch(const GemmPlan& plan, cudaStream_t stream) {
+  // SDB_GEMM_DEEP = all | none | auto (default) selects the one-CTA-per-SM variant (diagnostics)
+  static const int policy = [] {
+    const char* e = getenv("SDB_GEMM_DEEP");
+    return !e ? 2 : (!strcmp(e, "all") ? 1 : (!strcmp(e, "none") ? 0 : 2));
+  }();
   const long long total_tiles = (long long)plan.grid.x * plan.grid.y * plan.grid.z;
-  return total_tiles <= kNumSMs ? launch_v<BN, true>(plan, stream) : launch_v<BN, false>(plan, stream);
+  const bool deep = policy == 1 || (policy == 2 && total_tiles <= kNumSMs);
+  return deep ? launch_v<BN, true>(plan, stream) : launch_v<BN, false>(plan, stream);
 }
 
 }  // namespace
@@ -481,6 +500,10 @@ int gemm_splits(int M, int N, int K) {
 namespace {
 
 int pick_bn(int N) {
+  if (const char* e = getenv("SDB_GEMM_BN")) {  // diagnostics: force a tile width
+    const int bn = atoi(e);
+    if (bn == 64 || bn == 80 || bn == 128 || bn == 160) return bn;
+  }
   if (N % 160 == 0) return 160;
   if (N <= 64) return 64;
   return 128;

@@ -372,7 +372,7 @@ hyper_field_bwd_kernel(const __grid_constant__ GridMeta gm, const HfArgs a) {
       {
         const float* dcol = s.dht + warp * 32 + 8 * li;
         const float* wrow = s.w1t[net] + 4 * lj;
-#pragma unroll 4
+#pragma unroll 2
         for (int h = 0; h < kHidden; ++h) {
           const float4 d0 = *reinterpret_cast<const float4*>(dcol + h * kDhStride);
           const float4 d1 = *reinterpret_cast<const float4*>(dcol + h * kDhStride + 4);
@@ -390,7 +390,7 @@ hyper_field_bwd_kernel(const __grid_constant__ GridMeta gm, const HfArgs a) {
       __syncthreads();
 #pragma unroll 1
       for (int sub = 0; sub < 4; ++sub) {
-#pragma unroll 2
+#pragma unroll 1
         for (int s4 = 0; s4 < 8; ++s4) {
           float4 dv[4], ev[4];
 #pragma unroll

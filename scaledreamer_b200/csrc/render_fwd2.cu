@@ -25,7 +25,7 @@ struct Fwd2Smem {
 // Encodes this lane's point through all levels straight into column `lane` of the warp's tile.
 __device__ __forceinline__ void encode_to_tile(const float2* __restrict__ table, const GridMeta& gm, float x, float y,
                                                float z, bool valid, float* __restrict__ et_lane) {
-#pragma unroll 4
+#pragma unroll 2
   for (int l = 0; l < kMaxLevels; ++l) {
     float ax = 0.f, ay = 0.f;
     if (valid) {

@@ -46,7 +46,7 @@ __device__ __forceinline__ void hidden_tile(const float* __restrict__ ET, int es
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
-#pragma unroll 2
+#pragma unroll 1
   for (int k = 0; k < kEncDim; ++k) {
     const float4 e0 = *reinterpret_cast<const float4*>(ET + k * es + 8 * i);
     const float4 e1 = *reinterpret_cast<const float4*>(ET + k * es + 8 * i + 4);
