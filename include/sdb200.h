@@ -230,6 +230,19 @@ int sdb_triplane_sample_forward(const float* planes_cl, const float* points, int
 int sdb_triplane_sample_backward(const float* d_enc, const float* points, int n_prompts, int n_points, int height,
                                  int width, int channels, float* d_planes_cl, void* stream);
 
+/* ---- bias-free ReLU MLP d_in -> 64 -> 64 -> n_out (threestudio/models/networks.py:214-251 VanillaMLP with
+ * n_neurons 64, n_hidden_layers 2: the sdf / feature heads of "Triplane-transformer-sdf",
+ * custom/amortized/models/geometry/triplane_transformer_sdf.py:150-170). fp32; weights in nn.Linear layout
+ * (w1 [64,d_in], w2 [64,64], w3 [n_out,64]); x [n,d_in] row-major; d_in a multiple of 8 in [8,96]; n_out 1 or 3.
+ * The backward recomputes the hidden activations from x (nothing is saved by the forward). */
+int sdb_mlp3_forward(const float* x, long long n, int d_in, const float* w1, const float* w2, const float* w3,
+                     int n_out, float* y, void* stream);
+/* g_w1/g_w2/g_w3 += weight gradients (caller zeroes); d_x [n,d_in] is written, or accumulated into when
+ * accumulate_dx != 0 (two heads sharing one input); d_x may be NULL to skip the input gradient. */
+int sdb_mlp3_backward(const float* x, long long n, int d_in, const float* w1, const float* w2, const float* w3,
+                      int n_out, const float* d_y, float* d_x, int accumulate_dx, float* g_w1, float* g_w2,
+                      float* g_w3, void* stream);
+
 /* rays from cameras (threestudio/utils/ops.py:183-269 get_ray_directions + get_rays):
  * c2w [B,4,4], fovy [B] (radians) -> rays_o, rays_d [B,H,W,3] (normalised). */
 int sdb_raygen(const float* c2w, const float* fovy, int n_images, int height, int width, float* rays_o,

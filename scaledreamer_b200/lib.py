@@ -130,6 +130,8 @@ SIGNATURES = {
     "sdb_triplane_sample_backward": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "sdb_raygen": [_P, _P, _I, _I, _I, _P, _P, _P],
     "sdb_adamw_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
+    "sdb_mlp3_forward": [_P, _LL, _I, _P, _P, _P, _I, _P, _P],
+    "sdb_mlp3_backward": [_P, _LL, _I, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P],
     "sdb_adan_step": [_P, _P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _I, _F, _I, _P],
     # ---- include/sdb200_nn.h
     "sdb_gemm_f16": [C.POINTER(GemmArgsC), _P],

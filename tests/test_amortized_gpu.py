@@ -269,6 +269,62 @@ def test_triplane_sample_forward_backward(cuda_device, B, N, H):
     assert rel_l2(pl.grad.permute(0, 1, 4, 2, 3).cpu(), planes.grad) < 1e-5
 
 
+@pytest.mark.parametrize("n,d_in,k", [(1000, 96, 1), (1000, 96, 3), (129, 32, 3), (31, 8, 1), (20000, 64, 3), (0, 96, 1)])
+def test_tiny_mlp_forward_backward(cuda_device, n, d_in, k):
+    """The native 64-wide bias-free ReLU MLP (VanillaMLP, networks.py:214-251) through sdb_mlp3_forward/backward:
+    ragged row counts (not a multiple of the 32 / 128-row tiles), every supported head width, empty input."""
+    from scaledreamer_b200.amortized import _TinyMLP
+
+    g = torch.Generator().manual_seed(n + d_in + k)
+    x = torch.randn(n, d_in, generator=g, dtype=torch.float64).requires_grad_(True)
+    ws = [(torch.randn(o, i, generator=g, dtype=torch.float64) / math.sqrt(i)).requires_grad_(True)
+          for o, i in ((64, d_in), (64, 64), (k, 64))]
+    ref = ao.vanilla_mlp(x, ws)
+    go = torch.randn(n, k, generator=g, dtype=torch.float64)
+    (ref * go).sum().backward()
+    xd = x.detach().float().to(cuda_device).requires_grad_(True)
+    wd = [w.detach().float().to(cuda_device).requires_grad_(True) for w in ws]
+    y = _TinyMLP.apply(xd, *wd)
+    assert y.shape == (n, k)
+    if n == 0:
+        return
+    assert rel_l2(y.detach().cpu().double(), ref.detach()) < 1e-5
+    (y * go.float().to(cuda_device)).sum().backward()
+    # A pre-activation within fp32 rounding of zero flips its ReLU mask against the fp64 oracle and changes that ROW's
+    # gradient by O(1): all but a handful of rows must agree to 1e-4, the whole to 5e-3.
+    row_err = (xd.grad.cpu().double() - x.grad).norm(dim=1) / x.grad.norm(dim=1).clamp_min(1e-12)
+    assert (row_err > 1e-4).sum().item() <= max(2, n // 2000), row_err.max()
+    assert rel_l2(xd.grad.cpu().double(), x.grad) < 5e-3
+    for a, b in zip(wd, ws):
+        assert rel_l2(a.grad.cpu().double(), b.grad) < (1e-4 if n <= 1000 else 5e-3)
+
+
+def test_tiny_mlp_accumulates_input_gradient(cuda_device):
+    """accumulate_dx: the sdf and feature heads share one encoding, the second backward adds into d_x."""
+    from scaledreamer_b200 import lib as L
+
+    lib = L.load()
+    g = torch.Generator().manual_seed(5)
+    n, d = 300, 96
+    x = torch.randn(n, d, generator=g).to(cuda_device)
+    ws = [(torch.randn(o, i, generator=g) / math.sqrt(i)).to(cuda_device) for o, i in ((64, d), (64, 64), (3, 64))]
+    dy = torch.randn(n, 3, generator=g).to(cuda_device)
+    gs = [torch.zeros_like(w) for w in ws]
+    dx = torch.empty(n, d, device=cuda_device)
+    args = (L.ptr(x), n, d, L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(ws[2]), 3, L.ptr(dy))
+    L.check(lib.sdb_mlp3_backward(*args, L.ptr(dx), 0, *[L.ptr(t) for t in gs], L.stream_ptr()), "bwd")
+    once, g_once = dx.clone(), [t.clone() for t in gs]
+    L.check(lib.sdb_mlp3_backward(*args, L.ptr(dx), 1, *[L.ptr(t) for t in gs], L.stream_ptr()), "bwd")
+    assert rel_l2(dx.cpu(), 2 * once.cpu()) < 1e-6
+    for a, b in zip(gs, g_once):
+        assert rel_l2(a.cpu(), 2 * b.cpu()) < 1e-5
+    # no input gradient requested
+    L.check(lib.sdb_mlp3_backward(*args, None, 0, *[L.ptr(t) for t in gs], L.stream_ptr()), "bwd")
+    # unsupported widths are refused, not silently mis-computed
+    assert lib.sdb_mlp3_forward(L.ptr(x), n, 100, L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(ws[2]), 3, L.ptr(dy), L.stream_ptr()) != 0
+    assert lib.sdb_mlp3_forward(L.ptr(x), n, d, L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(ws[2]), 2, L.ptr(dy), L.stream_ptr()) != 0
+
+
 def test_adan_matches_reference_update(cuda_device):
     from scaledreamer_b200.systems import FusedAdan
 
