@@ -230,6 +230,44 @@ int sdb_triplane_sample_forward(const float* planes_cl, const float* points, int
 int sdb_triplane_sample_backward(const float* d_enc, const float* points, int n_prompts, int n_points, int height,
                                  int width, int channels, float* d_planes_cl, void* stream);
 
+/* ---- unfused ("packed") renderer stages (nerf_volume_renderer.py:139-180, 313-373) ----------------------------
+ * For geometries the fused renderer does not evaluate itself (C1: frequency encoding + VanillaMLP). Samples are
+ * packed and sorted by (ray, t); offsets [n_rays+1] (int64) delimit each ray's samples.
+ *   sdb_march_count : counts[ray] = candidate lattice samples in occupied cells (nerfacc OccGridEstimator.sampling,
+ *                     cone_angle 0, stratified jitter per ray)
+ *   sdb_march_fill  : ray_indices / t_starts / t_ends / positions [n,3] at offsets = exclusive cumsum of counts
+ *   sdb_packed_visibility : keep[s] = alpha >= min(alpha_thre, *occ_mean) && T >= early_stop_eps  (sigma_fn pruning,
+ *                     :153-180; occ_mean may be NULL), kept_counts[ray] = kept samples of the ray
+ *   sdb_packed_composite_forward : weights = T (1 - exp(-sigma dt)) (nerfacc render_weight_from_density) and the
+ *                     per-ray sums opacity, depth, comp_rgb_fg [n_rays,3], z_variance (:321-373); trans [n] is kept
+ *                     for the backward
+ *   sdb_packed_composite_backward : d_sigma [n], d_rgb [n,3] from g_opacity / g_depth / g_comp_rgb_fg (any may be
+ *                     NULL = zero) */
+int sdb_march_count(const sdb_march_cfg* march, float radius, const uint32_t* occ_bits, const float* rays_o,
+                    const float* rays_d, const float* jitter, int n_rays, int* counts, void* stream);
+int sdb_march_fill(const sdb_march_cfg* march, float radius, const uint32_t* occ_bits, const float* rays_o,
+                   const float* rays_d, const float* jitter, int n_rays, const long long* offsets, int* ray_indices,
+                   float* t_starts, float* t_ends, float* positions, void* stream);
+int sdb_packed_visibility(const float* sigma, const float* t_starts, const float* t_ends, const long long* offsets,
+                          int n_rays, float alpha_thre, const float* occ_mean, float early_stop_eps,
+                          unsigned char* keep, int* kept_counts, void* stream);
+int sdb_packed_composite_forward(const float* sigma, const float* rgb, const float* t_starts, const float* t_ends,
+                                 const long long* offsets, int n_rays, float* weights, float* trans, float* opacity,
+                                 float* depth, float* comp_rgb_fg, float* z_variance, void* stream);
+int sdb_packed_composite_backward(const float* rgb, const float* t_starts, const float* t_ends,
+                                  const long long* offsets, int n_rays, const float* weights, const float* trans,
+                                  const float* g_opacity, const float* g_depth, const float* g_comp_rgb_fg,
+                                  float* d_sigma, float* d_rgb, void* stream);
+/* ProgressiveBandFrequency (threestudio/models/networks.py:16-52) under CompositeEncoding (:170-190):
+ * out[i, lead + (2f+fn)*3 + c] = fn(2^f x01[i,c]) * mask[f], fn = sin, cos; lead = 3 columns of x01*2-1 when
+ * include_xyz; columns up to out_stride are zero (row padding for the MLP kernels). mask [n_frequencies] on device. */
+int sdb_freq_encode(const float* x01, long long n, int n_frequencies, const float* mask, int include_xyz,
+                    int out_stride, float* out, void* stream);
+/* Occupancy refresh from caller-evaluated values (= sigma * step at the jittered cell points):
+ * occs[cell] = max(occs[cell]*decay, value), then binarise as sdb_occgrid_update does. */
+int sdb_occgrid_update_values(const int* cell_idx, const float* values, int n_cells, int resolution, float ema_decay,
+                              float occ_thre, float* occs, uint32_t* occ_bits, float* occ_mean, void* stream);
+
 /* ---- bias-free ReLU MLP d_in -> 64 -> 64 -> n_out (threestudio/models/networks.py:214-251 VanillaMLP with
  * n_neurons 64, n_hidden_layers 2: the sdf / feature heads of "Triplane-transformer-sdf",
  * custom/amortized/models/geometry/triplane_transformer_sdf.py:150-170). fp32; weights in nn.Linear layout

@@ -108,6 +108,11 @@ class FieldCfg:
     color_activation: str = "sigmoid"
     bg_grid: GridCfg = field(default_factory=lambda: GridCfg(4, 2, 19, 4, 4.0))
     bg_color_activation: str = "sigmoid"
+    # C1 (vanilla-MLP implicit volume): pos_encoding_config.otype ProgressiveBandFrequency, deeper VanillaMLP
+    encoding: str = "hashgrid"  # "hashgrid" | "frequency"
+    n_frequencies: int = 0
+    include_xyz: bool = False
+    n_hidden_layers: int = 1
 
 
 def make_field_params(cfg: FieldCfg, seed: int = 0, table_scale: float = 1e-4) -> Dict[str, torch.Tensor]:
@@ -121,12 +126,54 @@ def make_field_params(cfg: FieldCfg, seed: int = 0, table_scale: float = 1e-4) -
 
     n = grid_meta(cfg.grid)["n_entries"]
     nb = grid_meta(cfg.bg_grid)["n_entries"]
-    return {
-        "table": (torch.rand(n, 2, generator=g) * 2 - 1) * table_scale,
-        "w1d": lin(64, 32), "w2d": lin(1, 64), "w1f": lin(64, 32), "w2f": lin(3, 64),
-        "bg_table": (torch.rand(nb, 2, generator=g) * 2 - 1) * table_scale,
-        "bg_w1": lin(16, 8), "bg_w2": lin(16, 16), "bg_w3": lin(3, 16),
-    }
+    if cfg.encoding == "frequency":
+        d = 6 * cfg.n_frequencies + (3 if cfg.include_xyz else 0)
+        P = {"w1d": lin(64, d), "w2d": lin(1, 64), "w1f": lin(64, d), "w2f": lin(3, 64)}
+    else:
+        P = {"table": (torch.rand(n, 2, generator=g) * 2 - 1) * table_scale,
+             "w1d": lin(64, 32), "w2d": lin(1, 64), "w1f": lin(64, 32), "w2f": lin(3, 64)}
+    if cfg.n_hidden_layers == 2:
+        P["wmd"], P["wmf"] = lin(64, 64), lin(64, 64)
+    P.update({"bg_table": (torch.rand(nb, 2, generator=g) * 2 - 1) * table_scale,
+              "bg_w1": lin(16, 8), "bg_w2": lin(16, 16), "bg_w3": lin(3, 16)})
+    return P
+
+
+def freq_encode(x01: torch.Tensor, n_frequencies: int, mask: Optional[torch.Tensor] = None,
+                include_xyz: bool = False) -> torch.Tensor:
+    """ProgressiveBandFrequency.forward (threestudio/models/networks.py:16-52) as get_encoding wraps it in
+    CompositeEncoding (:170-206): for every band 2^f, sin then cos of 2^f * x (3 channels each), times mask[f];
+    with include_xyz the block x*2-1 comes first."""
+    mask = torch.ones(n_frequencies) if mask is None else mask
+    out = [x01 * 2.0 - 1.0] if include_xyz else []
+    for f in range(n_frequencies):
+        for fn in (torch.sin, torch.cos):
+            out.append(fn((2.0 ** f) * x01) * mask[f])
+    return torch.cat(out, -1)
+
+
+def freq_mask(n_frequencies: int, n_masking_step: int, global_step: Optional[int]) -> torch.Tensor:
+    """ProgressiveBandFrequency.update_step (networks.py:36-52)."""
+    if n_masking_step <= 0 or global_step is None:
+        return torch.ones(n_frequencies)
+    ramp = (global_step / n_masking_step * n_frequencies - torch.arange(0, n_frequencies)).clamp(0, 1)
+    return (1.0 - torch.cos(math.pi * ramp)) / 2.0
+
+
+def _encode(points: torch.Tensor, P, cfg: FieldCfg) -> torch.Tensor:
+    r = cfg.radius
+    x01 = (points + r) / (2 * r)
+    if cfg.encoding == "frequency":
+        return freq_encode(x01, cfg.n_frequencies, P.get("freq_mask"), cfg.include_xyz)
+    return hashgrid_encode(x01, P["table"], cfg.grid)
+
+
+def _mlp(enc: torch.Tensor, P, head: str) -> torch.Tensor:
+    """VanillaMLP networks.py:214-251 (bias-free Linear + ReLU; 1 or 2 hidden layers)."""
+    h = torch.relu(enc @ P["w1" + head].T)
+    if ("wm" + head) in P:
+        h = torch.relu(h @ P["wm" + head].T)
+    return h @ P["w2" + head].T
 
 
 def _color_act(name: str, x: torch.Tensor) -> torch.Tensor:
@@ -139,11 +186,8 @@ def _color_act(name: str, x: torch.Tensor) -> torch.Tensor:
 def field_density(points: torch.Tensor, P: Dict[str, torch.Tensor], cfg: FieldCfg):
     """ImplicitVolume.forward_density (implicit_volume.py:198-207) + get_activated_density (:80-107) +
     contract_to_unisphere bounded branch (geometry/base.py:20-32). Returns (density [N], enc [N,32])."""
-    r = cfg.radius
-    x01 = (points + r) / (2 * r)
-    enc = hashgrid_encode(x01, P["table"], cfg.grid)
-    raw = torch.relu(enc @ P["w1d"].T) @ P["w2d"].T  # VanillaMLP networks.py:214-251
-    raw = raw[:, 0]
+    enc = _encode(points, P, cfg)
+    raw = _mlp(enc, P, "d")[:, 0]
     if cfg.density_bias == "blob_magic3d":
         raw = raw + cfg.density_blob_scale * (1 - torch.sqrt((points ** 2).sum(-1)) / cfg.density_blob_std)
     elif cfg.density_bias == "blob_dreamfusion":
@@ -160,7 +204,7 @@ def field_density(points: torch.Tensor, P: Dict[str, torch.Tensor], cfg: FieldCf
 def field_forward(points: torch.Tensor, P, cfg: FieldCfg, output_normal: bool = False):
     """ImplicitVolume.forward (implicit_volume.py:109-196): density, raw features, FD normals (:167-177)."""
     sigma, enc = field_density(points, P, cfg)
-    feat = torch.relu(enc @ P["w1f"].T) @ P["w2f"].T
+    feat = _mlp(enc, P, "f")
     out = {"density": sigma, "features": feat}
     if output_normal:
         eps = cfg.fd_eps

@@ -33,7 +33,7 @@ from . import lib as L
 from . import core
 from .core import BaseModule, BaseObject, find, get_rank, parse_structured, register
 from .data import RandomCameraDataModuleConfig, RandomCameraIterableDataset, RandomMultiviewCameraIterableDataset
-from .fields import DEFAULT_GRID, HashGridEncoding
+from .fields import DEFAULT_GRID, HashGridEncoding, _TinyMLP, tiny_mlp
 from .prompts import DIRECTIONS, PromptProcessorOutput, hash_prompt
 from .systems import BaseSystem, binary_cross_entropy
 
@@ -279,42 +279,6 @@ class _TriplaneSample(torch.autograd.Function):
         L.check(L.load().sdb_triplane_sample_backward(L.ptr(d_enc.contiguous().float()), L.ptr(points), B, N, H, W, Cc,
                                                       L.ptr(d_planes), L.stream_ptr()), "sdb_triplane_sample_backward")
         return d_planes, None
-
-
-class _TinyMLP(torch.autograd.Function):
-    """y [n, k] = W3 relu(W2 relu(W1 x)) for the bias-free 64-wide VanillaMLP heads (networks.py:214-251), native
-    fp32 kernels (csrc/tiny_mlp.cu). Nothing but x is kept for the backward: the hidden layers are recomputed."""
-
-    @staticmethod
-    def forward(ctx, x, w1, w2, w3):
-        lib = L.load()
-        x = x.contiguous().float()
-        w1, w2, w3 = (w.detach().contiguous().float() for w in (w1, w2, w3))
-        n, d_in, k = x.shape[0], x.shape[1], w3.shape[0]
-        y = torch.empty(n, k, device=x.device)
-        L.check(lib.sdb_mlp3_forward(L.ptr(x.detach()), n, d_in, L.ptr(w1), L.ptr(w2), L.ptr(w3), k, L.ptr(y),
-                                     L.stream_ptr()), "sdb_mlp3_forward")
-        ctx.save_for_backward(x.detach(), w1, w2, w3)
-        return y
-
-    @staticmethod
-    def backward(ctx, d_y):
-        x, w1, w2, w3 = ctx.saved_tensors
-        n, d_in, k = x.shape[0], x.shape[1], w3.shape[0]
-        d_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        g1, g2, g3 = torch.zeros_like(w1), torch.zeros_like(w2), torch.zeros_like(w3)
-        L.check(L.load().sdb_mlp3_backward(L.ptr(x), n, d_in, L.ptr(w1), L.ptr(w2), L.ptr(w3), k,
-                                           L.ptr(d_y.contiguous().float()), L.ptr(d_x) if d_x is not None else None,
-                                           0, L.ptr(g1), L.ptr(g2), L.ptr(g3), L.stream_ptr()), "sdb_mlp3_backward")
-        return d_x, g1, g2, g3
-
-
-def tiny_mlp(mlp, x: torch.Tensor) -> torch.Tensor:
-    """Evaluate a fields.VanillaMLP (64 neurons, 2 hidden layers) on x [..., d_in] with the native kernels."""
-    ws = mlp.weights()
-    if len(ws) != 3 or mlp.n_neurons != 64 or x.shape[-1] % 8 or not 8 <= x.shape[-1] <= 96 or ws[2].shape[0] not in (1, 3):
-        raise NotImplementedError("native tiny MLP: d_in -> 64 -> 64 -> {1,3} with d_in a multiple of 8 in [8, 96]")
-    return _TinyMLP.apply(x.reshape(-1, x.shape[-1]), *ws).view(*x.shape[:-1], ws[2].shape[0])
 
 
 class _Attention(nn.Module):

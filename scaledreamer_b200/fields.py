@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from . import lib as L
 from . import render_ops as R
-from .core import BaseModule, register
+from .core import BaseModule, Updateable, register
 
 DEFAULT_GRID = {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 19,
                 "base_resolution": 16, "per_level_scale": 1.447269237440378}
@@ -123,6 +123,76 @@ class VanillaMLP(nn.Module):
         return [m.weight for m in self.layers if isinstance(m, nn.Linear)]
 
 
+class _TinyMLP(torch.autograd.Function):
+    """y [n, k] = W3 relu(W2 relu(W1 x)) for the bias-free 64-wide VanillaMLP heads (networks.py:214-251), native
+    fp32 kernels (csrc/tiny_mlp.cu). Nothing but x is kept for the backward: the hidden layers are recomputed."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, w3):
+        lib = L.load()
+        x = x.contiguous().float()
+        w1, w2, w3 = (w.detach().contiguous().float() for w in (w1, w2, w3))
+        n, d_in, k = x.shape[0], x.shape[1], w3.shape[0]
+        y = torch.empty(n, k, device=x.device)
+        L.check(lib.sdb_mlp3_forward(L.ptr(x.detach()), n, d_in, L.ptr(w1), L.ptr(w2), L.ptr(w3), k, L.ptr(y),
+                                     L.stream_ptr()), "sdb_mlp3_forward")
+        ctx.save_for_backward(x.detach(), w1, w2, w3)
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        x, w1, w2, w3 = ctx.saved_tensors
+        n, d_in, k = x.shape[0], x.shape[1], w3.shape[0]
+        d_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        g1, g2, g3 = torch.zeros_like(w1), torch.zeros_like(w2), torch.zeros_like(w3)
+        L.check(L.load().sdb_mlp3_backward(L.ptr(x), n, d_in, L.ptr(w1), L.ptr(w2), L.ptr(w3), k,
+                                           L.ptr(d_y.contiguous().float()), L.ptr(d_x) if d_x is not None else None,
+                                           0, L.ptr(g1), L.ptr(g2), L.ptr(g3), L.stream_ptr()), "sdb_mlp3_backward")
+        return d_x, g1, g2, g3
+
+
+def tiny_mlp(mlp: "VanillaMLP", x: torch.Tensor) -> torch.Tensor:
+    """Evaluate a VanillaMLP (64 neurons, 1 or 2 hidden layers, 1 or 3 outputs) on x [..., d] with the native kernels.
+    x may carry zero padding columns beyond the MLP's input width (the first layer is padded to match). A single
+    hidden layer runs as the two-layer kernel with an identity second layer: relu(I relu(h)) == relu(h) exactly."""
+    ws = list(mlp.weights())
+    d = x.shape[-1]
+    if mlp.n_neurons != 64 or len(ws) not in (2, 3) or ws[-1].shape[0] not in (1, 3) or d % 8 or not 8 <= d <= 96 \
+            or ws[0].shape[1] > d:
+        raise NotImplementedError("native tiny MLP: d_in -> 64 [-> 64] -> {1,3}, d_in <= 96 (rows padded to 8)")
+    w1 = ws[0] if ws[0].shape[1] == d else torch.nn.functional.pad(ws[0], (0, d - ws[0].shape[1]))
+    w2 = ws[1] if len(ws) == 3 else torch.eye(64, device=x.device)
+    return _TinyMLP.apply(x.reshape(-1, d), w1, w2, ws[-1]).view(*x.shape[:-1], ws[-1].shape[0])
+
+
+class ProgressiveBandFrequency(nn.Module, Updateable):
+    """networks.py:16-52 wrapped as get_encoding does (CompositeEncoding, :170-206): sin / cos of 2^f x01 with the
+    coarse-to-fine mask, optional leading xyz*2-1 block. Parameter-free; rows come back zero-padded to a multiple of 8
+    columns (`padded_dims`) for the MLP kernels."""
+
+    def __init__(self, n_input_dims: int, config: dict):
+        super().__init__()
+        if n_input_dims != 3:
+            raise NotImplementedError("ProgressiveBandFrequency takes 3-D inputs")
+        self.N_freqs = int(config["n_frequencies"])
+        self.n_masking_step = int(config.get("n_masking_step", 0))
+        self.include_xyz = bool(config.get("include_xyz", False))
+        self.n_input_dims = n_input_dims
+        self.n_output_dims = 3 * int(self.include_xyz) + 6 * self.N_freqs
+        self.padded_dims = -(-self.n_output_dims // 8) * 8
+        self.register_buffer("mask", torch.ones(self.N_freqs), persistent=False)
+
+    def forward(self, x01: torch.Tensor) -> torch.Tensor:
+        return R.freq_encode(x01, self.N_freqs, self.mask, self.include_xyz)
+
+    def update_step(self, epoch, global_step, on_load_weights: bool = False):
+        if self.n_masking_step <= 0 or global_step is None:
+            self.mask.fill_(1.0)
+        else:
+            ramp = (global_step / self.n_masking_step * self.N_freqs - torch.arange(0, self.N_freqs)).clamp(0, 1)
+            self.mask.copy_((1.0 - torch.cos(math.pi * ramp)) / 2.0)
+
+
 @register("implicit-volume")
 class ImplicitVolume(BaseModule):
     @dataclass
@@ -156,19 +226,30 @@ class ImplicitVolume(BaseModule):
         self.register_buffer("bbox", torch.as_tensor([[-r, -r, -r], [r, r, r]], dtype=torch.float32))
         self.unbounded = False
         if self.cfg.n_feature_dims != 3:
-            raise NotImplementedError("the fused renderer evaluates a 3-channel feature network")
+            raise NotImplementedError("the renderers evaluate a 3-channel feature network")
         if self.cfg.normal_type not in (None, "finite_difference"):
             raise NotImplementedError(f"normal_type {self.cfg.normal_type} is not implemented (finite_difference only)")
-        mlp = self.cfg.mlp_network_config
-        if int(mlp["n_neurons"]) != 64 or int(mlp["n_hidden_layers"]) != 1:
-            raise NotImplementedError("the fused renderer is built for 32-64-{1,3} MLPs (n_neurons 64, 1 hidden layer)")
-        self.encoding = HashGridEncoding(self.cfg.n_input_dims, self.cfg.pos_encoding_config)
-        if self.encoding.n_output_dims != 32:
-            raise NotImplementedError("the fused renderer needs a 32-wide encoding (16 levels x 2 features)")
-        self.density_network = VanillaMLP(32, 1, mlp)
-        self.feature_network = VanillaMLP(32, self.cfg.n_feature_dims, mlp)
+        mlp, enc = self.cfg.mlp_network_config, self.cfg.pos_encoding_config
+        if int(mlp["n_neurons"]) != 64 or int(mlp["n_hidden_layers"]) not in (1, 2):
+            raise NotImplementedError("the sm_100a MLP kernels are built for n_neurons 64 and 1 or 2 hidden layers")
+        if enc.get("otype") == "ProgressiveBandFrequency":
+            self.encoding = ProgressiveBandFrequency(self.cfg.n_input_dims, enc)
+        else:
+            self.encoding = HashGridEncoding(self.cfg.n_input_dims, enc)
+        n_enc = self.encoding.n_output_dims
+        if n_enc > 96:
+            raise NotImplementedError("encodings wider than 96 are not covered by the MLP kernels")
+        # The fused ray-march + field + composite kernels cover the iNGP layout of the BASELINE configs C2/C3
+        # (32-wide hash grid, 32-64-{1,3} MLPs); anything else (C1: frequency encoding / deeper MLP) is rendered by
+        # the packed stages with this module's own forward().
+        self.fusable = isinstance(self.encoding, HashGridEncoding) and n_enc == 32 and int(mlp["n_hidden_layers"]) == 1
+        self.density_network = VanillaMLP(n_enc, 1, mlp)
+        self.feature_network = VanillaMLP(n_enc, self.cfg.n_feature_dims, mlp)
 
     def field_params(self) -> Dict[str, torch.Tensor]:
+        if not self.fusable:
+            raise NotImplementedError("this geometry is not in the fused renderer's layout (32-wide HashGrid, one "
+                                      "hidden layer); it renders through the packed stages")
         w1d, w2d = self.density_network.weights()
         w1f, w2f = self.feature_network.weights()
         return {"table": self.encoding.table, "w1d": w1d, "w2d": w2d, "w1f": w1f, "w2f": w2f}
@@ -182,10 +263,55 @@ class ImplicitVolume(BaseModule):
     def _spec(self) -> R.FieldSpec:
         return R.FieldSpec(bg_grid=self.encoding.grid_cfg, **self.field_spec_kwargs())
 
+    # ---- packed path: differentiable evaluation on arbitrary points (implicit_volume.py:80-107, 109-207)
+    def _encode(self, points: torch.Tensor) -> torch.Tensor:
+        x01 = ((points - self.bbox[0]) / (self.bbox[1] - self.bbox[0])).detach()  # contract_to_unisphere, bounded
+        if isinstance(self.encoding, HashGridEncoding):
+            return _HashGridFn.apply(x01, self.encoding.table.view(-1, 2), self.encoding.grid_cfg)
+        return self.encoding(x01)
+
+    def _activated_density(self, points: torch.Tensor, raw: torch.Tensor) -> torch.Tensor:
+        bias = self.cfg.density_bias
+        if bias == "blob_dreamfusion":
+            raw = raw + self.cfg.density_blob_scale * torch.exp(-0.5 * (points ** 2).sum(-1) / self.cfg.density_blob_std ** 2)
+        elif bias == "blob_magic3d":
+            raw = raw + self.cfg.density_blob_scale * (1 - torch.sqrt((points ** 2).sum(-1)) / self.cfg.density_blob_std)
+        elif isinstance(bias, (int, float)):
+            raw = raw + float(bias)
+        else:
+            raise ValueError(f"Unknown density bias {bias}")
+        act = self.cfg.density_activation or "softplus"
+        if act == "softplus":
+            return torch.nn.functional.softplus(raw)
+        if act == "exp":
+            return torch.exp(raw)
+        raise NotImplementedError(f"density_activation {act} is not implemented (softplus, exp)")
+
+    def _density(self, points: torch.Tensor, enc: Optional[torch.Tensor] = None) -> torch.Tensor:
+        enc = self._encode(points) if enc is None else enc
+        return self._activated_density(points, tiny_mlp(self.density_network, enc)[..., 0])
+
+    def _forward_packed(self, points: torch.Tensor, output_normal: bool) -> Dict[str, torch.Tensor]:
+        pts = points.reshape(-1, 3)
+        enc = self._encode(pts)
+        density = self._density(pts, enc)
+        out = {"density": density[:, None], "features": tiny_mlp(self.feature_network, enc)}
+        if output_normal:
+            eps, r = self.cfg.finite_difference_normal_eps, self.cfg.radius
+            offs = (pts[:, None, :] + eps * torch.eye(3, device=pts.device)).clamp(-r, r)
+            d_off = self._density(offs.reshape(-1, 3)).view(-1, 3)
+            normal = torch.nn.functional.normalize(-(d_off - density[:, None]) / eps, dim=-1)
+            out.update(normal=normal, shading_normal=normal)
+        return out
+
     def forward(self, points: torch.Tensor, output_normal: bool = False) -> Dict[str, torch.Tensor]:
-        """implicit_volume.py:109-196 on arbitrary points (no autograd: training gradients flow through the fused
-        renderer; this entry serves occupancy refresh, export and inspection)."""
+        """implicit_volume.py:109-196 on arbitrary points. In the fused layout this entry is gradient-free (training
+        gradients flow through the fused renderer; it serves occupancy refresh, export and inspection); otherwise it
+        is the differentiable field the packed renderer calls."""
         shp = points.shape[:-1]
+        if not self.fusable:
+            out = self._forward_packed(points, output_normal)
+            return {k: v.view(*shp, v.shape[-1]) for k, v in out.items()}
         P = {k: v.detach() for k, v in self.field_params().items()}
         d, f, n = R.field_forward(self._spec(), P, points.reshape(-1, 3), want_features=True, want_normal=output_normal)
         out = {"density": d.view(*shp, 1), "features": f.view(*shp, 3)}
@@ -196,6 +322,8 @@ class ImplicitVolume(BaseModule):
 
     def forward_density(self, points: torch.Tensor) -> torch.Tensor:
         shp = points.shape[:-1]
+        if not self.fusable:
+            return self._density(points.reshape(-1, 3)).view(*shp, 1)
         P = {k: v.detach() for k, v in self.field_params().items()}
         d, _, _ = R.field_forward(self._spec(), P, points.reshape(-1, 3), want_features=False)
         return d.view(*shp, 1)
@@ -362,6 +490,8 @@ class NeRFVolumeRenderer(BaseModule):
                             alpha_thre=0.01, grid_res=self.OCC_RES,
                             output_normal=bool(self.material.requires_normal and self.packed_capacity > 0))
         jitter = torch.rand(n_rays, device=dev) if self.randomized else None
+        if not getattr(self.geometry, "fusable", False):
+            return self._forward_packed(rays_o, rays_d, light_positions, bg_color, march, jitter)
         if bg_color is not None:
             bg_override = bg_color.to(dev, torch.float32).reshape(-1, 3).expand(B, 3).contiguous()
         else:
@@ -379,12 +509,48 @@ class NeRFVolumeRenderer(BaseModule):
                 res["normal"] = pk["normal"]
         return res
 
+    def _forward_packed(self, rays_o, rays_d, light_positions, bg_color, march: "R.MarchSpec", jitter):
+        """The reference's own stage order (nerf_volume_renderer.py:139-386) over packed samples, for geometries outside
+        the fused layout: march -> sigma_fn pruning -> geometry / material on the kept samples -> compositing."""
+        B, H, W = rays_o.shape[:3]
+        dev = rays_o.device
+        n_rays = B * H * W
+        ro, rd = rays_o.reshape(-1, 3).contiguous().float(), rays_d.reshape(-1, 3).contiguous().float()
+        occ = self._occ_grid(dev)
+        smp = R.march_packed(march, self.cfg.radius, occ, ro, rd, jitter)
+        if march.prune and smp["positions"].shape[0] > 0:
+            with torch.no_grad():
+                sigma = self.geometry.forward_density(smp["positions"])[..., 0]
+            smp = R.prune_packed(smp, sigma, march, occ)
+        ray_idx = smp["ray_indices"].long()
+        positions, t_dirs = smp["positions"], rd[ray_idx]
+        geo = self.geometry(positions, output_normal=bool(self.material.requires_normal))
+        lp = light_positions.reshape(-1, 1, 1, 3).expand(-1, H, W, -1).reshape(-1, 3)[ray_idx] \
+            if light_positions is not None else None
+        rgb_fg = self.material(viewdirs=t_dirs, positions=positions, light_positions=lp, **geo)
+        if bg_color is not None:
+            comp_rgb_bg = bg_color.to(dev, torch.float32).reshape(-1, 1, 1, 3).expand(B, H, W, 3)
+        else:
+            comp_rgb_bg = self.background(dirs=rays_d)
+        comp_rgb_bg = comp_rgb_bg.reshape(n_rays, 3)
+        acc = R.composite_packed(geo["density"][..., 0], rgb_fg, smp)
+        opacity = acc["opacity"][:, None]
+        comp_rgb = acc["comp_rgb_fg"] + comp_rgb_bg * (1.0 - opacity)
+        res = {"comp_rgb": comp_rgb.view(B, H, W, 3), "comp_rgb_fg": acc["comp_rgb_fg"].view(B, H, W, 3),
+               "comp_rgb_bg": comp_rgb_bg.view(B, H, W, 3), "opacity": opacity.view(B, H, W, 1),
+               "depth": acc["depth"].view(B, H, W, 1), "z_variance": acc["z_variance"].view(B, H, W, 1)}
+        if self.training:
+            res.update({"weights": acc["weights"][:, None], "t_points": (0.5 * (smp["t_starts"] + smp["t_ends"]))[:, None],
+                        "t_intervals": (smp["t_ends"] - smp["t_starts"])[:, None], "t_dirs": t_dirs,
+                        "ray_indices": ray_idx, "points": positions, **geo})
+        return res
+
     def update_step(self, epoch: int, global_step: int, on_load_weights: bool = False) -> None:
         """nerfacc OccGridEstimator.update_every_n_steps(step, occ_eval_fn = sigma * step_size, occ_thre=0.01,
         ema_decay=0.95, warmup_steps=256, n=16) (nerf_volume_renderer.py:430-444)."""
         if not (self.cfg.grid_prune and self.training and not on_load_weights) or global_step % 16 != 0:
             return
-        dev = self.geometry.encoding.table.device
+        dev = self.geometry.bbox.device
         occ = self._occ_grid(dev)
         n_cells = self.OCC_RES ** 3
         if global_step < 256:
@@ -396,8 +562,17 @@ class NeRFVolumeRenderer(BaseModule):
             if occupied.numel() > n:
                 occupied = occupied[torch.randint(occupied.numel(), (n,), device=dev)]
             idx = torch.cat([uniform, occupied]).to(torch.int32)
+        rand = torch.rand(idx.numel(), 3, device=dev)
+        if not getattr(self.geometry, "fusable", False):
+            res, r = self.OCC_RES, self.cfg.radius
+            i = idx.long()
+            cell = torch.stack([i // (res * res), (i // res) % res, i % res], -1).float()
+            with torch.no_grad():
+                sigma = self.geometry.forward_density(-r + (cell + rand) * (2.0 * r / res))
+            R.occgrid_update_values(occ, idx, sigma * self.render_step_size)
+            return
         P = {k: v.detach() for k, v in self._params().items()}
-        occ.update(self._spec(), P, idx, torch.rand(idx.numel(), 3, device=dev), self.render_step_size)
+        occ.update(self._spec(), P, idx, rand, self.render_step_size)
 
     def update_step_end(self, epoch: int, global_step: int) -> None:
         pass

@@ -132,6 +132,13 @@ SIGNATURES = {
     "sdb_adamw_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P],
     "sdb_mlp3_forward": [_P, _LL, _I, _P, _P, _P, _I, _P, _P],
     "sdb_mlp3_backward": [_P, _LL, _I, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P],
+    "sdb_march_count": [C.POINTER(MarchCfgC), _F, _P, _P, _P, _P, _I, _P, _P],
+    "sdb_march_fill": [C.POINTER(MarchCfgC), _F, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
+    "sdb_packed_visibility": [_P, _P, _P, _P, _I, _F, _P, _F, _P, _P, _P],
+    "sdb_packed_composite_forward": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+    "sdb_packed_composite_backward": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "sdb_freq_encode": [_P, _LL, _I, _P, _I, _I, _P, _P],
+    "sdb_occgrid_update_values": [_P, _P, _I, _I, _F, _F, _P, _P, _P, _P],
     "sdb_adan_step": [_P, _P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _I, _F, _I, _P],
     # ---- include/sdb200_nn.h
     "sdb_gemm_f16": [C.POINTER(GemmArgsC), _P],

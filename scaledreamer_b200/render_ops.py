@@ -374,3 +374,118 @@ def render_nerf(spec, march, occ, params, rays_o, rays_d, jitter, bg_override, r
     out = dict(holder)
     out["comp_rgb"], out["opacity"], out["depth"] = rgb, op, depth
     return out
+
+
+# ------------------------------------------------------------------------------------------------ packed (unfused) stages
+def freq_encode(x01: torch.Tensor, n_frequencies: int, mask: torch.Tensor, include_xyz: bool = False,
+                pad_to: int = 8) -> torch.Tensor:
+    """ProgressiveBandFrequency under CompositeEncoding (networks.py:16-52, 170-190) on x01 [N,3]; the rows are
+    zero-padded to a multiple of `pad_to` columns for the MLP kernels."""
+    x01 = x01.reshape(-1, 3).contiguous().float()
+    used = (3 if include_xyz else 0) + 6 * n_frequencies
+    stride = -(-used // pad_to) * pad_to
+    out = torch.empty(x01.shape[0], stride, device=x01.device)
+    mask = mask.to(x01.device, torch.float32).contiguous()
+    L.check(L.load().sdb_freq_encode(L.ptr(x01), x01.shape[0], int(n_frequencies), L.ptr(mask), int(include_xyz),
+                                     stride, L.ptr(out), L.stream_ptr()), "sdb_freq_encode")
+    return out
+
+
+def _offsets(counts: torch.Tensor) -> torch.Tensor:
+    off = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=counts.device)
+    torch.cumsum(counts, 0, out=off[1:])
+    return off
+
+
+def march_packed(march: MarchSpec, radius: float, occ: OccGrid, rays_o, rays_d, jitter) -> Dict[str, torch.Tensor]:
+    """Candidate samples of every ray, packed and sorted by (ray, t) (nerfacc OccGridEstimator.sampling without
+    sigma_fn). One host read of the total (the reference's packed tensors are sized the same way)."""
+    lib = L.load()
+    m = march.to_c()
+    rays_o, rays_d = rays_o.reshape(-1, 3).contiguous().float(), rays_d.reshape(-1, 3).contiguous().float()
+    n_rays, dev = rays_o.shape[0], rays_o.device
+    counts = torch.zeros(n_rays, dtype=torch.int32, device=dev)
+    L.check(lib.sdb_march_count(C.byref(m), float(radius), L.ptr(occ.bits), L.ptr(rays_o), L.ptr(rays_d),
+                                L.ptr(jitter), n_rays, L.ptr(counts), L.stream_ptr()), "sdb_march_count")
+    offsets = _offsets(counts)
+    n = int(offsets[-1].item())
+    out = {"offsets": offsets, "ray_indices": torch.empty(n, dtype=torch.int32, device=dev),
+           "t_starts": torch.empty(n, device=dev), "t_ends": torch.empty(n, device=dev),
+           "positions": torch.empty(n, 3, device=dev)}
+    if n:
+        L.check(lib.sdb_march_fill(C.byref(m), float(radius), L.ptr(occ.bits), L.ptr(rays_o), L.ptr(rays_d),
+                                   L.ptr(jitter), n_rays, L.ptr(offsets), L.ptr(out["ray_indices"]),
+                                   L.ptr(out["t_starts"]), L.ptr(out["t_ends"]), L.ptr(out["positions"]),
+                                   L.stream_ptr()), "sdb_march_fill")
+    return out
+
+
+def prune_packed(samples: Dict[str, torch.Tensor], sigma: torch.Tensor, march: MarchSpec,
+                 occ: Optional[OccGrid]) -> Dict[str, torch.Tensor]:
+    """sigma_fn visibility pruning (nerf_volume_renderer.py:153-180): drops samples with alpha < min(alpha_thre,
+    mean occupancy) or transmittance < early_stop_eps; returns the compacted packed samples."""
+    n_rays = samples["offsets"].numel() - 1
+    n = sigma.numel()
+    dev = sigma.device
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    kept = torch.zeros(n_rays, dtype=torch.int32, device=dev)
+    if n:
+        L.check(L.load().sdb_packed_visibility(
+            L.ptr(sigma.contiguous().float()), L.ptr(samples["t_starts"]), L.ptr(samples["t_ends"]),
+            L.ptr(samples["offsets"]), n_rays, float(march.alpha_thre), L.ptr(occ.mean) if occ is not None else None,
+            float(march.early_stop_eps), L.ptr(keep), L.ptr(kept), L.stream_ptr()), "sdb_packed_visibility")
+    idx = torch.nonzero(keep)[:, 0]
+    out = {k: samples[k][idx] for k in ("ray_indices", "t_starts", "t_ends", "positions")}
+    out["offsets"] = _offsets(kept)
+    return out
+
+
+class _PackedComposite(torch.autograd.Function):
+    """(opacity [R], depth [R], comp_rgb_fg [R,3]) = front-to-back compositing of packed samples; z_variance and the
+    per-sample weights come back through `holder` (not differentiable, as the fused renderer's)."""
+
+    @staticmethod
+    def forward(ctx, sigma, rgb, t_starts, t_ends, offsets, holder):
+        lib = L.load()
+        n_rays, dev = offsets.numel() - 1, offsets.device
+        sigma, rgb = sigma.contiguous().float(), rgb.contiguous().float()
+        n = sigma.numel()
+        weights, trans = torch.empty(n, device=dev), torch.empty(n, device=dev)
+        op, depth = torch.empty(n_rays, device=dev), torch.empty(n_rays, device=dev)
+        fg, zvar = torch.empty(n_rays, 3, device=dev), torch.empty(n_rays, device=dev)
+        L.check(lib.sdb_packed_composite_forward(
+            L.ptr(sigma.detach()), L.ptr(rgb.detach()), L.ptr(t_starts), L.ptr(t_ends), L.ptr(offsets), n_rays,
+            L.ptr(weights), L.ptr(trans), L.ptr(op), L.ptr(depth), L.ptr(fg), L.ptr(zvar), L.stream_ptr()),
+            "sdb_packed_composite_forward")
+        ctx.save_for_backward(rgb.detach(), t_starts, t_ends, offsets, weights, trans)
+        holder["weights"], holder["z_variance"] = weights, zvar
+        return op, depth, fg
+
+    @staticmethod
+    def backward(ctx, g_op, g_depth, g_fg):
+        rgb, t_starts, t_ends, offsets, weights, trans = ctx.saved_tensors
+        n_rays = offsets.numel() - 1
+        d_sigma, d_rgb = torch.zeros(weights.numel(), device=rgb.device), torch.zeros_like(rgb)
+        cg = lambda g: g.contiguous().float() if g is not None else None
+        g_op, g_depth, g_fg = cg(g_op), cg(g_depth), cg(g_fg)
+        L.check(L.load().sdb_packed_composite_backward(
+            L.ptr(rgb), L.ptr(t_starts), L.ptr(t_ends), L.ptr(offsets), n_rays, L.ptr(weights), L.ptr(trans),
+            L.ptr(g_op), L.ptr(g_depth), L.ptr(g_fg), L.ptr(d_sigma), L.ptr(d_rgb), L.stream_ptr()),
+            "sdb_packed_composite_backward")
+        return d_sigma, d_rgb, None, None, None, None
+
+
+def composite_packed(sigma, rgb, samples: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    holder: dict = {}
+    op, depth, fg = _PackedComposite.apply(sigma.reshape(-1), rgb.reshape(-1, 3), samples["t_starts"],
+                                           samples["t_ends"], samples["offsets"], holder)
+    return {"opacity": op, "depth": depth, "comp_rgb_fg": fg, "weights": holder["weights"],
+            "z_variance": holder["z_variance"]}
+
+
+def occgrid_update_values(occ: OccGrid, cell_idx: torch.Tensor, values: torch.Tensor, ema_decay: float = 0.95,
+                          occ_thre: float = 0.01) -> None:
+    cell_idx, values = cell_idx.to(torch.int32).contiguous(), values.reshape(-1).float().contiguous()
+    L.check(L.load().sdb_occgrid_update_values(L.ptr(cell_idx), L.ptr(values), cell_idx.numel(), occ.res,
+                                               float(ema_decay), float(occ_thre), L.ptr(occ.occs), L.ptr(occ.bits),
+                                               L.ptr(occ.mean), L.stream_ptr()), "sdb_occgrid_update_values")

@@ -224,8 +224,13 @@ class StableDreamer(BaseSystem):
             if name.startswith("loss_"):
                 loss = loss + value * self.C(lam[name.replace("loss_", "lambda_")])
         if self.C(lam.get("lambda_orient", 0.0)) > 0:
-            raise NotImplementedError("lambda_orient > 0 needs gradients through finite-difference normals, which the "
-                                      "fused renderer does not provide")
+            if "normal" not in out or not out["normal"].requires_grad:
+                raise NotImplementedError("lambda_orient > 0 needs gradients through finite-difference normals, which "
+                                          "the fused renderer does not provide")
+            cos = (out["normal"] * out["t_dirs"]).sum(-1, keepdim=True)  # scaledreamer.py:74-83
+            loss_orient = (out["weights"].detach() * cos.clamp_min(0.0) ** 2).sum() / (out["opacity"] > 0).sum()
+            self.log("train/loss_orient", loss_orient)
+            loss = loss + loss_orient * self.C(lam["lambda_orient"])
         if self.C(lam.get("lambda_sparsity", 0.0)) > 0:
             loss_sparsity = (out["opacity"] ** 2 + 0.01).sqrt().mean()
             self.log("train/loss_sparsity", loss_sparsity)

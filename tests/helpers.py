@@ -6,9 +6,9 @@ import torch
 from oracle import render_oracle as ro
 
 
-def scene(H=32, W=32, B=1, seed=0, table_scale=0.5, prune=True, n_samples=512):
+def scene(H=32, W=32, B=1, seed=0, table_scale=0.5, prune=True, n_samples=512, fcfg=None):
     """Random field + random cameras + one warm-up occupancy refresh, all on CPU (oracle side)."""
-    fcfg = ro.FieldCfg()
+    fcfg = ro.FieldCfg() if fcfg is None else fcfg
     mcfg = ro.MarchCfg(render_step_size=1.732 * 2 * fcfg.radius / n_samples, prune=prune)
     P = ro.make_field_params(fcfg, seed=seed, table_scale=table_scale)
     g = torch.Generator().manual_seed(seed + 1)
@@ -46,5 +46,5 @@ def march_spec_from_oracle(mcfg, output_normal=False):
 
 
 def rel_l2(a, b):
-    a, b = a.double().flatten(), b.double().flatten()
+    a, b = a.detach().double().flatten(), b.detach().double().flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))

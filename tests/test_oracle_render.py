@@ -94,3 +94,36 @@ def test_get_rays_unit_and_centered():
     torch.testing.assert_close(d.norm(dim=-1), torch.ones(1, 8, 8))
     centre = torch.nn.functional.normalize(d[0, 3:5, 3:5].mean((0, 1)), dim=0)
     torch.testing.assert_close(centre, torch.nn.functional.normalize(-o[0, 0, 0], dim=0), atol=1e-5, rtol=0)
+
+
+def test_frequency_field_matches_reference_golden():
+    """C1 field: the oracle's ProgressiveBandFrequency / VanillaMLP / density bias + activation restatement against
+    vectors produced by the reference's own class definitions (tests/golden/make_field_golden.py)."""
+    import os
+
+    import torch
+
+    from oracle import render_oracle as ro
+
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "field_golden.pt"))
+    assert set(gold) == {"f4", "f6_xyz_masked", "f12"}
+    for name, c in gold.items():
+        mask = ro.freq_mask(c["n_frequencies"], c["n_masking_step"], c["global_step"])
+        torch.testing.assert_close(mask, c["mask"], atol=1e-6, rtol=0)
+        bias = c["density_bias"]
+        fcfg = ro.FieldCfg(radius=c["radius"], encoding="frequency", n_frequencies=c["n_frequencies"],
+                           include_xyz=c["include_xyz"], n_hidden_layers=c["n_hidden_layers"],
+                           density_bias=bias if isinstance(bias, str) else "const",
+                           density_bias_const=0.0 if isinstance(bias, str) else bias,
+                           density_activation=c["density_activation"])
+        P = {"freq_mask": mask}
+        for head, ws in (("d", c["density_weights"]), ("f", c["feature_weights"])):
+            P["w1" + head], P["w2" + head] = ws[0], ws[-1]
+            if len(ws) == 3:
+                P["wm" + head] = ws[1]
+        x01 = (c["points"] + c["radius"]) / (2 * c["radius"])
+        enc = ro.freq_encode(x01, c["n_frequencies"], mask, c["include_xyz"])
+        torch.testing.assert_close(enc, c["enc"], atol=1e-6, rtol=1e-6)
+        out = ro.field_forward(c["points"], P, fcfg)
+        torch.testing.assert_close(out["density"], c["density"], atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(out["features"], c["features"], atol=1e-5, rtol=1e-5)
