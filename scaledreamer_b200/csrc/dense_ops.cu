@@ -2,6 +2,8 @@
 // Reference semantics: GroupNorm32 / Normalize (extern/mvdream/ldm/modules/diffusionmodules/util.py:229-231,
 // model.py:46-47, attention.py:88-89), nn.LayerNorm + GEGLU (attention.py:49-57,271-273), softmax
 // (attention.py:186), nearest Upsample (openaimodel.py:109-118), timestep_embedding (util.py:165-186).
+#include <cstdlib>
+
 #include "dense.h"
 
 namespace dense {
@@ -15,83 +17,119 @@ __device__ __forceinline__ float silu_grad(float x) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm
-// Block = PY pixel-lanes x P channel-pair threads. Thread (py, cp) owns channel pair cp for pixels py, py+PY, ...
-// mode 0: accumulate (sum x, sum x^2); mode 1 (backward): accumulate (sum dxhat, sum dxhat*xhat).
-template <int MODE>
-__global__ void gn_reduce_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
-                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
-                                 const float* __restrict__ stats, float* __restrict__ out, int HW, int C, int groups,
-                                 int P, int PY, int pix_per_block, float eps, int act_silu) {
-  extern __shared__ float sm[];  // [2][blockDim.x]
+// Thread mapping shared by the statistics and apply kernels: a block is PL pixel lanes x C8N channel octets; thread
+// (pl, c8) owns channels [8 c8, 8 c8 + 8) of pixels pl, pl + stride, ... of image blockIdx.y. The channel octet never
+// changes, so every per-channel constant (mean, rstd, gamma, beta) is computed once and lives in registers, and each
+// access is one 16-byte load / store, fully coalesced across the block (NHWC).
+struct GnChan {  // per-thread constants of the 4 channel pairs of an octet
+  float mean[4], rstd[4];
+};
+__device__ __forceinline__ GnChan gn_chan(const float* __restrict__ stats, int n, int groups, int cpg, int c8, float cnt,
+                                          float eps) {
+  GnChan k;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int g = (c8 * 8 + 2 * e) / cpg;
+    const float s = stats[(n * groups + g) * 2], ss = stats[(n * groups + g) * 2 + 1];
+    k.mean[e] = s / cnt;
+    k.rstd[e] = rsqrtf(fmaxf(ss / cnt - k.mean[e] * k.mean[e], 0.f) + eps);
+  }
+  return k;
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __half22float2(h[e]);
+    f[2 * e] = t.x, f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+  return v;
+}
+
+// mode 0: per-pair (sum x, sum x^2); mode 1 (backward): (sum dxhat, sum dxhat*xhat). Each block writes one partial per
+// group; gn_finalize_kernel sums them in a fixed order (bitwise reproducible statistics).
+template <int MODE, int UN>
+__global__ void __launch_bounds__(512)
+gn_reduce_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
+                 const __half* __restrict__ beta, const float* __restrict__ stats, float* __restrict__ out, int HW,
+                 int C, int groups, int C8N, int PL, int pix_per_block, float eps, int act_silu) {
+  extern __shared__ float sm[];  // [PL][C/2][2]
   const int n = blockIdx.y;
-  const int cp = threadIdx.x % P, py = threadIdx.x / P;
-  const int cpg = C / groups;  // channels per group (even)
-  const int p_begin = blockIdx.x * pix_per_block;
-  const int p_end = min(HW, p_begin + pix_per_block);
-  const int n_pairs = C / 2;
-  float a0 = 0.f, a1 = 0.f;
-  for (int c2 = cp; c2 < n_pairs; c2 += P) {  // P == n_pairs except for very wide tensors
-    float mean = 0.f, rstd = 0.f, g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
-    if (MODE == 1) {
-      const int g = (2 * c2) / cpg;
-      const float cnt = (float)HW * (float)cpg;
-      const float s = stats[(n * groups + g) * 2], ss = stats[(n * groups + g) * 2 + 1];
-      mean = s / cnt;
-      rstd = rsqrtf(fmaxf(ss / cnt - mean * mean, 0.f) + eps);
-      const float2 gg = __half22float2(reinterpret_cast<const __half2*>(gamma)[c2]);
-      const float2 bb = __half22float2(reinterpret_cast<const __half2*>(beta)[c2]);
-      g0 = gg.x, g1 = gg.y, b0 = bb.x, b1 = bb.y;
-    }
-    float s0 = 0.f, s1 = 0.f;
-    for (int p = p_begin + py; p < p_end; p += PY) {
-      const size_t off = ((size_t)n * HW + p) * n_pairs + c2;
-      const float2 v = __half22float2(reinterpret_cast<const __half2*>(x)[off]);
-      if (MODE == 0) {
-        s0 += v.x + v.y;
-        s1 += v.x * v.x + v.y * v.y;
-      } else {
-        const float2 d = __half22float2(reinterpret_cast<const __half2*>(dy)[off]);
-        const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
-        float dz0 = d.x, dz1 = d.y;
-        if (act_silu) {
-          dz0 *= silu_grad(xh0 * g0 + b0);
-          dz1 *= silu_grad(xh1 * g1 + b1);
-        }
-        const float dx0 = dz0 * g0, dx1 = dz1 * g1;
-        s0 += dx0 + dx1;
-        s1 += dx0 * xh0 + dx1 * xh1;
+  const int c8 = threadIdx.x % C8N, pl = threadIdx.x / C8N;
+  const int cpg = C / groups;
+  const int p_begin = blockIdx.x * pix_per_block, p_end = min(HW, p_begin + pix_per_block);
+  float g[8], b[8];
+  GnChan k;
+  if (MODE == 1) {
+    k = gn_chan(stats, n, groups, cpg, c8, (float)HW * (float)cpg, eps);
+    unpack8(reinterpret_cast<const uint4*>(gamma)[c8], g);
+    unpack8(reinterpret_cast<const uint4*>(beta)[c8], b);
+  }
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint4* xp = reinterpret_cast<const uint4*>(x) + (size_t)n * HW * C8N + c8;
+  const uint4* dp = reinterpret_cast<const uint4*>(dy) + (size_t)n * HW * C8N + c8;
+  auto accumulate = [&](const uint4& xv, const uint4& dv) {
+    float xf[8];
+    unpack8(xv, xf);
+    if (MODE == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s0[e] += xf[2 * e] + xf[2 * e + 1];
+        s1[e] = fmaf(xf[2 * e], xf[2 * e], fmaf(xf[2 * e + 1], xf[2 * e + 1], s1[e]));
+      }
+    } else {
+      float df[8];
+      unpack8(dv, df);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = j >> 1;
+        const float xh = (xf[j] - k.mean[e]) * k.rstd[e];
+        float dz = df[j];
+        if (act_silu) dz *= silu_grad(fmaf(xh, g[j], b[j]));
+        const float dxh = dz * g[j];
+        s0[e] += dxh;
+        s1[e] = fmaf(dxh, xh, s1[e]);
       }
     }
-    // pairs of one group are contiguous in c2: reduce through shared memory per c2-slot
-    sm[threadIdx.x] = s0;
-    sm[blockDim.x + threadIdx.x] = s1;
-    __syncthreads();
-    const int pairs_per_group = cpg / 2;
-    const int c2_base = c2 - cp;  // first pair handled in this sweep
-    // thread t < groups_in_sweep sums its group's slots over all pixel lanes
-    const int first_group = (2 * c2_base) / cpg;
-    const int sweep_pairs = min(P, n_pairs - c2_base);
-    const int groups_in_sweep = (sweep_pairs + pairs_per_group - 1) / pairs_per_group;
-    if ((int)threadIdx.x < groups_in_sweep) {
-      const int g = first_group + threadIdx.x;
-      const int lo = max(g * pairs_per_group - c2_base, 0), hi = min((g + 1) * pairs_per_group - c2_base, sweep_pairs);
-      float t0 = 0.f, t1 = 0.f;
-      for (int yy = 0; yy < PY; ++yy)
-        for (int q = lo; q < hi; ++q) {
-          t0 += sm[yy * P + q];
-          t1 += sm[blockDim.x + yy * P + q];
-        }
-      // per-block partial; summed in fixed order by gn_finalize_kernel (bitwise reproducible statistics)
-      float* po = out + (((size_t)n * gridDim.x + blockIdx.x) * groups + g) * 2;
-      po[0] = t0;
-      po[1] = t1;
+  };
+  int p = p_begin + pl;
+  for (; p + (UN - 1) * PL < p_end; p += UN * PL) {  // UN independent 16-byte loads in flight per operand
+    uint4 xv[UN], dv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      xv[u] = xp[(size_t)(p + u * PL) * C8N];
+      if (MODE == 1) dv[u] = dp[(size_t)(p + u * PL) * C8N];
     }
-    __syncthreads();
-    a0 += s0;
-    a1 += s1;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) accumulate(xv[u], dv[u]);
   }
-  (void)a0;
-  (void)a1;
+  for (; p < p_end; p += PL) {
+    uint4 dv = make_uint4(0, 0, 0, 0);
+    if (MODE == 1) dv = dp[(size_t)p * C8N];
+    accumulate(xp[(size_t)p * C8N], dv);
+  }
+  const int n_pairs = C / 2;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    sm[(pl * n_pairs + c8 * 4 + e) * 2] = s0[e];
+    sm[(pl * n_pairs + c8 * 4 + e) * 2 + 1] = s1[e];
+  }
+  __syncthreads();
+  // thread (gi, k) sums statistic k of group gi over pixel lanes and the group's pairs, in a fixed order
+  const int ppg = cpg / 2;
+  for (int t = threadIdx.x; t < groups * 2; t += blockDim.x) {
+    const int gi = t >> 1, kk = t & 1;
+    float acc = 0.f;
+    for (int yy = 0; yy < PL; ++yy)
+      for (int q = gi * ppg; q < (gi + 1) * ppg; ++q) acc += sm[(yy * n_pairs + q) * 2 + kk];
+    out[(((size_t)n * gridDim.x + blockIdx.x) * groups + gi) * 2 + kk] = acc;
+  }
 }
 
 // One warp per (n, group, k): lanes stride over the per-block partials, then a butterfly sum -- a fixed order, so the
@@ -102,68 +140,89 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __r
   const int lane = threadIdx.x & 31;
   if (i >= total) return;
   const int k = i & 1, g = (i >> 1) % groups, n = (i >> 1) / groups;
-  float acc = 0.f;
-  for (int b = lane; b < nblk; b += 32) acc += partial[(((size_t)n * nblk + b) * groups + g) * 2 + k];
-  acc = warp_sum(acc);
+  float a4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains: the loads are latency-bound, the order stays fixed
+  int b = lane;
+  for (; b + 96 < nblk; b += 128) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a4[u] += partial[(((size_t)n * nblk + b + 32 * u) * groups + g) * 2 + k];
+  }
+  for (; b < nblk; b += 32) a4[0] += partial[(((size_t)n * nblk + b) * groups + g) * 2 + k];
+  float acc = warp_sum((a4[0] + a4[1]) + (a4[2] + a4[3]));
   if (lane == 0) out[i] = acc;
 }
 
-// y = act(GN(x)) (MODE 0) or dx of it (MODE 1); 8 channels (16 bytes) per thread.
-template <int MODE>
-__global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
-                                const __half* __restrict__ gamma, const __half* __restrict__ beta,
-                                const float* __restrict__ stats, const float* __restrict__ red,
-                                __half* __restrict__ y, long long total8, int HW, int C, int groups, float eps,
-                                int act_silu) {
+// y = act(GN(x)) (MODE 0) or dx of it (MODE 1), same thread mapping as gn_reduce_kernel.
+template <int MODE, int UN>
+__global__ void __launch_bounds__(512)
+gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
+                const __half* __restrict__ beta, const float* __restrict__ stats, const float* __restrict__ red,
+                __half* __restrict__ y, int HW, int C, int groups, int C8N, int PL, float eps, int act_silu) {
+  const int n = blockIdx.y;
+  const int c8 = threadIdx.x % C8N, pl = threadIdx.x / C8N;
   const int cpg = C / groups;
   const float cnt = (float)HW * (float)cpg;
-  const int c8n = C / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % c8n);
-    const int n = (int)(i / ((long long)HW * c8n));
-    const uint4 xv = reinterpret_cast<const uint4*>(x)[i];
-    const uint4 gv = reinterpret_cast<const uint4*>(gamma)[c8];
-    const uint4 bv = reinterpret_cast<const uint4*>(beta)[c8];
-    uint4 dv = make_uint4(0, 0, 0, 0);
-    if (MODE == 1) dv = reinterpret_cast<const uint4*>(dy)[i];
-    uint4 ov;
-    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-    const __half2* gh = reinterpret_cast<const __half2*>(&gv);
-    const __half2* bh = reinterpret_cast<const __half2*>(&bv);
-    const __half2* dh = reinterpret_cast<const __half2*>(&dv);
-    __half2* oh = reinterpret_cast<__half2*>(&ov);
+  const GnChan k = gn_chan(stats, n, groups, cpg, c8, cnt, eps);
+  float g[8], b[8], r0[4], r1[4];
+  unpack8(reinterpret_cast<const uint4*>(gamma)[c8], g);
+  unpack8(reinterpret_cast<const uint4*>(beta)[c8], b);
+  if (MODE == 0) {  // fold the normalisation into one fma per element: y = x * g' + b'
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sc = k.rstd[j >> 1] * g[j];
+      b[j] = fmaf(-k.mean[j >> 1], sc, b[j]);
+      g[j] = sc;
+    }
+  } else {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int c = c8 * 8 + 2 * e;
-      const int g = c / cpg;
-      const float s = stats[(n * groups + g) * 2], ss = stats[(n * groups + g) * 2 + 1];
-      const float mean = s / cnt;
-      const float rstd = rsqrtf(fmaxf(ss / cnt - mean * mean, 0.f) + eps);
-      const float2 xf = __half22float2(xh[e]), gf = __half22float2(gh[e]), bf = __half22float2(bh[e]);
-      const float xh0 = (xf.x - mean) * rstd, xh1 = (xf.y - mean) * rstd;
-      float o0, o1;
-      if (MODE == 0) {
-        o0 = xh0 * gf.x + bf.x;
-        o1 = xh1 * gf.y + bf.y;
-        if (act_silu) {
-          o0 = silu(o0);
-          o1 = silu(o1);
-        }
-      } else {
-        const float2 df = __half22float2(dh[e]);
-        float dz0 = df.x, dz1 = df.y;
-        if (act_silu) {
-          dz0 *= silu_grad(xh0 * gf.x + bf.x);
-          dz1 *= silu_grad(xh1 * gf.y + bf.y);
-        }
-        const float r0 = red[(n * groups + g) * 2] / cnt, r1 = red[(n * groups + g) * 2 + 1] / cnt;
-        o0 = rstd * (dz0 * gf.x - r0 - xh0 * r1);
-        o1 = rstd * (dz1 * gf.y - r0 - xh1 * r1);
-      }
-      oh[e] = __floats2half2_rn(o0, o1);
+      const int gi = (c8 * 8 + 2 * e) / cpg;
+      r0[e] = red[(n * groups + gi) * 2] / cnt;
+      r1[e] = red[(n * groups + gi) * 2 + 1] / cnt;
     }
-    reinterpret_cast<uint4*>(y)[i] = ov;
+  }
+  const size_t img = (size_t)n * HW * C8N + c8;
+  const uint4* xp = reinterpret_cast<const uint4*>(x) + img;
+  const uint4* dp = reinterpret_cast<const uint4*>(dy) + img;
+  uint4* yp = reinterpret_cast<uint4*>(y) + img;
+  auto apply = [&](const uint4& xv, const uint4& dv) {
+    float xf[8], o[8];
+    unpack8(xv, xf);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = fmaf(xf[j], g[j], b[j]);
+        if (act_silu) o[j] = silu(o[j]);
+      }
+    } else {
+      float df[8];
+      unpack8(dv, df);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = j >> 1;
+        const float xh = (xf[j] - k.mean[e]) * k.rstd[e];
+        float dz = df[j];
+        if (act_silu) dz *= silu_grad(fmaf(xh, g[j], b[j]));
+        o[j] = k.rstd[e] * (dz * g[j] - r0[e] - xh * r1[e]);
+      }
+    }
+    return pack8(o);
+  };
+  const int step = gridDim.x * PL;
+  int p = blockIdx.x * PL + pl;
+  for (; p + (UN - 1) * step < HW; p += UN * step) {
+    uint4 xv[UN], dv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      xv[u] = xp[(size_t)(p + u * step) * C8N];
+      if (MODE == 1) dv[u] = dp[(size_t)(p + u * step) * C8N];
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) yp[(size_t)(p + u * step) * C8N] = apply(xv[u], dv[u]);
+  }
+  for (; p < HW; p += step) {
+    uint4 dv = make_uint4(0, 0, 0, 0);
+    if (MODE == 1) dv = dp[(size_t)p * C8N];
+    yp[(size_t)p * C8N] = apply(xp[(size_t)p * C8N], dv);
   }
 }
 
@@ -224,21 +283,21 @@ gn_fused_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, 
   }
 }
 
-void gn_geometry(int HW, int C, int N, int groups, int* P, int* PY, int* ppb, int* nblk) {
-  // one thread per channel pair; very wide tensors sweep in equal parts that hold whole groups
-  const int n_pairs = C / 2, ppg = C / groups / 2;
-  int d = 1;
-  while (n_pairs / d > 1024 || n_pairs % d || (n_pairs / d) % ppg) ++d;
-  const int p = n_pairs / d;
-  int py = 1;
-  while (p * py * 2 <= 256 && py * 2 <= HW) py *= 2;
-  // target ~4 waves of blocks over (N x splits)
-  int splits = (4 * kNumSMs + N - 1) / N;
+// Block shape (C8N channel octets x PL pixel lanes, 128..512 threads) and the pixel split of the statistics pass
+// (~4 waves of blocks over N x nblk).
+void gn_geometry(int HW, int C, int N, int* C8N, int* PL, int* ppb, int* nblk) {
+  static const int thr = getenv("SDB_GN_THREADS") ? atoi(getenv("SDB_GN_THREADS")) : 256;
+  static const int waves = getenv("SDB_GN_WAVES") ? atoi(getenv("SDB_GN_WAVES")) : 4;
+  const int c8n = C / 8;
+  int pl = thr / c8n;
+  if (pl < 1) pl = 1;
+  if (pl > HW) pl = HW;
+  int splits = (waves * kNumSMs + N - 1) / N;
   int pix = (HW + splits - 1) / splits;
-  if (pix < py * 4) pix = py * 4;
+  if (pix < pl * 8) pix = pl * 8;
   if (pix > HW) pix = HW;
-  *P = p;
-  *PY = py;
+  *C8N = c8n;
+  *PL = pl;
   *ppb = pix;
   *nblk = (HW + pix - 1) / pix;
 }
@@ -634,39 +693,56 @@ inline int ew_grid(long long total, int block = 256) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+inline bool gn_un8() {
+  static const bool v = getenv("SDB_GN_UNROLL") && atoi(getenv("SDB_GN_UNROLL")) == 8;
+  return v;
+}
+
+// Blocks per image of the apply pass: ~8 blocks per SM over the whole batch, at least 4 pixels per thread.
+inline int gn_apply_blocks(int HW, int pl, int N) {
+  static const int per_sm = getenv("SDB_GN_APPLY_BLOCKS") ? atoi(getenv("SDB_GN_APPLY_BLOCKS")) : 8;
+  const int want = (per_sm * kNumSMs + N - 1) / N, most = (HW + 4 * pl - 1) / (4 * pl);
+  return want < most ? want : (most > 0 ? most : 1);
+}
+
 }  // namespace
 
 long long groupnorm_workspace_floats(int N, int HW, int C, int groups) {
-  int P, PY, ppb, nblk;
-  gn_geometry(HW, C, N, groups, &P, &PY, &ppb, &nblk);
+  int c8n, pl, ppb, nblk;
+  gn_geometry(HW, C, N, &c8n, &pl, &ppb, &nblk);
   return (long long)N * groups * 2 * (1 + nblk);
 }
 
 int groupnorm_forward(const __half* x, const __half* gamma, const __half* beta, __half* y, float* stats, int N, int HW,
                       int C, int groups, float eps, int act_silu, cudaStream_t s) {
-  if (C % 8 || C % groups || (C / groups) % 2) {
-    sdb_set_error("groupnorm: C=%d must be a multiple of 8 with an even group size", C);
+  if (C % 8 || C % groups || (C / groups) % 2 || C > 4096) {
+    sdb_set_error("groupnorm: C=%d must be a multiple of 8 (<= 4096) with an even group size", C);
     return SDB_ERR_UNSUPPORTED;
   }
   const int cpg = C / groups;
-  if (N * groups >= 128 && cpg / 2 <= 256 && (long long)HW * cpg <= 262144) {
+  // One launch instead of three pays off only while the tensor is small enough for launch latency to dominate; its
+  // per-group slices are strided (cpg * 2 contiguous bytes per pixel), so above a few MB the coalesced passes win
+  // (C2 step: 30.0 ms with everything fused, 29.5 ms with nothing fused, 28.0 ms with the 8 MB switch).
+  static const long long fused_max = getenv("SDB_GN_FUSED_MAX") ? atoll(getenv("SDB_GN_FUSED_MAX")) : (8ll << 20);
+  if (N * groups >= 128 && cpg / 2 <= 256 && (long long)N * HW * C * 2 <= fused_max) {
     gn_fused_kernel<<<N * groups, 256, 0, s>>>(x, gamma, beta, y, stats, HW, C, groups, eps, act_silu);
     SDB_COUNT_LAUNCH();
     SDB_CHECK_LAUNCH("gn_fused");
     return SDB_OK;
   }
-  int P, PY, ppb, nblk;
-  gn_geometry(HW, C, N, groups, &P, &PY, &ppb, &nblk);
+  int c8n, pl, ppb, nblk;
+  gn_geometry(HW, C, N, &c8n, &pl, &ppb, &nblk);
   float* partial = stats + (size_t)N * groups * 2;
-  gn_reduce_kernel<0><<<dim3(nblk, N), P * PY, sizeof(float) * 2 * P * PY, s>>>(
-      x, nullptr, nullptr, nullptr, nullptr, partial, HW, C, groups, P, PY, ppb, eps, 0);
+  const int threads = c8n * pl;
+  const size_t smem = sizeof(float) * (size_t)pl * C;
+  (gn_un8() ? gn_reduce_kernel<0, 8> : gn_reduce_kernel<0, 4>)<<<dim3(nblk, N), threads, smem, s>>>(x, nullptr, nullptr, nullptr, nullptr, partial, HW, C, groups,
+                                                           c8n, pl, ppb, eps, 0);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_stats");
   gn_finalize_kernel<<<(N * groups * 2 + 3) / 4, 128, 0, s>>>(partial, stats, nblk, groups, N * groups * 2);
   SDB_COUNT_LAUNCH();
-  const long long total8 = (long long)N * HW * C / 8;
-  gn_apply_kernel<0><<<ew_grid(total8), 256, 0, s>>>(x, nullptr, gamma, beta, stats, nullptr, y, total8, HW, C, groups,
-                                                     eps, act_silu);
+  (gn_un8() ? gn_apply_kernel<0, 8> : gn_apply_kernel<0, 4>)<<<dim3(gn_apply_blocks(HW, pl, N), N), threads, 0, s>>>(x, nullptr, gamma, beta, stats, nullptr, y,
+                                                                             HW, C, groups, c8n, pl, eps, act_silu);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_apply");
   return SDB_OK;
@@ -675,18 +751,19 @@ int groupnorm_forward(const __half* x, const __half* gamma, const __half* beta, 
 int groupnorm_backward(const __half* x, const __half* gamma, const __half* beta, const float* stats, const __half* dy,
                        __half* dx, float* scratch2, int N, int HW, int C, int groups, float eps, int act_silu,
                        cudaStream_t s) {
-  int P, PY, ppb, nblk;
-  gn_geometry(HW, C, N, groups, &P, &PY, &ppb, &nblk);
+  int c8n, pl, ppb, nblk;
+  gn_geometry(HW, C, N, &c8n, &pl, &ppb, &nblk);
   float* partial = scratch2 + (size_t)N * groups * 2;
-  gn_reduce_kernel<1><<<dim3(nblk, N), P * PY, sizeof(float) * 2 * P * PY, s>>>(x, dy, gamma, beta, stats, partial, HW,
-                                                                               C, groups, P, PY, ppb, eps, act_silu);
+  const int threads = c8n * pl;
+  const size_t smem = sizeof(float) * (size_t)pl * C;
+  (gn_un8() ? gn_reduce_kernel<1, 8> : gn_reduce_kernel<1, 4>)<<<dim3(nblk, N), threads, smem, s>>>(x, dy, gamma, beta, stats, partial, HW, C, groups, c8n, pl,
+                                                           ppb, eps, act_silu);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_bwd_reduce");
   gn_finalize_kernel<<<(N * groups * 2 + 3) / 4, 128, 0, s>>>(partial, scratch2, nblk, groups, N * groups * 2);
   SDB_COUNT_LAUNCH();
-  const long long total8 = (long long)N * HW * C / 8;
-  gn_apply_kernel<1><<<ew_grid(total8), 256, 0, s>>>(x, dy, gamma, beta, stats, scratch2, dx, total8, HW, C, groups,
-                                                     eps, act_silu);
+  (gn_un8() ? gn_apply_kernel<1, 8> : gn_apply_kernel<1, 4>)<<<dim3(gn_apply_blocks(HW, pl, N), N), threads, 0, s>>>(x, dy, gamma, beta, stats, scratch2, dx, HW,
+                                                                             C, groups, c8n, pl, eps, act_silu);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_bwd_apply");
   return SDB_OK;
