@@ -29,6 +29,29 @@ CFG_YAML = os.path.join(ROOT, "tests", "configs", "asd_sd_nerf.yaml")
 H = W = 256
 
 
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel families the roofline objects
+    describe, from the newest committed ncu capture (profiles/*_traffic.json, written by tools/summarize_profiles.py from
+    one profiled step of the same workload). Empty when no capture is committed: traffic is then null."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_traffic.json")))
+    if not files:
+        return {}
+    t = json.load(open(files[-1]))
+    out = {}
+    fam = [t[k] for k in ("gemm", "flash_attn") if k in t]
+    if fam:
+        n = sum(f["launches_per_step"] for f in fam)
+        out["tensor"] = sum(f["dram_bytes_per_launch"] * f["launches_per_step"] for f in fam) / n
+    if "render_fwd" in t:
+        out["render_fwd"] = t["render_fwd"]["dram_bytes_per_launch"]
+    if "render_field_bwd" in t:
+        out["render_bwd"] = t["render_field_bwd"]["dram_bytes_per_launch"] + t.get("render_composite_bwd", {}).get(
+            "dram_bytes_per_launch", 0.0)
+    return out
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -373,20 +396,21 @@ def main() -> None:
             dist.destroy_process_group()
         return
     pk = peaks()
+    tr = ncu_traffic()
     gemm_tfs = prof["gemm_tflop_per_step"] / (prof["gemm_ms_per_step"] / 1e3)
     # algorithmic bytes of the render kernels: samples x 16 levels x 8 corners x 2 features x 4 B (SURVEY.md 8d, E = 1)
     rbytes_f = prof["render_samples_kept"] * 1024 + H * W * (24 + 28)
     rbytes_b = 2 * prof["render_samples_kept"] * 1024 + H * W * (24 + 28)
     roof_gemm = {"kernel": "gemm_f16_kernel + flash_attn_f16_kernel (tcgen05 GEMM / implicit conv / fused attention, all launches of one step)", "bound": "tensor",
                  "achieved": gemm_tfs, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tfs / pk["tf_sustained"],
-                 "traffic": None, "ms_per_step": prof["gemm_ms_per_step"], "peak_source": pk["src"] + " sustained bf16"}
+                 "traffic": tr.get("tensor"), "ms_per_step": prof["gemm_ms_per_step"], "peak_source": pk["src"] + " sustained bf16"}
     rb = rbytes_b / 1e9 / (prof["render_bwd_kernel_ms"] / 1e3)
     roof_rbwd = {"kernel": "render_composite_bwd_kernel + render_field_bwd_kernel (tape backward)", "bound": "hbm", "achieved": rb, "peak": pk["hbm"], "unit": "GB/s",
-                 "frac": rb / pk["hbm"], "traffic": None, "ms_per_step": prof["render_bwd_kernel_ms"],
+                 "frac": rb / pk["hbm"], "traffic": tr.get("render_bwd"), "ms_per_step": prof["render_bwd_kernel_ms"],
                  "peak_source": pk["src"] + " copy bandwidth"}
     rf = rbytes_f / 1e9 / (prof["render_fwd_kernel_ms"] / 1e3)
     roof_rfwd = {"kernel": "render_bg_kernel + render_nerf_fwd2_kernel (march + encode + MLPs + composite + tape)", "bound": "hbm", "achieved": rf, "peak": pk["hbm"], "unit": "GB/s",
-                 "frac": rf / pk["hbm"], "traffic": None, "ms_per_step": prof["render_fwd_kernel_ms"],
+                 "frac": rf / pk["hbm"], "traffic": tr.get("render_fwd"), "ms_per_step": prof["render_fwd_kernel_ms"],
                  "peak_source": pk["src"] + " copy bandwidth"}
     roofs = sorted([roof_gemm, roof_rbwd, roof_rfwd], key=lambda r: -r["ms_per_step"])
     line = {

@@ -252,16 +252,80 @@ class RandomMultiviewCameraIterableDataset(RandomCameraIterableDataset):
                 "_fovy_rad": fovy}
 
 
+class RandomCameraDataset:
+    """Evaluation orbit (uncond.py:347-467): n_val_views / n_test_views cameras at eval_elevation_deg,
+    eval_camera_distance, eval_fovy_deg; `val` spreads the azimuths so that the first and last view differ
+    (linspace(0, 360, n+1)[:n]), `test` closes the loop (linspace(0, 360, n)). Camera scalars live on the host; rays are
+    generated on device by `to_device` like the training batches."""
+
+    def __init__(self, cfg: Any, split: str) -> None:
+        self.cfg, self.split = cfg, split
+        n = self.n_views = cfg.n_val_views if split == "val" else cfg.n_test_views
+        azimuth_deg = torch.linspace(0, 360.0, n + 1)[:n] if split == "val" else torch.linspace(0, 360.0, n)
+        elevation_deg = torch.full_like(azimuth_deg, cfg.eval_elevation_deg)
+        camera_distances = torch.full_like(azimuth_deg, cfg.eval_camera_distance)
+        elevation, azimuth = elevation_deg * math.pi / 180, azimuth_deg * math.pi / 180
+        camera_positions = torch.stack([camera_distances * torch.cos(elevation) * torch.cos(azimuth),
+                                        camera_distances * torch.cos(elevation) * torch.sin(azimuth),
+                                        camera_distances * torch.sin(elevation)], dim=-1)
+        up = torch.as_tensor([0, 0, 1], dtype=torch.float32)[None, :].repeat(n, 1)
+        self.c2w = look_at(camera_positions, torch.zeros_like(camera_positions), up)
+        self.fovy = torch.full_like(azimuth_deg, cfg.eval_fovy_deg) * math.pi / 180
+        self.proj_mtx = get_projection_matrix(self.fovy, cfg.eval_width / cfg.eval_height, 0.01, 100.0)
+        self.mvp_mtx = get_mvp_matrix(self.c2w, self.proj_mtx)
+        self.camera_positions = self.light_positions = camera_positions
+        self.elevation_deg, self.azimuth_deg, self.camera_distances = elevation_deg, azimuth_deg, camera_distances
+
+    def __len__(self) -> int:
+        return self.n_views
+
+    def __getitem__(self, index: int) -> Dict[str, Any]:
+        return {"index": index, "mvp_mtx": self.mvp_mtx[index], "c2w": self.c2w[index],
+                "camera_positions": self.camera_positions[index], "light_positions": self.light_positions[index],
+                "elevation": self.elevation_deg[index], "azimuth": self.azimuth_deg[index],
+                "camera_distances": self.camera_distances[index], "height": self.cfg.eval_height,
+                "width": self.cfg.eval_width, "fovy": self.fovy[index], "proj_mtx": self.proj_mtx[index]}
+
+    def collate(self, items: List[Dict[str, Any]]) -> Dict[str, Any]:
+        out = {k: (torch.stack([it[k] for it in items]) if torch.is_tensor(items[0][k])
+                   else torch.as_tensor([it[k] for it in items])) for k in items[0] if k not in ("height", "width")}
+        out.update(height=self.cfg.eval_height, width=self.cfg.eval_width, _fovy_rad=out["fovy"])
+        return out
+
+    def to_device(self, batch: Dict[str, Any], device) -> Dict[str, Any]:
+        return RandomCameraIterableDataset.to_device(self, batch, device)
+
+
 class _CameraDataModule:
     dataset_cls = RandomCameraIterableDataset
+    eval_dataset_cls = RandomCameraDataset
 
     def __init__(self, cfg=None) -> None:
         self.cfg = parse_structured(self.dataset_cls.config_cls, cfg)
-        self.train_dataset = None
+        self.train_dataset = self.val_dataset = self.test_dataset = None
 
     def setup(self, stage=None) -> None:
         if stage in (None, "fit"):
             self.train_dataset = self.dataset_cls(self.cfg)
+        if stage in (None, "fit", "validate"):
+            self.val_dataset = self.eval_dataset_cls(self.cfg, "val")
+        if stage in (None, "test", "predict"):
+            self.test_dataset = self.eval_dataset_cls(self.cfg, "test")
+
+    def _eval_loader(self, ds):
+        bs = int(self.cfg.eval_batch_size)
+        for i in range(0, len(ds), bs):
+            yield ds.collate([ds[j] for j in range(i, min(i + bs, len(ds)))])
+
+    def val_dataloader(self):
+        if self.val_dataset is None:
+            self.setup("validate")
+        return self._eval_loader(self.val_dataset)
+
+    def test_dataloader(self):
+        if self.test_dataset is None:
+            self.setup("test")
+        return self._eval_loader(self.test_dataset)
 
     def train_dataloader(self):
         """Generator of host batches (num_workers=0, batch_size=None in the reference: uncond.py:489-502)."""

@@ -248,6 +248,28 @@ class StableDreamer(BaseSystem):
         return {"loss": loss}
 
 
+    def _eval_images(self, batch) -> Dict[str, Any]:
+        """validation_step / test_step (scaledreamer.py:172-300) up to the image grid: the rendered view, the opacity
+        map and the min-max normalised depth the reference writes to `it{step}-val/{index}.png`. Writing files / videos
+        is the saver's job and stays outside this package; the tensors are returned instead."""
+        out = self(batch)
+        res = {"index": batch["index"], "comp_rgb": out["comp_rgb"], "opacity": out["opacity"]}
+        if "comp_normal" in out:
+            res["comp_normal"] = out["comp_normal"]
+        if "depth" in out:
+            d = out["depth"][0, :, :, 0]
+            res["depth"] = (d - d.min()) / (d.max() - d.min())
+        return res
+
+    def validation_step(self, batch, batch_idx):
+        if self.cfg.visualize_samples:
+            raise NotImplementedError
+        return self._eval_images(batch)
+
+    def test_step(self, batch, batch_idx):
+        return self._eval_images(batch)
+
+
 # ------------------------------------------------------------------------------------------------ trainer
 class Trainer:
     """Minimal fit loop with Lightning's hook order; optional data-parallel gradient averaging over NCCL."""
@@ -284,6 +306,28 @@ class Trainer:
                 p.grad = view
             off += k
         self.dist.all_reduce(self._flat, op=self.dist.ReduceOp.SUM)
+
+    def _evaluate(self, system: BaseSystem, datamodule, split: str) -> List[Dict[str, Any]]:
+        """Lightning's validate / test loop for the evaluation orbit: eval mode (no jitter, no random background, no
+        tape), no autograd, one `*_step` per camera batch."""
+        device = core.get_device()
+        loader = datamodule.val_dataloader() if split == "val" else datamodule.test_dataloader()
+        dataset = datamodule.val_dataset if split == "val" else datamodule.test_dataset
+        was_training = system.training
+        system.eval()
+        outs = []
+        with torch.no_grad():
+            for i, host_batch in enumerate(loader):
+                batch = dataset.to_device(host_batch, device)
+                outs.append(system.validation_step(batch, i) if split == "val" else system.test_step(batch, i))
+        system.train(was_training)
+        return outs
+
+    def validate(self, system: BaseSystem, datamodule) -> List[Dict[str, Any]]:
+        return self._evaluate(system, datamodule, "val")
+
+    def test(self, system: BaseSystem, datamodule) -> List[Dict[str, Any]]:
+        return self._evaluate(system, datamodule, "test")
 
     def fit(self, system: BaseSystem, datamodule) -> None:
         device = core.get_device()

@@ -130,3 +130,42 @@ def test_mvdream_training_step_end_to_end(cuda_device):
     g = system.guidance
     assert g.unet_cfg["num_frames"] == 4 and g.buf["unet_x"].shape[0] == 12  # (cond, uncond, t+dt) x 4 views
     assert int(g._last["t"].unique().numel()) == 1                            # one timestep for the whole view batch
+
+
+def test_validation_and_test_loops(cuda_device):
+    """Evaluation orbit through the system (scaledreamer.py:172-300): eval-mode renders are deterministic (no jitter, no
+    random background, nothing taped), match a direct eval-mode renderer call on the same camera, and leave the module
+    in training mode afterwards."""
+    import scaledreamer_b200 as sd
+    from scaledreamer_b200.systems import Trainer
+
+    torch.manual_seed(3)
+    cfg = sd.load_config(CFG, cli_args=["system.prompt_processor.prompt=a DSLR photo of a hamburger",
+                                        "data.eval_height=40", "data.eval_width=56", "data.n_val_views=3",
+                                        "data.n_test_views=5"])
+    dm = sd.find(cfg.data_type)(cfg.data)
+    system = sd.find(cfg.system_type)(cfg.system)
+    system.train()
+    system.do_update_step(0, 0)  # warm-up occupancy refresh
+    tr = Trainer(**cfg.trainer)
+    v1, v2 = tr.validate(system, dm), tr.validate(system, dm)
+    assert len(v1) == 3 and system.training
+    for a, b in zip(v1, v2):
+        assert a["comp_rgb"].shape == (1, 40, 56, 3) and a["opacity"].shape == (1, 40, 56, 1)
+        assert a["depth"].shape == (40, 56) and float(a["depth"].min()) == 0.0 and float(a["depth"].max()) == 1.0
+        assert torch.equal(a["comp_rgb"], b["comp_rgb"]) and torch.equal(a["opacity"], b["opacity"])
+        assert not a["comp_rgb"].requires_grad
+    assert [int(o["index"][0]) for o in v1] == [0, 1, 2]
+    assert not torch.equal(v1[0]["comp_rgb"], v1[1]["comp_rgb"])  # different azimuths
+    t = tr.test(system, dm)
+    assert len(t) == 5
+    # test view 0 and the closing view (azimuth 360) see the same image; val view 0 is the same camera
+    assert (t[0]["comp_rgb"] - t[4]["comp_rgb"]).abs().max() < 2e-3
+    assert torch.equal(t[0]["comp_rgb"], v1[0]["comp_rgb"])
+    system.eval()
+    ds = dm.val_dataset
+    batch = ds.to_device(ds.collate([ds[1]]), cuda_device)
+    with torch.no_grad():
+        direct = system.renderer(**batch)
+    assert torch.equal(direct["comp_rgb"], v1[1]["comp_rgb"])
+    assert system.renderer.randomized is False
