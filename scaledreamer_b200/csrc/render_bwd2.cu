@@ -13,6 +13,8 @@
 //
 // Compositing gradient with the per-ray forward outputs saved: dL/dsigma_i = delta_i (g_i (T_i - w_i) - (R - P_i)),
 //   g_i = dL/dw_i = <gC, c_i> + gD t_i + gO,  R = <gC, C_fg> + gO op + gD depth,  P_i = sum_{j<=i} g_j w_j.
+#include <cstdlib>
+
 #include "render_tape.cuh"
 
 namespace {
@@ -213,7 +215,7 @@ struct FbSmem {
 
 __global__ void __launch_bounds__(kFbThreads, 2)
 render_field_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, const FieldGrads g,
-                        const RenderTape tape) {
+                        const RenderTape tape, const int scatter_on) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FbSmem& s = *reinterpret_cast<FbSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -406,24 +408,49 @@ render_field_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, 
     if (tile + (int)gridDim.x < n_tiles) issue_tile(tile + gridDim.x, buf ^ 1);
 
     // ---- scatter: this lane owns levels 2 lj, 2 lj + 1 of samples 8 li + a ----
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      const int sl = warp * 32 + 8 * li + a;
-      if (base + sl >= n) continue;
-      const float x = s.pos[buf][0][sl], y = s.pos[buf][1][sl], z = s.pos[buf][2][sl];
+    // The lane's eight samples are consecutive kept samples of (almost always) one ray, a step apart: on the coarse
+    // levels they fall into the same cell several times in a row. Contributions are summed per corner in registers
+    // and sent as one red.v2 per corner when the cell changes (levels 0-5 send 2-4 runs instead of 8 samples; the
+    // fine levels change cell every sample and behave as before).
+    if (scatter_on) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const float gx = dE[a][2 * q], gy = dE[a][2 * q + 1];
-        if (gx == 0.f && gy == 0.f) continue;
-        const LevelCell c = level_cell(lv_scale[q], x, y, z);
         float2* tl = g_table + lv_off[q];
+        uint32_t cx = 0u, cy = 0u, cz = 0u;
+        float ax[8], ay[8];
+        bool open = false;
+        auto flush = [&]() {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t idx = grid_index(lv_hashed[q], lv_res[q], lv_size[q], c.ix + (k & 1), c.iy + ((k >> 1) & 1),
-                                          c.iz + ((k >> 2) & 1));
-          const float w = corner_weight(c, k);
-          atomicAdd(tl + idx, make_float2(w * gx, w * gy));  // red.global.add.v2.f32
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t idx = grid_index(lv_hashed[q], lv_res[q], lv_size[q], cx + (k & 1), cy + ((k >> 1) & 1),
+                                            cz + ((k >> 2) & 1));
+            atomicAdd(tl + idx, make_float2(ax[k], ay[k]));  // red.global.add.v2.f32
+          }
+        };
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int sl = warp * 32 + 8 * li + a;
+          const float gx = dE[a][2 * q], gy = dE[a][2 * q + 1];
+          if (base + sl >= n || (gx == 0.f && gy == 0.f)) continue;
+          const LevelCell c = level_cell(lv_scale[q], s.pos[buf][0][sl], s.pos[buf][1][sl], s.pos[buf][2][sl]);
+          if (open && (c.ix != cx || c.iy != cy || c.iz != cz)) {
+            flush();
+            open = false;
+          }
+          if (!open) {
+            cx = c.ix, cy = c.iy, cz = c.iz;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ax[k] = ay[k] = 0.f;
+            open = true;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float w = corner_weight(c, k);
+            ax[k] = fmaf(w, gx, ax[k]);
+            ay[k] = fmaf(w, gy, ay[k]);
+          }
         }
+        if (open) flush();
       }
     }
   }
@@ -478,7 +505,8 @@ int launch_render_bwd2(const FieldMeta& f, const FieldPtrs& p, const FieldGrads&
   SDB_CHECK_LAUNCH("render_composite_bwd");
   const int max_tiles = (tape.capacity + kFbTile - 1) / kFbTile;
   const int grid_b = max(1, min(kNumSMs * 2, max_tiles));
-  render_field_bwd_kernel<<<grid_b, kFbThreads, sizeof(FbSmem), stream>>>(f, p, g, tape);
+  static const int scatter_on = getenv("SDB_FB_NOSCATTER") ? 0 : 1;  // diagnostics: time the MLP part alone
+  render_field_bwd_kernel<<<grid_b, kFbThreads, sizeof(FbSmem), stream>>>(f, p, g, tape, scatter_on);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("render_field_bwd");
   return SDB_OK;
