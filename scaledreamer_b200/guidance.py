@@ -15,7 +15,7 @@ from typing import Any, Optional
 
 import torch
 
-from . import core, lib as L, nets
+from . import checkpoints, core, lib as L, nets
 from .core import C, BaseObject, register
 
 NUM_TRAIN_TIMESTEPS = 1000
@@ -84,9 +84,17 @@ class _ASDGuidanceBase(BaseObject):
 
     # ---- network set-up (lazy: the batch size is only known at the first call) ----
     def _load_weights(self, vae: nets.VaeEncoder, unet: nets.UNet):
-        """Pretrained checkpoints in the vendored-LDM key layout load by name; none exist on this box, so the
-        default is seeded synthetic parameters."""
+        """Pretrained weights: a diffusers pipeline directory (unet/, vae/; keys renamed by checkpoints.py) or a
+        single LDM-layout checkpoint file load by name; none exist on this box, so the default is seeded synthetic
+        parameters."""
         path = getattr(self.cfg, "ckpt_path", None) or getattr(self.cfg, "pretrained_model_name_or_path", "")
+        if checkpoints.is_diffusers_dir(path):  # the layout StableDiffusionPipeline.from_pretrained reads (:68-114)
+            usd, vsd = checkpoints.load_diffusers_pipeline(path)
+            unet.load_state_dict(usd)
+            vae.load_state_dict({k: v for k, v in vsd.items() if k.startswith("encoder.")})
+            self.quant_w = vsd["quant_conv.weight"].reshape(8, 8).float().to(self.device).contiguous()
+            self.quant_b = vsd["quant_conv.bias"].float().to(self.device).contiguous()
+            return
         if path and os.path.isfile(path):
             sd = torch.load(path, map_location="cpu")
             sd = sd.get("state_dict", sd)
