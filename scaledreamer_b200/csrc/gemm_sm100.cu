@@ -36,7 +36,7 @@ struct Cfg {
   static constexpr int kBTileBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   // two CTAs share an SM (one CTA's epilogue overlaps the other's main loop): <= ~110 KB of ring per CTA
-  static constexpr int kStages = DEEP ? (BN <= 80 ? 8 : 6) : (BN <= 80 ? 4 : 3);
+  static constexpr int kStages = DEEP ? (BN <= 80 ? 8 : (BN <= 160 ? 6 : 4)) : (BN <= 80 ? 4 : 3);
   // DEEP: two accumulators in tensor memory (the MMA warp fills one while the epilogue drains the other) and two sets
   // of four epilogue warps that take alternate 32-column chunks of a tile.
   static constexpr int kAccBufs = DEEP ? 2 : 1;
@@ -485,13 +485,25 @@ int launch(const GemmPlan& plan, cudaStream_t stream) {
 
 }  // namespace
 
+// 128 x 256 tiles move 48 KB per K-block for 4.2 MFLOP (87 FLOP per operand byte, against 71 for 128 x 160 and 64 for
+// 128 x 128): the main loop is bound by L2 -> shared-memory delivery, so wide-N layers with a long K run on the wider
+// tile (one CTA per SM, two accumulators = all 512 tensor-memory columns).
+bool wide_tile(int M, int N, int K) {
+  static const bool on = !(getenv("SDB_GEMM_BN256") && atoi(getenv("SDB_GEMM_BN256")) == 0);
+  // only when the wider tiles still fill every SM: with fewer the extra CTAs of the narrow tiling win
+  // (measured: 1280 x 1280 x 1280, 50 wide tiles, 0.54 ms vs 0.45 ms; 65536 x 256 x 2304, 512 tiles, 0.46 vs 0.53 ms)
+  return on && N % 256 == 0 && K >= 1024 && (long long)((M + kBM - 1) / kBM) * (N / 256) >= kNumSMs;
+}
+
 int gemm_splits(int M, int N, int K) {
-  const int bn = N % 160 == 0 ? 160 : (N <= 64 ? 64 : 128);
+  const bool wide = wide_tile(M, N, K);
+  const int bn = wide ? 256 : (N % 160 == 0 ? 160 : (N <= 64 ? 64 : 128));
+  const int slots = wide ? kNumSMs : 2 * kNumSMs;  // the wide tile runs one CTA per SM
   const int tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
   const int nkb = (K + kBK - 1) / kBK;
-  // below one CTA per SM the TMA ring of a lone CTA is latency-bound: split K until ~2 CTAs per SM are in flight
+  // below one CTA per SM the TMA ring of a lone CTA is latency-bound: split K until the CTA slots are filled
   if (tiles >= kNumSMs || nkb < 48) return 1;
-  int sp = std::min(std::min(2 * kNumSMs / tiles, nkb / 4), 16);
+  int sp = std::min(std::min(slots / tiles, nkb / 4), 16);
   if (sp <= 1) return 1;
   const int per = (nkb + sp - 1) / sp;
   return (nkb + per - 1) / per;  // every split owns at least one K block
@@ -499,11 +511,12 @@ int gemm_splits(int M, int N, int K) {
 
 namespace {
 
-int pick_bn(int N) {
+int pick_bn(int M, int N, int K) {
   if (const char* e = getenv("SDB_GEMM_BN")) {  // diagnostics: force a tile width
     const int bn = atoi(e);
     if (bn == 64 || bn == 80 || bn == 128 || bn == 160) return bn;
   }
+  if (wide_tile(M, N, K)) return 256;
   if (N % 160 == 0) return 160;
   if (N <= 64) return 64;
   return 128;
@@ -615,7 +628,7 @@ int plan_gemm(GemmPlan* plan, const __half* A, long long lda, const __half* B, l
     return SDB_ERR_ARG;
   }
   memset(plan, 0, sizeof(*plan));
-  plan->bn = pick_bn(N);
+  plan->bn = pick_bn(M, N, K);
   GemmParams& p = plan->p;
   p.M = M;
   p.N = N;
@@ -676,7 +689,7 @@ int plan_conv3x3(GemmPlan* plan, const __half* x, int N, int H, int W, int Cin, 
     }
   }
   memset(plan, 0, sizeof(*plan));
-  plan->bn = pick_bn(Cout);
+  plan->bn = pick_bn(N * H * W, Cout, 9 * Cin);
   GemmParams& p = plan->p;
   p.M = N * H * W;
   p.N = Cout;
@@ -851,6 +864,7 @@ int run_gemm(const GemmPlan& plan, cudaStream_t stream) {
     case 80: return launch<80>(plan, stream);
     case 128: return launch<128>(plan, stream);
     case 160: return launch<160>(plan, stream);
+    case 256: return launch_v<256, true>(plan, stream);
   }
   sdb_set_error("gemm: unsupported BN %d", plan.bn);
   return SDB_ERR_UNSUPPORTED;

@@ -24,7 +24,11 @@ def rnd(*shape, dev, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 320, 320), (300, 200, 136), (4096, 1280, 2560),
-                                   (77, 640, 1024), (5, 64, 72)])
+                                   (77, 640, 1024), (5, 64, 72),
+                                   # 128 x 256 tiles (N % 256 == 0, K >= 1024, >= 148 tiles): ragged M, K tail, several
+                                   # tiles per CTA; and the same N / K below the tile-count threshold
+                                   (19000, 512, 1160), (40000, 256, 1088), (6400, 768, 1024), (300, 512, 1024),
+                                   (256, 1280, 11520)])
 def test_gemm_plain(cuda_device, M, N, K):
     from scaledreamer_b200 import nn_ops as O
 
@@ -35,13 +39,13 @@ def test_gemm_plain(cuda_device, M, N, K):
     assert rel(out, ref) < 1e-3
 
 
-def test_gemm_epilogue_and_fp32_out(cuda_device):
+@pytest.mark.parametrize("M,N,K", [(512, 320, 640), (19072, 256, 1152)])
+def test_gemm_epilogue_and_fp32_out(cuda_device, M, N, K):
     from scaledreamer_b200 import nn_ops as O
 
-    M, N, K = 512, 320, 640
     a, b = rnd(M, K, dev=cuda_device, seed=1, scale=0.5), rnd(N, K, dev=cuda_device, seed=2, scale=0.1)
     bias, res = rnd(N, dev=cuda_device, seed=3), rnd(M, N, dev=cuda_device, seed=4)
-    rowbias = torch.randn(4, N, device=cuda_device)
+    rowbias = torch.randn(M // 128, N, device=cuda_device)
     ref = a.float() @ b.float().T * 0.7 + bias.float() + rowbias.repeat_interleave(128, 0)
     out = O.gemm(a, b, bias=bias, rowbias=rowbias, rows_per_group=128, residual=res, alpha=0.7, act="silu", out_fp32=True)
     assert rel(out, F.silu(ref) + res.float()) < 1e-4
@@ -58,7 +62,8 @@ def test_gemm_batched(cuda_device):
 
 
 @pytest.mark.parametrize("N,H,W,Cin,Cout", [(1, 16, 16, 64, 128), (2, 32, 32, 128, 320), (5, 8, 8, 320, 320),
-                                            (3, 4, 4, 128, 64), (1, 128, 128, 64, 128), (1, 256, 256, 128, 128)])
+                                            (3, 4, 4, 128, 64), (1, 128, 128, 64, 128), (1, 256, 256, 128, 128),
+                                            (1, 256, 256, 128, 256), (2, 16, 16, 256, 512), (5, 8, 8, 1280, 1280)])
 def test_conv3x3(cuda_device, N, H, W, Cin, Cout):
     from scaledreamer_b200 import nn_ops as O
 
