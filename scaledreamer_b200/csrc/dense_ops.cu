@@ -303,11 +303,60 @@ void gn_geometry(int HW, int C, int N, int* C8N, int* PL, int* ppb, int* nblk) {
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
+// Warp per row. Rows of up to 32 * 8 * LN_ITEMS channels (multiple of 8) are read ONCE with 16-byte loads and stay in
+// registers between the mean / variance / apply passes; wider rows fall back to three strided passes.
+constexpr int LN_ITEMS = 5;  // 1280 channels
 __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                                  const __half* __restrict__ beta, __half* __restrict__ y, int rows, int C, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  if ((C & 7) == 0 && C <= 256 * LN_ITEMS) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * C);
+    const int n8 = C >> 3;
+    float v[LN_ITEMS][8];
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < LN_ITEMS; ++it) {
+      const int i = lane + 32 * it;
+      uint4 raw = make_uint4(0, 0, 0, 0);
+      if (i < n8) raw = xr[i];
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = __half22float2(h2[e]);
+        v[it][2 * e] = t.x, v[it][2 * e + 1] = t.y;
+        s += t.x + t.y;
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < LN_ITEMS; ++it)
+      if (lane + 32 * it < n8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss += (v[it][e] - mean) * (v[it][e] - mean);
+      }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * C);
+#pragma unroll
+    for (int it = 0; it < LN_ITEMS; ++it) {
+      const int i = lane + 32 * it;
+      if (i >= n8) continue;
+      const uint4 gr = reinterpret_cast<const uint4*>(gamma)[i], br = reinterpret_cast<const uint4*>(beta)[i];
+      const __half2* g2 = reinterpret_cast<const __half2*>(&gr);
+      const __half2* b2 = reinterpret_cast<const __half2*>(&br);
+      uint4 o;
+      __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 g = __half22float2(g2[e]), b = __half22float2(b2[e]);
+        o2[e] = __floats2half2_rn((v[it][2 * e] - mean) * rstd * g.x + b.x, (v[it][2 * e + 1] - mean) * rstd * g.y + b.y);
+      }
+      yr[i] = o;
+    }
+    return;
+  }
   const __half2* xr = reinterpret_cast<const __half2*>(x + (size_t)row * C);
   const int n2 = C / 2;
   float s = 0.f;

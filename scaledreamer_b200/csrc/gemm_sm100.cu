@@ -550,11 +550,28 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const GemmParams p
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / n4), nb = (int)(i % n4) * 4;
     float f[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < p.splits; ++s) {
-      const float* w = p.ws + ((long long)s * p.M + m) * p.N + nb;
+    const long long plane = (long long)p.M * p.N;
+    const float* w0 = p.ws + (long long)m * p.N + nb;
+    if (nb + 4 <= p.N && (p.N & 3) == 0) {
+      // four planes in flight (the loop is latency-bound otherwise); the additions keep the plane order
+      int s = 0;
+      for (; s + 4 <= p.splits; s += 4) {
+        float4 v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (nb + j < p.N) f[j] += w[j];
+        for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(w0 + (s + u) * plane);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) f[0] += v[u].x, f[1] += v[u].y, f[2] += v[u].z, f[3] += v[u].w;
+      }
+      for (; s < p.splits; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(w0 + s * plane);
+        f[0] += v.x, f[1] += v.y, f[2] += v.z, f[3] += v.w;
+      }
+    } else {
+      for (int s = 0; s < p.splits; ++s) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (nb + j < p.N) f[j] += w0[s * plane + j];
+      }
     }
     const float* rowb = p.rowbias ? p.rowbias + (long long)(m / p.rows_per_group) * p.rowbias_ld : nullptr;
 #pragma unroll

@@ -151,9 +151,11 @@ def test_groupnorm_forward_backward(cuda_device, N, HW, C, silu):
 def test_layernorm_geglu_upsample(cuda_device):
     from scaledreamer_b200 import nn_ops as O
 
-    x = rnd(300, 640, dev=cuda_device, seed=1)
-    g, b = rnd(640, dev=cuda_device, seed=2), rnd(640, dev=cuda_device, seed=3)
-    assert rel(O.layernorm(x, g, b), F.layer_norm(x.float(), (640,), g.float(), b.float())) < 1e-3
+    # register-resident rows (C <= 1280, incl. widths that leave lanes idle) and the strided fallback (wider / C % 8 != 0)
+    for C in (640, 320, 1280, 8, 264, 2560, 1284):
+        x = rnd(301, C, dev=cuda_device, seed=1) + 0.5
+        g, b = rnd(C, dev=cuda_device, seed=2), rnd(C, dev=cuda_device, seed=3)
+        assert rel(O.layernorm(x, g, b), F.layer_norm(x.float(), (C,), g.float(), b.float())) < 1e-3, C
     xg = rnd(100, 2 * 1280, dev=cuda_device, seed=4)
     a, gate = xg.float().chunk(2, -1)
     assert rel(O.geglu(xg), a * F.gelu(gate)) < 1e-3
