@@ -71,7 +71,7 @@ class PromptProcessorOutput:
         into the guidance's persistent buffers: one launch, no host sync."""
         emb, unc = self.tables(bool(pc.view_dependent))
         L.check(L.load().sdb_asd_text_embeddings(C_.byref(pc), L.ptr(emb), L.ptr(unc), L.ptr(elevation), L.ptr(azimuth),
-                                                 elevation.shape[0], 77, emb.shape[-1], L.ptr(ctx), L.ptr(neg_w),
+                                                 elevation.shape[0], emb.shape[-2], emb.shape[-1], L.ptr(ctx), L.ptr(neg_w),
                                                  L.stream_ptr()), "sdb_asd_text_embeddings")
 
     def _run(self, elevation, azimuth, view_dependent, perp_neg):
@@ -79,13 +79,14 @@ class PromptProcessorOutput:
         dev = self.text_embeddings_vd.device
         pc = self.prompt_cfg_c(view_dependent, perp_neg)
         n_rows = 5 * B if perp_neg else 3 * B
-        ctx = torch.empty(n_rows, 77, self.text_embeddings_vd.shape[-1], device=dev, dtype=torch.float16)
+        ctx = torch.empty(n_rows, self.text_embeddings_vd.shape[-2], self.text_embeddings_vd.shape[-1], device=dev,
+                          dtype=torch.float16)
         neg_w = torch.zeros(B, 2, device=dev)
         el = elevation.to(dev, torch.float32).contiguous()
         az = azimuth.to(dev, torch.float32).contiguous()
         emb, unc = self.tables(view_dependent)
-        L.check(L.load().sdb_asd_text_embeddings(C_.byref(pc), L.ptr(emb), L.ptr(unc), L.ptr(el), L.ptr(az), B, 77,
-                                                 emb.shape[-1], L.ptr(ctx), L.ptr(neg_w), L.stream_ptr()),
+        L.check(L.load().sdb_asd_text_embeddings(C_.byref(pc), L.ptr(emb), L.ptr(unc), L.ptr(el), L.ptr(az), B,
+                                                 emb.shape[-2], emb.shape[-1], L.ptr(ctx), L.ptr(neg_w), L.stream_ptr()),
                 "sdb_asd_text_embeddings")
         return ctx, neg_w
 
