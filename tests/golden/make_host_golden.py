@@ -11,7 +11,14 @@ math and inert stand-ins for the type annotations:
     threestudio/models/prompt_processors/base.py    DirectionConfig, PromptProcessorOutput, shift_azimuth_deg, the
                                                     `self.directions = [...]` list and the Perp-Neg defaults of
                                                     PromptProcessor.Config
-Output: tests/golden/host_golden.pt (a few tens of kB).
+    threestudio/models/guidance/stable_diffusion_asd_guidance.py   the methods __call__, get_latents, get_t_plus, get_eps
+                                                    of the SD ASD guidance, bound to a stand-in object whose UNet is a
+                                                    recorded random tensor and whose scheduler.add_noise is q_sample on the
+                                                    LDM linear beta schedule (extern/mvdream/ldm/.../util.py:37-40)
+    threestudio/models/guidance/mvdream_asd_guidance.py   __call__, get_latents, get_t_plus, get_camera_cond of the
+                                                    multi-view guidance with extern/mvdream/camera_utils.py normalize_camera,
+                                                    same stand-ins (model.q_sample = q_sample, model.apply_model = recorded)
+Output: tests/golden/host_golden.pt (about 0.5 MB).
 """
 import ast
 import math
@@ -74,6 +81,156 @@ def prompt_pieces(ns):
     assert len(lists) == 2
     expr = ast.get_source_segment(s, lists[1].value)
     return defaults, expr
+
+
+def methods(path, cls_name, names):
+    s, tree = _src(path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls_name)
+    out = {}
+    for n in cls.body:
+        if isinstance(n, ast.FunctionDef) and n.name in names:
+            body = "\n".join(s.splitlines()[n.lineno - 1:n.end_lineno])  # without decorators (autocast wrappers)
+            out[n.name] = "\n".join(line[4:] for line in body.splitlines())
+    assert set(out) == set(names), set(names) - set(out)
+    return out
+
+
+class _RecordingTorch:
+    """`torch` as the extracted methods see it: every random draw is recorded so the tests can replay it."""
+
+    def __init__(self):
+        self.draws = {}
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    def randn_like(self, x):
+        self.draws["noise"] = torch.randn_like(x)
+        return self.draws["noise"]
+
+    def randint(self, *a, **k):
+        self.draws["t"] = torch.randint(*a, **k)
+        return self.draws["t"]
+
+    def rand(self, *a, **k):
+        self.draws["u"] = torch.rand(*a, **k)
+        return self.draws["u"]
+
+
+def guidance_case(ns, prompt_utils, elevation, azimuth, dist):
+    """SDTimestepShiftedScoreDistillationGuidance.__call__ (:211-292) with rgb_as_latents=True on 64x64x4 inputs."""
+    gns = dict(ns)
+    rec = _RecordingTorch()
+    gns["torch"] = rec
+    gns["nn"] = torch.nn
+    gns["PromptProcessorOutput"] = ns["PromptProcessorOutput"]
+    top_level(f"{REF}/utils/ops.py", ["perpendicular_component"], gns)
+    src = methods(f"{REF}/models/guidance/stable_diffusion_asd_guidance.py",
+                  "SDTimestepShiftedScoreDistillationGuidance", ["__call__", "get_latents", "get_t_plus", "get_eps"])
+    for code in src.values():
+        exec(compile(code, "stable_diffusion_asd_guidance.py", "exec"), gns)
+    import numpy as np
+
+    lns = {"torch": torch, "np": np}
+    top_level("/root/reference/extern/mvdream/ldm/modules/diffusionmodules/util.py", ["make_beta_schedule"], lns)
+    betas = torch.as_tensor(lns["make_beta_schedule"]("linear", 1000, linear_start=0.00085, linear_end=0.0120))
+    alphas = torch.cumprod(1.0 - betas, dim=0).float()
+    B = elevation.shape[0]
+    gen = torch.Generator().manual_seed(21)
+    unet_out = torch.randn(5 * B, 4, 64, 64, generator=gen)
+    seen = {}
+
+    class Guidance:
+        pass
+
+    for name in src:
+        setattr(Guidance, name, gns[name])
+
+    def forward_unet(self, unet, latents, t, encoder_hidden_states):
+        seen.update(unet_x=latents.clone(), unet_t=t.clone(), ctx=encoder_hidden_states.clone())
+        return unet_out
+
+    Guidance.forward_unet = forward_unet
+    g = Guidance()
+    g.cfg = types.SimpleNamespace(guidance_scale=7.5, guidance_perp_neg=-0.5, plus_ratio=0.1, plus_random=True,
+                                  weighting_strategy="sds", view_dependent_prompting=True)
+    g.use_perp_neg, g.device, g.unet = True, torch.device("cpu"), None
+    g.num_train_timesteps, g.min_step, g.max_step, g.alphas, g.grad_clip_val = 1000, 20, 980, alphas, None
+    g.scheduler = types.SimpleNamespace(add_noise=lambda x, n, t: alphas[t].sqrt().view(-1, 1, 1, 1) * x
+                                        + (1 - alphas[t]).sqrt().view(-1, 1, 1, 1) * n)
+    latents = (torch.randn(B, 64, 64, 4, generator=gen) * 0.8).requires_grad_(True)  # "rgb" in BHWC, used as latents
+    torch.manual_seed(77)
+    out = g(latents, prompt_utils, elevation, azimuth, dist, rgb_as_latents=True)
+    out["loss_asd"].backward()
+    # the UNet stand-in output is reproducible from its seed (torch.Generator().manual_seed(21), drawn before the
+    # latents); a strided sample of it and of the UNet input batch is kept to check the replay
+    return {"latents_bhwc": latents.detach(), "noise": rec.draws["noise"], "t": rec.draws["t"], "u": rec.draws["u"],
+            "t_plus": seen["unet_t"][-B:].long(), "unet_t": seen["unet_t"], "ctx": seen["ctx"],
+            "unet_x_sample": seen["unet_x"].flatten()[::97].clone(), "unet_out_seed": 21,
+            "unet_out_sample": unet_out.flatten()[::97].clone(), "alphas_cumprod": alphas,
+            "loss_asd": out["loss_asd"].detach(), "grad_norm": out["grad_norm"].detach(),
+            "grad_bhwc": latents.grad.clone(), "min_step": 20, "max_step": 980, "guidance_scale": 7.5,
+            "guidance_perp_neg": -0.5, "plus_ratio": 0.1, "elevation": elevation, "azimuth": azimuth}
+
+
+def mv_guidance_case(ns, prompt_utils, c2w3):
+    """MVDreamTimestepShiftedScoreDistillationGuidance.__call__ (mvdream_asd_guidance.py:167-304): 4 views of one
+    object, one shared timestep, plain CFG, camera conditioning."""
+    gns = dict(ns)
+    rec = _RecordingTorch()
+    gns["torch"] = rec
+    gns["PromptProcessorOutput"] = ns["PromptProcessorOutput"]
+    import numpy as np
+
+    cns = {"torch": torch, "np": np}
+    top_level("/root/reference/extern/mvdream/camera_utils.py", ["normalize_camera"], cns)
+    gns["normalize_camera"] = cns["normalize_camera"]
+    src = methods(f"{REF}/models/guidance/mvdream_asd_guidance.py", "MVDreamTimestepShiftedScoreDistillationGuidance",
+                  ["__call__", "get_latents", "get_t_plus", "get_camera_cond"])
+    for code in src.values():
+        exec(compile(code, "mvdream_asd_guidance.py", "exec"), gns)
+    lns = {"torch": torch, "np": np}
+    top_level("/root/reference/extern/mvdream/ldm/modules/diffusionmodules/util.py", ["make_beta_schedule"], lns)
+    betas = torch.as_tensor(lns["make_beta_schedule"]("linear", 1000, linear_start=0.00085, linear_end=0.0120))
+    alphas = torch.cumprod(1.0 - betas, dim=0).float()
+    B = 4
+    gen = torch.Generator().manual_seed(33)
+    unet_out = torch.randn(3 * B, 4, 32, 32, generator=gen)
+    seen = {}
+
+    class Guidance:
+        pass
+
+    for name in src:
+        setattr(Guidance, name, gns[name])
+    g = Guidance()
+    g.cfg = types.SimpleNamespace(guidance_scale=7.5, plus_ratio=0.1, plus_random=True, weighting_strategy="sds",
+                                  view_dependent_prompting=False, camera_condition_type="rotation", n_view=4)
+    g.device, g.num_train_timesteps, g.min_step, g.max_step, g.alphas, g.grad_clip_val = \
+        torch.device("cpu"), 1000, 20, 980, alphas, None
+
+    def apply_model(x, t, context):
+        seen.update(unet_x=x.clone(), unet_t=t.clone(), ctx=context["context"].clone(), camera=context["camera"].clone(),
+                    num_frames=context["num_frames"])
+        return unet_out
+
+    g.model = types.SimpleNamespace(
+        q_sample=lambda x, t, noise: alphas[t].sqrt().view(-1, 1, 1, 1) * x + (1 - alphas[t]).sqrt().view(-1, 1, 1, 1) * noise,
+        apply_model=apply_model)
+    c2w = torch.cat([c2w3, c2w3[:1].flip(-1)], 0).clone()
+    c2w[:, 3, :] = torch.tensor([0.0, 0.0, 0.0, 1.0])
+    c2w[:, :3, 3] *= torch.tensor([0.7, 1.3, 2.0, 1.0])[:, None]
+    latents = (torch.randn(B, 32, 32, 4, generator=gen) * 0.8).requires_grad_(True)
+    el, az, dist = torch.tensor([15.0] * 4), torch.tensor([-100.0, -10.0, 80.0, 170.0]), torch.full((4,), 1.1)
+    torch.manual_seed(78)
+    out = g(latents, prompt_utils, el, az, dist, c2w.clone(), rgb_as_latents=True)
+    out["loss_asd"].backward()
+    return {"latents_bhwc": latents.detach(), "noise": rec.draws["noise"], "t": rec.draws["t"], "u": rec.draws["u"],
+            "unet_t": seen["unet_t"], "ctx": seen["ctx"], "camera": seen["camera"], "num_frames": seen["num_frames"],
+            "c2w": c2w, "unet_x_sample": seen["unet_x"].flatten()[::53].clone(), "unet_out_seed": 33,
+            "unet_out_sample": unet_out.flatten()[::53].clone(), "alphas_cumprod": alphas,
+            "loss_asd": out["loss_asd"].detach(), "grad_norm": out["grad_norm"].detach(),
+            "grad_bhwc": latents.grad.clone(), "min_step": 20, "max_step": 980, "guidance_scale": 7.5, "plus_ratio": 0.1}
 
 
 def main():
@@ -139,6 +296,8 @@ def main():
                       "global": out.get_text_embeddings(elevation, azimuth, dist, False).contiguous(),
                       "perp_neg": pn, "neg_weights": w.float(),
                       "decay_check": float(ns["shifted_expotional_decay"](1.0, 0.5, -0.606, torch.tensor(0.25)))}
+    gold["guidance"] = guidance_case(ns, out, elevation[[3, 8]], azimuth[[3, 8]], dist[[3, 8]])
+    gold["mv_guidance"] = mv_guidance_case(ns, out, gold["rays"]["c2w"])
     torch.save(gold, OUT)
     print("wrote", OUT, len(cases), "C cases;", "perp-neg", tuple(pn.shape), tuple(w.shape), coeff)
 

@@ -60,3 +60,106 @@ def test_perp_neg_embeddings_and_weights_match_reference(cuda_device):
     torch.testing.assert_close(w.cpu(), p["neg_weights"], atol=1e-6, rtol=1e-5)
     overhead = p["elevation"] > p["overhead_threshold"]
     assert overhead.any() and (w.cpu()[overhead] == 0).all()
+
+
+def test_asd_glue_kernels_match_reference_call(cuda_device):
+    """sdb_asd_t_plus / sdb_asd_prologue / sdb_asd_epilogue against the reference's own guidance __call__ (run with a
+    recorded UNet output, tests/golden/make_host_golden.py): timestep shift, q-sample batch assembly, Perp-Neg CFG,
+    w(t), loss, grad norm and the gradient that reaches the latents. The posterior is made a point mass (identity
+    quant_conv for the mean, log-variance -30, zero posterior noise, scaling factor 1) so that z equals the golden
+    latents."""
+    from scaledreamer_b200 import lib as L
+
+    lib = L.load()
+    g = GOLD["guidance"]
+    dev = cuda_device
+    B, HW, R = g["t"].shape[0], 64 * 64, 4
+    t = g["t"].to(dev, torch.int32)
+    u = g["u"].to(dev, torch.float32)
+    tp = torch.empty(B, dtype=torch.int32, device=dev)
+    L.check(lib.sdb_asd_t_plus(L.ptr(t), L.ptr(u), B, g["plus_ratio"], g["min_step"], 1000, L.ptr(tp), L.stream_ptr()), "t_plus")
+    assert torch.equal(tp.cpu().long(), g["t_plus"])
+
+    h = torch.cat([g["latents_bhwc"].reshape(B, HW, 4), torch.zeros(B, HW, 4)], -1).to(dev).contiguous()
+    qw = torch.zeros(8, 8)
+    qw[:4, :4] = torch.eye(4)
+    qb = torch.cat([torch.zeros(4), torch.full((4,), -30.0)])
+    qw, qb = qw.to(dev), qb.to(dev)
+    eps_post = torch.zeros(B, HW, 4, device=dev)
+    noise = g["noise"].permute(0, 2, 3, 1).reshape(B, HW, 4).to(dev).contiguous()
+    ac = g["alphas_cumprod"].to(dev)
+    latents = torch.empty(B, HW, 4, device=dev)
+    unet_x = torch.empty((R + 1) * B, HW, 4, device=dev, dtype=torch.float16)
+    unet_t = torch.empty((R + 1) * B, device=dev)
+    L.check(lib.sdb_asd_prologue(L.ptr(h), L.ptr(qw), L.ptr(qb), L.ptr(eps_post), L.ptr(noise), L.ptr(t), L.ptr(tp),
+                                 L.ptr(ac), 1.0, B, HW, R, L.ptr(latents), L.ptr(unet_x), L.ptr(unet_t), L.stream_ptr()),
+            "prologue")
+    torch.testing.assert_close(latents.cpu(), g["latents_bhwc"].reshape(B, HW, 4), atol=1e-6, rtol=0)
+    assert torch.equal(unet_t.cpu(), g["unet_t"].float())
+    x_nchw = unet_x.view((R + 1) * B, 64, 64, 4).permute(0, 3, 1, 2).float().cpu()
+    torch.testing.assert_close(x_nchw.flatten()[::97], g["unet_x_sample"], atol=4e-3, rtol=2e-3)  # fp16 UNet input
+
+    gen = torch.Generator().manual_seed(g["unet_out_seed"])
+    unet_out = torch.randn(5 * B, 4, 64, 64, generator=gen)
+    torch.testing.assert_close(unet_out.flatten()[::97], g["unet_out_sample"], atol=0, rtol=0)
+    eps = unet_out.permute(0, 2, 3, 1).reshape(5 * B, HW, 4).to(dev).contiguous()
+    neg_w = (GOLD["prompt"]["neg_weights"][[3, 8]] * -1 * g["guidance_perp_neg"]).to(dev).contiguous()
+    grad, d_h = torch.empty(B, HW, 4, device=dev), torch.empty(B, HW, 8, device=dev)
+    loss, gnorm = torch.empty(1, device=dev), torch.empty(1, device=dev)
+    L.check(lib.sdb_asd_epilogue(L.ptr(eps), L.ptr(h), L.ptr(qw), L.ptr(qb), L.ptr(eps_post), L.ptr(t), L.ptr(ac),
+                                 L.ptr(neg_w), g["guidance_scale"], 0, 0.0, 1.0, 1.0, B, HW, R, L.ptr(grad), L.ptr(d_h),
+                                 L.ptr(loss), L.ptr(gnorm), L.stream_ptr()), "epilogue")
+    torch.testing.assert_close(loss.cpu()[0], g["loss_asd"], atol=0, rtol=2e-5)
+    torch.testing.assert_close(gnorm.cpu()[0], g["grad_norm"], atol=0, rtol=2e-5)
+    # d loss / d latents = grad / B reaches h through the identity rows of quant_conv
+    ref = g["grad_bhwc"].reshape(B, HW, 4)
+    torch.testing.assert_close(d_h[..., :4].cpu(), ref, atol=2e-6, rtol=2e-5)
+    torch.testing.assert_close(grad.cpu() / B, ref, atol=2e-6, rtol=2e-5)
+
+
+def test_asd_glue_kernels_match_reference_mvdream_call(cuda_device):
+    """The same kernels in the multi-view arrangement (mvdream_asd_guidance.py:167-304): one shared timestep, UNet batch
+    [x_t, x_t, x_{t+}] (num_repeats 2), plain CFG (neg_weights NULL), 32x32 latents."""
+    from scaledreamer_b200 import lib as L
+
+    lib = L.load()
+    g = GOLD["mv_guidance"]
+    dev = cuda_device
+    B, HW, R = 4, 32 * 32, 2
+    t = g["t"].repeat(B).to(dev, torch.int32)
+    u = g["u"].repeat(B).to(dev, torch.float32)
+    tp = torch.empty(B, dtype=torch.int32, device=dev)
+    L.check(lib.sdb_asd_t_plus(L.ptr(t), L.ptr(u), B, g["plus_ratio"], g["min_step"], 1000, L.ptr(tp), L.stream_ptr()), "t_plus")
+    assert torch.equal(torch.cat([t, t, tp]).cpu().long(), g["unet_t"].long())
+    h = torch.cat([g["latents_bhwc"].reshape(B, HW, 4), torch.zeros(B, HW, 4)], -1).to(dev).contiguous()
+    qw = torch.zeros(8, 8)
+    qw[:4, :4] = torch.eye(4)
+    qw, qb = qw.to(dev), torch.cat([torch.zeros(4), torch.full((4,), -30.0)]).to(dev)
+    eps_post = torch.zeros(B, HW, 4, device=dev)
+    noise = g["noise"].permute(0, 2, 3, 1).reshape(B, HW, 4).to(dev).contiguous()
+    ac = g["alphas_cumprod"].to(dev)
+    latents = torch.empty(B, HW, 4, device=dev)
+    unet_x = torch.empty((R + 1) * B, HW, 4, device=dev, dtype=torch.float16)
+    unet_t = torch.empty((R + 1) * B, device=dev)
+    L.check(lib.sdb_asd_prologue(L.ptr(h), L.ptr(qw), L.ptr(qb), L.ptr(eps_post), L.ptr(noise), L.ptr(t), L.ptr(tp),
+                                 L.ptr(ac), 1.0, B, HW, R, L.ptr(latents), L.ptr(unet_x), L.ptr(unet_t), L.stream_ptr()),
+            "prologue")
+    assert torch.equal(unet_t.cpu(), g["unet_t"].float())
+    x_nchw = unet_x.view((R + 1) * B, 32, 32, 4).permute(0, 3, 1, 2).float().cpu()
+    torch.testing.assert_close(x_nchw.flatten()[::53], g["unet_x_sample"], atol=4e-3, rtol=2e-3)
+    gen = torch.Generator().manual_seed(g["unet_out_seed"])
+    unet_out = torch.randn(3 * B, 4, 32, 32, generator=gen)
+    eps = unet_out.permute(0, 2, 3, 1).reshape(3 * B, HW, 4).to(dev).contiguous()
+    grad, d_h = torch.empty(B, HW, 4, device=dev), torch.empty(B, HW, 8, device=dev)
+    loss, gnorm = torch.empty(1, device=dev), torch.empty(1, device=dev)
+    L.check(lib.sdb_asd_epilogue(L.ptr(eps), L.ptr(h), L.ptr(qw), L.ptr(qb), L.ptr(eps_post), L.ptr(t), L.ptr(ac),
+                                 None, g["guidance_scale"], 0, 0.0, 1.0, 1.0, B, HW, R, L.ptr(grad), L.ptr(d_h),
+                                 L.ptr(loss), L.ptr(gnorm), L.stream_ptr()), "epilogue")
+    torch.testing.assert_close(loss.cpu()[0], g["loss_asd"], atol=0, rtol=2e-5)
+    torch.testing.assert_close(gnorm.cpu()[0], g["grad_norm"], atol=0, rtol=2e-5)
+    torch.testing.assert_close(d_h[..., :4].cpu(), g["grad_bhwc"].reshape(B, HW, 4), atol=2e-6, rtol=2e-5)
+    # camera conditioning of the plugin (normalize_camera, flattened 4x4 per view, repeated for the three UNet blocks)
+    from scaledreamer_b200.guidance import normalize_camera
+
+    cam = normalize_camera(g["c2w"].to(dev))
+    torch.testing.assert_close(cam.repeat(3, 1).cpu(), g["camera"], atol=1e-6, rtol=1e-6)
