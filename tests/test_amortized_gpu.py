@@ -406,3 +406,32 @@ def test_triplane_multiview_system_training_step(cuda_device, tmp_path, monkeypa
         opt.zero_grad(set_to_none=False)
     assert (system.geometry.space_generator.deconv.weight.detach() - w0).abs().max() > 0
     assert "train/loss_eikonal" in system.logged and "train/loss_asd" in system.logged
+
+
+def _amortized_gold():
+    return torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "amortized_golden.pt"))
+
+
+@pytest.mark.parametrize("tag", ["prox", "no_prox", "plain"])
+def test_fused_adan_matches_reference_optimizer(cuda_device, tag):
+    """sdb_adan_step through the FusedAdan plugin optimizer against six steps of the reference's own Adan class
+    (threestudio/systems/optimizers.py, executed by tests/golden/make_amortized_golden.py)."""
+    from scaledreamer_b200.systems import FusedAdan
+
+    c = _amortized_gold()[f"adan_{tag}"]
+    p = torch.nn.Parameter(c["p0"].clone().to(cuda_device))
+    opt = FusedAdan([p], lr=c["lr"], betas=c["betas"], eps=c["eps"], weight_decay=c["weight_decay"], no_prox=c["no_prox"])
+    for i in range(6):
+        p.grad = c["grads"][i].to(cuda_device)
+        opt.step()
+        torch.testing.assert_close(p.detach().cpu(), c["params"][i], atol=1e-6, rtol=1e-5)
+
+
+def test_triplane_kernel_matches_reference_sample_from_planes(cuda_device):
+    """sdb_triplane_sample_forward on non-square planes (H != W) against the reference's own sample_from_planes."""
+    from scaledreamer_b200.amortized import _TriplaneSample
+
+    c = _amortized_gold()["triplane"]
+    pl = c["planes"].permute(0, 1, 3, 4, 2).contiguous().to(cuda_device)
+    enc = _TriplaneSample.apply(pl, c["points"].to(cuda_device))
+    torch.testing.assert_close(enc.cpu(), c["out"], atol=2e-6, rtol=1e-5)
