@@ -232,7 +232,7 @@ class RandomMultiviewCameraIterableDataset(RandomCameraIterableDataset):
         camera_distances = rep(torch.rand(R) * (self.camera_distance_range[1] - self.camera_distance_range[0])
                                + self.camera_distance_range[0])
         if cfg.relative_radius:
-            camera_distances = camera_distances / torch.tan(0.5 * fovy)
+            camera_distances = (1 / torch.tan(0.5 * fovy)) * camera_distances  # the reference's rounding order
         zoom = rep(torch.rand(R) * (self.zoom_range[1] - self.zoom_range[0]) + self.zoom_range[0])
         fovy, fovy_deg = fovy * zoom, fovy_deg * zoom
         camera_positions = torch.stack([camera_distances * torch.cos(elevation) * torch.cos(azimuth),

@@ -163,3 +163,28 @@ def test_asd_glue_kernels_match_reference_mvdream_call(cuda_device):
 
     cam = normalize_camera(g["c2w"].to(dev))
     torch.testing.assert_close(cam.repeat(3, 1).cpu(), g["camera"], atol=1e-6, rtol=1e-6)
+
+
+@pytest.mark.parametrize("case,plugin", [("c2", "random-camera-datamodule"), ("generic", "random-camera-datamodule"),
+                                          ("mv", "mvdream-random-multiview-camera-datamodule"),
+                                          ("mv_zoom", "mvdream-random-multiview-camera-datamodule")])
+def test_device_rays_of_training_batches_match_reference_datasets(cuda_device, case, plugin):
+    """collate (host scalars, bit-identical to the reference under the same seeds: tests/test_data_cpu.py) + to_device
+    (sdb_raygen) against the rays the reference's own data sets put into the same batches (tests/golden/data_golden.pt)."""
+    import random
+
+    import scaledreamer_b200 as sd
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data_golden.pt"))[case]
+    dm = sd.find(plugin)(dict(g["config"]))
+    dm.setup("fit")
+    ds = dm.train_dataset
+    for rec in g["batches"]:
+        ds.update_step(0, rec["step"])
+        random.seed(rec["seed"])
+        torch.manual_seed(rec["seed"])
+        b = ds.to_device(ds.collate({}), cuda_device)
+        ref = rec["batch"]
+        assert b["rays_o"].shape == (ds.batch_size, ref["height"], ref["width"], 3)
+        torch.testing.assert_close(b["rays_o"].reshape(-1, 3)[::37].cpu(), ref["rays_o_sample"], atol=0, rtol=0)
+        torch.testing.assert_close(b["rays_d"].reshape(-1, 3)[::37].cpu(), ref["rays_d_sample"], atol=1e-6, rtol=1e-5)
