@@ -1,0 +1,45 @@
+"""Loss aggregation of the two systems against the reference's own training_step methods (tests/golden/
+make_system_golden.py): lambda schedules through C(), orientation / sparsity / opaque / eikonal terms, logging names."""
+import os
+
+import pytest
+import torch
+
+GOLD = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "system_golden.pt"))
+
+
+@pytest.mark.parametrize("i", range(len(GOLD)))
+def test_training_step_losses_match_reference(i):
+    from scaledreamer_b200 import core
+    from scaledreamer_b200.amortized import MultipromptRadienceFieldGeneratorSystem
+    from scaledreamer_b200.systems import StableDreamer
+
+    c = GOLD[i]
+    out = {k: (v.clone().requires_grad_(True) if k == "normal" else v) for k, v in c["out"].items()}
+    logged = {}
+
+    class System:
+        cfg = type("Cfg", (), {"loss": dict(c["loss_cfg"]), "visualize_samples": False})()
+        prompt_utils = None
+
+        def __call__(self, batch):
+            return out
+
+        def C(self, v):
+            return core.C(v, 0, c["global_step"])
+
+        def log(self, name, value, **kw):
+            logged[name] = float(value.detach()) if torch.is_tensor(value) else float(value)
+
+        def guidance(self, rgb, prompt_utils, **kw):
+            assert rgb is out["comp_rgb"] and kw["rgb_as_latents"] is False
+            return {"loss_asd": torch.tensor(1.25 + c["global_step"] * 1e-4), "grad_norm": torch.tensor(3.0),
+                    "min_step": 20, "max_step": 980}
+
+    cls = StableDreamer if c["system"] == "scaledreamer" else MultipromptRadienceFieldGeneratorSystem
+    System.training_step = cls.training_step
+    res = System().training_step({"elevation": torch.zeros(2)}, 0)
+    torch.testing.assert_close(res["loss"].detach(), c["loss"], atol=0, rtol=1e-6)
+    assert set(logged) == set(c["logged"]), (sorted(logged), sorted(c["logged"]))
+    for k, v in c["logged"].items():
+        assert abs(logged[k] - v) <= 1e-6 * max(1.0, abs(v)), k
