@@ -850,15 +850,16 @@ class MultiPromptProcessorOutput:
         unc = p.uncond_vd if pc.view_dependent else p.uncond
         idx = self._idx_for(elevation.shape[0])
         L.check(L.load().sdb_asd_text_embeddings_multi(C.byref(pc), L.ptr(table), L.ptr(unc), L.ptr(idx), table.shape[0],
-                                                       L.ptr(elevation), L.ptr(azimuth), elevation.shape[0], 77,
-                                                       table.shape[-1], L.ptr(ctx), L.ptr(neg_w), L.stream_ptr()),
+                                                       L.ptr(elevation), L.ptr(azimuth), elevation.shape[0],
+                                                       table.shape[-2], table.shape[-1], L.ptr(ctx), L.ptr(neg_w),
+                                                       L.stream_ptr()),
                 "sdb_asd_text_embeddings_multi")
 
     def _run(self, elevation, azimuth, view_dependent, perp_neg):
         B = elevation.shape[0]
         dev = self.proc.vd_table.device
         pc = self.prompt_cfg_c(view_dependent, perp_neg)
-        ctx = torch.empty((5 if perp_neg else 3) * B, 77, 1024, device=dev, dtype=torch.float16)
+        ctx = torch.empty((5 if perp_neg else 3) * B, *self.proc.vd_table.shape[-2:], device=dev, dtype=torch.float16)
         neg_w = torch.zeros(B, 2, device=dev)
         self.fill_context(pc, elevation.to(dev, torch.float32).contiguous(), azimuth.to(dev, torch.float32).contiguous(),
                           ctx, neg_w)

@@ -11,6 +11,7 @@ math and inert stand-ins for the type annotations:
     threestudio/models/prompt_processors/base.py    DirectionConfig, PromptProcessorOutput, shift_azimuth_deg, the
                                                     `self.directions = [...]` list and the Perp-Neg defaults of
                                                     PromptProcessor.Config
+    custom/amortized/models/prompt_processors/base.py   MultiPromptProcessorOutput (per-sample prompt tables)
     threestudio/models/guidance/stable_diffusion_asd_guidance.py   the methods __call__, get_latents, get_t_plus, get_eps
                                                     of the SD ASD guidance, bound to a stand-in object whose UNet is a
                                                     recorded random tensor and whose scheduler.add_noise is q_sample on the
@@ -296,6 +297,28 @@ def main():
                       "global": out.get_text_embeddings(elevation, azimuth, dist, False).contiguous(),
                       "perp_neg": pn, "neg_weights": w.float(),
                       "decay_check": float(ns["shifted_expotional_decay"](1.0, 0.5, -0.606, torch.tensor(0.25)))}
+    # ---- multi-prompt batches: custom/amortized/models/prompt_processors/base.py:409-568
+    mns = dict(ns)
+    top_level("/root/reference/custom/amortized/models/prompt_processors/base.py", ["MultiPromptProcessorOutput"], mns)
+    P, Bm = 3, 6
+    vd_table = half(torch.randn(P, 4, T, D, generator=g))
+    local_table = half(torch.randn(P, T, D, generator=g))
+    global_table = half(torch.randn(P, D, generator=g))
+    prompt_idx = torch.tensor([2, 0, 1, 1, 0, 2])
+    mout = mns["MultiPromptProcessorOutput"](
+        global_text_embeddings=[global_table[i] for i in prompt_idx], local_text_embeddings=[local_table[i] for i in prompt_idx],
+        uncond_text_embeddings=tables["uncond_text_embeddings"][0], text_embeddings_vd=[vd_table[i] for i in prompt_idx],
+        uncond_text_embeddings_vd=tables["uncond_text_embeddings_vd"], directions=directions_list,
+        direction2idx={d.name: i for i, d in enumerate(directions_list)}, use_perp_neg=True, device="cpu", **coeff)
+    el_m, az_m = elevation[[0, 4, 8, 3, 10, 12]], azimuth[[0, 4, 8, 3, 10, 12]]
+    pn_m, w_m = mout.get_text_embeddings_perp_neg(el_m, az_m, dist[:Bm], True)
+    gold["multi_prompt"] = {"vd_table": vd_table, "local_table": local_table, "global_table": global_table,
+                            "prompt_idx": prompt_idx, "elevation": el_m, "azimuth": az_m,
+                            "uncond": tables["uncond_text_embeddings"][0], "uncond_vd": tables["uncond_text_embeddings_vd"],
+                            "vd": mout.get_text_embeddings(el_m, az_m, dist[:Bm], True),
+                            "local": mout.get_text_embeddings(el_m, az_m, dist[:Bm], False).contiguous(),
+                            "global": mout.get_global_text_embeddings(), "perp_neg": pn_m, "neg_weights": w_m.float(),
+                            "perp_neg_scaled": mout.get_text_embeddings_perp_neg(el_m, az_m, dist[:Bm], True, 0.5)[1].float()}
     gold["guidance"] = guidance_case(ns, out, elevation[[3, 8]], azimuth[[3, 8]], dist[[3, 8]])
     gold["mv_guidance"] = mv_guidance_case(ns, out, gold["rays"]["c2w"])
     torch.save(gold, OUT)

@@ -188,3 +188,33 @@ def test_device_rays_of_training_batches_match_reference_datasets(cuda_device, c
         assert b["rays_o"].shape == (ds.batch_size, ref["height"], ref["width"], 3)
         torch.testing.assert_close(b["rays_o"].reshape(-1, 3)[::37].cpu(), ref["rays_o_sample"], atol=0, rtol=0)
         torch.testing.assert_close(b["rays_d"].reshape(-1, 3)[::37].cpu(), ref["rays_d_sample"], atol=1e-6, rtol=1e-5)
+
+
+def test_multi_prompt_embeddings_match_reference(cuda_device):
+    """sdb_asd_text_embeddings_multi through the plugin's MultiPromptProcessorOutput against the reference's own
+    MultiPromptProcessorOutput (custom/amortized/models/prompt_processors/base.py:409-568): every sample of the batch
+    has its own prompt (index into the stacked table), view-dependent selection, local / global embeddings, Perp-Neg
+    interpolation and weights (default and explicit guidance_scale_neg)."""
+    from scaledreamer_b200.amortized import MultiPromptProcessorOutput
+
+    m, p = GOLD["multi_prompt"], GOLD["prompt"]
+    dev = cuda_device
+    h = lambda t: t.to(dev, torch.float16).contiguous()
+    cfg = types.SimpleNamespace(use_perp_neg=True, use_local_text_embeddings=False, front_threshold=p["front_threshold"],
+                                back_threshold=p["back_threshold"], overhead_threshold=p["overhead_threshold"],
+                                **{k: p[k] for k in ("perp_neg_f_sb", "perp_neg_f_fsb", "perp_neg_f_fs", "perp_neg_f_sf")})
+    proc = types.SimpleNamespace(cfg=cfg, vd_table=h(m["vd_table"]), local_table=h(m["local_table"][:, None]),
+                                 uncond=h(m["uncond"][None]), uncond_vd=h(m["uncond_vd"]),
+                                 global_table=m["global_table"].to(dev))
+    out = MultiPromptProcessorOutput(proc, m["prompt_idx"].to(dev, torch.int32), ["p"] * 6)
+    el, az = m["elevation"].to(dev), m["azimuth"].to(dev)
+    B = el.shape[0]
+    assert torch.equal(out.get_text_embeddings(el, az, None, True).float().cpu(), m["vd"])
+    assert torch.equal(out.get_text_embeddings(el, az, None, False).float().cpu(), m["local"])
+    torch.testing.assert_close(out.get_global_text_embeddings().cpu(), m["global"], atol=0, rtol=0)
+    ctx, w = out.get_text_embeddings_perp_neg(el, az, None, True)
+    torch.testing.assert_close(ctx[:B].float().cpu(), m["perp_neg"][:B], atol=2e-3, rtol=1e-3)
+    assert torch.equal(ctx[B:].float().cpu(), m["perp_neg"][B:])
+    torch.testing.assert_close(w.cpu(), m["neg_weights"], atol=1e-6, rtol=1e-5)
+    _, w2 = out.get_text_embeddings_perp_neg(el, az, None, True, 0.5)
+    torch.testing.assert_close(w2.cpu(), m["perp_neg_scaled"], atol=1e-6, rtol=1e-5)
