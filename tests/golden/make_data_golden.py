@@ -98,6 +98,31 @@ def main():
                 batches.append({"step": step, "seed": seed, "batch": keep(ds.collate({}))})
         cases.append(name)
         gold[name] = {"config": cfg_kw, "batches": batches}
+    # multi-prompt variants (custom/amortized/data/multiprompt.py:61-83, multiview_multiprompt.py:51-77): base collate +
+    # generator noise + prompts drawn with random.choices / random.sample
+    pieces("/root/reference/custom/amortized/data/multiprompt.py",
+           ["MultipromptRandomCameraDataModuleConfig", "MultipromptRandomCameraIterableDataset"], ns)
+    pieces("/root/reference/custom/amortized/data/multiview_multiprompt.py",
+           ["MultiviewMultipromptRandomCameraDataModuleConfig", "MultiviewMultipromptRandomCameraIterableDataset"], ns)
+    library = {"train": [f"prompt number {i}" for i in range(5)]}
+    for name, cfg_cls, cls, cfg_kw in (
+            ("multiprompt", "MultipromptRandomCameraDataModuleConfig", "MultipromptRandomCameraIterableDataset",
+             # batch_size 3 is avoided on purpose: the reference calls torch.cross(lookat, up) without `dim`, which picks the
+             # FIRST axis of size 3 -- for a [3, 3] batch that is the batch axis, and the cameras come out wrong
+             dict(batch_size=4, width=16, height=16, dim_gaussian=8)),
+            ("multiprompt_more_than_library", "MultipromptRandomCameraDataModuleConfig",
+             "MultipromptRandomCameraIterableDataset", dict(batch_size=7, width=16, height=16, dim_gaussian=4)),
+            ("multiview_multiprompt", "MultiviewMultipromptRandomCameraDataModuleConfig",
+             "MultiviewMultipromptRandomCameraIterableDataset",
+             dict(batch_size=8, n_view=4, width=16, height=16, dim_gaussian=8, camera_distance_range=[0.8, 1.0],
+                  fovy_range=[15, 60], elevation_range=[0, 30], camera_perturb=0.0, center_perturb=0.0, up_perturb=0.0))):
+        ds = ns[cls](ns[cfg_cls](**cfg_kw), library)
+        batches = []
+        for seed in (21, 22, 23):
+            random.seed(seed)
+            torch.manual_seed(seed)
+            batches.append({"step": 0, "seed": seed, "batch": keep(ds.collate({}))})
+        gold[name] = {"config": cfg_kw, "library": library, "batches": batches}
     # evaluation orbit
     cfg = ns["RandomCameraDataModuleConfig"](eval_height=20, eval_width=28, n_val_views=5, n_test_views=7,
                                              eval_elevation_deg=15.0, eval_camera_distance=1.2, eval_fovy_deg=70.0)

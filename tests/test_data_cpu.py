@@ -107,3 +107,30 @@ def test_eval_orbit_matches_reference_dataset():
                       "camera_distances", "fovy", "proj_mtx"):
                 torch.testing.assert_close(it[k], ref[k], atol=0, rtol=0, msg=lambda m: f"{split} {i} {k}: {m}")
             assert it["index"] == ref["index"] and it["height"] == ref["height"] and it["width"] == ref["width"]
+
+
+@pytest.mark.parametrize("case", ["multiprompt", "multiprompt_more_than_library", "multiview_multiprompt"])
+def test_multiprompt_batches_match_reference_datasets(case):
+    """custom/amortized/data/multiprompt.py:61-83 and multiview_multiprompt.py:51-77: camera block as above plus the
+    generator noise and the prompts drawn from the library (random.sample, or random.choices when the batch is larger
+    than the library)."""
+    import random
+
+    from scaledreamer_b200 import amortized as A
+    from scaledreamer_b200.core import parse_structured
+
+    g = DATA_GOLD[case]
+    mv = case.startswith("multiview")
+    cfg_cls = A.MultiviewMultipromptRandomCameraDataModuleConfig if mv else A.MultipromptRandomCameraDataModuleConfig
+    ds_cls = A.MultiviewMultipromptRandomCameraIterableDataset if mv else A.MultipromptRandomCameraIterableDataset
+    ds = ds_cls(parse_structured(cfg_cls, dict(g["config"])), g["library"])
+    for rec in g["batches"]:
+        random.seed(rec["seed"])
+        torch.manual_seed(rec["seed"])
+        b = ds.collate({})
+        ref = rec["batch"]
+        assert b["prompt"] == ref["prompt"]
+        torch.testing.assert_close(b["noise"], ref["noise"], atol=0, rtol=0)
+        for k in TENSOR_KEYS:
+            if k in ref:
+                torch.testing.assert_close(b[k], ref[k], atol=0, rtol=0, msg=lambda m: f"{case} {k}: {m}")
