@@ -359,6 +359,6 @@ class Trainer:
                 system.true_global_step = self.global_step
             system.do_update_step_end(system.true_current_epoch, system.true_global_step)
             if self.log_every_n_steps and self.global_step % self.log_every_n_steps == 0 and micro % self.accumulate == 0:
-                rec = {k: (float(v) if torch.is_tensor(v) else v) for k, v in system.logged.items()}
+                rec = {k: (float(v.detach()) if torch.is_tensor(v) else v) for k, v in system.logged.items()}
                 rec["step"] = self.global_step
                 self.history.append(rec)

@@ -57,8 +57,17 @@ def namespace():
     net = definitions(f"{REF}/models/networks.py", ["ProgressiveBandFrequency", "CompositeEncoding", "VanillaMLP"])
     for name in ("ProgressiveBandFrequency", "CompositeEncoding", "VanillaMLP"):
         exec(compile(net[name], "networks.py", "exec"), ns)
-    geo = definitions(f"{REF}/models/geometry/implicit_volume.py", ["ImplicitVolume.get_activated_density"])
-    exec(compile(geo["ImplicitVolume.get_activated_density"], "implicit_volume.py", "exec"), ns)
+    ns.update({"Dict": _Any(), "Num": _Any(), "ValidScale": object})
+    ops2 = definitions(f"{REF}/utils/ops.py", ["scale_tensor"])
+    exec(compile(ops2["scale_tensor"], "ops.py", "exec"), ns)
+    base = definitions(f"{REF}/models/geometry/base.py", ["contract_to_unisphere"])
+    exec(compile(base["contract_to_unisphere"], "base.py", "exec"), ns)
+    geo = definitions(f"{REF}/models/geometry/implicit_volume.py",
+                      ["ImplicitVolume.get_activated_density", "ImplicitVolume.forward", "ImplicitVolume.forward_density"])
+    for name in ("get_activated_density", "forward", "forward_density"):
+        code = geo["ImplicitVolume." + name]
+        code = "\n".join(line[4:] if line.startswith("    ") else line for line in code.splitlines())
+        exec(compile(code, "implicit_volume.py", "exec"), ns)
     return ns
 
 
@@ -89,10 +98,23 @@ def main():
             e = comp(x01)
             raw, density = ns["get_activated_density"](holder, points, dnet(e))
             feat = fnet(e)
+            # the whole ImplicitVolume.forward (implicit_volume.py:109-196) with finite-difference normals, bound to a
+            # stand-in that carries the reference encoding / networks
+            vol = types.SimpleNamespace(
+                cfg=types.SimpleNamespace(n_input_dims=3, n_feature_dims=3, normal_type="finite_difference",
+                                          finite_difference_normal_eps=0.01, radius=radius, density_bias=bias,
+                                          density_blob_scale=10.0, density_blob_std=0.5, density_activation=act),
+                bbox=torch.tensor([[-radius] * 3, [radius] * 3]), unbounded=False, encoding=comp, density_network=dnet,
+                feature_network=fnet)
+            vol.get_activated_density = types.MethodType(ns["get_activated_density"], vol)
+            vol.forward_density = types.MethodType(ns["forward_density"], vol)
+            full = ns["forward"](vol, points.clone(), output_normal=True)
+            assert torch.equal(full["density"][:, 0], density[:, 0]) and torch.equal(full["features"], feat)
         cases[name] = {
             "n_frequencies": n_freq, "include_xyz": include_xyz, "n_masking_step": n_mask, "global_step": step,
             "n_hidden_layers": n_hidden, "density_bias": bias, "density_activation": act, "radius": radius,
             "points": points, "mask": enc.mask.clone(), "enc": e, "density": density[:, 0], "features": feat,
+            "normal": full["normal"], "fd_eps": 0.01,
             "density_weights": [m.weight.detach().clone() for m in dnet.layers if isinstance(m, nn.Linear)],
             "feature_weights": [m.weight.detach().clone() for m in fnet.layers if isinstance(m, nn.Linear)],
         }

@@ -124,6 +124,12 @@ def test_frequency_field_matches_reference_golden():
         x01 = (c["points"] + c["radius"]) / (2 * c["radius"])
         enc = ro.freq_encode(x01, c["n_frequencies"], mask, c["include_xyz"])
         torch.testing.assert_close(enc, c["enc"], atol=1e-6, rtol=1e-6)
-        out = ro.field_forward(c["points"], P, fcfg)
+        fcfg.fd_eps = c["fd_eps"]
+        out = ro.field_forward(c["points"], P, fcfg, output_normal=True)
         torch.testing.assert_close(out["density"], c["density"], atol=1e-5, rtol=1e-5)
         torch.testing.assert_close(out["features"], c["features"], atol=1e-5, rtol=1e-5)
+        # finite-difference normals of the reference's own ImplicitVolume.forward (implicit_volume.py:167-177): offsets
+        # clamped to the box, -(sigma(x + eps e_k) - sigma(x)) / eps, normalised. fp32 differences of nearly equal
+        # densities: compared by direction
+        cos = (out["normal"] * c["normal"]).sum(-1)
+        assert cos.min() > 0.999 and cos.median() > 0.99999, (name, float(cos.min()))

@@ -58,6 +58,10 @@ def test_frequency_field_matches_reference_golden(cuda_device, case):
     assert rel_l2(out["density"][:, 0].cpu(), c["density"]) < 1e-5
     assert rel_l2(out["features"].cpu(), c["features"]) < 1e-5
     assert rel_l2(geo.forward_density(pts)[:, 0].cpu(), c["density"]) < 1e-5
+    # finite-difference normals against the reference's own ImplicitVolume.forward(output_normal=True)
+    nrm = geo(pts, output_normal=True)["normal"].detach().cpu()
+    cos = (nrm * c["normal"]).sum(-1)
+    assert cos.min() > 0.99 and cos.median() > 0.9999, float(cos.min())
 
 
 def _c1_scene(H, W, B=1, seed=3, prune=True, n_hidden=2, n_samples=256):
