@@ -59,6 +59,71 @@ def scene(seed, with_sdf):
     return out
 
 
+def toy_model(seed=0):
+    """Module tree with the attribute paths the C2 optimizer block addresses (asd_sd_nerf.yaml:110-125)."""
+    import torch.nn as nn
+
+    g = torch.Generator().manual_seed(seed)
+
+    class Enc(nn.Module):
+        def __init__(self, n):
+            super().__init__()
+            self.params = nn.Parameter(torch.randn(n, generator=g) * 0.1)
+
+    class Net(nn.Module):
+        def __init__(self, i, o):
+            super().__init__()
+            self.layers = nn.Sequential(nn.Linear(i, 8, bias=False), nn.ReLU(), nn.Linear(8, o, bias=False))
+            for p in self.parameters():
+                p.data = torch.randn(p.shape, generator=g) * 0.3
+
+    class Part(nn.Module):
+        def __init__(self, with_feature):
+            super().__init__()
+            self.encoding = Enc(37)
+            self.network = Net(4, 3)
+            if with_feature:
+                self.density_network, self.feature_network = Net(4, 1), Net(4, 3)
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.geometry, self.background = Part(True), Part(False)
+
+    return Model()
+
+
+def optimizer_case():
+    """parse_optimizer (threestudio/systems/utils.py:19-53) -> torch.optim.AdamW with the C2 groups, five steps."""
+    import types as _t
+
+    import torch.nn as nn
+
+    ns = {"torch": torch, "nn": nn, "threestudio": _t.SimpleNamespace(debug=lambda *a, **k: None)}
+    top(f"{ROOT}/threestudio/systems/utils.py", ["getattr_recursive", "get_parameters", "parse_optimizer"], ns)
+    cfg_dict = {"name": "AdamW", "args": {"betas": [0.0, 0.99], "eps": 1e-15},
+                "params": {"geometry.encoding": {"lr": 0.01}, "geometry.density_network": {"lr": 0.001},
+                           "geometry.feature_network": {"lr": 0.001}, "background.encoding": {"lr": 0.01},
+                           "background.network": {"lr": 0.001}}}
+    cfg = AttrDict(name=cfg_dict["name"], args=cfg_dict["args"], params=cfg_dict["params"])
+    model = toy_model()
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    opt = ns["parse_optimizer"](cfg, model)
+    groups = [{"name": gr["name"], "lr": gr["lr"], "n": sum(p.numel() for p in gr["params"])} for gr in opt.param_groups]
+    g = torch.Generator().manual_seed(4)
+    grads = []
+    for _ in range(5):
+        step = {}
+        for k, p in model.named_parameters():
+            p.grad = torch.randn(p.shape, generator=g)
+            step[k] = p.grad.clone()
+        grads.append(step)
+        opt.step()
+    return {"config": cfg_dict, "init": init, "groups": groups, "grads": grads,
+            "final": {k: v.clone() for k, v in model.state_dict().items()},
+            "untouched": ["geometry.network.layers.0.weight", "geometry.network.layers.2.weight"]}
+
+
 def main():
     ns = {"torch": torch, "F": F, "math": math, "config_to_primitive": lambda v: list(v) if isinstance(v, (list, tuple)) else v,
           "Any": object}
@@ -110,8 +175,9 @@ def main():
             res = System().training_step({"elevation": torch.zeros(2)}, 0)
             gold.append({"system": sysname, "loss_cfg": losses[lossname], "global_step": step, "out": out,
                          "loss": res["loss"].detach().clone(), "logged": logged})
+    gold = {"training_step": gold, "optimizer": optimizer_case()}
     torch.save(gold, OUT)
-    print("wrote", OUT, len(gold), "cases;", [(c["system"], c["global_step"], round(float(c["loss"]), 4)) for c in gold][:6])
+    print("wrote", OUT, len(gold["training_step"]), "cases;", list(gold["optimizer"]))
 
 
 if __name__ == "__main__":

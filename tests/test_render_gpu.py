@@ -303,3 +303,28 @@ def test_adamw_matches_torch(cuda_device):
                                         0.99, 1e-15, 0.01, step, 1.0, L.stream_ptr()), "adamw")
         torch.cuda.synchronize()
     torch.testing.assert_close(p.cpu(), ref.detach(), atol=1e-6, rtol=1e-5)
+
+
+def test_fused_adamw_matches_reference_parse_optimizer_trajectory(cuda_device):
+    """Five steps of the optimizer the reference's own parse_optimizer builds for the C2 block (torch.optim.AdamW, betas
+    (0, 0.99), eps 1e-15, per-module lr; tests/golden/make_system_golden.py) against parse_optimizer -> FusedAdamW
+    (sdb_adamw_step) on the same parameters and gradients; parameters outside every group stay untouched."""
+    import os
+
+    from scaledreamer_b200.systems import parse_optimizer
+    from tests.test_system_golden_cpu import toy_model
+
+    o = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "system_golden.pt"))["optimizer"]
+    model = toy_model()
+    model.load_state_dict(o["init"])
+    model.to(cuda_device)
+    opt = parse_optimizer(o["config"], model)
+    params = dict(model.named_parameters())
+    for step in o["grads"]:
+        for k, g in step.items():
+            params[k].grad = g.to(cuda_device)
+        opt.step()
+    for k, ref in o["final"].items():
+        torch.testing.assert_close(model.state_dict()[k].cpu(), ref, atol=1e-6, rtol=1e-5, msg=lambda m: f"{k}: {m}")
+    for k in o["untouched"]:
+        assert torch.equal(model.state_dict()[k].cpu(), o["init"][k])

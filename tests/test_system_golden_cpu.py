@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-GOLD = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "system_golden.pt"))
+GOLD = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "system_golden.pt"))["training_step"]
 
 
 @pytest.mark.parametrize("i", range(len(GOLD)))
@@ -43,3 +43,50 @@ def test_training_step_losses_match_reference(i):
     assert set(logged) == set(c["logged"]), (sorted(logged), sorted(c["logged"]))
     for k, v in c["logged"].items():
         assert abs(logged[k] - v) <= 1e-6 * max(1.0, abs(v)), k
+
+
+def toy_model():
+    """The module tree of tests/golden/make_system_golden.py (attribute paths of the C2 optimizer block)."""
+    import torch.nn as nn
+
+    class Enc(nn.Module):
+        def __init__(self, n):
+            super().__init__()
+            self.params = nn.Parameter(torch.zeros(n))
+
+    class Net(nn.Module):
+        def __init__(self, i, o):
+            super().__init__()
+            self.layers = nn.Sequential(nn.Linear(i, 8, bias=False), nn.ReLU(), nn.Linear(8, o, bias=False))
+
+    class Part(nn.Module):
+        def __init__(self, with_feature):
+            super().__init__()
+            self.encoding = Enc(37)
+            self.network = Net(4, 3)
+            if with_feature:
+                self.density_network, self.feature_network = Net(4, 1), Net(4, 3)
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.geometry, self.background = Part(True), Part(False)
+
+    return Model()
+
+
+def test_optimizer_groups_match_reference_parse_optimizer():
+    """parse_optimizer (threestudio/systems/utils.py:19-53): one group per dotted module path, in config order, with
+    its own lr; parameters not named by any group are left out."""
+    from scaledreamer_b200.systems import parse_optimizer
+
+    o = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "system_golden.pt"))["optimizer"]
+    model = toy_model()
+    model.load_state_dict(o["init"])
+    opt = parse_optimizer(o["config"], model)
+    got = [{"name": g["name"], "lr": g["lr"], "n": sum(p.numel() for p in g["params"])} for g in opt.param_groups]
+    assert got == o["groups"]
+    named = {id(p) for g in opt.param_groups for p in g["params"]}
+    for k in o["untouched"]:
+        assert id(dict(model.named_parameters())[k]) not in named
+    assert opt.defaults["betas"] == (0.0, 0.99) or tuple(opt.param_groups[0]["betas"]) == (0.0, 0.99)
