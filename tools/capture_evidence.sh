@@ -12,8 +12,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
   --clock-control none --csv --log-file $OUT/${TAG}_step_traffic.csv python tools/profile_step.py 3 > /dev/null 2>&1
 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
-  -k regex:"render_field_bwd|render_nerf_fwd2|render_composite_bwd|flash_attn|gn_apply|gn_reduce" -c 14 \
+  -k regex:"render_field_bwd|render_nerf_fwd2|render_composite_bwd|flash_attn" -c 8 \
   -o $OUT/${TAG}_full_misc -f python tools/profile_step.py 3 > /dev/null 2>&1
 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
-  -k regex:gemm_f16_kernel -s 70 -c 10 -o $OUT/${TAG}_full_gemm -f python tools/profile_step.py 3 > /dev/null 2>&1
+  -k regex:gemm_f16_kernel -s 70 -c 8 -o $OUT/${TAG}_full_gemm -f python tools/profile_step.py 3 > /dev/null 2>&1
 ls -la $OUT | tail -8
