@@ -6,7 +6,12 @@ Run in the build container only (it reads /root/reference):
     threestudio/models/renderers/neus_volume_renderer.py     volsdf_density
     threestudio/utils/ops.py                                 binary_cross_entropy, get_activation
     custom/amortized/models/geometry/hyper_iNGP.py           LinearHyperNetwork
-    custom/amortized/models/geometry/utils.py                planes, project_onto_planes, sample_from_planes
+    custom/amortized/models/geometry/utils.py                planes, project_onto_planes, sample_from_planes,
+                                                             contract_to_unisphere_custom
+    custom/amortized/models/geometry/triplane_transformer.py TriplaneTransformerSDF.forward / forward_sdf /
+                                                             interpolate_encodings / get_shifted_sdf (+ networks.py VanillaMLP)
+    custom/amortized/models/geometry/hyper_iNGP.py           Hypernet_Sdf.forward / forward_sdf / hypernet_forward /
+                                                             get_shifted_sdf (encoding = the oracle's hash grid: tcnn is absent)
 (definitions taken out by name with `ast` where the module itself cannot be imported).
 Output: tests/golden/amortized_golden.pt (about 100 kB).
 """
@@ -42,6 +47,11 @@ def pieces(path, names, ns):
             exec(compile(ast.get_source_segment(s, node), path, "exec"), ns)
             found.add(name)
     assert found == set(names), set(names) - found
+
+
+def dict_update(d, **kw):
+    d.update(kw)
+    return d
 
 
 def main():
@@ -101,8 +111,81 @@ def main():
     pts[0, :4] = torch.tensor([[1.0, -1.0, 0.0], [-1.0, 1.0, 1.0], [0.3, -0.7, 0.99], [0.0, 0.0, 0.0]])
     gold["triplane"] = {"planes": feats, "points": pts, "out": ns["sample_from_planes"](feats, pts),
                         "proj": ns["project_onto_planes"](ns["planes"], pts[:, :5])}
+    # ---- TriplaneTransformerSDF.forward / forward_sdf / interpolate_encodings / get_shifted_sdf
+    # (custom/amortized/models/geometry/triplane_transformer.py:103-239) bound to a stand-in that carries a recorded space
+    # cache and the reference's own VanillaMLP heads: sdf + sphere bias, features, finite-difference sdf_grad / normals
+    import types
+
+    tns = dict(ns, Updateable=object, Sized=(list, tuple), Dict=_Any(), Any=object, Tuple=_Any(), Optional=_Any(),
+               Union=_Any(), threestudio=types.SimpleNamespace(debug=lambda *a, **k: None))
+    pieces(f"{ROOT}/threestudio/models/networks.py", ["VanillaMLP"], tns)
+    pieces(f"{ROOT}/custom/amortized/models/geometry/utils.py", ["contract_to_unisphere_custom"], tns)
+    pieces(f"{ROOT}/threestudio/utils/ops.py", ["scale_tensor"], dict_update(tns, Num=_Any(), ValidScale=object))
+    src = open(f"{ROOT}/custom/amortized/models/geometry/triplane_transformer.py").read()
+    cls = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "TriplaneTransformerSDF")
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ("forward", "forward_sdf", "interpolate_encodings", "get_shifted_sdf"):
+            body = "\n".join(src.splitlines()[fn.lineno - 1:fn.end_lineno])
+            exec(compile("\n".join(line[4:] for line in body.splitlines()), "triplane_transformer.py", "exec"), tns)
+    torch.manual_seed(13)
+    mlp_cfg = {"otype": "VanillaMLP", "activation": "ReLU", "output_activation": "none", "n_neurons": 64, "n_hidden_layers": 2}
+    C3 = 8
+    sdf_net, feat_net = tns["VanillaMLP"](3 * C3, 1, mlp_cfg), tns["VanillaMLP"](3 * C3, 3, mlp_cfg)
+    radius = 1.0
+    geo = types.SimpleNamespace(
+        cfg=types.SimpleNamespace(normal_type="finite_difference", n_feature_dims=3, radius=radius, sdf_bias="sphere",
+                                  sdf_bias_params=0.8),
+        bbox=torch.tensor([[-radius] * 3, [radius] * 3]), unbounded=False, finite_difference_normal_eps=0.01,
+        sdf_network=sdf_net, feature_network=feat_net)
+    for name in ("forward_sdf", "interpolate_encodings", "get_shifted_sdf"):
+        setattr(geo, name, types.MethodType(tns[name], geo))
+    cache = torch.randn(2, 3, C3, 16, 16, generator=g) * 0.5
+    pts3 = (torch.rand(2, 200, 3, generator=g) * 2 - 1) * 0.98
+    with torch.no_grad():
+        out = tns["forward"](geo, pts3.clone(), cache, output_normal=True)
+    gold["triplane_geometry"] = {
+        "space_cache": cache, "points": pts3, "radius": radius, "sdf_bias_radius": 0.8, "fd_eps": 0.01,
+        "sdf_weights": [m.weight.detach().clone() for m in sdf_net.layers if isinstance(m, nn.Linear)],
+        "feature_weights": [m.weight.detach().clone() for m in feat_net.layers if isinstance(m, nn.Linear)],
+        "out": {k: v.clone() for k, v in out.items()}}
+    # ---- Hypernet_Sdf.forward / forward_sdf / hypernet_forward / get_shifted_sdf (hyper_iNGP.py:206-349) bound to a stand-in.
+    # tiny-cuda-nn is not installable here, so `self.encoding` is the ORACLE's hash-grid restatement: this pins the per-prompt
+    # bmm chain, the sphere bias, the clamped finite-difference sdf_grad and the output layout -- not the encoding itself.
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle import render_oracle as ro
+
+    hns = dict(tns, Callable=_Any())
+    pieces(f"{ROOT}/threestudio/models/geometry/base.py", ["contract_to_unisphere"], hns)
+    src = open(f"{ROOT}/custom/amortized/models/geometry/hyper_iNGP.py").read()
+    cls = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "Hypernet_Sdf")
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ("forward", "forward_sdf", "hypernet_forward", "get_shifted_sdf"):
+            body = "\n".join(src.splitlines()[fn.lineno - 1:fn.end_lineno])
+            exec(compile("\n".join(line[4:] for line in body.splitlines()), "hyper_iNGP.py", "exec"), hns)
+    grid = ro.GridCfg(n_levels=16, n_features_per_level=2, log2_hashmap_size=10, base_resolution=4, per_level_scale=1.3)
+    table = (torch.rand(ro.grid_meta(grid)["n_entries"], 2, generator=g) * 2 - 1) * 0.3
+    enc_mod = types.SimpleNamespace(n_output_dims=32)
+    encoding = lambda x: ro.hashgrid_encode(x, table, grid)
+    hradius = 2.0
+    hgeo = types.SimpleNamespace(
+        cfg=types.SimpleNamespace(normal_type="finite_difference", n_feature_dims=3, n_input_dims=3, radius=hradius,
+                                  sdf_bias="sphere", sdf_bias_params=0.5),
+        bbox=torch.tensor([[-hradius] * 3, [hradius] * 3]), unbounded=False, finite_difference_normal_eps=0.01)
+    hgeo.encoding = type("Enc", (), {"n_output_dims": 32, "__call__": lambda self, x: encoding(x)})()
+    for name in ("forward_sdf", "hypernet_forward", "get_shifted_sdf"):
+        setattr(hgeo, name, types.MethodType(hns[name], hgeo))
+    Bh = 2
+    hcache = {"sdf_weights": [torch.randn(Bh, 32, 64, generator=g) * 0.3, torch.randn(Bh, 64, 1, generator=g) * 0.3],
+              "feature_weights": [torch.randn(Bh, 32, 64, generator=g) * 0.3, torch.randn(Bh, 64, 3, generator=g) * 0.3]}
+    hpts = (torch.rand(Bh, 150, 3, generator=g) * 2 - 1) * 1.98
+    with torch.no_grad():
+        hout = hns["forward"](hgeo, hpts.clone(), hcache, output_normal=True)
+    gold["hyper_geometry"] = {"grid": vars(grid), "table": table, "cache": hcache, "points": hpts, "radius": hradius,
+                              "sdf_bias_radius": 0.5, "fd_eps": 0.01, "out": {k: v.clone() for k, v in hout.items()}}
     torch.save(gold, OUT)
-    print("wrote", OUT, {k: (tuple(v["out"].shape) if torch.is_tensor(v.get("out")) else "-") for k, v in gold.items()})
+    print("wrote", OUT, list(gold))
 
 
 if __name__ == "__main__":

@@ -56,3 +56,34 @@ def test_triplane_lookup_oracle_matches_reference():
     torch.testing.assert_close(p[:, 0], pts[..., [0, 1]])
     torch.testing.assert_close(p[:, 1], pts[..., [0, 2]])
     torch.testing.assert_close(p[:, 2], pts[..., [2, 1]])
+
+
+def test_triplane_field_oracle_matches_reference_forward():
+    """ao.triplane_field against the reference's own TriplaneTransformerSDF.forward(output_normal=True): contraction to
+    [-1, 1], plane lookup, VanillaMLP heads, sphere sdf bias, finite-difference sdf_grad with clamped offsets, normals."""
+    c = GOLD["triplane_geometry"]
+    out = ao.triplane_field(c["points"], c["space_cache"], c["sdf_weights"], c["feature_weights"], c["radius"],
+                            c["sdf_bias_radius"], c["fd_eps"], output_normal=True)
+    ref = c["out"]
+    torch.testing.assert_close(out["sdf"], ref["sdf"], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(out["features"], ref["features"], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(out["sdf_grad"], ref["sdf_grad"], atol=2e-4, rtol=1e-3)  # differences divided by 0.01
+    cos = (out["normal"] * ref["normal"]).sum(-1)
+    assert cos.min() > 0.9999
+    assert torch.equal(ref["normal"], ref["shading_normal"])
+
+
+def test_hyper_field_oracle_matches_reference_forward():
+    """ao.hyper_field against the reference's own Hypernet_Sdf.forward(output_normal=True) (per-prompt bmm chain, sphere
+    bias, clamped finite differences, [B*N, .] layout). The encoding inside that golden is the oracle's own hash grid
+    (tiny-cuda-nn is not installable), so this pins everything around the encoding, not the encoding."""
+    from oracle import render_oracle as ro
+
+    c = GOLD["hyper_geometry"]
+    cfg = ao.HyperCfg(grid=ro.GridCfg(**c["grid"]), radius=c["radius"], sdf_bias_radius=c["sdf_bias_radius"], fd_eps=c["fd_eps"])
+    out = ao.hyper_field(c["points"], c["table"], c["cache"], cfg, output_normal=True)
+    ref = c["out"]
+    torch.testing.assert_close(out["sdf"], ref["sdf"], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(out["features"], ref["features"], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(out["sdf_grad"], ref["sdf_grad"], atol=2e-4, rtol=1e-3)
+    assert ((out["normal"] * ref["normal"]).sum(-1)).min() > 0.9999

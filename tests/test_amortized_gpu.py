@@ -435,3 +435,56 @@ def test_triplane_kernel_matches_reference_sample_from_planes(cuda_device):
     pl = c["planes"].permute(0, 1, 3, 4, 2).contiguous().to(cuda_device)
     enc = _TriplaneSample.apply(pl, c["points"].to(cuda_device))
     torch.testing.assert_close(enc.cpu(), c["out"], atol=2e-6, rtol=1e-5)
+
+
+def test_triplane_geometry_matches_reference_forward(cuda_device):
+    """The "Triplane-transformer-sdf" plugin (triplane kernel + native MLP heads + FD sdf_grad) against the reference's
+    own TriplaneTransformerSDF.forward run on a recorded space cache (tests/golden/make_amortized_golden.py)."""
+    import scaledreamer_b200 as sd
+
+    c = _amortized_gold()["triplane_geometry"]
+    dev = cuda_device
+    Cp = c["space_cache"].shape[2]
+    geo = sd.find("Triplane-transformer-sdf")({
+        "radius": c["radius"], "sdf_bias": "sphere", "sdf_bias_params": c["sdf_bias_radius"],
+        "finite_difference_normal_eps": c["fd_eps"],
+        "space_generator_config": {"inner_dim": 64, "condition_dim": 1024, "triplane_low_res": 8, "triplane_high_res": 16,
+                                   "triplane_dim": Cp, "num_layers": 1, "num_heads": 4, "mlp_ratio": 4, "local_text": True}}).to(dev)
+    geo.update_step(0, 0)
+    for net, ws in ((geo.sdf_network, c["sdf_weights"]), (geo.feature_network, c["feature_weights"])):
+        for p, w in zip(net.weights(), ws):
+            p.data.copy_(w)
+    out = geo(c["points"].to(dev), c["space_cache"].to(dev), output_normal=True)
+    ref = c["out"]
+    assert set(ref) <= set(out)
+    torch.testing.assert_close(out["sdf"].detach().cpu(), ref["sdf"], atol=2e-6, rtol=1e-5)
+    torch.testing.assert_close(out["features"].detach().cpu(), ref["features"], atol=2e-6, rtol=1e-5)
+    torch.testing.assert_close(out["sdf_grad"].detach().cpu(), ref["sdf_grad"], atol=5e-4, rtol=2e-3)
+    cos = (out["normal"].detach().cpu() * ref["normal"]).sum(-1)
+    assert cos.min() > 0.9995
+
+
+def test_hyper_geometry_matches_reference_forward(cuda_device):
+    """The "Hyper-iNGP" plugin (fused per-prompt field kernel, FD sdf_grad) against the reference's own
+    Hypernet_Sdf.forward run with recorded per-prompt weights (tests/golden/make_amortized_golden.py; the encoding inside
+    that golden is the oracle's hash grid)."""
+    import scaledreamer_b200 as sd
+
+    c = _amortized_gold()["hyper_geometry"]
+    dev = cuda_device
+    geo = sd.find("Hyper-iNGP")({"radius": c["radius"], "sdf_bias": "sphere", "sdf_bias_params": c["sdf_bias_radius"],
+                                 "finite_difference_normal_eps": c["fd_eps"],
+                                 "pos_encoding_config": {"otype": "HashGrid", **c["grid"]},
+                                 "hypernet_config": {"c_dim": 1024, "out_dims": {"sdf_weights": [64, 1], "feature_weights": [64, 3]},
+                                                     "spectral_norm": False, "n_neurons": 64, "n_hidden_layers": 1}}).to(dev)
+    geo.update_step(0, 0)
+    with torch.no_grad():
+        geo.encoding.encoding.params.copy_(c["table"].reshape(-1).to(dev))
+    cache = {k: [m.to(dev) for m in v] for k, v in c["cache"].items()}
+    out = geo(c["points"].to(dev), cache, output_normal=True)
+    ref = c["out"]
+    assert set(out) == set(ref)
+    torch.testing.assert_close(out["sdf"].detach().cpu(), ref["sdf"], atol=5e-6, rtol=1e-4)
+    torch.testing.assert_close(out["features"].detach().cpu(), ref["features"], atol=5e-6, rtol=1e-4)
+    torch.testing.assert_close(out["sdf_grad"].detach().cpu(), ref["sdf_grad"], atol=1e-3, rtol=2e-3)
+    assert ((out["normal"].detach().cpu() * ref["normal"]).sum(-1)).min() > 0.999
