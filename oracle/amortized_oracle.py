@@ -9,6 +9,9 @@ Restates, in plain fp32 PyTorch on the CPU, the reference's
   GenerativeSpaceVolSDFVolumeRenderer    custom/amortized/models/renderers/generative_space_volsdf_volume_renderer.py:89-446
   eikonal / sparsity / opaque losses     custom/amortized/systems/multiprompt_radience_field_generator.py:127-216
 
+PINNED against the reference's own code (tests/golden/make_amortized_golden.py -> tests/test_amortized_golden_cpu.py):
+Adan, volsdf_density, LinearHyperNetwork, sample_from_planes, and the complete Hypernet_Sdf.forward /
+TriplaneTransformerSDF.forward (heads, sphere bias, clamped finite-difference sdf_grad, normals).
 PARITY UNPINNED for the nerfacc pieces (nerfacc v0.5.2 is an un-vendored dependency, not installable here):
 `importance_sampling` is restated as inverse-CDF sampling at u_j = (j + b) / (n + 1), j = 0..n, with one offset b per
 ray (U[0,1) when stratified, 0.5 otherwise) and linear interpolation inside a CDF bin; `render_weight_from_alpha` as

@@ -9,10 +9,13 @@ Plain fp32 PyTorch restatement of the frozen networks and of the guidance arithm
                       Downsample :80-87, AttnBlock :179-203)
   asd_*               stable_diffusion_asd_guidance.py:211-316,333-428 / mvdream_asd_guidance.py:141-304
 
-PARITY STATUS: **pinned** for the two networks -- tests/test_oracle_ldm.py checks this file against
-tests/golden/ldm_golden.pt, which tests/golden/make_ldm_golden.py produced by running the REFERENCE's own vendored
-modules in this container. The guidance arithmetic (CFG / Perp-Neg / t+dt) has no reference fixture (the reference
-needs diffusers + CUDA to run it) and is restated from the cited lines: parity unpinned for that part.
+PARITY STATUS: **pinned**.  Networks: tests/test_oracle_ldm.py checks this file against tests/golden/ldm_golden.pt,
+which tests/golden/make_ldm_golden.py produced by running the REFERENCE's own vendored modules in this container.
+Guidance arithmetic (schedule, t+dt, q-sample batch, CFG / Perp-Neg, w(t), loss and gradient):
+tests/test_host_golden_cpu.py checks it against tests/golden/host_golden.pt, produced by the reference's own SD and
+MVDream guidance `__call__` / `get_t_plus` / `get_eps` methods (taken out of the guidance files with `ast`, executed
+unchanged with a recorded UNet output; tests/golden/make_host_golden.py).  Not executable here: the diffusers VAE / UNet
+classes themselves (their vendored LDM twins are) and DDPMScheduler.add_noise (== q_sample on the same schedule).
 """
 from __future__ import annotations
 

@@ -3,11 +3,14 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
 module; the product path (scaledreamer_b200/) never does.
 
-PARITY STATUS: **unpinned**.  The reference has no tests or golden vectors for this path and
-its arithmetic lives in two un-vendored CUDA extensions that are absent from /root/reference and from this
-image: tiny-cuda-nn @ master (README.md:65) and nerfacc v0.5.2 (README.md:66).  This file restates their
-published algorithms and drives them with the reference's own formulas, each cited below
-(paths relative to /root/reference).  Everything is plain differentiable float32 torch on the CPU, so
+PARITY STATUS: **unpinned** for the hash grid and the occupancy-grid sampling / compositing.  The reference has no
+tests or golden vectors for this path and that arithmetic lives in two un-vendored CUDA extensions that
+are absent from /root/reference and from this image: tiny-cuda-nn @ master (README.md:65) and nerfacc v0.5.2
+(README.md:66).  This file restates their published algorithms and drives them with the reference's own formulas,
+each cited below (paths relative to /root/reference).  **Pinned** where the reference's own code can run here
+(tests/golden/make_field_golden.py, make_host_golden.py: definitions taken out of the reference files with `ast` and
+executed unchanged): the frequency encoding + VanillaMLP field incl. density bias / activation and finite-difference
+normals (ImplicitVolume.forward), and get_rays / look-at cameras.  Everything is plain differentiable float32 torch on the CPU, so
 torch.autograd of these functions is the gradient oracle as well.
 
 One documented choice where nerfacc's exact behaviour cannot be checked here: the lattice of candidate
