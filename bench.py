@@ -201,7 +201,17 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3"],
+                    help="C2 = the BASELINE metric's configuration (default); C3 = ASD-MVDream, 4 views of 256x256 per step "
+                         "(informational: same loop, not the headline line)")
     args = ap.parse_args()
+    global WORKLOAD, CFG_YAML
+    extra_cli = []
+    if args.workload == "C3":
+        WORKLOAD = ("C3: single-prompt ASD-MVDream, hash-grid iNGP NeRF, 256x256x4 views, multi-view UNet batch 12 @32x32 "
+                    "latents (cond/uncond/t+dt x 4 views), VAE @256x256")
+        CFG_YAML = os.path.join(ROOT, "tests", "configs", "asd_mv_nerf.yaml")
+        extra_cli = ["data.batch_size=[4,4]"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -230,7 +240,7 @@ def main() -> None:
     torch.manual_seed(1234 + rank)
     random.seed(1234 + rank)
     cfg = sd.load_config(CFG_YAML, cli_args=["system.prompt_processor.prompt=a DSLR photo of a hamburger",
-                                             f"data.width=[{W},{W}]", f"data.height=[{H},{H}]"])
+                                             f"data.width=[{W},{W}]", f"data.height=[{H},{H}]"] + extra_cli)
     dm = sd.find(cfg.data_type)(cfg.data)
     system = sd.find(cfg.system_type)(cfg.system)
     dm.setup("fit")
@@ -364,9 +374,10 @@ def main() -> None:
         b = ds.to_device(host_batch(), dev)
         P = {k: v.detach() for k, v in rr._params().items()}
         march = R.MarchSpec(render_step_size=rr.render_step_size, prune=True, grid_res=32)
-        jit = torch.rand(H * W, device=dev)
         ro_, rd_ = b["rays_o"].reshape(-1, 3).contiguous(), b["rays_d"].reshape(-1, 3).contiguous()
-        tape = R.RenderTape.acquire(march, rr._spec().radius, H * W, dev)
+        n_rays = ro_.shape[0]  # views x H x W
+        jit = torch.rand(n_rays, device=dev)
+        tape = R.RenderTape.acquire(march, rr._spec().radius, n_rays, dev)
         o = R.render_forward_v2_raw(rr._spec(), march, P, rr._occ_grid(dev), ro_, rd_, jit, None, H * W, tape)
         samples_kept = int(tape.counter[0].item())
         tape.check_overflow()
@@ -399,8 +410,9 @@ def main() -> None:
     tr = ncu_traffic()
     gemm_tfs = prof["gemm_tflop_per_step"] / (prof["gemm_ms_per_step"] / 1e3)
     # algorithmic bytes of the render kernels: samples x 16 levels x 8 corners x 2 features x 4 B (SURVEY.md 8d, E = 1)
-    rbytes_f = prof["render_samples_kept"] * 1024 + H * W * (24 + 28)
-    rbytes_b = 2 * prof["render_samples_kept"] * 1024 + H * W * (24 + 28)
+    n_views = 4 if args.workload == "C3" else 1
+    rbytes_f = prof["render_samples_kept"] * 1024 + n_views * H * W * (24 + 28)
+    rbytes_b = 2 * prof["render_samples_kept"] * 1024 + n_views * H * W * (24 + 28)
     roof_gemm = {"kernel": "gemm_f16_kernel + flash_attn_f16_kernel (tcgen05 GEMM / implicit conv / fused attention, all launches of one step)", "bound": "tensor",
                  "achieved": gemm_tfs, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tfs / pk["tf_sustained"],
                  "traffic": tr.get("tensor"), "ms_per_step": prof["gemm_ms_per_step"], "peak_source": pk["src"] + " sustained bf16"}
@@ -426,6 +438,7 @@ def main() -> None:
         "gpu_launches": int(launches), "gpu_launches_per_step": int(launches // args.steps),
         "clocks": clk, "roofline": roofs[0], "roofline_other_kernels": roofs[1:], "profile": prof,
     }
+    line["views_per_s"] = line["value"] * n_views
     if world == 1 and not args.no_cpu_baseline:
         step_s, sample, cores = cpu_baseline_step_seconds()
         line["cpu_baseline"] = {"value": 1.0 / step_s, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
