@@ -574,10 +574,11 @@ __global__ void col2im_s2_kernel(const __half* __restrict__ col, __half* __restr
   }
 }
 
-// Direct 3x3 conv, small Cin (3 or 4): thread = (pixel, 8 consecutive output channels). CIN is a template parameter
-// so the 9*CIN input taps stay in registers and the 8 x 9*CIN FMAs unroll; weights sit in shared memory as fp32,
-// transposed to [k][Cout] so the eight channels of a thread are two float4 reads shared by the whole warp column.
-template <typename TIn, int CIN>
+// Direct 3x3 conv for tiny Cin (3 / 4 / 8: the RGB / latent / moment ends of the networks). Thread = PX consecutive
+// pixels of a row x 8 output channels: the (3 x (PX+2) x CIN) input window stays in registers and every pair of
+// LDS.128 weight reads feeds 8 * PX FMAs (the first version, one pixel per thread, was bound by the shared-memory
+// pipe at one LDS.128 per four FMAs). Weights sit in shared memory as fp32, transposed to [k][CT].
+template <typename TIn, int CIN, int PX>
 __global__ void __launch_bounds__(128)
 conv_small_cin_kernel(const TIn* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                       void* __restrict__ y, int y_fp32, int N, int H, int W, int Cout, int CT) {
@@ -589,60 +590,151 @@ conv_small_cin_kernel(const TIn* __restrict__ x, const __half* __restrict__ w, c
     swf[k * CT + co] = __half2float(w[(size_t)(co0 + co) * K + k]);
   }
   __syncthreads();
-  const int co8n = CT / 8;
-  const long long total = (long long)N * H * W * co8n;
+  const int co8n = CT / 8, wq = (W + PX - 1) / PX;
+  const long long total = (long long)N * H * wq * co8n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(i % co8n);
     long long r = i / co8n;
-    const int px = (int)(r % W);
-    r /= W;
+    const int px0 = (int)(r % wq) * PX;
+    r /= wq;
     const int py = (int)(r % H);
     const int n = (int)(r / H);
-    float in[K];
+    float in[3][PX + 2][CIN];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
-      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = py + ky - 1;
 #pragma unroll
-      for (int c = 0; c < CIN; ++c)
-        in[tap * CIN + c] = ok ? (float)x[(((long long)n * H + iy) * W + ix) * CIN + c] : 0.f;
+      for (int q = 0; q < PX + 2; ++q) {
+        const int ix = px0 + q - 1;
+        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+          in[ky][q][c] = ok ? (float)x[(((long long)n * H + iy) * W + ix) * CIN + c] : 0.f;
+      }
     }
-    float acc[8];
+    float acc[PX][8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = bias ? __half2float(bias[co0 + cg * 8 + o]) : 0.f;
+    for (int o = 0; o < 8; ++o) {
+      const float bv = bias ? __half2float(bias[co0 + cg * 8 + o]) : 0.f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const float4 w0 = *reinterpret_cast<const float4*>(swf + k * CT + cg * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(swf + k * CT + cg * 8 + 4);
-      acc[0] = fmaf(in[k], w0.x, acc[0]);
-      acc[1] = fmaf(in[k], w0.y, acc[1]);
-      acc[2] = fmaf(in[k], w0.z, acc[2]);
-      acc[3] = fmaf(in[k], w0.w, acc[3]);
-      acc[4] = fmaf(in[k], w1.x, acc[4]);
-      acc[5] = fmaf(in[k], w1.y, acc[5]);
-      acc[6] = fmaf(in[k], w1.z, acc[6]);
-      acc[7] = fmaf(in[k], w1.w, acc[7]);
+      for (int p = 0; p < PX; ++p) acc[p][o] = bv;
     }
-    const long long ob = (((long long)n * H + py) * W + px) * Cout + co0 + cg * 8;
-    if (y_fp32) {
-      reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + ob)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + ob)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    } else {
-      uint4 ov;
-      __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(y) + ob) = ov;
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          const int k = (ky * 3 + kx) * CIN + c;
+          const float4 w0 = *reinterpret_cast<const float4*>(swf + k * CT + cg * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(swf + k * CT + cg * 8 + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[p][o] = fmaf(in[ky][kx + p][c], wv[o], acc[p][o]);
+        }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      if (px0 + p >= W) break;
+      const long long ob = (((long long)n * H + py) * W + px0 + p) * Cout + co0 + cg * 8;
+      if (y_fp32) {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + ob)[0] = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + ob)[1] = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
+      } else {
+        uint4 ov;
+        __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(acc[p][2 * e], acc[p][2 * e + 1]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(y) + ob) = ov;
+      }
     }
   }
 }
 
-// Direct 3x3 conv, small Cout (<= 8): one warp per pixel, lanes split Cin (fp16 input only).
+// Direct 3x3 conv for tiny Cout (3 / 4 / 8: the last convolution of the UNet, conv_out of the VAE, and the data
+// gradients of their first convolutions) on LARGE images. Thread = PX consecutive pixels of a row x all COUT outputs, looping over
+// taps and 8-channel chunks: one 16-byte load per pixel and 2 * COUT LDS.128 (broadcast) feed 32 * COUT FMAs. The first
+// warp-per-pixel kernel below stays for small images, where a thread per PX pixels would leave the GPU empty
+// (64 x 64: 1024 threads).
+template <int COUT, int PX>
+__global__ void __launch_bounds__(128)
+conv_small_cout_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+                       void* __restrict__ y, int y_fp32, int N, int H, int W, int Cin) {
+  extern __shared__ float swo[];  // [9][Cin][COUT] fp32
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < COUT * K; i += blockDim.x) {
+    const int o = i / K, k = i - o * K;
+    swo[k * COUT + o] = __half2float(w[(size_t)o * K + k]);
+  }
+  __syncthreads();
+  const int wq = (W + PX - 1) / PX, c8n = Cin / 8;
+  const long long total = (long long)N * H * wq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int px0 = (int)(i % wq) * PX;
+    const int py = (int)((i / wq) % H);
+    const int n = (int)(i / ((long long)wq * H));
+    float acc[PX][COUT];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) acc[p][o] = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = py + tap / 3 - 1, dx = tap % 3 - 1;
+      if (iy < 0 || iy >= H) continue;
+      const uint4* row = reinterpret_cast<const uint4*>(x + ((long long)n * H + iy) * W * Cin);
+      const float* wt = swo + (size_t)tap * Cin * COUT;
+#pragma unroll 1
+      for (int c8 = 0; c8 < c8n; ++c8) {
+        uint4 xv[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const int ix = px0 + p + dx;
+          xv[p] = (ix >= 0 && ix < W) ? row[(long long)ix * c8n + c8] : make_uint4(0, 0, 0, 0);
+        }
+        float wv[8 * COUT];  // the chunk's weights, [e][o] contiguous: 2 * COUT LDS.128
+#pragma unroll
+        for (int q = 0; q < 2 * COUT; ++q) {
+          const float4 t = reinterpret_cast<const float4*>(wt + (size_t)c8 * 8 * COUT)[q];
+          wv[4 * q] = t.x, wv[4 * q + 1] = t.y, wv[4 * q + 2] = t.z, wv[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&xv[p]);
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 xf = __half22float2(h2[e2]);
+#pragma unroll
+            for (int o = 0; o < COUT; ++o)
+              acc[p][o] = fmaf(xf.x, wv[(2 * e2) * COUT + o], fmaf(xf.y, wv[(2 * e2 + 1) * COUT + o], acc[p][o]));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      if (px0 + p >= W) break;
+      const long long pix = ((long long)n * H + py) * W + px0 + p;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float v = acc[p][o] + (bias ? __half2float(bias[o]) : 0.f);
+        if (y_fp32)
+          reinterpret_cast<float*>(y)[pix * COUT + o] = v;
+        else
+          reinterpret_cast<__half*>(y)[pix * COUT + o] = __float2half_rn(v);
+      }
+    }
+  }
+}
+
+// Small images: one warp per pixel, lanes split Cin, warp-shuffle reduction of the COUT sums.
 template <int COUT>
-__global__ void conv_small_cout_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
-                                       const __half* __restrict__ bias, void* __restrict__ y, int y_fp32, int N, int H,
-                                       int W, int Cin) {
+__global__ void conv_small_cout_warp_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                                            const __half* __restrict__ bias, void* __restrict__ y, int y_fp32, int N,
+                                            int H, int W, int Cin) {
   const int lane = threadIdx.x & 31;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -905,28 +997,54 @@ int conv3x3_small(const void* x, int x_fp32, const __half* w, const __half* bias
     int CT = 128;  // output-channel slice per block: the largest multiple of 8 <= 128 dividing Cout
     while (Cout % CT) CT -= 8;
     const size_t smem = sizeof(float) * CT * 9 * Cin;  // <= 36 KB
-    const long long total = (long long)N * H * W * (CT / 8);
+    const int px = Cin == 8 ? 2 : 4;  // pixels per thread (register budget: 3 x (px + 2) x Cin inputs)
+    const long long total = (long long)N * H * ((W + px - 1) / px) * (CT / 8);
     const dim3 grid(ew_grid(total, 128), Cout / CT);
-#define SDB_SMALL_CIN(T, CI) \
-  conv_small_cin_kernel<T, CI><<<grid, 128, smem, s>>>(reinterpret_cast<const T*>(x), w, bias, y, y_fp32, N, H, W, Cout, CT)
+#define SDB_SMALL_CIN(T, CI, PX) \
+  conv_small_cin_kernel<T, CI, PX><<<grid, 128, smem, s>>>(reinterpret_cast<const T*>(x), w, bias, y, y_fp32, N, H, W, Cout, CT)
     if (x_fp32) {
-      if (Cin == 3) SDB_SMALL_CIN(float, 3);
-      else if (Cin == 4) SDB_SMALL_CIN(float, 4);
-      else SDB_SMALL_CIN(float, 8);
+      if (Cin == 3) SDB_SMALL_CIN(float, 3, 4);
+      else if (Cin == 4) SDB_SMALL_CIN(float, 4, 4);
+      else SDB_SMALL_CIN(float, 8, 2);
     } else {
-      if (Cin == 3) SDB_SMALL_CIN(__half, 3);
-      else if (Cin == 4) SDB_SMALL_CIN(__half, 4);
-      else SDB_SMALL_CIN(__half, 8);
+      if (Cin == 3) SDB_SMALL_CIN(__half, 3, 4);
+      else if (Cin == 4) SDB_SMALL_CIN(__half, 4, 4);
+      else SDB_SMALL_CIN(__half, 8, 2);
     }
 #undef SDB_SMALL_CIN
+  } else if (Cout <= 8 && !x_fp32 && Cin % 8 == 0 && (size_t)Cout * 9 * Cin * 4 <= 200 * 1024 &&
+             (long long)N * H * W >= 131072) {
+    // large images: thread per PX pixels (2 until there are >= 512 k pixels, so that >= 64 k threads exist)
+    const int px = (long long)N * H * W >= 524288 ? 4 : 2;
+    const long long total = (long long)N * H * ((W + px - 1) / px);
+    const int grid = ew_grid(total, 128);
+    const size_t smem = sizeof(float) * Cout * 9 * Cin;
+    const __half* xh = reinterpret_cast<const __half*>(x);
+#define SDB_SMALL_COUT(CO, PX)                                                                                     \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(conv_small_cout_kernel<CO, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    conv_small_cout_kernel<CO, PX><<<grid, 128, smem, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin);                  \
+  } while (0)
+    switch (Cout * 10 + px) {
+      case 32: SDB_SMALL_COUT(3, 2); break;
+      case 34: SDB_SMALL_COUT(3, 4); break;
+      case 42: SDB_SMALL_COUT(4, 2); break;
+      case 44: SDB_SMALL_COUT(4, 4); break;
+      case 82: SDB_SMALL_COUT(8, 2); break;
+      case 84: SDB_SMALL_COUT(8, 4); break;
+      default:
+        sdb_set_error("conv3x3_small: Cout=%d not instantiated", Cout);
+        return SDB_ERR_UNSUPPORTED;
+    }
+#undef SDB_SMALL_COUT
   } else if (Cout <= 8 && !x_fp32 && Cin % 2 == 0) {
     const long long total = (long long)N * H * W;
     const int grid = ew_grid(total * 32);
     const __half* xh = reinterpret_cast<const __half*>(x);
     switch (Cout) {
-      case 3: conv_small_cout_kernel<3><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
-      case 4: conv_small_cout_kernel<4><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
-      case 8: conv_small_cout_kernel<8><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
+      case 3: conv_small_cout_warp_kernel<3><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
+      case 4: conv_small_cout_warp_kernel<4><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
+      case 8: conv_small_cout_warp_kernel<8><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
       default:
         sdb_set_error("conv3x3_small: Cout=%d not instantiated", Cout);
         return SDB_ERR_UNSUPPORTED;

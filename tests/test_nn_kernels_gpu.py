@@ -83,10 +83,24 @@ def test_conv3x3(cuda_device, N, H, W, Cin, Cout):
 def test_conv3x3_small(cuda_device, cin, cout, fp32in):
     from scaledreamer_b200 import nn_ops as O
 
-    x = rnd(2, 12, 20, cin, dev=cuda_device, seed=1)
+    x = rnd(2, 12, 21, cin, dev=cuda_device, seed=1)  # width not a multiple of the 2 / 4 pixels a thread owns
     if fp32in:
         x = x.float()
     w = rnd(cout, 3, 3, cin, dev=cuda_device, seed=2, scale=0.1)
+    bias = rnd(cout, dev=cuda_device, seed=3)
+    out = O.conv3x3_small(x, w, bias, out_fp32=True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias.float(), padding=1)
+    assert rel(out, ref.permute(0, 2, 3, 1)) < 1e-4
+
+
+@pytest.mark.parametrize("H,W,cout", [(363, 365, 3), (363, 365, 8), (725, 727, 3), (725, 727, 4)])
+def test_conv3x3_small_cout_large_images(cuda_device, H, W, cout):
+    """The thread-per-2/4-pixels kernels that take over from the warp-per-pixel one above 128 k / 512 k pixels
+    (VAE conv_in data gradient at 512 x 512); odd widths leave a ragged last pixel group."""
+    from scaledreamer_b200 import nn_ops as O
+
+    x = rnd(1, H, W, 16, dev=cuda_device, seed=1)
+    w = rnd(cout, 3, 3, 16, dev=cuda_device, seed=2, scale=0.1)
     bias = rnd(cout, dev=cuda_device, seed=3)
     out = O.conv3x3_small(x, w, bias, out_fp32=True)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias.float(), padding=1)
