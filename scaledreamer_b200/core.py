@@ -75,17 +75,26 @@ def _resolver_table(n_gpus: int):
         "tuple2": lambda s: [float(s), float(s)],
         "gt0": lambda s: s > 0,
         "cmaxgt0": lambda s: _cmax(s) > 0,
+        "cmaxgt0orcmaxgt0": lambda a, b: _cmax(a) > 0 or _cmax(b) > 0,
         "not": lambda s: not s,
         "n_gpus": lambda: n_gpus,
     }
 
 
 def _cmax(value):
+    """C_max (threestudio/utils/config.py:31-49): the largest value a scheduled scalar reaches."""
     if isinstance(value, (int, float)):
         return value
     value = list(value)
+    if len(value) >= 6:
+        max_value = value[2]
+        for i in range(4, len(value), 2):
+            max_value = max(max_value, value[i])
+        value = [value[0], value[1], max_value, value[3]]
     if len(value) == 3:
         value = [0] + value
+    if len(value) != 4:
+        raise TypeError(f"Scalar specification must have 3, 4 or >= 6 entries, got {value}")
     return max(value[1], value[2])
 
 

@@ -6,6 +6,7 @@ The reference modules cannot be imported (pytorch-lightning, tinycudann, igl ...
 are taken out of the files by name with `ast`, compiled unchanged and run against a namespace that holds only torch /
 math and inert stand-ins for the type annotations:
     threestudio/utils/misc.py                       C  (scheduled scalars)
+    threestudio/utils/config.py                     C_max and the OmegaConf resolver lambdas
     threestudio/utils/ops.py                        get_ray_directions, get_rays, get_projection_matrix, get_mvp_matrix,
                                                     shifted_expotional_decay
     threestudio/models/prompt_processors/base.py    DirectionConfig, PromptProcessorOutput, shift_azimuth_deg, the
@@ -254,6 +255,25 @@ def main():
                 cases.append({"value": spec, "epoch": epoch, "global_step": step, "interpolation": interp,
                               "out": float(ns["C"](spec, epoch, step, interp))})
     gold["C"] = cases
+
+    # ---- OmegaConf resolvers and C_max: threestudio/utils/config.py:10-49 (the lambdas handed to
+    # OmegaConf.register_new_resolver are taken out of the call expressions)
+    rns = dict(ns, os=os)
+    top_level(f"{REF}/utils/config.py", ["C_max"], rns)
+    src_cfg, tree_cfg = _src(f"{REF}/utils/config.py")
+    resolvers = {}
+    for node in ast.walk(tree_cfg):
+        if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "register_new_resolver":
+            resolvers[node.args[0].value] = eval(compile(ast.Expression(node.args[1]), "config.py", "eval"), rns)
+    sched = [0, 0.0, 0.5, 100, 2.0, 300, -1.0, 1000]
+    calls = [("calc_exp_lr_decay_rate", (0.1, 25000)), ("add", (3, 4.5)), ("sub", (3, 4.5)), ("mul", (3, 4.5)),
+             ("div", (7, 2)), ("idiv", (7, 2)), ("basename", ("a/b/c.yaml",)), ("rmspace", ("a DSLR photo", "_")),
+             ("tuple2", ("1.5",)), ("gt0", (0.0,)), ("gt0", (0.1,)), ("cmaxgt0", ([10000, 0.0, 100.0, 10001],)),
+             ("cmaxgt0", (0.0,)), ("cmaxgt0", ([0.0, 0.0, 5],)), ("cmaxgt0", (sched,)), ("not", (True,)), ("not", (0,)),
+             ("cmaxgt0orcmaxgt0", (0.0, [0, 0.0, 1.0, 10])), ("cmaxgt0orcmaxgt0", (0.0, 0.0))]
+    gold["resolvers"] = {"names": sorted(resolvers), "calls": [(n, a, resolvers[n](*a)) for n, a in calls],
+                         "c_max": [(v, rns["C_max"](v)) for v in (0.5, 3, [0, 0.5, 0.02, 25000], [0.98, 0.5, 25000], sched,
+                                                                  [0, 1.0, 0.1, 10, 4.0, 20])]}
 
     # ---- rays / projection: threestudio/utils/ops.py:183-300, used as data/uncond.py:302-328 uses them
     ns = base_namespace()

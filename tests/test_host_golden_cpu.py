@@ -117,3 +117,17 @@ def test_oracle_mvdream_guidance_matches_reference_call():
     torch.testing.assert_close(g["ctx"][:4], p["text_embeddings"].expand(4, -1, -1))
     torch.testing.assert_close(g["ctx"][4:8], p["uncond_text_embeddings"].expand(4, -1, -1))
     assert torch.equal(g["ctx"][:4], g["ctx"][8:])
+
+
+def test_config_resolvers_match_reference():
+    """The `${name:args}` resolvers of the yaml configs and C_max (threestudio/utils/config.py:10-49)."""
+    from scaledreamer_b200 import core
+
+    r = GOLD["resolvers"]
+    table = core._resolver_table(1)
+    assert set(r["names"]) <= set(table), set(r["names"]) - set(table)
+    for name, args, ref in r["calls"]:
+        got = table[name](*args)
+        assert got == ref and type(got) is type(ref), (name, args, got, ref)
+    for v, ref in r["c_max"]:
+        assert core._cmax(v) == ref, (v, core._cmax(v), ref)
