@@ -1,6 +1,8 @@
 """Command-line entry with the reference's contract (launch.py:267-299 there):
     python launch.py --config configs/x.yaml --train [--gpu 0] key=value ...
-Only --train is implemented (the ASD hot path); validate / test / export are outside the scope of this repo.
+--train runs the ASD hot path; --validate / --test render the evaluation orbit (scaledreamer.py:172-300) and write the
+views as PNG files under <trial_dir>/save/ (rgb | opacity | depth side by side, like the reference's image grid);
+--export (mesh extraction) is outside the scope of this repo. `resume=<ckpt>` loads a Lightning-style state dict.
 """
 import argparse
 import os
@@ -18,8 +20,8 @@ def main() -> None:
     g.add_argument("--export", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args, extras = ap.parse_known_args()
-    if not args.train:
-        raise NotImplementedError("only --train is implemented")
+    if args.export:
+        raise NotImplementedError("--export (mesh extraction) is not implemented")
     if "LOCAL_RANK" not in os.environ:
         os.environ.setdefault("CUDA_VISIBLE_DEVICES", args.gpu)
     import torch
@@ -44,9 +46,34 @@ def main() -> None:
     dm = sd.find(cfg.data_type)(cfg.data)
     system = sd.find(cfg.system_type)(cfg.system)
     trainer = Trainer(**cfg.trainer)
-    trainer.fit(system, dm)
-    if get_rank() == 0 and trainer.history:
-        print(trainer.history[-1])
+    if getattr(cfg, "resume", None):
+        ckpt = torch.load(cfg.resume, map_location="cpu")
+        system.load_state_dict(ckpt.get("state_dict", ckpt), strict=False)
+        system.do_update_step(ckpt.get("epoch", 0), ckpt.get("global_step", 0), on_load_weights=True)
+    if args.train:
+        trainer.fit(system, dm)
+        if get_rank() == 0 and trainer.history:
+            print(trainer.history[-1])
+        return
+    outs = trainer.validate(system, dm) if args.validate else trainer.test(system, dm)
+    if get_rank() == 0:
+        save_views(outs, os.path.join(cfg.trial_dir, "save", "val" if args.validate else "test"))
+
+
+def save_views(outs, out_dir: str) -> None:
+    """One PNG per evaluation view: rgb | opacity | normalised depth (the reference's save_image_grid row)."""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    os.makedirs(out_dir, exist_ok=True)
+    for o in outs:
+        rgb = o["comp_rgb"][0].clamp(0, 1)
+        gray = lambda t: t.reshape(rgb.shape[0], rgb.shape[1], 1).clamp(0, 1).expand(-1, -1, 3)
+        row = torch.cat([rgb, gray(o["opacity"][0])] + ([gray(o["depth"])] if "depth" in o else []), dim=1)
+        img = (row * 255.0).round().to(torch.uint8).cpu().numpy()
+        Image.fromarray(np.ascontiguousarray(img)).save(os.path.join(out_dir, f"{int(o['index'][0])}.png"))
+    print(f"wrote {len(outs)} views to {out_dir}")
 
 
 if __name__ == "__main__":

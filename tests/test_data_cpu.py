@@ -134,3 +134,29 @@ def test_multiprompt_batches_match_reference_datasets(case):
         for k in TENSOR_KEYS:
             if k in ref:
                 torch.testing.assert_close(b[k], ref[k], atol=0, rtol=0, msg=lambda m: f"{case} {k}: {m}")
+
+
+def test_launch_save_views_writes_rgb_opacity_depth_rows(tmp_path):
+    """launch.save_views: one PNG per evaluation view, rgb | opacity | depth side by side."""
+    import sys
+
+    from PIL import Image
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import launch
+
+    H, W = 6, 10
+    outs = [{"index": torch.tensor([i]), "comp_rgb": torch.rand(1, H, W, 3), "opacity": torch.rand(1, H, W, 1),
+             "depth": torch.rand(H, W)} for i in (0, 3)]
+    outs[1].pop("depth")
+    launch.save_views(outs, str(tmp_path / "val"))
+    assert sorted(os.listdir(tmp_path / "val")) == ["0.png", "3.png"]
+    a = Image.open(tmp_path / "val" / "0.png")
+    assert a.size == (3 * W, H)
+    assert Image.open(tmp_path / "val" / "3.png").size == (2 * W, H)
+    import numpy as np
+
+    px = torch.from_numpy(np.asarray(a).copy()).float() / 255.0
+    torch.testing.assert_close(px[:, :W], outs[0]["comp_rgb"][0], atol=0.5 / 255 + 1e-6, rtol=0)
+    torch.testing.assert_close(px[:, W:2 * W, 0], outs[0]["opacity"][0, :, :, 0], atol=0.5 / 255 + 1e-6, rtol=0)
+    torch.testing.assert_close(px[:, 2 * W:, 1], outs[0]["depth"], atol=0.5 / 255 + 1e-6, rtol=0)

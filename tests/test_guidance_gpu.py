@@ -169,3 +169,24 @@ def test_validation_and_test_loops(cuda_device):
         direct = system.renderer(**batch)
     assert torch.equal(direct["comp_rgb"], v1[1]["comp_rgb"])
     assert system.renderer.randomized is False
+
+
+def test_launch_validate_writes_the_evaluation_views(cuda_device, tmp_path):
+    """`launch.py --config ... --validate` (the reference's CLI contract): renders the evaluation orbit in eval mode and
+    writes one rgb | opacity | depth PNG per view under <trial_dir>/save/val/."""
+    import subprocess
+    import sys
+
+    from PIL import Image
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "launch.py"), "--config", CFG, "--validate",
+                        "system.prompt_processor.prompt=a DSLR photo of a hamburger", "data.eval_height=32",
+                        "data.eval_width=48", "data.n_val_views=2", f"exp_root_dir={tmp_path}"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out_dir = os.path.join(str(tmp_path), "asd_sd_nerf", "a_DSLR_photo_of_a_hamburger", "save", "val")
+    files = sorted(os.listdir(out_dir))
+    assert files == ["0.png", "1.png"], files
+    im = Image.open(os.path.join(out_dir, "0.png"))
+    assert im.size == (3 * 48, 32) and im.mode == "RGB"
