@@ -71,7 +71,7 @@ def test_sd_asd_guidance_matches_oracle(cuda_device):
     e_eps = rel(g.buf["eps"].permute(0, 3, 1, 2), eps)
     e_grad = rel(g.buf["grad"].view(B, 16, 16, 4).permute(0, 3, 1, 2), grad)
     e_drgb = rel(rgb_d.grad, x.grad)
-    print(f"guidance parity: eps {e_eps:.2e} grad {e_grad:.2e} loss {float(out['loss_asd']):.4f}/{float(loss):.4f} "
+    print(f"guidance parity: eps {e_eps:.2e} grad {e_grad:.2e} loss {float(out['loss_asd'].detach()):.4f}/{float(loss.detach()):.4f} "
           f"d_rgb {e_drgb:.2e}")
     assert int(g.buf["t_plus"][0]) == int(tp[0])
     assert e_eps < 5e-3 and e_grad < 2e-2
