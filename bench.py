@@ -269,8 +269,8 @@ def main() -> None:
         return out["loss"]
 
     def host_batch():
-        b = ds.collate({})
-        return {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
+        # host tensors; ds.to_device packs them into a pinned staging slot and uploads them with one asynchronous copy
+        return ds.collate({})
 
     def sync_all():
         torch.cuda.synchronize()
