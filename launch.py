@@ -2,7 +2,9 @@
     python launch.py --config configs/x.yaml --train [--gpu 0] key=value ...
 --train runs the ASD hot path; --validate / --test render the evaluation orbit (scaledreamer.py:172-300) and write the
 views as PNG files under <trial_dir>/save/ (rgb | opacity | depth side by side, like the reference's image grid);
---export (mesh extraction) is outside the scope of this repo. `resume=<ckpt>` loads a Lightning-style state dict.
+--export (mesh extraction) is outside the scope of this repo. Checkpoints follow the reference's `checkpoint:` yaml
+section (<trial_dir>/ckpts/last.ckpt, epoch=E-step=N.ckpt; Lightning's dict layout and the reference's state-dict keys);
+`resume=<ckpt>` restores module state, occupancy grid, step counters and optimizer moments.
 """
 import argparse
 import os
@@ -45,11 +47,9 @@ def main() -> None:
     random.seed(seed), np.random.seed(seed), torch.manual_seed(seed)
     dm = sd.find(cfg.data_type)(cfg.data)
     system = sd.find(cfg.system_type)(cfg.system)
-    trainer = Trainer(**cfg.trainer)
+    trainer = Trainer(**cfg.trainer, ckpt_dir=os.path.join(cfg.trial_dir, "ckpts"), checkpoint=cfg.checkpoint)
     if getattr(cfg, "resume", None):
-        ckpt = torch.load(cfg.resume, map_location="cpu")
-        system.load_state_dict(ckpt.get("state_dict", ckpt), strict=False)
-        system.do_update_step(ckpt.get("epoch", 0), ckpt.get("global_step", 0), on_load_weights=True)
+        trainer.load_checkpoint(cfg.resume, system)  # module state, step counters, schedules; optimizer state in fit()
     if args.train:
         trainer.fit(system, dm)
         if get_rank() == 0 and trainer.history:

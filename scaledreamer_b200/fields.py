@@ -40,8 +40,23 @@ class _GridParams(nn.Module):
         self.params = nn.Parameter((torch.rand(n_params, generator=g) * 2 - 1) * 1e-4)
 
 
+class _TCNNEncoding(nn.Module):
+    """Stands where networks.py:55-64 (TCNNEncoding) stands: `.encoding` is the tcnn.Encoding stand-in, so the
+    parameter's state-dict path below a geometry is `encoding.encoding.encoding.params`, as in the reference's
+    checkpoints. `.params` is kept as a shortcut to the same Parameter."""
+
+    def __init__(self, n_params: int):
+        super().__init__()
+        self.encoding = _GridParams(n_params)
+
+    @property
+    def params(self) -> nn.Parameter:
+        return self.encoding.params
+
+
 class HashGridEncoding(nn.Module):
-    """networks.py:55-64 (TCNNEncoding): `.encoding.params`, n_output_dims = n_levels * n_features_per_level."""
+    """networks.py:194-211 (get_encoding): CompositeEncoding(`.encoding` = TCNNEncoding(`.encoding` = tcnn.Encoding
+    with the flat `params`)), include_xyz false. n_output_dims = n_levels * n_features_per_level."""
 
     def __init__(self, n_input_dims: int, config: dict):
         super().__init__()
@@ -55,11 +70,20 @@ class HashGridEncoding(nn.Module):
         self.n_input_dims = n_input_dims
         self.n_output_dims = int(config["n_levels"]) * int(config["n_features_per_level"])
         self.n_entries = L.grid_num_entries(self.grid_cfg)
-        self.encoding = _GridParams(self.n_entries * int(config["n_features_per_level"]))
+        self.encoding = _TCNNEncoding(self.n_entries * int(config["n_features_per_level"]))
+        self._register_load_state_dict_pre_hook(self._accept_flat_key)
+
+    @staticmethod
+    def _accept_flat_key(state_dict, prefix, *unused) -> None:
+        """Checkpoints written by earlier builds of this package held the table one level higher
+        (`<prefix>encoding.params`); move it to the reference's path before the regular load."""
+        old, new = prefix + "encoding.params", prefix + "encoding.encoding.params"
+        if old in state_dict and new not in state_dict:
+            state_dict[new] = state_dict.pop(old)
 
     @property
     def table(self) -> torch.Tensor:
-        return self.encoding.params
+        return self.encoding.encoding.params
 
     def forward(self, x01: torch.Tensor) -> torch.Tensor:
         return R.hashgrid_forward(x01.reshape(-1, 3), self.table.detach().view(-1, 2), self.grid_cfg)
@@ -466,7 +490,38 @@ class NeRFVolumeRenderer(BaseModule):
     def _occ_grid(self, device) -> R.OccGrid:
         if self.occ is None:
             self.occ = R.OccGrid(self.OCC_RES, device, all_occupied=not self.cfg.grid_prune)
+        elif self.occ.occs.device.type != torch.device(device).type:  # module moved after the grid was created
+            self.occ.occs, self.occ.bits, self.occ.mean = (t.to(device) for t in (self.occ.occs, self.occ.bits,
+                                                                                   self.occ.mean))
         return self.occ
+
+    # The occupancy state travels in checkpoints under the names of nerfacc.OccGridEstimator's persistent buffers
+    # (nerfacc 0.5.2 estimators/occ_grid.py; `self.estimator` at nerf_volume_renderer.py:60-65): `estimator.resolution`
+    # int32 [3], `estimator.aabbs` [1,6], `estimator.occs` float [res^3] (cell = (x*res + y)*res + z) and
+    # `estimator.binaries` bool [1,res,res,res], so a Lightning checkpoint of the reference resumes here with its grid.
+    def _save_to_state_dict(self, destination, prefix, keep_vars) -> None:
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        occ, res, dev = self._occ_grid(self.bbox.device), self.OCC_RES, self.bbox.device
+        destination[prefix + "estimator.resolution"] = torch.full((3,), res, dtype=torch.int32, device=dev)
+        destination[prefix + "estimator.aabbs"] = self.bbox.detach().reshape(1, 6).clone()
+        destination[prefix + "estimator.occs"] = occ.occs.detach().clone()
+        destination[prefix + "estimator.binaries"] = occ.binaries().reshape(1, res, res, res)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs) -> None:
+        est = {k[len(prefix) + len("estimator."):]: state_dict.pop(k)
+               for k in [k for k in state_dict if k.startswith(prefix + "estimator.")]}
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
+        if "occs" in est and "binaries" in est:
+            n = self.OCC_RES ** 3
+            if est["occs"].numel() != n or est["binaries"].numel() != n:
+                error_msgs.append(f"{prefix}estimator: occupancy grid of {est['occs'].numel()} cells, expected {n} "
+                                  f"(resolution {self.OCC_RES}, one level)")
+                return
+            self._occ_grid(self.bbox.device).set_binaries(est["binaries"].reshape(-1).bool(), est["occs"].float())
+        elif strict and est.keys() & {"occs", "binaries"}:
+            missing_keys.append(prefix + ("estimator.binaries" if "occs" in est else "estimator.occs"))
 
     def _spec(self) -> R.FieldSpec:
         return R.FieldSpec(bg_grid=self.background.encoding.grid_cfg,

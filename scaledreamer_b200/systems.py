@@ -275,10 +275,19 @@ class Trainer:
     """Minimal fit loop with Lightning's hook order; optional data-parallel gradient averaging over NCCL."""
 
     def __init__(self, max_steps: int = 1, log_every_n_steps: int = 50, accumulate_grad_batches: int = 1,
-                 distributed: Optional[bool] = None, **unused) -> None:
+                 distributed: Optional[bool] = None, ckpt_dir: Optional[str] = None, checkpoint: Optional[dict] = None,
+                 **unused) -> None:
         self.max_steps = int(max_steps)
         self.log_every_n_steps = int(log_every_n_steps)
         self.accumulate = int(accumulate_grad_batches)
+        # launch.py:201-206 of the reference: ModelCheckpoint(dirpath=<trial_dir>/ckpts, **cfg.checkpoint) with
+        # `save_last`, `every_n_train_steps` (the yaml keys of configs/*/asd_*.yaml `checkpoint:`)
+        self.ckpt_dir = ckpt_dir
+        ck = dict(checkpoint or {})
+        self.ckpt_every = int(ck.get("every_n_train_steps") or 0)
+        self.ckpt_save_last = bool(ck.get("save_last", False))
+        self._resume: Optional[Dict[str, Any]] = None
+        self._last_saved_step = -1
         import torch.distributed as dist
 
         self.dist = dist if (distributed if distributed is not None else dist.is_initialized()) else None
@@ -306,6 +315,56 @@ class Trainer:
                 p.grad = view
             off += k
         self.dist.all_reduce(self._flat, op=self.dist.ReduceOp.SUM)
+
+    # ---- checkpoints in the layout Lightning 2.0 writes (what `resume=` / `system.weights=` of the reference read)
+    def checkpoint_dict(self, system: BaseSystem, optimizer: Optional[torch.optim.Optimizer] = None) -> Dict[str, Any]:
+        ckpt = {"epoch": system.true_current_epoch, "global_step": self.global_step,
+                "pytorch-lightning_version": "2.0.0", "state_dict": system.state_dict()}
+        if optimizer is not None:
+            ckpt["optimizer_states"] = [optimizer.state_dict()]
+            ckpt["lr_schedulers"] = []
+        return ckpt
+
+    def save_checkpoint(self, path: str, system: BaseSystem, optimizer: Optional[torch.optim.Optimizer] = None) -> None:
+        """Rank 0 writes (every rank holds the same parameters after the all-reduce); atomic rename so an interrupted
+        write never leaves a truncated `last.ckpt`."""
+        if core.get_rank() != 0:
+            return
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        tmp = path + ".part"
+        torch.save(self.checkpoint_dict(system, optimizer), tmp)
+        os.replace(tmp, path)
+
+    def load_checkpoint(self, path: str, system: BaseSystem) -> Dict[str, Any]:
+        """`trainer.fit(ckpt_path=cfg.resume)` of the reference (launch.py:246-248): restores the module state, the step
+        counters, re-runs the step-dependent schedules (`on_load_weights`) and keeps the optimizer state for `fit`."""
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        sd = ckpt.get("state_dict", ckpt)
+        missing, unexpected = system.load_state_dict(sd, strict=False)
+        own = {k.split(".")[0] for k in system.state_dict()}
+        # entries of modules that are not ours (guidance / prompt processor) and empty tensors (tcnn encodings without
+        # parameters, e.g. SphericalHarmonics `params` of size 0) carry nothing to restore
+        unexpected = [k for k in unexpected if k.split(".")[0] in own and sd[k].numel() > 0]
+        if missing or unexpected:
+            raise RuntimeError(f"checkpoint {path} does not match the system: missing {missing[:8]}, "
+                               f"unexpected {unexpected[:8]}")
+        self.global_step = int(ckpt.get("global_step", 0))
+        system.true_global_step = self.global_step
+        system.true_current_epoch = int(ckpt.get("epoch", 0))
+        system.do_update_step(system.true_current_epoch, system.true_global_step, on_load_weights=True)
+        self._resume = ckpt
+        return ckpt
+
+    def _maybe_checkpoint(self, system: BaseSystem, optimizer, last: bool = False) -> None:
+        if not self.ckpt_dir:
+            return
+        periodic = bool(self.ckpt_every) and self.global_step % self.ckpt_every == 0
+        if periodic and not last:
+            name = f"epoch={system.true_current_epoch}-step={self.global_step}.ckpt"
+            self.save_checkpoint(os.path.join(self.ckpt_dir, name), system, optimizer)
+        if self.ckpt_save_last and (periodic or last) and self._last_saved_step != self.global_step:
+            self.save_checkpoint(os.path.join(self.ckpt_dir, "last.ckpt"), system, optimizer)
+            self._last_saved_step = self.global_step
 
     def _evaluate(self, system: BaseSystem, datamodule, split: str) -> List[Dict[str, Any]]:
         """Lightning's validate / test loop for the evaluation orbit: eval mode (no jitter, no random background, no
@@ -340,6 +399,9 @@ class Trainer:
         if isinstance(optimizer, (FusedAdamW, FusedAdan)):
             optimizer.grad_scale = 1.0 / (self.world_size * self.accumulate)
         params = [p for g in optimizer.param_groups for p in g["params"]]
+        if self._resume is not None and self._resume.get("optimizer_states"):
+            optimizer.load_state_dict(self._resume["optimizer_states"][0])  # moments land on each parameter's device
+        self._resume = None
         micro = 0
         while self.global_step < self.max_steps:
             batch = next(loader)
@@ -357,8 +419,10 @@ class Trainer:
                 optimizer.zero_grad(set_to_none=False)
                 self.global_step += 1
                 system.true_global_step = self.global_step
+                self._maybe_checkpoint(system, optimizer)
             system.do_update_step_end(system.true_current_epoch, system.true_global_step)
             if self.log_every_n_steps and self.global_step % self.log_every_n_steps == 0 and micro % self.accumulate == 0:
                 rec = {k: (float(v.detach()) if torch.is_tensor(v) else v) for k, v in system.logged.items()}
                 rec["step"] = self.global_step
                 self.history.append(rec)
+        self._maybe_checkpoint(system, optimizer, last=True)

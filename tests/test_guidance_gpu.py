@@ -91,8 +91,8 @@ def test_training_step_end_to_end_with_reference_schema_yaml(cuda_device):
     dm = sd.find(cfg.data_type)(cfg.data)
     system = sd.find(cfg.system_type)(cfg.system)
     before = {k: v.detach().clone() for k, v in system.state_dict().items() if v.numel() > 0}
-    assert {"geometry.encoding.encoding.params", "geometry.density_network.layers.0.weight",
-            "geometry.feature_network.layers.2.weight", "background.encoding.encoding.params",
+    assert {"geometry.encoding.encoding.encoding.params", "geometry.density_network.layers.0.weight",
+            "geometry.feature_network.layers.2.weight", "background.encoding.encoding.encoding.params",
             "background.network.layers.4.weight"} <= set(before)
     tr = Trainer(**cfg.trainer)
     tr.fit(system, dm)
@@ -102,7 +102,7 @@ def test_training_step_end_to_end_with_reference_schema_yaml(cuda_device):
     assert all(k in last for k in ("train/loss_asd", "train/grad_norm", "train/min_step", "train/max_step"))
     assert last["train/loss_asd"] > 0 and last["train/loss_asd"] == last["train/loss_asd"]
     after = system.state_dict()
-    assert (after["geometry.encoding.encoding.params"] != before["geometry.encoding.encoding.params"]).any()
+    assert (after["geometry.encoding.encoding.encoding.params"] != before["geometry.encoding.encoding.encoding.params"]).any()
     assert (after["geometry.feature_network.layers.2.weight"] != before["geometry.feature_network.layers.2.weight"]).any()
 
 
