@@ -190,3 +190,45 @@ def test_launch_validate_writes_the_evaluation_views(cuda_device, tmp_path):
     assert files == ["0.png", "1.png"], files
     im = Image.open(os.path.join(out_dir, "0.png"))
     assert im.size == (3 * 48, 32) and im.mode == "RGB"
+
+
+def test_checkpoint_resume_on_the_device(cuda_device, tmp_path):
+    """Two optimizer steps write <ckpt_dir>/last.ckpt in Lightning's layout with the reference's state-dict keys; a fresh
+    system resumed from it holds the same hash table, MLPs, occupancy grid (bit for bit) and AdamW moments, renders the
+    same evaluation view, and continues from step 2."""
+    import scaledreamer_b200 as sd
+    from scaledreamer_b200.systems import Trainer
+
+    cli = ["system.prompt_processor.prompt=a DSLR photo of a hamburger", "data.width=[64,64]", "data.height=[64,64]",
+           "data.eval_height=32", "data.eval_width=32", "data.n_val_views=1", "trainer.max_steps=2",
+           "trainer.log_every_n_steps=1"]
+    torch.manual_seed(2)
+    cfg = sd.load_config(CFG, cli_args=cli)
+    dm = sd.find(cfg.data_type)(cfg.data)
+    system = sd.find(cfg.system_type)(cfg.system)
+    tr = Trainer(**cfg.trainer, ckpt_dir=str(tmp_path), checkpoint={"save_last": True, "every_n_train_steps": 2})
+    tr.fit(system, dm)
+    torch.cuda.synchronize()
+    assert sorted(os.listdir(tmp_path)) == ["epoch=0-step=2.ckpt", "last.ckpt"]
+    ck = torch.load(tmp_path / "last.ckpt", map_location="cpu", weights_only=False)
+    assert ck["global_step"] == 2 and ck["state_dict"]["renderer.estimator.binaries"].shape == (1, 32, 32, 32)
+    assert ck["state_dict"]["renderer.estimator.binaries"].any()  # the warm-up refresh marked the blob
+    view = tr.validate(system, dm)[0]["comp_rgb"]
+
+    torch.manual_seed(99)
+    fresh = sd.find(cfg.system_type)(cfg.system)
+    tr2 = Trainer(**{**cfg.trainer, "max_steps": 3}, ckpt_dir=str(tmp_path / "second"), checkpoint={})
+    tr2.load_checkpoint(str(tmp_path / "last.ckpt"), fresh)
+    assert tr2.global_step == 2 and fresh.true_global_step == 2
+    a, b = system.state_dict(), fresh.state_dict()
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(fresh.renderer.occ.bits, system.renderer.occ.bits)
+    assert torch.equal(tr2.validate(fresh, dm)[0]["comp_rgb"], view)
+    tr2.fit(fresh, dm)
+    torch.cuda.synchronize()
+    assert tr2.global_step == 3 and tr2.history[-1]["step"] == 3
+    assert not os.path.exists(tmp_path / "second")  # an empty `checkpoint:` section writes nothing
+    table = "geometry.encoding.encoding.encoding.params"
+    assert (fresh.state_dict()[table] != a[table]).any()
