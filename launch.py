@@ -61,19 +61,30 @@ def main() -> None:
 
 
 def save_views(outs, out_dir: str) -> None:
-    """One PNG per evaluation view: rgb | opacity | normalised depth (the reference's save_image_grid row)."""
+    """One PNG per evaluation view: rgb | [normal |] opacity | normalised depth (the reference's save_image_grid row). The
+    multi-prompt systems return several views per batch and a `name`: those go to <out_dir>/<name>/<index>.png
+    (multiprompt_radience_field_generator.py:236-240)."""
     import numpy as np
     import torch
     from PIL import Image
 
-    os.makedirs(out_dir, exist_ok=True)
+    n = 0
     for o in outs:
-        rgb = o["comp_rgb"][0].clamp(0, 1)
-        gray = lambda t: t.reshape(rgb.shape[0], rgb.shape[1], 1).clamp(0, 1).expand(-1, -1, 3)
-        row = torch.cat([rgb, gray(o["opacity"][0])] + ([gray(o["depth"])] if "depth" in o else []), dim=1)
-        img = (row * 255.0).round().to(torch.uint8).cpu().numpy()
-        Image.fromarray(np.ascontiguousarray(img)).save(os.path.join(out_dir, f"{int(o['index'][0])}.png"))
-    print(f"wrote {len(outs)} views to {out_dir}")
+        sub = os.path.join(out_dir, o["name"]) if "name" in o else out_dir
+        os.makedirs(sub, exist_ok=True)
+        for v in range(o["comp_rgb"].shape[0]):
+            rgb = o["comp_rgb"][v].clamp(0, 1)
+            gray = lambda t: t.reshape(rgb.shape[0], rgb.shape[1], 1).clamp(0, 1).expand(-1, -1, 3)
+            cells = [rgb]
+            if "comp_normal" in o:
+                cells.append(o["comp_normal"][v].clamp(0, 1))
+            cells.append(gray(o["opacity"][v]))
+            if "depth" in o:
+                cells.append(gray(o["depth"] if o["depth"].dim() == 2 else o["depth"][v]))
+            img = (torch.cat(cells, dim=1) * 255.0).round().to(torch.uint8).cpu().numpy()
+            Image.fromarray(np.ascontiguousarray(img)).save(os.path.join(sub, f"{int(o['index'][v])}.png"))
+            n += 1
+    print(f"wrote {n} views to {out_dir}")
 
 
 if __name__ == "__main__":

@@ -32,7 +32,8 @@ import torch.nn.functional as F
 from . import lib as L
 from . import core
 from .core import BaseModule, BaseObject, find, get_rank, parse_structured, register
-from .data import RandomCameraDataModuleConfig, RandomCameraIterableDataset, RandomMultiviewCameraIterableDataset
+from .data import (RandomCameraDataModuleConfig, RandomCameraDataset, RandomCameraIterableDataset,
+                   RandomMultiviewCameraIterableDataset)
 from .fields import DEFAULT_GRID, HashGridEncoding, _TinyMLP, tiny_mlp
 from .prompts import DIRECTIONS, PromptProcessorOutput, hash_prompt
 from .systems import BaseSystem, binary_cross_entropy
@@ -641,6 +642,20 @@ class GenerativeSpaceVolSDFVolumeRenderer(BaseModule):
         Bc = text_embed.shape[0] if text_embed is not None else B
         if space_cache is None:
             space_cache = self.geometry.generate_space_cache(styles=noise, text_embed=text_embed)
+        if Bc != B and not self.training:
+            # inference over an orbit of ONE generated space: one view at a time (the reference's chunk_batch_original
+            # with chunk_size 1, generative_space_volsdf_volume_renderer.py:131-157), so an evaluation batch of 120
+            # 512x512 views never holds more than one view's samples
+            assert Bc == 1, "batch_size of space_cache must be 1 or equal to batch_size of rays_o"
+            per_view = lambda t, i, n: t[i * n:(i + 1) * n] if torch.is_tensor(t) else t
+            outs = [self.forward(rays_o[i:i + 1], rays_d[i:i + 1],
+                                 None if light_positions is None else light_positions[i:i + 1],
+                                 bg_color=per_view(bg_color, i, 1) if torch.is_tensor(bg_color) and bg_color.dim() > 1
+                                 and bg_color.shape[0] == B else bg_color,
+                                 noise=noise, space_cache=space_cache, text_embed=text_embed,
+                                 u_coarse=per_view(u_coarse, i, H * W), u_fine=per_view(u_fine, i, H * W))
+                    for i in range(B)]
+            return {k: torch.cat([o[k] for o in outs], dim=0) for k in outs[0]}
         if Bc != B:
             if not self.training:
                 assert Bc == 1, "batch_size of space_cache must be 1 or equal to batch_size of rays_o"
@@ -744,23 +759,130 @@ class MultipromptRandomCameraIterableDataset(RandomCameraIterableDataset):
         return out
 
 
-@register("multiprompt-camera-datamodule")
-class MultipromptCameraDataModule:
-    def __init__(self, cfg=None) -> None:
-        self.cfg = parse_structured(MultipromptRandomCameraDataModuleConfig, cfg)
-        rank, world = _world()
-        self.prompt_library = load_prompt_library(self.cfg, rank, world)
-        self.train_dataset = None
+class MultipromptRandomCameraDataset4Test:
+    """Evaluation set of the multi-prompt data modules (multiprompt.py:85-122): one batch per prompt of the split holding
+    the WHOLE evaluation orbit (all n_val_views / n_test_views cameras) and one noise row; the renderer walks the views
+    one at a time against the single generated space."""
+
+    def __init__(self, cfg: Any, split: str, prompt_library: Dict) -> None:
+        self.dataset = RandomCameraDataset(cfg, split)
+        self.cfg, self.n_views = cfg, self.dataset.n_views
+        start_point = torch.randn(cfg.dim_gaussian)
+        end_point = torch.randn(cfg.dim_gaussian)
+        self.noises = torch.stack([start_point + (end_point - start_point) * i / self.n_views
+                                   for i in range(self.n_views)])
+        self.prompt_library = prompt_library[split] if split in prompt_library else prompt_library["val"]
+        self._views: Optional[Dict[str, Any]] = None
+
+    def __len__(self) -> int:
+        return len(self.prompt_library)
+
+    def __iter__(self):
+        for prompt in self.prompt_library:
+            yield {"prompt": [prompt]}
+
+    def collate(self, batch: Dict[str, Any]) -> Dict[str, Any]:
+        if self._views is None:
+            self._views = self.dataset.collate([self.dataset[i] for i in range(self.n_views)])
+        out = dict(self._views)
+        out["noise"] = self.noises[0][None, :]
+        out.update(batch)
+        return out
+
+    def to_device(self, batch: Dict[str, Any], device) -> Dict[str, Any]:
+        return self.dataset.to_device(batch, device)
+
+
+class MultipromptRandomCameraDataset4FixPrompt:
+    """`data.eval_prompt=...` (multiprompt.py:125-164): one view per batch, always the same prompt and a zero noise row;
+    with `target_prompt` the text embedding is interpolated along the orbit (`ratio` = linspace(0, 1, n_views)), with
+    `eval_fix_camera` every batch uses that one camera. Batches are collated with batch size 1 (multiprompt.py:230-234)."""
+
+    def __init__(self, cfg: Any, split: str) -> None:
+        self.dataset = RandomCameraDataset(cfg, split)
+        self.cfg, self.n_views = cfg, self.dataset.n_views
+        self.noise = torch.zeros(cfg.dim_gaussian)
+        self.eval_prompt, self.target_prompt = cfg.eval_prompt, cfg.target_prompt
+        self.ratios = torch.linspace(0, 1, self.n_views)
+        self.fix_camera = cfg.eval_fix_camera
+
+    def __len__(self) -> int:
+        return self.n_views
+
+    def __getitem__(self, idx: int) -> Dict[str, Any]:
+        item = self.dataset[self.fix_camera] if self.fix_camera else self.dataset[idx]
+        item.update(noise=self.noise, prompt=self.eval_prompt, index=idx)
+        if self.target_prompt is not None:
+            item.update(prompt_target=self.target_prompt, ratio=self.ratios[idx])
+        item["name"] = "_to_".join([self.eval_prompt, self.target_prompt]) if self.target_prompt is not None \
+            else self.eval_prompt
+        return item
+
+    def __iter__(self):
+        for idx in range(self.n_views):
+            yield self.collate([self[idx]])
+
+    def collate(self, items: List[Dict[str, Any]]) -> Dict[str, Any]:
+        strings = {k: [it[k] for it in items] for k in ("prompt", "prompt_target", "name") if k in items[0]}
+        out = self.dataset.collate([{k: v for k, v in it.items() if k not in strings} for it in items])
+        out.update(strings)
+        return out
+
+    def to_device(self, batch: Dict[str, Any], device) -> Dict[str, Any]:
+        return self.dataset.to_device(batch, device)
+
+
+class _MultipromptEvalLoaders:
+    """setup / val_dataloader / test_dataloader shared by the two multi-prompt data modules (multiprompt.py:189-238,
+    multiview_multiprompt.py:100-111)."""
+
+    train_cls: Any = None
 
     def setup(self, stage=None) -> None:
         if stage in (None, "fit"):
-            self.train_dataset = MultipromptRandomCameraIterableDataset(self.cfg, self.prompt_library)
+            self.train_dataset = self.train_cls(self.cfg, self.prompt_library)
+        if stage in (None, "fit", "validate"):
+            self.val_dataset = MultipromptRandomCameraDataset4Test(self.cfg, "val", self.prompt_library)
+        if stage in (None, "test", "predict"):
+            if self.cfg.eval_prompt is not None:
+                self.test_dataset = MultipromptRandomCameraDataset4FixPrompt(self.cfg, "test")
+            else:
+                self.test_dataset = MultipromptRandomCameraDataset4Test(self.cfg, "test", self.prompt_library)
+
+    @staticmethod
+    def _loader(ds):
+        if isinstance(ds, MultipromptRandomCameraDataset4FixPrompt):
+            yield from ds
+        else:
+            for item in ds:
+                yield ds.collate(item)
+
+    def val_dataloader(self):
+        if getattr(self, "val_dataset", None) is None:
+            self.setup("validate")
+        return self._loader(self.val_dataset)
+
+    def test_dataloader(self):
+        if getattr(self, "test_dataset", None) is None:
+            self.setup("test")
+        return self._loader(self.test_dataset)
 
     def train_dataloader(self):
         if self.train_dataset is None:
             self.setup("fit")
         while True:
             yield self.train_dataset.collate({})
+
+
+@register("multiprompt-camera-datamodule")
+class MultipromptCameraDataModule(_MultipromptEvalLoaders):
+    train_cls = MultipromptRandomCameraIterableDataset
+
+    def __init__(self, cfg=None) -> None:
+        self.cfg = parse_structured(MultipromptRandomCameraDataModuleConfig, cfg)
+        rank, world = _world()
+        self.prompt_library = load_prompt_library(self.cfg, rank, world)
+        self.train_dataset = self.val_dataset = self.test_dataset = None
 
 
 @dataclass
@@ -791,22 +913,14 @@ class MultiviewMultipromptRandomCameraIterableDataset(RandomMultiviewCameraItera
 
 
 @register("multiprompt-multiview-camera-datamodule")
-class MultiviewMultipromptCameraDataModule:
+class MultiviewMultipromptCameraDataModule(_MultipromptEvalLoaders):
+    train_cls = MultiviewMultipromptRandomCameraIterableDataset
+
     def __init__(self, cfg=None) -> None:
         self.cfg = parse_structured(MultiviewMultipromptRandomCameraDataModuleConfig, cfg)
         rank, world = _world()
         self.prompt_library = load_prompt_library(self.cfg, rank, world)
-        self.train_dataset = None
-
-    def setup(self, stage=None) -> None:
-        if stage in (None, "fit"):
-            self.train_dataset = MultiviewMultipromptRandomCameraIterableDataset(self.cfg, self.prompt_library)
-
-    def train_dataloader(self):
-        if self.train_dataset is None:
-            self.setup("fit")
-        while True:
-            yield self.train_dataset.collate({})
+        self.train_dataset = self.val_dataset = self.test_dataset = None
 
 
 # ------------------------------------------------------------------------------------------------ prompts
@@ -1004,6 +1118,14 @@ class MultipromptRadienceFieldGeneratorSystem(BaseSystem):
             self.geometry.initialize_shape()
         self.prompt_processor = find(self.cfg.prompt_processor_type)(self.cfg.prompt_processor)
 
+    def on_test_start(self) -> None:
+        """multiprompt_radience_field_generator.py:83-91: evaluation without a preceding fit only needs the prompt processor
+        (the guidance networks are never built for --validate / --test)."""
+        if not hasattr(self, "prompt_processor"):
+            self.prompt_processor = find(self.cfg.prompt_processor_type)(self.cfg.prompt_processor)
+
+    on_validation_start = on_predict_start = on_test_start
+
     def forward(self, batch: Dict[str, Any]) -> Dict[str, Any]:
         self.prompt_utils = self.prompt_processor(prompt=batch["prompt"])
         if "prompt_target" in batch:
@@ -1049,3 +1171,27 @@ class MultipromptRadienceFieldGeneratorSystem(BaseSystem):
             loss = loss + loss_eikonal * self.C(lam["lambda_eikonal"])
             self.log("train/inv_std", out["inv_std"])
         return {"loss": loss}
+
+    def _eval_images(self, batch, name_key: str) -> Dict[str, Any]:
+        """validation_step / test_step (multiprompt_radience_field_generator.py:218-300, 318-385) up to the image grid:
+        every view of the batch as rgb | normal | opacity | per-view min-max normalised depth, filed under the prompt
+        (`it{step}-val/{name}/{index}.png` in the reference). Writing files / videos stays with the caller."""
+        out = self(batch)
+        label = batch[name_key][0] if name_key in batch else batch["prompt"][0]
+        res = {"name": label.replace(",", "").replace(".", "").replace(" ", "_"), "index": batch["index"],
+               "comp_rgb": out["comp_rgb"], "opacity": out["opacity"]}
+        if "comp_normal" in out:
+            res["comp_normal"] = out["comp_normal"]
+        if "depth" in out:
+            d = out["depth"][..., 0]
+            lo, hi = d.amin(dim=(1, 2), keepdim=True), d.amax(dim=(1, 2), keepdim=True)
+            res["depth"] = (d - lo) / (hi - lo)
+        return res
+
+    def validation_step(self, batch, batch_idx):
+        if self.cfg.visualize_samples:
+            raise NotImplementedError
+        return self._eval_images(batch, "prompt")
+
+    def test_step(self, batch, batch_idx):
+        return self._eval_images(batch, "name")

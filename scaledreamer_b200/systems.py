@@ -374,6 +374,9 @@ class Trainer:
         dataset = datamodule.val_dataset if split == "val" else datamodule.test_dataset
         was_training = system.training
         system.eval()
+        hook = getattr(system, "on_validation_start" if split == "val" else "on_test_start", None)
+        if hook is not None:
+            hook()
         outs = []
         with torch.no_grad():
             for i, host_batch in enumerate(loader):

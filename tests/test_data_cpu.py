@@ -160,3 +160,40 @@ def test_launch_save_views_writes_rgb_opacity_depth_rows(tmp_path):
     torch.testing.assert_close(px[:, :W], outs[0]["comp_rgb"][0], atol=0.5 / 255 + 1e-6, rtol=0)
     torch.testing.assert_close(px[:, W:2 * W, 0], outs[0]["opacity"][0, :, :, 0], atol=0.5 / 255 + 1e-6, rtol=0)
     torch.testing.assert_close(px[:, 2 * W:, 1], outs[0]["depth"], atol=0.5 / 255 + 1e-6, rtol=0)
+
+
+EVAL_GOLD = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_data_golden.pt"))
+EVAL_KEYS = ("mvp_mtx", "c2w", "camera_positions", "light_positions", "elevation", "azimuth", "camera_distances", "fovy",
+             "proj_mtx", "noise", "ratio")
+
+
+@pytest.mark.parametrize("i", range(len(EVAL_GOLD["cases"])))
+def test_multiprompt_evaluation_batches_match_reference_datasets(i, tmp_path, monkeypatch):
+    """custom/amortized/data/multiprompt.py:85-164 through the data modules' val / test loaders: per-prompt batches that
+    hold the whole orbit (library split), or one view per batch for `eval_prompt` (with `target_prompt` interpolation
+    ratios and `eval_fix_camera`, including the reference's `if self.fix_camera` treatment of camera 0)."""
+    import json
+
+    import scaledreamer_b200 as sd
+
+    c = EVAL_GOLD["cases"][i]
+    os.makedirs(tmp_path / "load")
+    json.dump(EVAL_GOLD["library"], open(tmp_path / "load" / "lib.json", "w"))
+    monkeypatch.chdir(tmp_path)
+    for name in ("multiprompt-camera-datamodule", "multiprompt-multiview-camera-datamodule"):
+        dm = sd.find(name)(dict(c["config"], prompt_library="lib"))
+        if "seed" in c:
+            torch.manual_seed(c["seed"])
+        dm.setup("validate" if c["split"] == "val" else "test")
+        loader = dm.val_dataloader() if c["split"] == "val" else dm.test_dataloader()
+        batches = list(loader)
+        assert len(batches) == len(c["batches"])
+        for b, ref in zip(batches, c["batches"]):
+            for k in ("prompt", "prompt_target", "name"):
+                assert b.get(k) == ref.get(k), k
+            assert b["index"].tolist() == ref["index"].tolist()
+            assert b["height"] == int(ref["height"][0]) and b["width"] == int(ref["width"][0])
+            for k in EVAL_KEYS:
+                assert (k in b) == (k in ref), k
+                if k in ref:
+                    torch.testing.assert_close(b[k], ref[k], atol=0, rtol=0, msg=lambda m: f"{c['kind']} {k}: {m}")

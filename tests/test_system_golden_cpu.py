@@ -90,3 +90,45 @@ def test_optimizer_groups_match_reference_parse_optimizer():
     for k in o["untouched"]:
         assert id(dict(model.named_parameters())[k]) not in named
     assert opt.defaults["betas"] == (0.0, 0.99) or tuple(opt.param_groups[0]["betas"]) == (0.0, 0.99)
+
+
+def test_multiprompt_evaluation_steps_and_saved_views(tmp_path):
+    """validation_step / test_step of the multi-prompt system (multiprompt_radience_field_generator.py:218-385): views
+    filed under the sanitised prompt (test: under `name` when the fix-prompt data set supplies one), depth normalised
+    per view; launch.save_views writes <name>/<index>.png rows of rgb | normal | opacity | depth."""
+    import sys
+
+    from PIL import Image
+
+    from scaledreamer_b200.amortized import MultipromptRadienceFieldGeneratorSystem as Sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import launch
+
+    B, H, W = 3, 5, 7
+    g = torch.Generator().manual_seed(0)
+    out = {"comp_rgb": torch.rand(B, H, W, 3, generator=g), "comp_normal": torch.rand(B, H, W, 3, generator=g),
+           "opacity": torch.rand(B, H, W, 1, generator=g), "depth": torch.rand(B, H, W, 1, generator=g) * 4 + 1}
+
+    class Stub:
+        cfg = type("Cfg", (), {"visualize_samples": False})()
+        _eval_images = Sys._eval_images
+        validation_step = Sys.validation_step
+        test_step = Sys.test_step
+
+        def __call__(self, batch):
+            return out
+
+    batch = {"prompt": ["a red apple, on a table."], "index": torch.arange(B)}
+    v = Stub().validation_step(batch, 0)
+    assert v["name"] == "a_red_apple_on_a_table" and v["index"].tolist() == [0, 1, 2]
+    for i in range(B):
+        d = out["depth"][i, :, :, 0]
+        torch.testing.assert_close(v["depth"][i], (d - d.min()) / (d.max() - d.min()))
+    t = Stub().test_step({**batch, "name": ["a corgi_to_a cat"]}, 0)
+    assert t["name"] == "a_corgi_to_a_cat"
+    assert Stub().test_step(batch, 0)["name"] == v["name"]  # library test set: no `name`, the prompt is used
+    launch.save_views([v, t], str(tmp_path))
+    assert sorted(os.listdir(tmp_path)) == ["a_corgi_to_a_cat", "a_red_apple_on_a_table"]
+    assert sorted(os.listdir(tmp_path / "a_red_apple_on_a_table")) == ["0.png", "1.png", "2.png"]
+    assert Image.open(tmp_path / "a_red_apple_on_a_table" / "2.png").size == (4 * W, H)
