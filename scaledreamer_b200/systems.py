@@ -380,6 +380,12 @@ class Trainer:
         outs = []
         with torch.no_grad():
             for i, host_batch in enumerate(loader):
+                # on_validation_batch_start / on_test_batch_start (systems/base.py:186-196): the step-dependent state
+                # (finite-difference eps, progressive bands, ...) is refreshed before every evaluation batch; in eval
+                # mode the renderers leave their occupancy grids alone
+                if hasattr(dataset, "update_step"):
+                    dataset.update_step(system.true_current_epoch, system.true_global_step)
+                system.do_update_step(system.true_current_epoch, system.true_global_step)
                 batch = dataset.to_device(host_batch, device)
                 outs.append(system.validation_step(batch, i) if split == "val" else system.test_step(batch, i))
         system.train(was_training)
