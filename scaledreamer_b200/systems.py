@@ -118,6 +118,27 @@ def parse_optimizer(config: dict, model: nn.Module) -> torch.optim.Optimizer:
     raise NotImplementedError(f"optimizer {name}")
 
 
+def parse_scheduler(config: dict, optimizer: torch.optim.Optimizer) -> Dict[str, Any]:
+    """threestudio/systems/utils.py:74-104: `{name, args, interval}` -> torch.optim.lr_scheduler instance; `SequentialLR`
+    (with `schedulers`, `milestones`) and `ChainedScheduler` (with `schedulers`) nest. interval is "epoch" (default) or
+    "step"."""
+    from torch.optim import lr_scheduler
+
+    interval = config.get("interval", "epoch")
+    assert interval in ["epoch", "step"]
+    name = config["name"]
+    if name == "SequentialLR":
+        sched = lr_scheduler.SequentialLR(optimizer, [parse_scheduler(c, optimizer)["scheduler"] for c in config["schedulers"]],
+                                          milestones=list(config["milestones"]))
+    elif name == "ChainedScheduler":
+        sched = lr_scheduler.ChainedScheduler([parse_scheduler(c, optimizer)["scheduler"] for c in config["schedulers"]])
+    elif hasattr(lr_scheduler, name):
+        sched = getattr(lr_scheduler, name)(optimizer, **dict(config.get("args", {})))
+    else:
+        raise NotImplementedError(f"scheduler {name}")
+    return {"scheduler": sched, "interval": interval}
+
+
 # ------------------------------------------------------------------------------------------------ system
 def binary_cross_entropy(input, target):
     """threestudio/utils/ops.py:365-369"""
@@ -162,6 +183,10 @@ class BaseSystem(nn.Module, Updateable):
 
     def configure_optimizers(self):
         return parse_optimizer(self.cfg.optimizer, self)
+
+    def configure_scheduler(self, optimizer) -> Optional[Dict[str, Any]]:
+        """The `lr_scheduler` half of the reference's configure_optimizers (systems/base.py:101-112)."""
+        return parse_scheduler(self.cfg.scheduler, optimizer) if self.cfg.scheduler is not None else None
 
     def on_fit_start(self) -> None:
         pass
@@ -288,6 +313,7 @@ class Trainer:
         self.ckpt_save_last = bool(ck.get("save_last", False))
         self._resume: Optional[Dict[str, Any]] = None
         self._last_saved_step = -1
+        self._scheduler: Optional[Dict[str, Any]] = None
         import torch.distributed as dist
 
         self.dist = dist if (distributed if distributed is not None else dist.is_initialized()) else None
@@ -322,7 +348,7 @@ class Trainer:
                 "pytorch-lightning_version": "2.0.0", "state_dict": system.state_dict()}
         if optimizer is not None:
             ckpt["optimizer_states"] = [optimizer.state_dict()]
-            ckpt["lr_schedulers"] = []
+            ckpt["lr_schedulers"] = [self._scheduler["scheduler"].state_dict()] if self._scheduler else []
         return ckpt
 
     def save_checkpoint(self, path: str, system: BaseSystem, optimizer: Optional[torch.optim.Optimizer] = None) -> None:
@@ -408,8 +434,14 @@ class Trainer:
         if isinstance(optimizer, (FusedAdamW, FusedAdan)):
             optimizer.grad_scale = 1.0 / (self.world_size * self.accumulate)
         params = [p for g in optimizer.param_groups for p in g["params"]]
+        # Lightning's order: schedulers are built with the optimizer (their constructors already rewrite the learning
+        # rates), THEN the saved optimizer state (moments and the learning rates in force) and scheduler state are loaded
+        configure_scheduler = getattr(system, "configure_scheduler", None)
+        self._scheduler = configure_scheduler(optimizer) if configure_scheduler is not None else None
         if self._resume is not None and self._resume.get("optimizer_states"):
             optimizer.load_state_dict(self._resume["optimizer_states"][0])  # moments land on each parameter's device
+        if self._scheduler and self._resume is not None and self._resume.get("lr_schedulers"):
+            self._scheduler["scheduler"].load_state_dict(self._resume["lr_schedulers"][0])
         self._resume = None
         micro = 0
         while self.global_step < self.max_steps:
@@ -426,6 +458,10 @@ class Trainer:
                     self._allreduce_grads(params)
                 optimizer.step()
                 optimizer.zero_grad(set_to_none=False)
+                # Lightning steps "step"-interval schedulers after every optimizer step; "epoch"-interval ones at epoch
+                # end, which an endless camera stream (IterableDataset without a length) never reaches
+                if self._scheduler and self._scheduler["interval"] == "step":
+                    self._scheduler["scheduler"].step()
                 self.global_step += 1
                 system.true_global_step = self.global_step
                 self._maybe_checkpoint(system, optimizer)

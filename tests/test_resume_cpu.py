@@ -170,3 +170,59 @@ def test_resume_refuses_a_checkpoint_of_another_model(tmp_path, monkeypatch):
     torch.save({"state_dict": sd, "global_step": 2, "epoch": 0}, tmp_path / "ok.ckpt")
     tr.load_checkpoint(str(tmp_path / "ok.ckpt"), system)
     assert tr.global_step == 2
+
+
+def test_lr_scheduler_follows_torch_and_survives_a_resume(tmp_path, monkeypatch):
+    """`system.scheduler` (threestudio/systems/utils.py:74-104, systems/base.py:101-112): nested SequentialLR with
+    interval "step" drives the optimizer's learning rate exactly like the torch schedulers built by hand, its state is
+    written to `lr_schedulers` and a resumed run continues the curve; an "epoch" scheduler never steps on the endless
+    camera stream."""
+    from torch.optim import lr_scheduler
+
+    from scaledreamer_b200 import core
+    from scaledreamer_b200.systems import parse_scheduler
+
+    monkeypatch.setattr(core, "get_device", lambda: torch.device("cpu"))
+    sched_cfg = {"name": "SequentialLR", "interval": "step", "milestones": [3],
+                 "schedulers": [{"name": "LinearLR", "interval": "step", "args": {"start_factor": 0.1, "total_iters": 3}},
+                                {"name": "ExponentialLR", "interval": "step", "args": {"gamma": 0.8}}]}
+
+    def run(path, steps, resume=None):
+        _, system, data, tr = _toy(path, steps, checkpoint={"save_last": True})
+        system.cfg.scheduler = sched_cfg
+        lrs = []
+        step = system.training_step
+
+        def spy(batch, i):
+            lrs.append(tr._opt.param_groups[0]["lr"])
+            return step(batch, i)
+
+        system.training_step = spy
+        make_opt = system.configure_optimizers
+        system.configure_optimizers = lambda: setattr(tr, "_opt", make_opt()) or tr._opt
+        if resume:
+            tr.load_checkpoint(resume, system)
+        tr.fit(system, data)
+        return lrs, tr
+
+    lrs, tr = run(tmp_path / "a", 7)
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=0.05)
+    ref = lr_scheduler.SequentialLR(opt, [lr_scheduler.LinearLR(opt, start_factor=0.1, total_iters=3),
+                                          lr_scheduler.ExponentialLR(opt, gamma=0.8)], milestones=[3])
+    expect = []
+    for _ in range(7):
+        expect.append(opt.param_groups[0]["lr"])
+        opt.step()
+        ref.step()
+    assert lrs == pytest.approx(expect, rel=1e-12) and len(set(lrs)) == 7
+    ck = torch.load(tmp_path / "a" / "ckpts" / "last.ckpt", weights_only=False)
+    assert len(ck["lr_schedulers"]) == 1 and ck["lr_schedulers"][0]["last_epoch"] == 7
+    first, _ = run(tmp_path / "b", 4)
+    second, tr2 = run(tmp_path / "c", 7, resume=str(tmp_path / "b" / "ckpts" / "last.ckpt"))
+    assert first + second == pytest.approx(expect, rel=1e-12) and tr2.global_step == 7
+    # "epoch" interval: constructed, never stepped
+    p2 = torch.optim.SGD([p], lr=1.0)
+    assert parse_scheduler({"name": "ExponentialLR", "args": {"gamma": 0.5}}, p2)["interval"] == "epoch"
+    with pytest.raises(NotImplementedError):
+        parse_scheduler({"name": "NoSuchLR"}, p2)
