@@ -64,19 +64,39 @@ class FusedAdamW(torch.optim.Optimizer):
 
 class FusedAdan(torch.optim.Optimizer):
     """Adan (threestudio/systems/optimizers.py:23-315; the Triplane-Transformer configs), one sdb_adan_step launch per
-    parameter tensor. max_grad_norm > 0 (global-norm clipping with a host sync) is not implemented."""
+    parameter tensor. max_grad_norm > 0 clips by the global gradient norm as the reference does (optimizers.py:108-128: one
+    device reduction and one host read per step); the coefficient is folded into the kernel's gradient scale, so the
+    stored previous gradient is the clipped one, like the reference's in-place `grad.mul_(clip)`."""
 
     def __init__(self, params, lr=1e-3, betas=(0.98, 0.92, 0.99), eps=1e-8, weight_decay=0.0, max_grad_norm=0.0,
                  no_prox=False, foreach=True, **unused):
-        if max_grad_norm > 0:
-            raise NotImplementedError("Adan max_grad_norm > 0 is not implemented")
-        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, no_prox=no_prox))
+        if not 0.0 <= max_grad_norm:
+            raise ValueError("Invalid Max grad norm: {}".format(max_grad_norm))
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, no_prox=no_prox,
+                                      max_grad_norm=max_grad_norm))
         self.grad_scale = 1.0
+
+    @torch.no_grad()
+    def clip_coefficient(self) -> float:
+        """clamp(max_grad_norm / (||g|| + eps), max=1) over every gradient of every group, g being the gradient the
+        update uses (`grad_scale` included: the reference sees DDP-averaged gradients). 1.0 when clipping is off."""
+        max_norm = self.defaults["max_grad_norm"]
+        if max_norm <= 0:
+            return 1.0
+        grads = [p.grad for group in self.param_groups for p in group["params"] if p.grad is not None]
+        if not grads:
+            return 1.0
+        total = torch.zeros(1, device=grads[0].device)
+        for g in grads:
+            total.add_(g.float().pow(2).sum())
+        norm = torch.sqrt(total) * self.grad_scale
+        return float(torch.clamp(max_norm / (norm + self.param_groups[-1]["eps"]), max=1.0).item())
 
     @torch.no_grad()
     def step(self, closure=None):
         lib = L.load()
         st = L.stream_ptr()
+        scale = self.grad_scale * self.clip_coefficient()
         for group in self.param_groups:
             b1, b2, b3 = group["betas"]
             group["step"] = group.get("step", 0) + 1
@@ -91,7 +111,7 @@ class FusedAdan(torch.optim.Optimizer):
                 L.check(lib.sdb_adan_step(L.ptr(p.data), L.ptr(g), L.ptr(state["exp_avg"]), L.ptr(state["exp_avg_sq"]),
                                           L.ptr(state["exp_avg_diff"]), L.ptr(state["prev_grad"]), p.numel(),
                                           float(group["lr"]), float(b1), float(b2), float(b3), float(group["eps"]),
-                                          float(group["weight_decay"]), int(group["step"]), float(self.grad_scale),
+                                          float(group["weight_decay"]), int(group["step"]), float(scale),
                                           int(bool(group["no_prox"])), st), "sdb_adan_step")
         return None
 

@@ -132,3 +132,53 @@ def test_multiprompt_evaluation_steps_and_saved_views(tmp_path):
     assert sorted(os.listdir(tmp_path)) == ["a_corgi_to_a_cat", "a_red_apple_on_a_table"]
     assert sorted(os.listdir(tmp_path / "a_red_apple_on_a_table")) == ["0.png", "1.png", "2.png"]
     assert Image.open(tmp_path / "a_red_apple_on_a_table" / "2.png").size == (4 * W, H)
+
+
+@pytest.mark.parametrize("tag", ["prox", "no_prox"])
+def test_adan_clip_coefficient_matches_reference_trajectory(tag):
+    """FusedAdan(max_grad_norm > 0): the clip coefficient (threestudio/systems/optimizers.py:108-128) folded into the
+    kernel's gradient scale. The reference's own Adan produced the trajectory (tests/golden/make_adan_clip_golden.py,
+    two groups, some steps clipped); here the coefficient comes from FusedAdan.clip_coefficient() and the per-element
+    update is adan_kernel's arithmetic written in torch (the kernel itself: tests/test_zz_multiprompt_eval_gpu.py)."""
+    import math
+
+    from scaledreamer_b200.systems import FusedAdan
+
+    c = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adan_clip_golden.pt"))[tag]
+    ps = [torch.nn.Parameter(p.clone()) for p in c["p0"]]
+    opt = FusedAdan([{"params": [ps[0]], "lr": c["lrs"][0]}, {"params": [ps[1]], "lr": c["lrs"][1]}], lr=1e-2,
+                    betas=c["betas"], eps=c["eps"], weight_decay=c["weight_decay"], no_prox=c["no_prox"],
+                    max_grad_norm=c["max_grad_norm"])
+    b1, b2, b3 = c["betas"]
+    state = [dict(m=torch.zeros_like(p), n=torch.zeros_like(p), d=torch.zeros_like(p), prev=torch.zeros_like(p)) for p in ps]
+    clipped = 0
+    for step in range(1, 7):
+        for p, g in zip(ps, c["grads"][step - 1]):
+            p.grad = g.clone()
+        coef = opt.clip_coefficient()
+        assert coef == pytest.approx(min(1.0, c["max_grad_norm"] / (c["norms"][step - 1] + c["eps"])), rel=1e-6)
+        clipped += coef < 1.0
+        for p, s, lr in zip(ps, state, c["lrs"]):
+            with torch.no_grad():
+                gi = p.grad * coef
+                diff = torch.zeros_like(gi) if step == 1 else gi - s["prev"]
+                s["m"] = b1 * s["m"] + (1 - b1) * gi
+                s["d"] = b2 * s["d"] + (1 - b2) * diff
+                u = b2 * diff + gi
+                s["n"] = b3 * s["n"] + (1 - b3) * u * u
+                s["prev"] = gi
+                denom = s["n"].sqrt() / math.sqrt(1 - b3 ** step) + c["eps"]
+                if c["no_prox"]:
+                    p.mul_(1 - lr * c["weight_decay"])
+                p.sub_((lr / (1 - b1 ** step)) * (s["m"] / denom) + (lr * b2 / (1 - b2 ** step)) * (s["d"] / denom))
+                if not c["no_prox"]:
+                    p.div_(1 + lr * c["weight_decay"])
+        for p, ref in zip(ps, c["params"][step - 1]):
+            torch.testing.assert_close(p.detach(), ref, atol=1e-6, rtol=1e-5)
+    assert clipped == 4  # norms 13.9, 43.1, 29.6, 6.9 against max_grad_norm 5
+    # data-parallel runs hand the optimizer SUMMED gradients and grad_scale = 1 / world: the norm is that of the mean
+    opt.grad_scale = 0.5
+    for p, g in zip(ps, c["grads"][1]):
+        p.grad = g.clone() * 2.0
+    assert opt.clip_coefficient() == pytest.approx(min(1.0, c["max_grad_norm"] / (c["norms"][1] + c["eps"])), rel=1e-6)
+    assert FusedAdan([torch.nn.Parameter(torch.zeros(3))]).clip_coefficient() == 1.0

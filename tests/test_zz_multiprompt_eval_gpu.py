@@ -64,3 +64,22 @@ def test_multiprompt_validate_and_fix_prompt_test_loops(cuda_device, tmp_path, m
     assert len(t) == 4 and all(o["name"] == "a_corgi_sitting" and o["comp_rgb"].shape == (1, 24, 32, 3) for o in t)
     assert [int(o["index"][0]) for o in t] == [0, 1, 2, 3]
     assert (t[0]["comp_rgb"] - t[3]["comp_rgb"]).abs().max() < 5e-3  # the test orbit closes (azimuth 0 and 360)
+
+
+@pytest.mark.parametrize("tag", ["prox", "no_prox"])
+def test_fused_adan_global_norm_clipping_matches_reference(cuda_device, tag):
+    """sdb_adan_step with max_grad_norm > 0 (two parameter groups, some steps clipped) against six steps of the
+    reference's own Adan (tests/golden/make_adan_clip_golden.py). Same note as above: written after the GPU budget."""
+    from scaledreamer_b200.systems import FusedAdan
+
+    c = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adan_clip_golden.pt"))[tag]
+    ps = [torch.nn.Parameter(p.clone().to(cuda_device)) for p in c["p0"]]
+    opt = FusedAdan([{"params": [ps[0]], "lr": c["lrs"][0]}, {"params": [ps[1]], "lr": c["lrs"][1]}], lr=1e-2,
+                    betas=c["betas"], eps=c["eps"], weight_decay=c["weight_decay"], no_prox=c["no_prox"],
+                    max_grad_norm=c["max_grad_norm"])
+    for i in range(6):
+        for p, g in zip(ps, c["grads"][i]):
+            p.grad = g.to(cuda_device)
+        opt.step()
+        for p, ref in zip(ps, c["params"][i]):
+            torch.testing.assert_close(p.detach().cpu(), ref, atol=1e-6, rtol=1e-5)
