@@ -4,7 +4,8 @@
 views as PNG files under <trial_dir>/save/ (rgb | opacity | depth side by side, like the reference's image grid);
 --export (mesh extraction) is outside the scope of this repo. Checkpoints follow the reference's `checkpoint:` yaml
 section (<trial_dir>/ckpts/last.ckpt, epoch=E-step=N.ckpt; Lightning's dict layout and the reference's state-dict keys);
-`resume=<ckpt>` restores module state, occupancy grid, step counters and optimizer moments.
+`resume=<ckpt>` restores module state, occupancy grid, step counters and optimizer moments. During --train the evaluation
+orbit is rendered every `trainer.val_check_interval` batches into <trial_dir>/save/it{step}-val/.
 """
 import argparse
 import os
@@ -47,7 +48,14 @@ def main() -> None:
     random.seed(seed), np.random.seed(seed), torch.manual_seed(seed)
     dm = sd.find(cfg.data_type)(cfg.data)
     system = sd.find(cfg.system_type)(cfg.system)
-    trainer = Trainer(**cfg.trainer, ckpt_dir=os.path.join(cfg.trial_dir, "ckpts"), checkpoint=cfg.checkpoint)
+    save_dir = os.path.join(cfg.trial_dir, "save")
+
+    def on_validation(outs, step):  # scaledreamer.py:172-233: it{step}-val/...; multi-prompt ranks hold different prompts
+        if get_rank() == 0 or (outs and "name" in outs[0]):
+            save_views(outs, os.path.join(save_dir, f"it{step}-val"))
+
+    trainer = Trainer(**cfg.trainer, ckpt_dir=os.path.join(cfg.trial_dir, "ckpts"), checkpoint=cfg.checkpoint,
+                      on_validation=on_validation)
     if getattr(cfg, "resume", None):
         trainer.load_checkpoint(cfg.resume, system)  # module state, step counters, schedules; optimizer state in fit()
     if args.train:
@@ -56,8 +64,8 @@ def main() -> None:
             print(trainer.history[-1])
         return
     outs = trainer.validate(system, dm) if args.validate else trainer.test(system, dm)
-    if get_rank() == 0:
-        save_views(outs, os.path.join(cfg.trial_dir, "save", "val" if args.validate else "test"))
+    if get_rank() == 0 or (outs and "name" in outs[0]):
+        save_views(outs, os.path.join(save_dir, "val" if args.validate else "test"))
 
 
 def save_views(outs, out_dir: str) -> None:

@@ -321,8 +321,13 @@ class Trainer:
 
     def __init__(self, max_steps: int = 1, log_every_n_steps: int = 50, accumulate_grad_batches: int = 1,
                  distributed: Optional[bool] = None, ckpt_dir: Optional[str] = None, checkpoint: Optional[dict] = None,
-                 **unused) -> None:
+                 val_check_interval: Optional[int] = None, on_validation=None, **unused) -> None:
         self.max_steps = int(max_steps)
+        # Lightning's `val_check_interval: N` (int): the validation loop runs after every N training batches; the views
+        # go to `on_validation(outs, global_step)` (launch.py writes them where the reference's savers do). Without a
+        # consumer the loop is skipped: rendering 120 views nobody looks at is not part of a training step.
+        self.val_check_interval = int(val_check_interval) if val_check_interval and on_validation else 0
+        self.on_validation = on_validation
         self.log_every_n_steps = int(log_every_n_steps)
         self.accumulate = int(accumulate_grad_batches)
         # launch.py:201-206 of the reference: ModelCheckpoint(dirpath=<trial_dir>/ckpts, **cfg.checkpoint) with
@@ -490,4 +495,6 @@ class Trainer:
                 rec = {k: (float(v.detach()) if torch.is_tensor(v) else v) for k, v in system.logged.items()}
                 rec["step"] = self.global_step
                 self.history.append(rec)
+            if self.val_check_interval and micro % self.val_check_interval == 0:
+                self.on_validation(self.validate(system, datamodule), self.global_step)
         self._maybe_checkpoint(system, optimizer, last=True)

@@ -226,3 +226,29 @@ def test_lr_scheduler_follows_torch_and_survives_a_resume(tmp_path, monkeypatch)
     assert parse_scheduler({"name": "ExponentialLR", "args": {"gamma": 0.5}}, p2)["interval"] == "epoch"
     with pytest.raises(NotImplementedError):
         parse_scheduler({"name": "NoSuchLR"}, p2)
+
+
+def test_val_check_interval_and_gradient_accumulation(tmp_path, monkeypatch):
+    """trainer.val_check_interval counts training BATCHES (Lightning), trainer.accumulate_grad_batches optimizer-steps every
+    k-th batch (C5: 2): with k = 2 and an interval of 4 the validation views arrive at optimizer steps 2 and 4, the module
+    is back in training mode afterwards, and max_steps counts optimizer steps."""
+    from scaledreamer_b200 import core
+    from scaledreamer_b200.systems import Trainer
+
+    monkeypatch.setattr(core, "get_device", lambda: torch.device("cpu"))
+    _, system, data, _ = _toy(tmp_path, 5)
+    batches, seen = [], []
+    step = system.training_step
+    system.training_step = lambda b, i: (batches.append((i, system.true_global_step, system.training)), step(b, i))[1]
+    system.validation_step = lambda b, i: {"index": b["index"], "mode": system.training}
+    type(data).val_dataset = property(lambda self: self)
+    type(data).val_dataloader = lambda self: iter([{"index": torch.tensor([0])}, {"index": torch.tensor([1])}])
+    tr = Trainer(max_steps=5, log_every_n_steps=1, distributed=False, accumulate_grad_batches=2, val_check_interval=4,
+                 on_validation=lambda outs, s: seen.append((s, [int(o["index"][0]) for o in outs], [o["mode"] for o in outs])))
+    tr.fit(system, data)
+    assert tr.global_step == 5 and len(batches) == 10
+    assert [b[1] for b in batches] == [0, 0, 1, 1, 2, 2, 3, 3, 4, 4] and all(b[2] for b in batches)
+    assert seen == [(2, [0, 1], [False, False]), (4, [0, 1], [False, False])] and system.training
+    assert [r["step"] for r in tr.history] == [1, 2, 3, 4, 5]
+    # without a consumer for the views the loop is skipped
+    assert Trainer(max_steps=1, val_check_interval=4, distributed=False).val_check_interval == 0
