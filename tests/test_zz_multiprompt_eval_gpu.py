@@ -15,6 +15,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.skipif(os.environ.get("SDB_UNVERIFIED_TESTS") != "1",
+                    reason="not yet green on a device: it ran once when the round-1 GPU budget ran out (found and fixed a "
+                           "missing per-batch do_update_step) and has not run since; first item of round 2: "
+                           "SDB_UNVERIFIED_TESTS=1 python -m pytest tests/test_zz_multiprompt_eval_gpu.py")
 def test_multiprompt_validate_and_fix_prompt_test_loops(cuda_device, tmp_path, monkeypatch):
     import scaledreamer_b200 as sd
     from scaledreamer_b200.systems import Trainer
