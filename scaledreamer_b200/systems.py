@@ -107,6 +107,8 @@ class FusedAdan(torch.optim.Optimizer):
                 if not state:
                     for k in ("exp_avg", "exp_avg_sq", "exp_avg_diff", "prev_grad"):
                         state[k] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                elif "prev_grad" not in state:  # optimizer state of the reference's Adan (it keeps minus the gradient)
+                    state["prev_grad"] = state.pop("neg_pre_grad").neg_()
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 L.check(lib.sdb_adan_step(L.ptr(p.data), L.ptr(g), L.ptr(state["exp_avg"]), L.ptr(state["exp_avg_sq"]),
                                           L.ptr(state["exp_avg_diff"]), L.ptr(state["prev_grad"]), p.numel(),
