@@ -59,3 +59,20 @@ def test_product_path_refuses_cpu_tensors():
 
     with pytest.raises(RuntimeError, match="no CPU path"):
         L.ptr(torch.zeros(3))
+
+
+def test_integration_appendix_lists_every_exported_function():
+    """INTEGRATION.md's appendix (tools/abi_table.py) names every function of include/*.h with the line it is declared on."""
+    import subprocess
+    import sys
+
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    table = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "abi_table.py")], capture_output=True, text=True,
+                           check=True).stdout
+    rows = [r for r in table.splitlines() if r.startswith("| `sdb_")]
+    assert len(rows) >= 60
+    missing = [r for r in rows if r not in doc]
+    assert not missing, "run `python tools/abi_table.py` and refresh INTEGRATION.md's appendix:\n" + "\n".join(missing[:5])
+    functions = {re.match(r"\| `(sdb_\w+)`", r).group(1) for r in rows}
+    types = {"sdb_gemm_args", "sdb_grid_cfg", "sdb_prompt_cfg", "sdb_unet_cfg", "sdb_vae_cfg", "sdb_packed_samples"}
+    assert set(declared_symbols()) - types <= functions, sorted(set(declared_symbols()) - types - functions)
