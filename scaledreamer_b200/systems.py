@@ -458,8 +458,12 @@ class Trainer:
         system.train()
         system.on_fit_start()
         optimizer = system.configure_optimizers()
-        if isinstance(optimizer, (FusedAdamW, FusedAdan)):
-            optimizer.grad_scale = 1.0 / (self.world_size * self.accumulate)
+        # gradients arrive SUMMED over ranks and micro-batches; Lightning / DDP hand the optimizer their mean. The fused
+        # optimizers take the factor as a kernel argument, any other optimizer gets its gradients scaled in place.
+        mean_scale = 1.0 / (self.world_size * self.accumulate)
+        fused = isinstance(optimizer, (FusedAdamW, FusedAdan))
+        if fused:
+            optimizer.grad_scale = mean_scale
         params = [p for g in optimizer.param_groups for p in g["params"]]
         # Lightning's order: schedulers are built with the optimizer (their constructors already rewrite the learning
         # rates), THEN the saved optimizer state (moments and the learning rates in force) and scheduler state are loaded
@@ -483,6 +487,8 @@ class Trainer:
             if micro % self.accumulate == 0:
                 if self.dist is not None:
                     self._allreduce_grads(params)
+                if not fused and mean_scale != 1.0:
+                    torch._foreach_mul_([p.grad for p in params if p.grad is not None], mean_scale)
                 optimizer.step()
                 optimizer.zero_grad(set_to_none=False)
                 # Lightning steps "step"-interval schedulers after every optimizer step; "epoch"-interval ones at epoch

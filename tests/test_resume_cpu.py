@@ -252,3 +252,26 @@ def test_val_check_interval_and_gradient_accumulation(tmp_path, monkeypatch):
     assert [r["step"] for r in tr.history] == [1, 2, 3, 4, 5]
     # without a consumer for the views the loop is skipped
     assert Trainer(max_steps=1, val_check_interval=4, distributed=False).val_check_interval == 0
+
+
+def test_accumulated_gradients_reach_a_plain_optimizer_as_their_mean(tmp_path, monkeypatch):
+    """accumulate_grad_batches = k with an optimizer that is not one of the fused kernels: k micro-batch gradients are
+    summed by autograd and divided by k before the step (Lightning divides the loss by k), so one SGD step over two
+    batches equals a step on the mean gradient."""
+    from scaledreamer_b200 import core
+    from scaledreamer_b200.systems import Trainer
+
+    monkeypatch.setattr(core, "get_device", lambda: torch.device("cpu"))
+    _, system, data, _ = _toy(tmp_path, 1)
+    system.configure_optimizers = lambda: torch.optim.SGD(system.geometry.parameters(), lr=0.1)
+    w0 = system.geometry.weight.detach().clone()
+    loader = data.train_dataloader()
+    grads = []
+    for _ in range(2):
+        x = next(loader)["x"]
+        w = w0.clone().requires_grad_(True)
+        ((x @ w.T + system.geometry.bias.detach()) ** 2).mean().backward()
+        grads.append(w.grad)
+    tr = Trainer(max_steps=1, log_every_n_steps=1, distributed=False, accumulate_grad_batches=2)
+    tr.fit(system, data)
+    torch.testing.assert_close(system.geometry.weight.detach(), w0 - 0.1 * (grads[0] + grads[1]) / 2, rtol=1e-6, atol=1e-7)
