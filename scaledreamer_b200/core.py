@@ -374,7 +374,9 @@ def load_module_weights(path, module_name=None, ignore_modules=None, map_locatio
     """Selects `module_name.*` entries of a Lightning-style checkpoint (threestudio/utils/misc.py:33-63)."""
     if module_name is not None and ignore_modules is not None:
         raise ValueError("module_name and ignore_modules cannot be both set")
-    ckpt = torch.load(path, map_location=map_location)
+    # Lightning checkpoints carry more than tensors (hyper-parameters, callback state): the full unpickler, as the
+    # reference (torch < 2.6 semantics) uses
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
     sd = ckpt["state_dict"]
     out = {}
     if ignore_modules is not None:

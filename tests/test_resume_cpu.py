@@ -275,3 +275,34 @@ def test_accumulated_gradients_reach_a_plain_optimizer_as_their_mean(tmp_path, m
     tr = Trainer(max_steps=1, log_every_n_steps=1, distributed=False, accumulate_grad_batches=2)
     tr.fit(system, data)
     torch.testing.assert_close(system.geometry.weight.detach(), w0 - 0.1 * (grads[0] + grads[1]) / 2, rtol=1e-6, atol=1e-7)
+
+
+def test_system_weights_and_ignore_modules(cpu_system, tmp_path):
+    """`system.weights=<ckpt>` with `system.weights_ignore_modules` (systems/base.py:54-60, utils/misc.py:33-63): the named
+    modules keep their fresh initialisation, everything else (occupancy grid included) comes from the checkpoint, and the
+    step-dependent state is replayed at the checkpoint's step with on_load_weights."""
+    import scaledreamer_b200 as sd
+    from scaledreamer_b200.systems import Trainer
+
+    donor = cpu_system("C2")
+    with torch.no_grad():
+        for p in donor.parameters():
+            p.add_(1.0)
+    donor_sd = donor.state_dict()
+    donor_sd["renderer.estimator.binaries"] = torch.ones(1, 32, 32, 32, dtype=torch.bool)
+    donor_sd["renderer.estimator.occs"] = torch.full((32 ** 3,), 0.5)
+    donor.load_state_dict(donor_sd)
+    tr = Trainer(max_steps=0, distributed=False)
+    tr.global_step = 1234
+    donor.true_global_step = 1234
+    path = str(tmp_path / "donor.ckpt")
+    tr.save_checkpoint(path, donor)
+    cfg = sd.load_config(os.path.join(HERE, "configs", "asd_sd_nerf.yaml"),
+                         cli_args=["system.prompt_processor.prompt=a hamburger", f"system.weights={path}",
+                                   "system.weights_ignore_modules=[background]"])
+    system = sd.find(cfg.system_type)(cfg.system)
+    mine, ref = system.state_dict(), donor.state_dict()
+    for k in ref:
+        same = torch.equal(mine[k], ref[k])
+        assert same != k.startswith("background."), k
+    assert bool(system.renderer.occ.binaries().all())
