@@ -5,7 +5,8 @@ views as PNG files under <trial_dir>/save/ (rgb | opacity | depth side by side, 
 --export (mesh extraction) is outside the scope of this repo. Checkpoints follow the reference's `checkpoint:` yaml
 section (<trial_dir>/ckpts/last.ckpt, epoch=E-step=N.ckpt; Lightning's dict layout and the reference's state-dict keys);
 `resume=<ckpt>` restores module state, occupancy grid, step counters and optimizer moments. During --train the evaluation
-orbit is rendered every `trainer.val_check_interval` batches into <trial_dir>/save/it{step}-val/.
+orbit is rendered every `trainer.val_check_interval` batches into <trial_dir>/save/it{step}-val/, and the test orbit once
+after the last step into save/it{step}-test/ (the reference's --train ends with trainer.test).
 """
 import argparse
 import os
@@ -62,6 +63,9 @@ def main() -> None:
         trainer.fit(system, dm)
         if get_rank() == 0 and trainer.history:
             print(trainer.history[-1])
+        outs = trainer.test(system, dm)  # the reference's --train ends with trainer.test (launch.py:247-248)
+        if get_rank() == 0 or (outs and "name" in outs[0]):
+            save_views(outs, os.path.join(save_dir, f"it{trainer.global_step}-test"))
         return
     outs = trainer.validate(system, dm) if args.validate else trainer.test(system, dm)
     if get_rank() == 0 or (outs and "name" in outs[0]):

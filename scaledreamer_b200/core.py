@@ -370,6 +370,22 @@ class BaseModule(nn.Module, Updateable):
         pass
 
 
+def find_last_path(path: Optional[str]) -> Optional[str]:
+    """threestudio/utils/misc.py:143-161: `outputs/exp/prompt@LAST/ckpts/last.ckpt` -> the lexicographically last
+    directory starting with `outputs/exp/prompt@` (trial directories carry a timestamp), spaces read as underscores."""
+    if path is None or "LAST" not in path:
+        return path
+    path = path.replace(" ", "_")
+    prefix, suffix = path.split("LAST", 1)
+    base_dir = os.path.dirname(prefix)
+    prefix = os.path.join(base_dir, os.path.split(prefix)[-1])
+    candidates = sorted((os.path.join(base_dir, d) for d in os.listdir(base_dir)), reverse=True)
+    candidates = [d for d in candidates if d.startswith(prefix)]
+    if not candidates or not os.path.exists(candidates[0] + suffix):
+        raise FileNotFoundError((candidates[0] if candidates else prefix) + suffix)
+    return candidates[0] + suffix
+
+
 def load_module_weights(path, module_name=None, ignore_modules=None, map_location="cpu"):
     """Selects `module_name.*` entries of a Lightning-style checkpoint (threestudio/utils/misc.py:33-63)."""
     if module_name is not None and ignore_modules is not None:

@@ -189,6 +189,7 @@ class BaseSystem(nn.Module, Updateable):
         self.true_current_epoch = 0
         self.logged: Dict[str, Any] = {}
         self.configure()
+        self.cfg.weights = core.find_last_path(self.cfg.weights)  # systems/base.py:250-251
         if self.cfg.weights is not None:
             sd, epoch, step = core.load_module_weights(self.cfg.weights, ignore_modules=self.cfg.weights_ignore_modules)
             self.load_state_dict(sd, strict=False)

@@ -306,3 +306,18 @@ def test_system_weights_and_ignore_modules(cpu_system, tmp_path):
         same = torch.equal(mine[k], ref[k])
         assert same != k.startswith("background."), k
     assert bool(system.renderer.occ.binaries().all())
+
+
+def test_find_last_path_picks_the_newest_trial(tmp_path):
+    """threestudio/utils/misc.py:143-161, used for `system.weights` (systems/base.py:250-251)."""
+    from scaledreamer_b200.core import find_last_path
+
+    for stamp in ("20240101-000000", "20240301-120000", "20240201-000000"):
+        os.makedirs(tmp_path / "exp" / f"a_corgi@{stamp}" / "ckpts")
+        open(tmp_path / "exp" / f"a_corgi@{stamp}" / "ckpts" / "last.ckpt", "w").close()
+    os.makedirs(tmp_path / "exp" / "zebra@20250101-000000")
+    got = find_last_path(str(tmp_path / "exp" / "a corgi@LAST" / "ckpts" / "last.ckpt"))
+    assert got == str(tmp_path / "exp" / "a_corgi@20240301-120000" / "ckpts" / "last.ckpt")
+    assert find_last_path(None) is None and find_last_path("x/y.ckpt") == "x/y.ckpt"
+    with pytest.raises(FileNotFoundError):
+        find_last_path(str(tmp_path / "exp" / "a_corgi@LAST" / "ckpts" / "missing.ckpt"))
