@@ -45,6 +45,15 @@ def _worker(rank: int, world: int, port: int, tmp: str):
         tr._allreduce_grads(params)
         assert tr._flat.numel() == params[0].numel() + params[1].numel()
 
+        # ---- checkpoints: every rank calls save, rank 0 alone writes (parameters are identical after the all-reduce)
+        model = torch.nn.Linear(3, 2)
+        model.true_current_epoch = 0
+        tr.global_step = 5
+        tr.save_checkpoint(os.path.join(tmp, f"ckpt_rank{rank}", "last.ckpt"), model)
+        dist.barrier()
+        assert os.path.exists(os.path.join(tmp, "ckpt_rank0", "last.ckpt"))
+        assert not os.path.exists(os.path.join(tmp, "ckpt_rank1"))
+
         # ---- prompt sharding: rank r keeps library[r::world] of every split
         assert _world() == (rank, world)
         cfg = MultipromptRandomCameraDataModuleConfig(prompt_library="lib", prompt_library_dir=os.path.join(tmp, "load"))
