@@ -771,7 +771,8 @@ class MultipromptRandomCameraDataset4Test:
         end_point = torch.randn(cfg.dim_gaussian)
         self.noises = torch.stack([start_point + (end_point - start_point) * i / self.n_views
                                    for i in range(self.n_views)])
-        self.prompt_library = prompt_library[split] if split in prompt_library else prompt_library["val"]
+        # the reference indexes prompt_library["val"] as the fall-back; a train-only library simply has nothing to evaluate
+        self.prompt_library = prompt_library[split] if split in prompt_library else prompt_library.get("val", [])
         self._views: Optional[Dict[str, Any]] = None
 
     def __len__(self) -> int:
