@@ -2,10 +2,8 @@
 Trainer.validate / test): one batch per prompt holding the whole orbit, rendered view by view against ONE generated space
 (generative_space_volsdf_volume_renderer.py:131-157), deterministic in eval mode.
 
-NOTE (round 1): written when the round's GPU budget was all but spent — it ran once on the device (and found the missing
-per-batch `do_update_step`, since fixed) but not since; the file name sorts it last so that `pytest -x` reaches every
-verified test first. The host side of the same path is covered on the CPU (tests/test_data_cpu.py,
-tests/test_system_golden_cpu.py)."""
+Green on a B200 since round 2 (gpurun_out/r2a_unverified.log: 3 passed). The host side of the same path is covered on the
+CPU (tests/test_data_cpu.py, tests/test_system_golden_cpu.py)."""
 import json
 import os
 
@@ -15,10 +13,6 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.skipif(os.environ.get("SDB_UNVERIFIED_TESTS") != "1",
-                    reason="not yet green on a device: it ran once when the round-1 GPU budget ran out (found and fixed a "
-                           "missing per-batch do_update_step) and has not run since; first item of round 2: "
-                           "SDB_UNVERIFIED_TESTS=1 python -m pytest tests/test_zz_multiprompt_eval_gpu.py")
 def test_multiprompt_validate_and_fix_prompt_test_loops(cuda_device, tmp_path, monkeypatch):
     import scaledreamer_b200 as sd
     from scaledreamer_b200.systems import Trainer
