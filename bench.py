@@ -22,6 +22,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# no checkpoints on the box: the benchmark runs on seeded synthetic weights and says so in its JSON line
+os.environ.setdefault("SDB_SYNTHETIC_WEIGHTS", "1")
 
 METRIC = "ASD steps/sec (256^2 render->UNet)"
 WORKLOAD = "C2: single-prompt ASD-SD, hash-grid iNGP NeRF, 256x256x1 view, Perp-Neg UNet batch 5 @64x64 latents, VAE @512x512"

@@ -1058,6 +1058,7 @@ class StableDiffusionMultiPromptProcessor(BaseObject):
         shape = (self.n_tokens, self.embed_dim) if kind == "local" else (self.embed_dim,)
         if self.cfg.use_cache and os.path.exists(path):
             return torch.load(path, map_location="cpu").reshape(shape).float()
+        core.synthetic_or_raise("text embeddings", path)
         g = torch.Generator().manual_seed(int(key[:8], 16) % (2 ** 31))
         return torch.randn(*shape, generator=g)
 

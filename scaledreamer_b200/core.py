@@ -50,6 +50,25 @@ def find(name: str):
 
 
 # ----------------------------------------------------------------------------------------------- environment
+_SYNTH_WARNED = set()
+
+
+def synthetic_or_raise(what: str, path: str):
+    """Pretrained weights / cached text embeddings that cannot be found are an ERROR (the reference fails in
+    `from_pretrained` / runs CLIP). Seeded synthetic stand-ins are used only when SDB_SYNTHETIC_WEIGHTS=1 is set
+    (bench.py, smoke() and the tests set it: there are no checkpoints on the box), with one warning per kind."""
+    if os.environ.get("SDB_SYNTHETIC_WEIGHTS") != "1":
+        raise FileNotFoundError(f"{what}: '{path}' not found. Point the config at real weights / a populated "
+                                ".threestudio_cache, or set SDB_SYNTHETIC_WEIGHTS=1 to run on seeded synthetic "
+                                "parameters (benchmarks and tests only: training against them optimises noise).")
+    if what not in _SYNTH_WARNED:
+        _SYNTH_WARNED.add(what)
+        import warnings
+
+        warnings.warn(f"SDB_SYNTHETIC_WEIGHTS=1: {what} replaced by seeded synthetic values ('{path}' not found)",
+                      RuntimeWarning, stacklevel=3)
+
+
 def get_rank() -> int:
     for key in ("RANK", "LOCAL_RANK", "SLURM_PROCID", "JSM_NAMESPACE_RANK"):
         if os.environ.get(key) is not None:

@@ -85,8 +85,8 @@ class _ASDGuidanceBase(BaseObject):
     # ---- network set-up (lazy: the batch size is only known at the first call) ----
     def _load_weights(self, vae: nets.VaeEncoder, unet: nets.UNet):
         """Pretrained weights: a diffusers pipeline directory (unet/, vae/; keys renamed by checkpoints.py) or a
-        single LDM-layout checkpoint file load by name; none exist on this box, so the default is seeded synthetic
-        parameters."""
+        single LDM-layout checkpoint file load by name. Anything else raises FileNotFoundError unless
+        SDB_SYNTHETIC_WEIGHTS=1 asks for seeded synthetic parameters (none exist on this box)."""
         path = getattr(self.cfg, "ckpt_path", None) or getattr(self.cfg, "pretrained_model_name_or_path", "")
         if checkpoints.is_diffusers_dir(path):  # the layout StableDiffusionPipeline.from_pretrained reads (:68-114)
             usd, vsd = checkpoints.load_diffusers_pipeline(path)
@@ -105,6 +105,7 @@ class _ASDGuidanceBase(BaseObject):
             self.quant_w = sd["first_stage_model.quant_conv.weight"].reshape(8, 8).float().to(self.device).contiguous()
             self.quant_b = sd["first_stage_model.quant_conv.bias"].float().to(self.device).contiguous()
             return
+        core.synthetic_or_raise("UNet / VAE weights", path)
         unet.load_state_dict(nets.random_state_dict(unet.specs, self.weights_seed))
         vae.load_state_dict(nets.random_state_dict(vae.specs, self.weights_seed + 1))
         q = nets.random_state_dict([("quant_conv.weight", (8, 8)), ("quant_conv.bias", (8,))], self.weights_seed + 2)

@@ -17,7 +17,7 @@ from typing import List, Optional, Tuple
 
 import torch
 
-from . import lib as L
+from . import core, lib as L
 from .core import BaseObject, register
 
 DIRECTIONS = ("side", "front", "back", "overhead")
@@ -172,6 +172,7 @@ class StableDiffusionPromptProcessor(BaseObject):
         path = os.path.join(CACHE_DIR, f"{key}.pt")
         if self.cfg.use_cache and os.path.exists(path):
             return torch.load(path, map_location="cpu").reshape(self.n_tokens, self.embed_dim).float()
+        core.synthetic_or_raise("text embeddings", path)
         g = torch.Generator().manual_seed(int(key[:8], 16) % (2 ** 31))
         return torch.randn(self.n_tokens, self.embed_dim, generator=g)
 

@@ -370,6 +370,21 @@ class Trainer:
             off += k
         self.dist.all_reduce(self._flat, op=self.dist.ReduceOp.SUM)
 
+    def sync_initial_state(self, system: nn.Module) -> None:
+        """What DistributedDataParallel does when Lightning wraps the module (launch.py:233-240 of the reference): rank
+        0's parameters and buffers (occupancy grid included, through the state dict) overwrite every other rank's, so
+        replicas seeded with `seed + rank` start from one generator. A no-op without a process group."""
+        if self.dist is None or self.world_size == 1:
+            return
+        with torch.no_grad():
+            tensors = [t for t in list(system.parameters()) + list(system.buffers()) if t.numel() > 0]
+            for t in tensors:
+                self.dist.broadcast(t.data, src=0)
+            occ = getattr(getattr(system, "renderer", None), "occ", None)
+            if occ is not None:
+                for t in (occ.occs, occ.bits, occ.mean):
+                    self.dist.broadcast(t, src=0)
+
     # ---- checkpoints in the layout Lightning 2.0 writes (what `resume=` / `system.weights=` of the reference read)
     def checkpoint_dict(self, system: BaseSystem, optimizer: Optional[torch.optim.Optimizer] = None) -> Dict[str, Any]:
         ckpt = {"epoch": system.true_current_epoch, "global_step": self.global_step,
@@ -458,6 +473,7 @@ class Trainer:
         loader = datamodule.train_dataloader()
         system.train()
         system.on_fit_start()
+        self.sync_initial_state(system)
         optimizer = system.configure_optimizers()
         # gradients arrive SUMMED over ranks and micro-batches; Lightning / DDP hand the optimizer their mean. The fused
         # optimizers take the factor as a kernel argument, any other optimizer gets its gradients scaled in place.

@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# no checkpoints / CLIP caches exist on the box: the tests opt in to seeded synthetic weights (core.synthetic_or_raise)
+os.environ.setdefault("SDB_SYNTHETIC_WEIGHTS", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -45,6 +45,19 @@ def _worker(rank: int, world: int, port: int, tmp: str):
         tr._allreduce_grads(params)
         assert tr._flat.numel() == params[0].numel() + params[1].numel()
 
+        # ---- initial state: replicas seeded with seed + rank (launch.py) must start from rank 0's generator
+        torch.manual_seed(100 + rank)
+        net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))
+        net[1].running_mean.fill_(float(rank))
+        before = [t.clone() for t in list(net.parameters()) + list(net.buffers())]
+        tr.sync_initial_state(net)
+        mine = torch.cat([t.detach().float().reshape(-1) for t in list(net.parameters()) + list(net.buffers())])
+        both = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(both, mine)
+        assert torch.equal(both[0], both[1]), "parameters / buffers differ across ranks after sync_initial_state"
+        if rank == 0:
+            assert all(torch.equal(a, b) for a, b in zip(before, list(net.parameters()) + list(net.buffers())))
+
         # ---- checkpoints: every rank calls save, rank 0 alone writes (parameters are identical after the all-reduce)
         model = torch.nn.Linear(3, 2)
         model.true_current_epoch = 0
