@@ -175,6 +175,31 @@ int sdb_render_nerf_backward_tape(const sdb_field* field, const sdb_field_grads*
                                   const float* depth, const float* g_comp_rgb, const float* g_opacity,
                                   const float* g_depth, const sdb_render_tape* tape, void* stream);
 
+/* Same, with the gradient of the z-variance output (HiFA loss, threestudio/systems/scaledreamer.py:93-102 on
+ * nerf_volume_renderer.py:335-349): d z_variance / d w_i = ((t_i - zbar)^2 - z_variance) / opacity on rays with
+ * opacity > 0.5. z_variance / g_z_variance [n_rays] may both be NULL (then identical to the call above). */
+int sdb_render_nerf_backward_tape_zv(const sdb_field* field, const sdb_field_grads* grads, const sdb_march_cfg* march,
+                                     const float* rays_d, const float* bg_override, int n_rays, int rays_per_image,
+                                     const float* comp_rgb_fg, const float* comp_rgb_bg, const float* opacity,
+                                     const float* depth, const float* z_variance, const float* g_comp_rgb,
+                                     const float* g_opacity, const float* g_depth, const float* g_z_variance,
+                                     const sdb_render_tape* tape, void* stream);
+
+/* Orientation term on the taped samples of sdb_render_nerf_forward_v2 (call it before the backward, which overwrites
+ * tape plane 0): orient[ray] = sum_i w_i relu(n_i . d_ray)^2 with the finite-difference normals
+ * n = normalize(-(sigma(clamp(x + eps e_k)) - sigma(x)) / eps) of threestudio/models/geometry/implicit_volume.py:137-177;
+ * the numerator of loss_orient (threestudio/systems/scaledreamer.py:70-80; the weights are detached there, so only the
+ * density network and the table receive a gradient). og [4*capacity] receives d term / d raw density at the sample
+ * and its three offset points. */
+int sdb_render_orient_forward(const sdb_field* field, const float* rays_d, int n_rays, const sdb_render_tape* tape,
+                              float* orient, float* og, void* stream);
+
+/* Backward of the orientation term: og is scaled by g_orient[ray] in place, then the density-network backward and the
+ * hash-grid scatter run on the four points of every sample. Accumulates into grads->table / w1_density / w2_density
+ * (the other members are ignored). */
+int sdb_render_orient_backward(const sdb_field* field, const sdb_field_grads* grads, int n_rays,
+                               const sdb_render_tape* tape, float* og, const float* g_orient, void* stream);
+
 /* ---- prompt-conditioned hash-grid field (amortized generators) -------------------------------------------
  * out = relu(enc(x) W1[b]) W2[b], weights per prompt b from a hypernetwork, two optional heads on one encoding:
  *   head a 32->64->1: SDF of "Hyper-iNGP" (custom/amortized/models/geometry/hyper_iNGP.py:261-349, torch.bmm);

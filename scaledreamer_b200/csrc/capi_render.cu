@@ -474,6 +474,18 @@ int sdb_render_nerf_backward_tape(const sdb_field* field, const sdb_field_grads*
                                   const float* comp_rgb_fg, const float* comp_rgb_bg, const float* opacity,
                                   const float* depth, const float* g_comp_rgb, const float* g_opacity,
                                   const float* g_depth, const sdb_render_tape* tape, void* stream) {
+  return sdb_render_nerf_backward_tape_zv(field, grads, march, rays_d, bg_override, n_rays, rays_per_image, comp_rgb_fg,
+                                          comp_rgb_bg, opacity, depth, nullptr, g_comp_rgb, g_opacity, g_depth, nullptr,
+                                          tape, stream);
+}
+
+int sdb_render_nerf_backward_tape_zv(const sdb_field* field, const sdb_field_grads* grads, const sdb_march_cfg* march,
+                                     const float* rays_d, const float* bg_override, int n_rays, int rays_per_image,
+                                     const float* comp_rgb_fg, const float* comp_rgb_bg, const float* opacity,
+                                     const float* depth, const float* z_variance, const float* g_comp_rgb,
+                                     const float* g_opacity, const float* g_depth, const float* g_z_variance,
+                                     const sdb_render_tape* tape, void* stream) {
+  SDB_CHECK_ARG(!g_z_variance || z_variance, "render_backward_tape: g_z_variance needs the forward's z_variance");
   FieldMeta fm;
   FieldPtrs fp;
   MarchMeta mm;
@@ -504,6 +516,8 @@ int sdb_render_nerf_backward_tape(const sdb_field* field, const sdb_field_grads*
   io.g_comp_rgb = g_comp_rgb;
   io.g_opacity = g_opacity;
   io.g_depth = g_depth;
+  io.z_variance = const_cast<float*>(z_variance);
+  io.g_z_variance = g_z_variance;
   FieldGrads fg;
   fg.table = grads->table;
   fg.w1d = grads->w1_density;
@@ -515,6 +529,45 @@ int sdb_render_nerf_backward_tape(const sdb_field* field, const sdb_field_grads*
   fg.bg_w2 = grads->bg_w2;
   fg.bg_w3 = grads->bg_w3;
   return launch_render_bwd2(fm, fp, fg, mm, io, t, (cudaStream_t)stream);
+}
+
+static int orient_common(const sdb_field* field, const sdb_render_tape* tape, int n_rays, FieldMeta* fm, FieldPtrs* fp,
+                         RenderTape* t) {
+  int rc = resolve_field(field, fm, fp, true);
+  if (rc) return rc;
+  SDB_CHECK_ARG(tape && n_rays >= 0, "render_orient: bad arguments");
+  SDB_CHECK_ARG(fm->fd_eps > 0.f, "render_orient: finite_difference_normal_eps must be > 0");
+  return resolve_tape(tape, n_rays, t);
+}
+
+int sdb_render_orient_forward(const sdb_field* field, const float* rays_d, int n_rays, const sdb_render_tape* tape,
+                              float* orient, float* og, void* stream) {
+  FieldMeta fm;
+  FieldPtrs fp;
+  RenderTape t;
+  int rc = orient_common(field, tape, n_rays, &fm, &fp, &t);
+  if (rc) return rc;
+  SDB_CHECK_ARG(rays_d && orient && og, "render_orient_forward: NULL buffer");
+  if (n_rays == 0) return SDB_OK;
+  return launch_render_orient_fwd(fm, fp, rays_d, n_rays, t, orient, og, (cudaStream_t)stream);
+}
+
+int sdb_render_orient_backward(const sdb_field* field, const sdb_field_grads* grads, int n_rays,
+                               const sdb_render_tape* tape, float* og, const float* g_orient, void* stream) {
+  FieldMeta fm;
+  FieldPtrs fp;
+  RenderTape t;
+  int rc = orient_common(field, tape, n_rays, &fm, &fp, &t);
+  if (rc) return rc;
+  SDB_CHECK_ARG(grads && grads->table && grads->w1_density && grads->w2_density && og && g_orient,
+                "render_orient_backward: NULL buffer");
+  if (n_rays == 0) return SDB_OK;
+  FieldGrads fg;
+  memset(&fg, 0, sizeof(fg));
+  fg.table = grads->table;
+  fg.w1d = grads->w1_density;
+  fg.w2d = grads->w2_density;
+  return launch_render_orient_bwd(fm, fp, fg, n_rays, t, og, g_orient, (cudaStream_t)stream);
 }
 
 long long sdb_hyper_field_tape_floats(int n_prompts, int n_points) {

@@ -54,6 +54,7 @@ render_composite_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs
     float md[3] = {0.f, 0.f, 1.f};
     float gC[3] = {0.f, 0.f, 0.f}, gO = 0.f, gD = 0.f, Rtot = 0.f;
     float dbg[3] = {0.f, 0.f, 0.f};
+    float gZ = 0.f, zbar = 0.f, zvar = 0.f;  // z-variance gradient (nerf_volume_renderer.py:335-349), see below
     if (my_valid) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -73,6 +74,13 @@ render_composite_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs
       }
       Rtot = fmaf(gO, op, Rtot);
       Rtot = fmaf(gD, dp, Rtot);
+      // z_variance = sum_i (w_i / op) (t_i - zbar)^2 on rays with op > 0.5, zbar = depth / op:
+      //   d z_variance / d w_i = ((t_i - zbar)^2 - z_variance) / op, which sums to zero against w (R is unchanged)
+      if (io.g_z_variance && op > 0.5f) {
+        gZ = __ldg(io.g_z_variance + my_ray) / op;
+        zbar = dp / op;
+        zvar = __ldg(io.z_variance + my_ray);
+      }
     }
     if (!io.bg_override) {  // random-colour augmentation detaches the environment map (color * 0 + rand)
       BgActs a;
@@ -145,6 +153,8 @@ render_composite_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs
                   rgC2 = __shfl_sync(kFullMask, gC[2], r);
       const float rgO = __shfl_sync(kFullMask, gO, r), rgD = __shfl_sync(kFullMask, gD, r);
       const float rR = __shfl_sync(kFullMask, Rtot, r);
+      const float rgZ = __shfl_sync(kFullMask, gZ, r), rzbar = __shfl_sync(kFullMask, zbar, r),
+                  rzvar = __shfl_sync(kFullMask, zvar, r);
       const uint32_t* chunks = tape.ray_chunks + (size_t)ray * tape.max_chunks;
       float P = 0.f;
       for (int c0 = 0; c0 < nch; c0 += 32) {
@@ -166,6 +176,7 @@ render_composite_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs
             const float k0 = color_activation(f.color_act, o0), k1 = color_activation(f.color_act, o1),
                         k2 = color_activation(f.color_act, o2);
             g_w = fmaf(rgC0, k0, fmaf(rgC1, k1, fmaf(rgC2, k2, fmaf(rgD, tm, rgO))));
+            g_w = fmaf(rgZ, (tm - rzbar) * (tm - rzbar) - rzvar, g_w);
             gw_w = g_w * w;
             df0 = w * rgC0 * color_activation_grad(f.color_act, o0);
             df1 = w * rgC1 * color_activation_grad(f.color_act, o1);

@@ -22,32 +22,6 @@ struct Fwd2Smem {
   float et[kF2Warps][kEncDim * 32];  // per-warp encoding tile, feature-major: et[k][sample]
 };
 
-// Encodes this lane's point through all levels straight into column `lane` of the warp's tile.
-__device__ __forceinline__ void encode_to_tile(const float2* __restrict__ table, const GridMeta& gm, float x, float y,
-                                               float z, bool valid, float* __restrict__ et_lane) {
-#pragma unroll 2
-  for (int l = 0; l < kMaxLevels; ++l) {
-    float ax = 0.f, ay = 0.f;
-    if (valid) {
-      const uint32_t res = gm.res[l], size = gm.size[l], hashed = gm.hashed[l];
-      const float2* tl = table + gm.offset[l];
-      const LevelCell c = level_cell(gm.scale[l], x, y, z);
-      float2 v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        v[k] = __ldg(tl + grid_index(hashed, res, size, c.ix + (k & 1), c.iy + ((k >> 1) & 1), c.iz + ((k >> 2) & 1)));
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float w = corner_weight(c, k);
-        ax = fmaf(w, v[k].x, ax);
-        ay = fmaf(w, v[k].y, ay);
-      }
-    }
-    et_lane[(2 * l) * 32] = ax;
-    et_lane[(2 * l + 1) * 32] = ay;
-  }
-}
-
 // Environment map (or the random-colour override) for every ray, thread per ray -> comp_rgb_bg.
 __global__ void __launch_bounds__(128)
 render_bg_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, const RayIO io) {

@@ -106,7 +106,41 @@ __device__ __forceinline__ float corner_weight(const LevelCell& c, int k) {
   return ((k & 1) ? c.wx : 1.f - c.wx) * (((k >> 1) & 1) ? c.wy : 1.f - c.wy) * (((k >> 2) & 1) ? c.wz : 1.f - c.wz);
 }
 
+// Encodes this lane's point through all levels straight into column `lane` of the warp's tile.
+// `kStride` = floats per feature row of the tile (32 for the forward's per-warp tile).
+template <int kStride = 32>
+__device__ __forceinline__ void encode_to_tile(const float2* __restrict__ table, const GridMeta& gm, float x, float y,
+                                               float z, bool valid, float* __restrict__ et_lane) {
+#pragma unroll 2
+  for (int l = 0; l < kMaxLevels; ++l) {
+    float ax = 0.f, ay = 0.f;
+    if (valid) {
+      const uint32_t res = gm.res[l], size = gm.size[l], hashed = gm.hashed[l];
+      const float2* tl = table + gm.offset[l];
+      const LevelCell c = level_cell(gm.scale[l], x, y, z);
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        v[k] = __ldg(tl + grid_index(hashed, res, size, c.ix + (k & 1), c.iy + ((k >> 1) & 1), c.iz + ((k >> 2) & 1)));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float w = corner_weight(c, k);
+        ax = fmaf(w, v[k].x, ax);
+        ay = fmaf(w, v[k].y, ay);
+      }
+    }
+    et_lane[(2 * l) * kStride] = ax;
+    et_lane[(2 * l + 1) * kStride] = ay;
+  }
+}
+
 int launch_render_fwd2(const FieldMeta& f, const FieldPtrs& p, const MarchMeta& m, const RayIO& io,
                        const RenderTape* tape, cudaStream_t stream);
 int launch_render_bwd2(const FieldMeta& f, const FieldPtrs& p, const FieldGrads& g, const MarchMeta& m, const RayIO& io,
                        const RenderTape& tape, cudaStream_t stream);
+// Orientation term on the taped samples (render_orient.cu): orient[ray] = sum_i w_i relu(n_i . d)^2 with finite-difference
+// normals; og [4][capacity] receives d term / d raw density at the sample and its three offset points.
+int launch_render_orient_fwd(const FieldMeta& f, const FieldPtrs& p, const float* rays_d, int n_rays,
+                             const RenderTape& tape, float* orient, float* og, cudaStream_t stream);
+int launch_render_orient_bwd(const FieldMeta& f, const FieldPtrs& p, const FieldGrads& g, int n_rays,
+                             const RenderTape& tape, float* og, const float* g_orient, cudaStream_t stream);

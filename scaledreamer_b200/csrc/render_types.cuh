@@ -101,5 +101,6 @@ struct RayIO {
   const float* g_comp_rgb;  // [Nr,3]
   const float* g_opacity;   // [Nr] or null
   const float* g_depth;     // [Nr] or null
+  const float* g_z_variance;  // [Nr] or null (tape backward only; needs z_variance)
   int* work_counter;        // [1] zeroed before launch
 };

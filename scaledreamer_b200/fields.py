@@ -482,6 +482,9 @@ class NeRFVolumeRenderer(BaseModule):
         self.randomized = self.cfg.randomized
         self.occ: Optional[R.OccGrid] = None
         self.packed_capacity = 0  # set > 0 by a system that consumes per-sample outputs
+        # set by the system while loss.lambda_orient > 0: the fused path then returns `orient` [B,H,W,1], the per-ray
+        # sum_i w_i relu(n_i . d)^2 (gradients through the finite-difference normals), instead of per-sample tensors
+        self.orient_loss = False
 
     geometry = property(lambda self: self.sub_modules.geometry)
     material = property(lambda self: self.sub_modules.material)
@@ -551,11 +554,14 @@ class NeRFVolumeRenderer(BaseModule):
             bg_override = bg_color.to(dev, torch.float32).reshape(-1, 3).expand(B, 3).contiguous()
         else:
             bg_override = self.background.sample_override(B, dev)
+        want_orient = bool(self.orient_loss and self.training and self.material.requires_normal)
         out = R.render_nerf(self._spec(), march, self._occ_grid(dev), self._params(), rays_o.reshape(-1, 3),
-                            rays_d.reshape(-1, 3), jitter, bg_override, H * W, self.packed_capacity)
+                            rays_d.reshape(-1, 3), jitter, bg_override, H * W, self.packed_capacity, want_orient)
         res = {"comp_rgb": out["comp_rgb"].view(B, H, W, 3), "comp_rgb_fg": out["comp_rgb_fg"].view(B, H, W, 3),
                "comp_rgb_bg": out["comp_rgb_bg"].view(B, H, W, 3), "opacity": out["opacity"].view(B, H, W, 1),
                "depth": out["depth"].view(B, H, W, 1), "z_variance": out["z_variance"].view(B, H, W, 1)}
+        if "orient" in out:
+            res["orient"] = out["orient"].view(B, H, W, 1)
         pk = out.get("packed")
         if self.training and pk is not None:
             res.update({"weights": pk["weights"], "t_starts": pk["t_starts"], "t_ends": pk["t_ends"],

@@ -119,6 +119,10 @@ SIGNATURES = {
                                    _P, _P, _P, _P, _P, _P, C.POINTER(RenderTapeC), _P, _P],
     "sdb_render_nerf_backward_tape": [C.POINTER(FieldC), C.POINTER(FieldGradsC), C.POINTER(MarchCfgC), _P, _P, _I, _I,
                                       _P, _P, _P, _P, _P, _P, _P, C.POINTER(RenderTapeC), _P],
+    "sdb_render_nerf_backward_tape_zv": [C.POINTER(FieldC), C.POINTER(FieldGradsC), C.POINTER(MarchCfgC), _P, _P, _I,
+                                         _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(RenderTapeC), _P],
+    "sdb_render_orient_forward": [C.POINTER(FieldC), _P, _I, C.POINTER(RenderTapeC), _P, _P, _P],
+    "sdb_render_orient_backward": [C.POINTER(FieldC), C.POINTER(FieldGradsC), _I, C.POINTER(RenderTapeC), _P, _P, _P],
     "sdb_hyper_field_tape_floats": [_I, _I],
     "sdb_hyper_field_forward": [C.POINTER(GridCfgC), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "sdb_hyper_field_backward": [C.POINTER(GridCfgC), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],

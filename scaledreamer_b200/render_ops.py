@@ -238,6 +238,14 @@ class RenderTape:
         self.ray_chunks = torch.empty(n_rays * max_chunks, dtype=torch.int32, device=device)
         self.ray_nchunks = torch.zeros(n_rays, dtype=torch.int32, device=device)
         self.key = None
+        self._og = None
+
+    @property
+    def og(self) -> torch.Tensor:
+        """[4][capacity] partial derivatives of the orientation term (allocated on first use: 16 B per slot)."""
+        if self._og is None:
+            self._og = torch.empty(4 * self.capacity, device=self.enc.device)
+        return self._og
 
     def to_c(self) -> L.RenderTapeC:
         return L.RenderTapeC(self.capacity, self.max_chunks, L.ptr(self.counter), L.ptr(self.enc), L.ptr(self.pos),
@@ -289,9 +297,37 @@ def render_forward_v2_raw(spec: FieldSpec, march: MarchSpec, params, occ: OccGri
     return out
 
 
+def _grads_c(grads) -> L.FieldGradsC:
+    g = L.FieldGradsC()
+    for name, key in (("table", "table"), ("w1_density", "w1d"), ("w2_density", "w2d"), ("w1_feature", "w1f"),
+                      ("w2_feature", "w2f"), ("bg_table", "bg_table"), ("bg_w1", "bg_w1"), ("bg_w2", "bg_w2"),
+                      ("bg_w3", "bg_w3")):
+        setattr(g, name, L.ptr(grads[key]))
+    return g
+
+
+def render_orient_forward_raw(spec: FieldSpec, params, rays_d, tape: RenderTape) -> torch.Tensor:
+    """sdb_render_orient_forward on the tape of the forward that just ran: per-ray sum_i w_i relu(n_i . d)^2 (the
+    numerator of loss_orient, scaledreamer.py:70-80); the partial derivatives stay in tape.og for the backward."""
+    f = make_field_c(spec, params)
+    orient = torch.empty(rays_d.shape[0], device=rays_d.device)
+    tc = tape.to_c()
+    L.check(L.load().sdb_render_orient_forward(C.byref(f), L.ptr(rays_d), rays_d.shape[0], C.byref(tc), L.ptr(orient),
+                                               L.ptr(tape.og), L.stream_ptr()), "sdb_render_orient_forward")
+    return orient
+
+
+def render_orient_backward_raw(spec: FieldSpec, params, grads, tape: RenderTape, g_orient: torch.Tensor) -> None:
+    f = make_field_c(spec, params)
+    g = _grads_c(grads)
+    tc = tape.to_c()
+    L.check(L.load().sdb_render_orient_backward(C.byref(f), C.byref(g), g_orient.numel(), C.byref(tc), L.ptr(tape.og),
+                                                L.ptr(g_orient), L.stream_ptr()), "sdb_render_orient_backward")
+
+
 def render_backward_tape_raw(spec: FieldSpec, march: MarchSpec, params, grads, rays_d, bg_override,
                              rays_per_image: int, saved, tape: RenderTape, g_comp_rgb, g_opacity=None,
-                             g_depth=None) -> None:
+                             g_depth=None, g_z_variance=None) -> None:
     """Runs sdb_render_nerf_backward_tape; accumulates into `grads` (dict keyed like params)."""
     lib = L.load()
     f = make_field_c(spec, params)
@@ -302,11 +338,12 @@ def render_backward_tape_raw(spec: FieldSpec, march: MarchSpec, params, grads, r
                       ("bg_w3", "bg_w3")):
         setattr(g, name, L.ptr(grads[key]))
     tc = tape.to_c()
-    L.check(lib.sdb_render_nerf_backward_tape(
+    zv = saved.get("z_variance") if g_z_variance is not None else None
+    L.check(lib.sdb_render_nerf_backward_tape_zv(
         C.byref(f), C.byref(g), C.byref(m), L.ptr(rays_d), L.ptr(bg_override), rays_d.shape[0], int(rays_per_image),
         L.ptr(saved["comp_rgb_fg"]), L.ptr(saved["comp_rgb_bg"]), L.ptr(saved["opacity"]), L.ptr(saved["depth"]),
-        L.ptr(g_comp_rgb), L.ptr(g_opacity), L.ptr(g_depth), C.byref(tc), L.stream_ptr()),
-        "sdb_render_nerf_backward_tape")
+        L.ptr(zv), L.ptr(g_comp_rgb), L.ptr(g_opacity), L.ptr(g_depth), L.ptr(g_z_variance), C.byref(tc),
+        L.stream_ptr()), "sdb_render_nerf_backward_tape_zv")
 
 
 class _RenderNeRF(torch.autograd.Function):
@@ -322,6 +359,9 @@ class _RenderNeRF(torch.autograd.Function):
         ctx.spec, ctx.march, ctx.occ, ctx.rpi = spec, march, occ, rays_per_image
         ctx.has_jitter, ctx.has_bg = jitter is not None, bg_override is not None
         ctx.tape = None
+        ctx.set_materialize_grads(False)
+        want_orient = bool(holder.pop("want_orient", False))
+        ctx.has_orient = False
         need_grad = any(ctx.needs_input_grad[10:])
         if packed_capacity > 0:
             out = render_forward_raw(spec, march, params, occ, rays_o, rays_d, jitter, bg_override, rays_per_image,
@@ -333,26 +373,40 @@ class _RenderNeRF(torch.autograd.Function):
                 ctx.tape = RenderTape.acquire(march, spec.radius, rays_o.shape[0], rays_o.device)
             out = render_forward_v2_raw(spec, march, params, occ, rays_o, rays_d, jitter, bg_override,
                                         rays_per_image, ctx.tape)
+        # orientation term (scaledreamer.py:70-80) on the tape, before anything can overwrite its raw densities
+        if want_orient and ctx.tape is not None:
+            orient = render_orient_forward_raw(spec, params, rays_d, ctx.tape)
+            ctx.has_orient = True
+        else:
+            orient = torch.zeros(rays_o.shape[0], device=rays_o.device)
         ctx.save_for_backward(rays_o, rays_d, jitter if jitter is not None else rays_o.new_zeros(0),
                               bg_override if bg_override is not None else rays_o.new_zeros(0),
-                              out["comp_rgb_fg"], out["comp_rgb_bg"], out["opacity"], out["depth"], *param_tensors)
-        holder.update(out)  # non-differentiable extras (fg/bg/z_variance/packed) for the caller
+                              out["comp_rgb_fg"], out["comp_rgb_bg"], out["opacity"], out["depth"], out["z_variance"],
+                              *param_tensors)
+        holder.update(out)  # non-differentiable extras (fg / bg / packed) for the caller
         holder["tape"] = ctx.tape
-        ctx.mark_non_differentiable(out["comp_rgb_fg"], out["comp_rgb_bg"], out["z_variance"])
-        return out["comp_rgb"], out["opacity"], out["depth"]
+        non_diff = [out["comp_rgb_fg"], out["comp_rgb_bg"]]
+        if ctx.tape is None:  # the re-marching (v1) backward has no z-variance / orientation gradient
+            non_diff += [out["z_variance"], orient]
+        elif not ctx.has_orient:
+            non_diff.append(orient)
+        ctx.mark_non_differentiable(*non_diff)
+        return out["comp_rgb"], out["opacity"], out["depth"], out["z_variance"], orient
 
     @staticmethod
-    def backward(ctx, g_rgb, g_op, g_depth):
-        rays_o, rays_d, jitter, bg_override, fg, bg, op, depth, *param_tensors = ctx.saved_tensors
+    def backward(ctx, g_rgb, g_op, g_depth, g_zv=None, g_orient=None):
+        rays_o, rays_d, jitter, bg_override, fg, bg, op, depth, zvar, *param_tensors = ctx.saved_tensors
         params = dict(zip(PARAM_KEYS, param_tensors))
         grads = {k: torch.zeros_like(v) for k, v in params.items()}
+        cg = lambda g: g.contiguous().float() if g is not None else None
         g_rgb = g_rgb.contiguous() if g_rgb is not None else torch.zeros_like(fg)
-        g_op = g_op.contiguous() if g_op is not None else None
-        g_depth = g_depth.contiguous() if g_depth is not None else None
-        saved = {"comp_rgb_fg": fg, "comp_rgb_bg": bg, "opacity": op, "depth": depth}
+        g_op, g_depth, g_zv, g_orient = cg(g_op), cg(g_depth), cg(g_zv), cg(g_orient)
+        saved = {"comp_rgb_fg": fg, "comp_rgb_bg": bg, "opacity": op, "depth": depth, "z_variance": zvar}
         if ctx.tape is not None:
+            if ctx.has_orient and g_orient is not None:
+                render_orient_backward_raw(ctx.spec, params, grads, ctx.tape, g_orient)
             render_backward_tape_raw(ctx.spec, ctx.march, params, grads, rays_d, bg_override if ctx.has_bg else None,
-                                     ctx.rpi, saved, ctx.tape, g_rgb, g_op, g_depth)
+                                     ctx.rpi, saved, ctx.tape, g_rgb, g_op, g_depth, g_zv)
             ctx.tape.release()
             ctx.tape = None
         else:
@@ -365,14 +419,19 @@ class _RenderNeRF(torch.autograd.Function):
         return (None,) * 10 + tuple(grads[k] for k in PARAM_KEYS)
 
 
-def render_nerf(spec, march, occ, params, rays_o, rays_d, jitter, bg_override, rays_per_image, packed_capacity=0):
-    """Differentiable fused render. Returns dict with comp_rgb / opacity / depth (grad) and the extras."""
-    holder: dict = {}
-    rgb, op, depth = _RenderNeRF.apply(spec, march, occ, rays_o.contiguous(), rays_d.contiguous(), jitter,
-                                       bg_override, rays_per_image, packed_capacity, holder,
-                                       *[params[k] for k in PARAM_KEYS])
+def render_nerf(spec, march, occ, params, rays_o, rays_d, jitter, bg_override, rays_per_image, packed_capacity=0,
+                want_orient=False):
+    """Differentiable fused render. Returns dict with comp_rgb / opacity / depth / z_variance (grad) and the extras;
+    with want_orient (tape path, gradients on) also `orient` [Nr] = sum_i w_i relu(n_i . d)^2 per ray, differentiable
+    with respect to the density network and the table through the finite-difference normals."""
+    holder: dict = {"want_orient": want_orient and packed_capacity == 0}
+    rgb, op, depth, zvar, orient = _RenderNeRF.apply(spec, march, occ, rays_o.contiguous(), rays_d.contiguous(), jitter,
+                                                     bg_override, rays_per_image, packed_capacity, holder,
+                                                     *[params[k] for k in PARAM_KEYS])
     out = dict(holder)
-    out["comp_rgb"], out["opacity"], out["depth"] = rgb, op, depth
+    out["comp_rgb"], out["opacity"], out["depth"], out["z_variance"] = rgb, op, depth, zvar
+    if want_orient and holder.get("tape") is not None:
+        out["orient"] = orient
     return out
 
 

@@ -263,6 +263,8 @@ class StableDreamer(BaseSystem):
         self.prompt_utils = self.prompt_processor()
 
     def training_step(self, batch, batch_idx):
+        # the fused renderer evaluates the orientation term itself (no per-sample normal / weights / t_dirs tensors)
+        self.renderer.orient_loss = self.C(self.cfg.loss.get("lambda_orient", 0.0)) > 0
         out = self(batch)
         guidance_out = self.guidance(out["comp_rgb"], self.prompt_utils, **batch, rgb_as_latents=False)
         loss = 0.0
@@ -272,11 +274,13 @@ class StableDreamer(BaseSystem):
             if name.startswith("loss_"):
                 loss = loss + value * self.C(lam[name.replace("loss_", "lambda_")])
         if self.C(lam.get("lambda_orient", 0.0)) > 0:
-            if "normal" not in out or not out["normal"].requires_grad:
-                raise NotImplementedError("lambda_orient > 0 needs gradients through finite-difference normals, which "
-                                          "the fused renderer does not provide")
-            cos = (out["normal"] * out["t_dirs"]).sum(-1, keepdim=True)  # scaledreamer.py:74-83
-            loss_orient = (out["weights"].detach() * cos.clamp_min(0.0) ** 2).sum() / (out["opacity"] > 0).sum()
+            if "orient" in out:  # fused renderer: per-ray sums of w relu(n . d)^2 (csrc/render_orient.cu)
+                loss_orient = out["orient"].sum() / (out["opacity"] > 0).sum()
+            else:
+                if "normal" not in out:
+                    raise ValueError("Normal is required for orientation loss, no normal is found in the output.")
+                cos = (out["normal"] * out["t_dirs"]).sum(-1, keepdim=True)  # scaledreamer.py:74-83
+                loss_orient = (out["weights"].detach() * cos.clamp_min(0.0) ** 2).sum() / (out["opacity"] > 0).sum()
             self.log("train/loss_orient", loss_orient)
             loss = loss + loss_orient * self.C(lam["lambda_orient"])
         if self.C(lam.get("lambda_sparsity", 0.0)) > 0:
@@ -288,9 +292,13 @@ class StableDreamer(BaseSystem):
             loss_opaque = binary_cross_entropy(op, op)
             self.log("train/loss_opaque", loss_opaque)
             loss = loss + loss_opaque * self.C(lam["lambda_opaque"])
-        if self.C(lam.get("lambda_z_variance", 0.0)) > 0:
-            raise NotImplementedError("lambda_z_variance > 0: z_variance is a non-differentiable output of the fused "
-                                      "renderer")
+        if self.C(lam.get("lambda_z_variance", 0.0)) > 0:  # scaledreamer.py:93-102 (HiFA)
+            if not out["z_variance"].requires_grad:
+                raise NotImplementedError("lambda_z_variance > 0 needs the tape renderer (fused geometry, "
+                                          "packed_capacity 0): this renderer's z_variance carries no gradient")
+            loss_z_variance = out["z_variance"][out["opacity"] > 0.5].mean()
+            self.log("train/loss_z_variance", loss_z_variance)
+            loss = loss + loss_z_variance * self.C(lam["lambda_z_variance"])
         if self.C(lam.get("lambda_eikonal", 0.0)) > 0:
             raise ValueError("sdf is required for eikonal loss, no sdf is found in the output.")
         return {"loss": loss}

@@ -132,6 +132,38 @@ def test_mvdream_training_step_end_to_end(cuda_device):
     assert int(g._last["t"].unique().numel()) == 1                            # one timestep for the whole view batch
 
 
+def test_mvdream_yaml_survives_its_orientation_schedule(cuda_device):
+    """configs/single-prompt_benchmark/asd_mv_nerf.yaml:100-102 switch lambda_orient / lambda_opaque from 0 to 100 at step
+    10001. The fit loop is started at step 10000 and runs across that boundary on the FUSED renderer: loss_orient is
+    logged, finite and positive, and training keeps moving the density network (round 1 raised NotImplementedError)."""
+    import scaledreamer_b200 as sd
+    from scaledreamer_b200.systems import Trainer
+
+    torch.manual_seed(3)
+    cfg_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs", "asd_mv_nerf.yaml")
+    cfg = sd.load_config(cfg_path, cli_args=["system.prompt_processor.prompt=a DSLR photo of a hamburger",
+                                             "data.width=[64,64]", "data.height=[64,64]", "trainer.max_steps=10003",
+                                             "trainer.log_every_n_steps=1"])
+    assert cfg.system["loss"]["lambda_orient"] == [10000, 0.0, 100.0, 10001]
+    dm = sd.find(cfg.data_type)(cfg.data)
+    system = sd.find(cfg.system_type)(cfg.system)
+    assert system.geometry.fusable
+    with torch.no_grad():
+        system.geometry.encoding.table.mul_(2000.0)  # 1e-4 init -> 0.2: the hash features shape the density
+    tr = Trainer(**cfg.trainer)
+    tr.global_step = system.true_global_step = 10000
+    tr.fit(system, dm)
+    torch.cuda.synchronize()
+    assert tr.global_step == 10003
+    by_step = {int(r["step"]): r for r in tr.history}
+    assert "train/loss_orient" not in by_step[10001]          # the batch of step 10000 still ran with lambda 0
+    for st in (10002, 10003):
+        lo_ = by_step[st]["train/loss_orient"]
+        assert lo_ == lo_ and lo_ > 0, (st, lo_)
+        assert by_step[st]["train/loss_opaque"] == by_step[st]["train/loss_opaque"]
+    assert system.geometry.density_network.layers[0].weight.grad is not None
+
+
 def test_validation_and_test_loops(cuda_device):
     """Evaluation orbit through the system (scaledreamer.py:172-300): eval-mode renders are deterministic (no jitter, no
     random background, nothing taped), match a direct eval-mode renderer call on the same camera, and leave the module

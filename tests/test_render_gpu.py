@@ -251,6 +251,71 @@ def test_render_autograd_function_and_bg_detach(cuda_device):
     assert P["bg_table"].grad.abs().sum() == 0 and P["bg_w3"].grad.abs().sum() == 0
 
 
+def test_orientation_and_z_variance_losses_match_oracle(cuda_device):
+    """loss_orient (scaledreamer.py:70-80: detached weights x relu(n . d)^2 through the finite-difference normals of
+    implicit_volume.py:137-177) and the z-variance loss (scaledreamer.py:93-102) of the FUSED renderer, values and
+    gradients to every trainable tensor, against autograd through oracle.render(output_normal=True). 5e-3 on gradients:
+    ReLU-mask flips at fp32 rounding, and the FD quotient divides differences of nearly equal densities by eps."""
+    from scaledreamer_b200 import render_ops as R
+
+    sc = scene(H=20, W=20, seed=31)
+    spec, march = field_spec_from_oracle(sc["fcfg"]), march_spec_from_oracle(sc["mcfg"])
+    occ = R.OccGrid(32, cuda_device)
+    occ.set_binaries(sc["binary"], sc["occs"])
+    lam_o, lam_z = 100.0, 3.0
+
+    def losses(out, orient_sum):
+        lo_ = orient_sum / (out["opacity"] > 0).sum()
+        m = out["opacity"] > 0.5
+        lz_ = out["z_variance"][m].mean()
+        return lo_, lz_
+
+    P = {k: v.clone().requires_grad_(True) for k, v in sc["P"].items()}
+    ref = ro.render(sc["rays_o"], sc["rays_d"], sc["jitter"], None, sc["binary"].numpy(), float(sc["occs"].mean()), P,
+                    sc["fcfg"], sc["mcfg"], 400, output_normal=True)
+    cos = (ref["normal"] * sc["rays_d"][ref["ray_indices"]]).sum(-1)
+    ref_orient = (ref["weights"].detach() * cos.clamp_min(0.0) ** 2).sum()
+    lo_ref, lz_ref = losses(ref, ref_orient)
+    assert float(lo_ref) > 0 and float(lz_ref) > 0
+    (lam_o * lo_ref + lam_z * lz_ref + ref["comp_rgb"].square().sum()).backward()
+
+    Pd = {k: v.to(cuda_device).requires_grad_(True) for k, v in sc["P"].items()}
+    out = R.render_nerf(spec, march, occ, Pd, sc["rays_o"].to(cuda_device), sc["rays_d"].to(cuda_device),
+                        sc["jitter"].to(cuda_device), None, 400, want_orient=True)
+    assert out["orient"].shape == (400,) and out["orient"].requires_grad and out["z_variance"].requires_grad
+    lo_gpu, lz_gpu = losses(out, out["orient"].sum())
+    (lam_o * lo_gpu + lam_z * lz_gpu + out["comp_rgb"].square().sum()).backward()
+    torch.cuda.synchronize()
+    print(f"loss_orient {float(lo_gpu):.6f} vs {float(lo_ref):.6f}; loss_z_variance {float(lz_gpu):.6f} vs {float(lz_ref):.6f}")
+    assert abs(float(lo_gpu) - float(lo_ref)) / float(lo_ref) < 5e-3
+    assert abs(float(lz_gpu) - float(lz_ref)) / float(lz_ref) < 1e-3
+    # per-ray orientation sums
+    ref_rays = torch.zeros(400).index_add(0, ref["ray_indices"], (ref["weights"] * cos.clamp_min(0.0) ** 2).detach())
+    assert rel_l2(out["orient"].cpu(), ref_rays) < 5e-3
+    for k in R.PARAM_KEYS:
+        err = rel_l2(Pd[k].grad.cpu(), P[k].grad)
+        print(k, err)
+        assert err < 5e-3, (k, err)
+
+    # the orientation term alone: only the density network and the table receive a gradient (weights are detached)
+    P2 = {k: v.clone().requires_grad_(True) for k, v in sc["P"].items()}
+    ref2 = ro.render(sc["rays_o"], sc["rays_d"], sc["jitter"], None, sc["binary"].numpy(), float(sc["occs"].mean()), P2,
+                     sc["fcfg"], sc["mcfg"], 400, output_normal=True)
+    cos2 = (ref2["normal"] * sc["rays_d"][ref2["ray_indices"]]).sum(-1)
+    (ref2["weights"].detach() * cos2.clamp_min(0.0) ** 2).sum().backward()
+    Pd2 = {k: v.to(cuda_device).requires_grad_(True) for k, v in sc["P"].items()}
+    out2 = R.render_nerf(spec, march, occ, Pd2, sc["rays_o"].to(cuda_device), sc["rays_d"].to(cuda_device),
+                         sc["jitter"].to(cuda_device), None, 400, want_orient=True)
+    out2["orient"].sum().backward()
+    torch.cuda.synchronize()
+    for k in ("table", "w1d", "w2d"):
+        err = rel_l2(Pd2[k].grad.cpu(), P2[k].grad)
+        print("orient only", k, err)
+        assert err < 5e-3, (k, err)
+    for k in ("w1f", "w2f", "bg_table", "bg_w1"):
+        assert float(Pd2[k].grad.abs().sum()) == 0.0, k
+
+
 def test_occgrid_update_parity(cuda_device):
     from scaledreamer_b200 import render_ops as R
 
