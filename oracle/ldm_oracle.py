@@ -201,3 +201,28 @@ def asd_grad(eps, latents, t, ac, B, guidance_scale, neg_w=None, weighting="sds"
     target = (latents - grad).detach()
     loss = 0.5 * F.mse_loss(latents, target, reduction="sum") / B
     return grad, loss, grad.norm()
+
+
+def seeded_state_dict(kind: str, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic parameters for `unet_forward` ("unet_sd") / `vae_encoder_forward` ("vae") from the committed
+    name -> shape table oracle/ldm_param_specs.json (the reference modules' state-dict names; 3x3 kernels listed as
+    [Co,3,3,Ci] and returned as [Co,Ci,3,3]). Lets the CPU baseline run without touching the product library."""
+    import json
+    import math
+    import os
+    import zlib
+
+    specs = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ldm_param_specs.json")))[kind]
+    sd = {}
+    for name, shape in specs:
+        rs = (shape[0], shape[3], shape[1], shape[2]) if len(shape) == 4 else tuple(shape)
+        g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + 7919 * seed) % (2 ** 31))
+        if len(rs) >= 2:
+            t = torch.randn(rs, generator=g) / math.sqrt(math.prod(rs[1:]))
+        elif name.endswith(".weight"):
+            t = 1.0 + 0.1 * torch.randn(rs, generator=g)
+        else:
+            t = 0.05 * torch.randn(rs, generator=g)
+        sd[name] = t
+    return sd
+

@@ -605,9 +605,14 @@ class GenerativeSpaceVolSDFVolumeRenderer(BaseModule):
         if self.cfg.trainable_variance:
             raise NotImplementedError("trainable_variance=true: the compositing kernels take inv_std as a constant "
                                       "(the multi-prompt configs freeze it)")
-        if self.cfg.train_chunk_size > 0:
-            raise NotImplementedError("train_chunk_size > 0 (chunked training) is not needed with 180 GB of HBM")
         self.randomized = self.cfg.randomized
+        # Training memory: the per-sample tensors of one step (encodings, MLP activations, their gradients) grow with
+        # rays x 193 intervals x 4 field evaluations. `train_chunk_size` (the reference's key, rays per chunk; its
+        # chunk_batch_original at generative_space_volsdf_volume_renderer.py:241-250) bounds them: rays are rendered in
+        # chunks whose intermediates are dropped after the forward and recomputed chunk by chunk in the backward. With
+        # 0 (the yaml default) the chunk is chosen so that a chunk's intermediates stay under CHUNK_BUDGET_BYTES; a
+        # batch that fits is rendered in one piece (BASELINE C4 does, C5 at 256 x 256 x 4 views needs ~80 GB and does not).
+        self.last_chunk_rays = 0
 
     geometry = property(lambda self: self.sub_modules.geometry)
     material = property(lambda self: self.sub_modules.material)
@@ -668,23 +673,39 @@ class GenerativeSpaceVolSDFVolumeRenderer(BaseModule):
                 text_embed = text_embed.repeat_interleave(B // Bc, dim=0)
         Nr, HW = B * H * W, H * W
         o, d = rays_o.reshape(Nr, 3).contiguous(), rays_d.reshape(Nr, 3).contiguous()
-        t = self.sample_intervals(o, d, HW, space_cache, u_coarse, u_fine)
-        t_mid, delta = 0.5 * (t[:, :-1] + t[:, 1:]), t[:, 1:] - t[:, :-1]
-        S = t_mid.shape[1]
-        positions = o[:, None, :] + d[:, None, :] * t_mid[..., None]
-        geo = self.geometry(positions.view(B, HW * S, 3), space_cache=space_cache, output_normal=True)
-        inv_std = float(self.variance.inv_std.clamp(1.0e-6, 1.0e6))
-        color_act = {"sigmoid": 0, "sigmoid-mipnerf": 1}.get(self.material.cfg.color_activation)
-        if color_act is None or type(self.material).__name__ != "NoMaterial":
-            raise NotImplementedError("the VolSDF compositing kernel fuses no-material with a sigmoid / sigmoid-mipnerf "
-                                      "colour activation")
-        fg, opacity, depth, z_var, weights, comp_normal = _VolSDFComposite.apply(
-            geo["sdf"].view(Nr, S), geo["features"].view(Nr, S, 3), geo["normal"].view(Nr, S, 3), t_mid, delta, inv_std,
-            color_act)
-        if getattr(self.background, "enabling_hypernet", False):
-            comp_rgb_bg = self.background(dirs=rays_d, text_embed=text_embed)
+        dev = o.device
+        if u_coarse is None:
+            u_coarse = torch.rand(Nr, device=dev) if self.randomized else torch.full((Nr,), 0.5, device=dev)
+        if u_fine is None:
+            u_fine = torch.rand(Nr, device=dev) if self.randomized else torch.full((Nr,), 0.5, device=dev)
+        S = self.cfg.num_samples_per_ray_importance + self.cfg.num_samples_per_ray + 1
+        chunk = self._chunk_rays(B, HW, S) if (self.training and torch.is_grad_enabled()) else 0
+        self.last_chunk_rays = chunk
+        extras = None
+        if chunk <= 0 or chunk >= HW:
+            fg, opacity, depth, z_var, comp_normal, sdf_grad, extras = self._render_rays(o, d, u_coarse, u_fine,
+                                                                                       space_cache, B, True)
         else:
-            comp_rgb_bg = self.background(dirs=rays_d)
+            # rays [B, HW] -> chunks [B, c]: every chunk keeps the batch grouping the geometry's space cache needs
+            from torch.utils.checkpoint import checkpoint
+
+            o3, d3 = o.view(B, HW, 3), d.view(B, HW, 3)
+            uc2, uf2 = u_coarse.view(B, HW), u_fine.view(B, HW)
+            parts = []
+            for s0 in range(0, HW, chunk):
+                s1 = min(HW, s0 + chunk)
+                args = (o3[:, s0:s1].reshape(-1, 3).contiguous(), d3[:, s0:s1].reshape(-1, 3).contiguous(),
+                        uc2[:, s0:s1].reshape(-1).contiguous(), uf2[:, s0:s1].reshape(-1).contiguous())
+                fn = lambda a, b_, c_, e_: self._render_rays(a, b_, c_, e_, space_cache, B, False)[:6]
+                parts.append(checkpoint(fn, *args, use_reentrant=False, preserve_rng_state=False))
+            cat = lambda i: torch.cat([p[i].view(B, -1, *p[i].shape[1:]) for p in parts], dim=1)
+            fg, opacity, depth, z_var, comp_normal = (cat(i).reshape(Nr, *parts[0][i].shape[1:]) for i in range(5))
+            sdf_grad = torch.cat([p[5].view(B, -1, S, 3) for p in parts], dim=1).reshape(-1, 3)
+        color_bg_module = self.background
+        if getattr(color_bg_module, "enabling_hypernet", False):
+            comp_rgb_bg = color_bg_module(dirs=rays_d, text_embed=text_embed)
+        else:
+            comp_rgb_bg = color_bg_module(dirs=rays_d)
         if bg_color is None:
             bg_color = comp_rgb_bg
         bg_flat = bg_color.reshape(Nr, -1) if bg_color.shape[:-1] == (B, H, W) else bg_color
@@ -694,12 +715,54 @@ class GenerativeSpaceVolSDFVolumeRenderer(BaseModule):
                "depth": depth.view(B, H, W, 1), "z_variance": z_var.view(B, H, W, 1),
                "comp_normal": comp_normal.view(B, H, W, 3)}
         if self.training:
-            ray_indices = torch.arange(Nr, device=o.device).unsqueeze(-1).expand(-1, S).reshape(-1)
-            out.update({"weights": weights.reshape(-1, 1), "t_points": t_mid.reshape(-1, 1),
-                        "t_intervals": delta.reshape(-1, 1), "t_dirs": d[ray_indices], "ray_indices": ray_indices,
-                        "points": positions.reshape(-1, 3), **geo})
+            if extras is not None:
+                out.update(extras)
+            else:  # chunked: the per-sample tensors are not kept (only what the eikonal loss reads)
+                out["sdf_grad"] = sdf_grad
             out["inv_std"] = self.variance.inv_std
         return out
+
+    CHUNK_BUDGET_BYTES = 24 << 30
+
+    def _chunk_rays(self, B: int, HW: int, S: int) -> int:
+        """Rays per batch element and chunk (0: render everything at once)."""
+        if self.cfg.train_chunk_size > 0:
+            return max(1, int(self.cfg.train_chunk_size) // B)
+        # bytes of intermediates per field evaluation: encodings kept for the MLP backward (fp32 x width), their
+        # gradient, hidden-layer recompute scratch and the outputs; the hash-grid field keeps a 128-byte tape instead
+        width = 96 if type(self.geometry).__name__ == "TriplaneTransformerSDF" else 32
+        per_point = 3 * 4 * width + 96
+        total = B * HW * S * 4 * per_point
+        if total <= self.CHUNK_BUDGET_BYTES:
+            return 0
+        c = max(256, int(self.CHUNK_BUDGET_BYTES // (B * S * 4 * per_point)))
+        return 1 << (c.bit_length() - 1)  # power of two: equal chunks for the usual image sizes
+
+    def _render_rays(self, o, d, u_coarse, u_fine, space_cache, B: int, want_extras: bool):
+        """Importance sampling -> geometry (centres + finite-difference offsets) -> VolSDF compositing for rays grouped
+        by batch element ([B * c, 3]); generative_space_volsdf_volume_renderer.py:209-424."""
+        Nr = o.shape[0]
+        c = Nr // B
+        t = self.sample_intervals(o, d, c, space_cache, u_coarse, u_fine)
+        t_mid, delta = 0.5 * (t[:, :-1] + t[:, 1:]), t[:, 1:] - t[:, :-1]
+        S = t_mid.shape[1]
+        positions = o[:, None, :] + d[:, None, :] * t_mid[..., None]
+        geo = self.geometry(positions.view(B, c * S, 3), space_cache=space_cache, output_normal=True)
+        inv_std = float(self.variance.inv_std.clamp(1.0e-6, 1.0e6))
+        color_act = {"sigmoid": 0, "sigmoid-mipnerf": 1}.get(self.material.cfg.color_activation)
+        if color_act is None or type(self.material).__name__ != "NoMaterial":
+            raise NotImplementedError("the VolSDF compositing kernel fuses no-material with a sigmoid / sigmoid-mipnerf "
+                                      "colour activation")
+        fg, opacity, depth, z_var, weights, comp_normal = _VolSDFComposite.apply(
+            geo["sdf"].view(Nr, S), geo["features"].view(Nr, S, 3), geo["normal"].view(Nr, S, 3), t_mid, delta, inv_std,
+            color_act)
+        extras = None
+        if want_extras and self.training:
+            ray_indices = torch.arange(Nr, device=o.device).unsqueeze(-1).expand(-1, S).reshape(-1)
+            extras = {"weights": weights.reshape(-1, 1), "t_points": t_mid.reshape(-1, 1),
+                      "t_intervals": delta.reshape(-1, 1), "t_dirs": d[ray_indices], "ray_indices": ray_indices,
+                      "points": positions.reshape(-1, 3), **geo}
+        return fg, opacity, depth, z_var, comp_normal, geo["sdf_grad"], extras
 
     def update_step(self, epoch: int, global_step: int, on_load_weights: bool = False) -> None:
         pass

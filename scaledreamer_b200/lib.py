@@ -99,6 +99,51 @@ def load() -> C.CDLL:
     return lib
 
 
+class _TimedLib:
+    """Measurement aid (bench.py's per-kernel breakdown): every C-ABI call that takes a stream is bracketed by CUDA
+    events on the CURRENT stream, summed per entry point. Installed by call_timer_begin(), removed by call_timer_end();
+    the product path never sees it otherwise."""
+
+    def __init__(self, lib: C.CDLL):
+        self._lib = lib
+        self.records = {}
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        sig = SIGNATURES.get(name)
+        if not name.startswith("sdb_") or not sig or sig[-1] is not _P or name.startswith("sdb_gemm_profile"):
+            return fn
+
+        def timed(*args):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = self._lib.sdb_launch_count()
+            a.record()
+            rc = fn(*args)
+            b.record()
+            self.records.setdefault(name, []).append((a, b, self._lib.sdb_launch_count() - n0))
+            return rc
+
+        return timed
+
+
+def call_timer_begin() -> None:
+    global _lib
+    lib = load()
+    if not isinstance(lib, _TimedLib):
+        _lib = _TimedLib(lib)
+
+
+def call_timer_end() -> dict:
+    """-> {entry point: {"calls": n, "ms": total device time, "launches": kernels launched}} since call_timer_begin()."""
+    global _lib
+    if not isinstance(_lib, _TimedLib):
+        return {}
+    timed, _lib = _lib, _lib._lib
+    torch.cuda.synchronize()
+    return {k: {"calls": len(v), "ms": sum(a.elapsed_time(b) for a, b, _ in v), "launches": int(sum(n for _, _, n in v))}
+            for k, v in timed.records.items()}
+
+
 _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> argtypes; every function returns int unless listed in load() above. Pointers are void* so that

@@ -357,6 +357,7 @@ class Trainer:
         self.global_step = 0
         self.history: List[Dict[str, float]] = []
         self._flat = None
+        self._ar_stream = None
 
     def _allreduce_grads(self, params: List[torch.Tensor]) -> None:
         """One collective per optimizer step on a flat fp32 buffer (replaces DDP's bucketed reducer). After the first
@@ -376,7 +377,22 @@ class Trainer:
                 view.copy_(g)
                 p.grad = view
             off += k
-        self.dist.all_reduce(self._flat, op=self.dist.ReduceOp.SUM)
+        # The collective runs on a side stream: it starts when the backward's last kernel has finished and the optimizer
+        # kernels wait for it, while the compute stream stays free for work that does not read the gradients (the
+        # update hooks and the next batch's upload / ray generation are enqueued behind the optimizer only).
+        if with_grad[0].is_cuda:
+            if self._ar_stream is None:
+                self._ar_stream = torch.cuda.Stream()
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(self._ar_stream):
+                self._ar_stream.wait_event(ready)
+                self.dist.all_reduce(self._flat, op=self.dist.ReduceOp.SUM)
+                done = torch.cuda.Event()
+                done.record()
+            torch.cuda.current_stream().wait_event(done)
+        else:
+            self.dist.all_reduce(self._flat, op=self.dist.ReduceOp.SUM)
 
     def sync_initial_state(self, system: nn.Module) -> None:
         """What DistributedDataParallel does when Lightning wraps the module (launch.py:233-240 of the reference): rank

@@ -150,6 +150,68 @@ def _write_library(tmp_path, prompts):
     json.dump({"train": prompts, "val": prompts[:1], "test": prompts[:1]}, open(tmp_path / "load" / "lib.json", "w"))
 
 
+@pytest.mark.parametrize("kind", ["hyper", "triplane"])
+def test_chunked_training_render_equals_unchunked(cuda_device, kind):
+    """`train_chunk_size` (generative_space_volsdf_volume_renderer.py:241-250; here: chunks recomputed in the backward so
+    that BASELINE C5 fits in HBM at 256 x 256 x 4 views): images, eikonal input and every gradient equal the one-piece
+    render on the same random draws."""
+    import scaledreamer_b200 as sd
+
+    dev = cuda_device
+    torch.manual_seed(0)
+    if kind == "hyper":
+        geo = sd.find("Hyper-iNGP")({"radius": 2.0, "sdf_bias": "sphere", "sdf_bias_params": 0.5,
+                                     "hypernet_config": {"c_dim": 1024, "out_dims": {"sdf_weights": [64, 1], "feature_weights": [64, 3]},
+                                                         "spectral_norm": False, "n_neurons": 64, "n_hidden_layers": 1}}).to(dev)
+        with torch.no_grad():
+            geo.encoding.encoding.params.mul_(500.0)
+        emb = torch.randn(2, 1024, device=dev)
+    else:
+        geo = sd.find("Triplane-transformer-sdf")({"radius": 1.0, "sdf_bias": "sphere", "sdf_bias_params": 0.8,
+                                                   "space_generator_config": {"inner_dim": 128, "condition_dim": 1024,
+                                                                              "triplane_low_res": 8, "triplane_high_res": 16,
+                                                                              "triplane_dim": 32, "num_layers": 1, "num_heads": 2,
+                                                                              "flash_attention": False, "local_text": True}}).to(dev)
+        emb = torch.randn(2, 77, 1024, device=dev)
+    mat = sd.find("no-material")({"n_output_dims": 3, "color_activation": "sigmoid", "requires_normal": True}).to(dev)
+    bgm = sd.find("neural-environment-map-background")({"color_activation": "sigmoid", "random_aug": False}).to(dev)
+
+    def run(chunk):
+        ren = sd.find("generative-space-volsdf-volume-renderer")(
+            {"radius": 2.0 if kind == "hyper" else 1.0, "use_volsdf": True, "trainable_variance": False,
+             "learned_variance_init": 0.340119, "estimator": "importance", "num_samples_per_ray": 64,
+             "num_samples_per_ray_importance": 128, "near_plane": 0.1, "far_plane": 4.0, "train_chunk_size": chunk},
+            geometry=geo, material=mat, background=bgm).to(dev)
+        ren.train()
+        geo.update_step(0, 0)
+        for p in list(geo.parameters()) + list(bgm.parameters()):
+            p.grad = None
+        B, H, W = 2, 8, 8
+        g = torch.Generator().manual_seed(3)
+        o = (torch.tensor([0.0, -1.6, 0.3]) + 0.05 * torch.randn(B, 1, 1, 3, generator=g)).expand(B, H, W, 3).contiguous()
+        d = torch.nn.functional.normalize(torch.tensor([0.0, 1.0, -0.15]) + 0.2 * torch.randn(B, H, W, 3, generator=g), dim=-1)
+        uc, uf = torch.rand(B * H * W, generator=g), torch.rand(B * H * W, generator=g)
+        kw = dict(text_embed=emb) if kind == "hyper" else dict(text_embed=emb)
+        out = ren(o.to(dev), d.to(dev), None, u_coarse=uc.to(dev), u_fine=uf.to(dev), **kw)
+        gimg = torch.randn(B, H, W, 3, generator=g).to(dev)
+        loss = (out["comp_rgb"] * gimg).sum() + out["opacity"].sum() + 0.3 * out["depth"].sum() \
+            + 0.1 * ((out["sdf_grad"].norm(dim=-1) - 1.0) ** 2).mean()
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = {n: p.grad.detach().clone() for n, p in geo.named_parameters() if p.grad is not None}
+        return ren.last_chunk_rays, {k: out[k].detach().clone() for k in ("comp_rgb", "opacity", "depth", "sdf_grad")}, grads
+
+    c0, out0, g0 = run(0)
+    c1, out1, g1 = run(48)  # 24 rays per batch element and chunk: 3 chunks, the last one ragged (64 = 24 + 24 + 16)
+    assert c0 == 0 and c1 == 24
+    assert "weights" not in out1
+    for k in out0:
+        assert rel_l2(out1[k], out0[k]) < 1e-5, k
+    assert set(g0) == set(g1) and len(g0) >= 3
+    for n in g0:
+        assert rel_l2(g1[n], g0[n]) < 2e-4, n
+
+
 def test_volsdf_renderer_plugin_matches_oracle(cuda_device):
     """Geometry + background + renderer plugins (reference names / Config keys) against the oracle render on the same
     random draws, including the gradients of an image + eikonal loss w.r.t. hash table and hypernetwork output."""

@@ -23,11 +23,26 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"].startswith("ASD steps/sec") and d["unit"] == "steps/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
-    assert d["value"] > 0 and abs(d["ms_per_step"] - 1e3 / d["value"]) < 1e-6 * d["ms_per_step"]
+    # every step really runs one bounded sample: ms_per_step is ITS measured time (steps x ms_per_step = wall clock of the
+    # loop), `value` is the full-step rate extrapolated by the stated factors and labelled as such
+    assert d["value"] > 0 and d["extrapolated"] is True
     assert d["config"]["workload"].startswith("C2")
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "render" in cb["sample"]
+    assert cb["extrapolated"] is True and cb["full_step_seconds"] > cb["sample_seconds"] > 0
+    assert abs(cb["full_step_seconds"] - 1.0 / d["value"]) < 1e-6 * cb["full_step_seconds"]
+    assert 0.5 * cb["sample_seconds"] * 1e3 < d["ms_per_step"] < 3.0 * cb["sample_seconds"] * 1e3 + 5e3
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """The CPU baseline is the oracle alone: the process that runs it must not load libsdb200.so."""
+    code = ("import sys, os; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0']; "
+            "sys.path.insert(0, %r); import bench; bench.main(); "
+            "maps=open('/proc/self/maps').read(); assert 'libsdb200' not in maps, 'product library mapped'; "
+            "assert 'scaledreamer_b200.lib' not in sys.modules or sys.modules['scaledreamer_b200.lib']._lib is None") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
 
 
 def test_reference_arm_is_silent_on_other_ranks():
