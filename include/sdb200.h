@@ -200,6 +200,22 @@ int sdb_render_orient_forward(const sdb_field* field, const float* rays_d, int n
 int sdb_render_orient_backward(const sdb_field* field, const sdb_field_grads* grads, int n_rays,
                                const sdb_render_tape* tape, float* og, const float* g_orient, void* stream);
 
+/* ---- hypernetwork of the amortized generators ----------------------------------------------------------------
+ * LinearHyperNetwork (custom/amortized/models/geometry/hyper_iNGP.py:18-111, n_hidden_layers 1, n_neurons 64; also the
+ * environment map's, custom/amortized/models/background/multiprompt_neural_environment_hashgrid_map_background.py:82-99):
+ *   out[b] = w1 silu(LayerNorm(w0 x[b])) + b1,  x [n_prompts, c_dim], w0 [64, c_dim] (no bias), w1 [n_out, 64], fp32.
+ * `hidden` [n_prompts, 64] keeps w0 x for the backward. n_prompts <= 64. */
+int sdb_hypernet_forward(const float* x, int n_prompts, int c_dim, const float* w0, const float* ln_weight,
+                         const float* ln_bias, float ln_eps, const float* w1, const float* b1, int n_out,
+                         float* hidden, float* out, void* stream);
+/* Host-only: floats of the backward's scratch buffer. */
+long long sdb_hypernet_scratch_floats(int n_prompts, int n_out);
+/* Gradients of every parameter (WRITTEN, not accumulated; fixed summation order). g_b1 may be NULL. */
+int sdb_hypernet_backward(const float* x, int n_prompts, int c_dim, const float* ln_weight, const float* ln_bias,
+                          float ln_eps, const float* w1, int n_out, const float* hidden, const float* d_out,
+                          float* g_w0, float* g_ln_weight, float* g_ln_bias, float* g_w1, float* g_b1, float* scratch,
+                          void* stream);
+
 /* ---- prompt-conditioned hash-grid field (amortized generators) -------------------------------------------
  * out = relu(enc(x) W1[b]) W2[b], weights per prompt b from a hypernetwork, two optional heads on one encoding:
  *   head a 32->64->1: SDF of "Hyper-iNGP" (custom/amortized/models/geometry/hyper_iNGP.py:261-349, torch.bmm);

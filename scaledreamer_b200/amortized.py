@@ -95,6 +95,43 @@ def hyper_field(grid_cfg: dict, pts01: torch.Tensor, table: torch.Tensor, head_a
 
 
 # ------------------------------------------------------------------------------------------------ hypernetwork
+class _HyperNet(torch.autograd.Function):
+    """out = W1 silu(LayerNorm(W0 x)) + b1 (sdb_hypernet_forward / sdb_hypernet_backward): one launch forward, two
+    backward, fixed summation order. x (the text embedding) receives no gradient, as in the reference."""
+
+    @staticmethod
+    def forward(ctx, x, w0, ln_w, ln_b, w1, b1, eps):
+        lib = L.load()
+        B, c_dim = x.shape
+        n_out = w1.shape[0]
+        w0c, w1c = w0.detach().contiguous(), w1.detach().contiguous()
+        hidden = torch.empty(B, 64, device=x.device)
+        out = torch.empty(B, n_out, device=x.device)
+        L.check(lib.sdb_hypernet_forward(L.ptr(x), B, c_dim, L.ptr(w0c), L.ptr(ln_w.detach()), L.ptr(ln_b.detach()),
+                                         float(eps), L.ptr(w1c), L.ptr(b1.detach()) if b1 is not None else None, n_out,
+                                         L.ptr(hidden), L.ptr(out), L.stream_ptr()), "sdb_hypernet_forward")
+        ctx.save_for_backward(x, ln_w.detach(), ln_b.detach(), w1c, hidden)
+        ctx.eps, ctx.has_bias, ctx.w0_shape = float(eps), b1 is not None, tuple(w0.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = L.load()
+        x, ln_w, ln_b, w1, hidden = ctx.saved_tensors
+        B, c_dim = x.shape
+        n_out = w1.shape[0]
+        dev = x.device
+        g_w0, g_w1 = torch.empty(ctx.w0_shape, device=dev), torch.empty_like(w1)
+        g_lw, g_lb = torch.empty(64, device=dev), torch.empty(64, device=dev)
+        g_b1 = torch.empty(n_out, device=dev) if ctx.has_bias else None
+        scratch = torch.empty(lib.sdb_hypernet_scratch_floats(B, n_out), device=dev)
+        L.check(lib.sdb_hypernet_backward(L.ptr(x), B, c_dim, L.ptr(ln_w), L.ptr(ln_b), ctx.eps, L.ptr(w1), n_out,
+                                          L.ptr(hidden), L.ptr(d_out.contiguous().float()), L.ptr(g_w0), L.ptr(g_lw),
+                                          L.ptr(g_lb), L.ptr(g_w1), L.ptr(g_b1), L.ptr(scratch), L.stream_ptr()),
+                "sdb_hypernet_backward")
+        return None, g_w0, g_lw, g_lb, g_w1, g_b1, None
+
+
 class LinearHyperNetwork(nn.Module):
     """hyper_iNGP.py:18-111: text embedding -> flat weight vector, split into [in, out] matrices per head."""
 
@@ -124,8 +161,18 @@ class LinearHyperNetwork(nn.Module):
         nn.init.xavier_normal_(layer.weight, gain=1.0)
         return layer
 
+    def _native_layout(self, x: torch.Tensor) -> bool:
+        """Linear(no bias) -> LayerNorm(64) -> SiLU -> Linear: the layout of every BASELINE config (csrc/hypernet.cu)."""
+        return (x.is_cuda and x.dim() == 2 and len(self.layers) == 4 and self.layers[0].out_features == 64
+                and 0 < x.shape[0] <= 64 and x.shape[1] * 4 <= 48 * 1024)
+
     def forward(self, x: torch.Tensor) -> Dict[str, List[torch.Tensor]]:
-        out = self.layers(x.float())
+        if self._native_layout(x):
+            lin0, ln, _, lin1 = self.layers
+            out = _HyperNet.apply(x.float().contiguous(), lin0.weight, ln.weight, ln.bias, lin1.weight, lin1.bias,
+                                  float(ln.eps))
+        else:  # deeper hypernetworks (n_hidden_layers > 1) and CPU inspection: torch modules
+            out = self.layers(x.float())
         res, start = {}, 0
         for name, ch in self.out_dims.items():
             mats = []

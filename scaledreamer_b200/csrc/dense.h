@@ -54,6 +54,12 @@ struct GemmParams {
   int tiles_m, tiles_n, tiles_z;  // tile grid walked by the persistent CTAs (filled at launch)
   unsigned long long* dbg;  // optional [gridDim.x][4] globaltimer stamps: entry, setup done, first accumulator, exit
   int row_softmax;     // BN == 80 only: the epilogue applies softmax over the (single-tile) row of N <= 80 scores
+  // Stream-K (z == 1 launches whose tile count does not fill the CTA slots evenly): the tiles x k-blocks iteration space
+  // is cut into gridDim.x equal ranges; a CTA whose range ends inside a tile leaves an fp32 partial accumulator in its
+  // workspace slot, the CTA that owns the tile's last k-block adds the partials (fixed order) and runs the epilogue.
+  int streamk;
+  float* sk_ws;          // [gridDim.x][BN/32 chunks][128 rows][32] fp32
+  unsigned int* sk_flags;  // [gridDim.x] 0 = empty, 1 = partial ready (reset by the consumer)
 };
 
 struct GemmPlan {

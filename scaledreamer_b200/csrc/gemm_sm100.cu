@@ -67,9 +67,52 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* tm, const Operan
 }
 
 // Epilogue of one 128 x BN tile for the 32 rows of TMEM lane quadrant wq (one row per thread).
+// Stream-K bookkeeping of one segment's epilogue: sk_mode 0 = ordinary tile; 1 = leave the raw accumulator in workspace slot
+// `sk_slot`; 2 = add the partials of slots [sk_first, sk_slot) before the ordinary epilogue.
+struct SkEpi {
+  int mode, slot, first;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// barrier over the epilogue warps of one set only (ids 1, 2; barrier 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar_sync(int set) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int wq, int lane, int m0, int n0,
-                                              int z, int zsplit, int set, int nsets) {
+                                              int z, int zsplit, int set, int nsets, const SkEpi sk = SkEpi{0, 0, 0}) {
+  constexpr int kChunks = (BN + 31) / 32;
+  const size_t sk_slot_floats = (size_t)kChunks * kBM * 32;
+  if (sk.mode == 1) {  // raw fp32 accumulator -> this CTA's workspace slot, chunk-major: a warp writes 4 KB contiguous
+    float* dst = p.sk_ws + (size_t)sk.slot * sk_slot_floats + (size_t)(wq * 32 + lane) * 32;
+#pragma unroll 1
+    for (int c = 32 * set; c < BN; c += 32 * nsets) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, v);
+      ptx::tmem_ld_wait();
+      float* o = dst + (size_t)(c >> 5) * kBM * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        __stcg(reinterpret_cast<uint4*>(o) + q, make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    }
+    __threadfence();
+    return;
+  }
+  if (sk.mode == 2) {  // wait for every contributor once (lane 0 polls, the warp follows)
+    for (int s = sk.first; s < sk.slot; ++s) {
+      if (lane == 0)
+        while (ld_acquire_gpu(p.sk_flags + s) == 0u) __nanosleep(64);
+      __syncwarp();
+    }
+  }
   const int m = m0 + wq * 32 + lane;
   const bool m_ok = m < p.M;
   const long long zoff = (long long)(z / p.out_zdiv) * p.out_zs_hi + (long long)(z % p.out_zdiv) * p.out_zs_lo;
@@ -175,6 +218,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       if (c + cstep < BN) load_res(c + cstep, rnext);
     }
     ptx::tmem_ld_wait();
+    if (sk.mode == 2) {  // partial accumulators of the CTAs that own the tile's earlier k-blocks, in slot order
+      for (int s = sk.first; s < sk.slot; ++s) {
+        const float* src = p.sk_ws + (size_t)s * sk_slot_floats + ((size_t)(c >> 5) * kBM + wq * 32 + lane) * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = __ldcg(reinterpret_cast<const float4*>(src) + q);
+          v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + t.x);
+          v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + t.y);
+          v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + t.z);
+          v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + t.w);
+        }
+      }
+    }
     if (!m_ok || nb >= p.N) continue;
     if (p.splits > 1) {  // raw fp32 partial sums; splitk_finalize_kernel applies the epilogue
       float* o = p.ws + ((long long)zsplit * p.M + m) * p.N + nb;
@@ -327,20 +383,50 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int kb0 = zs * per_split;                                                    \
   const int nkb = p.splits > 1 ? min(per_split, p.num_k_blocks - kb0) : p.num_k_blocks;
 
+  // Stream-K: this CTA's share of the tiles x k-blocks iteration space, walked from its END towards its beginning, so
+  // that the piece of a tile it shares with the next CTA (a partial accumulator another CTA is waiting for) is produced
+  // first and the tile it finishes itself (which waits for the previous CTAs' partials) comes last.
+  const long long sk_iters = (long long)tiles_mn * p.num_k_blocks;
+  const long long sk_begin = p.streamk ? sk_iters * blockIdx.x / gridDim.x : 0;
+  const long long sk_end = p.streamk ? sk_iters * (blockIdx.x + 1) / gridDim.x : 0;
+  struct SkSeg {
+    long long cur_end, begin;
+    int nkb_tile, tile, kb0, kb1;
+    __device__ __forceinline__ bool next() {
+      if (cur_end <= begin) return false;
+      tile = (int)((cur_end - 1) / nkb_tile);
+      const long long first = (long long)tile * nkb_tile;
+      const long long sb = begin > first ? begin : first;
+      kb0 = (int)(sb - first);
+      kb1 = (int)(cur_end - first);
+      cur_end = sb;
+      return true;
+    }
+  };
+
   if (warp == 0) {
     if (ptx::elect_one()) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        SDB_DECODE_TILE(tile)
-        (void)zs;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+      auto produce = [&](int m0, int n0, int z, int kb_first, int count) {
+        for (int kb = 0; kb < count; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1u);
           ptx::mbar_arrive_expect_tx(&full[s], C::kStageBytes);
           uint8_t* sa = base + s * C::kStageBytes;
-          load_operand(&tmA, p.a, sa, &full[s], kb0 + kb, m0, z);
-          load_operand(&tmB, p.b, sa + kATileBytes, &full[s], kb0 + kb, n0, z);
+          load_operand(&tmA, p.a, sa, &full[s], kb_first + kb, m0, z);
+          load_operand(&tmB, p.b, sa + kATileBytes, &full[s], kb_first + kb, n0, z);
+        }
+      };
+      if (p.streamk) {
+        SkSeg sg{sk_end, sk_begin, p.num_k_blocks, 0, 0, 0};
+        while (sg.next())
+          produce((sg.tile % p.tiles_m) * kBM, (sg.tile / p.tiles_m) * BN, 0, sg.kb0, sg.kb1 - sg.kb0);
+      } else {
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+          SDB_DECODE_TILE(tile)
+          (void)zs;
+          produce(m0, n0, z, kb0, nkb);
         }
       }
     }
@@ -348,14 +434,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_f16(kBM, BN, 0, 0, p.b.mn_major);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
-        SDB_DECODE_TILE(tile)
-        (void)m0; (void)n0; (void)z; (void)zs; (void)kb0;
+      auto mma_segment = [&](int count) {
         const uint32_t buf = tcount % C::kAccBufs, use = tcount / C::kAccBufs;
         const uint32_t tmem_acc = tmem_base + buf * C::kAccStride;
         ptx::mbar_wait(&accum_empty[buf], (use & 1) ^ 1u);  // the epilogue warps drained this accumulator
         ptx::tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = 0; kb < count; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           ptx::mbar_wait(&full[s], ph);
@@ -374,21 +458,65 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::umma_commit(&empty[s]);
         }
         ptx::umma_commit(&accum_full[buf]);
+        ++tcount;
+      };
+      if (p.streamk) {
+        SkSeg sg{sk_end, sk_begin, p.num_k_blocks, 0, 0, 0};
+        while (sg.next()) mma_segment(sg.kb1 - sg.kb0);
+      } else {
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+          SDB_DECODE_TILE(tile)
+          (void)m0; (void)n0; (void)z; (void)zs; (void)kb0;
+          mma_segment(nkb);
+        }
       }
     }
   } else if (warp >= 4) {
     const int wq = warp & 3, set = (warp - 4) >> 2;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
-      SDB_DECODE_TILE(tile)
-      (void)kb0; (void)nkb;
+    auto epilogue_segment = [&](int m0, int n0, int z, int zs, const SkEpi sk) {
       const uint32_t buf = tcount % C::kAccBufs, use = tcount / C::kAccBufs;
       ptx::mbar_wait(&accum_full[buf], use & 1);
       ptx::tc_fence_after();
       if (tcount == 0) stamp(2);
-      epilogue_tile<BN>(p, tmem_base + buf * C::kAccStride, wq, lane, m0, n0, z, zs, set, C::kEpiSets);
+      epilogue_tile<BN>(p, tmem_base + buf * C::kAccStride, wq, lane, m0, n0, z, zs, set, C::kEpiSets, sk);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&accum_empty[buf]);
+      ++tcount;
+    };
+    if (p.streamk) {
+      SkSeg sg{sk_end, sk_begin, p.num_k_blocks, 0, 0, 0};
+      while (sg.next()) {
+        const int m0 = (sg.tile % p.tiles_m) * kBM, n0 = (sg.tile / p.tiles_m) * BN;
+        SkEpi sk{0, (int)blockIdx.x, 0};
+        if (sg.kb1 < p.num_k_blocks) {
+          sk.mode = 1;  // the tile's last k-blocks belong to a later CTA: leave a partial
+        } else if (sg.kb0 > 0) {
+          sk.mode = 2;  // this CTA finishes the tile: contributors are the CTAs from the owner of its first k-block on
+          const long long first = (long long)sg.tile * p.num_k_blocks;
+          long long ga = first * gridDim.x / sk_iters;
+          while (ga > 0 && sk_iters * ga / gridDim.x > first) --ga;
+          while (sk_iters * (ga + 1) / gridDim.x <= first) ++ga;
+          sk.first = (int)ga;
+        }
+        epilogue_segment(m0, n0, 0, 0, sk);
+        if (sk.mode != 0) {  // publish / retire flags once every epilogue warp is done with the workspace
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * C::kEpiSets) : "memory");
+          if (threadIdx.x == 128) {
+            if (sk.mode == 1) {
+              st_release_gpu(p.sk_flags + blockIdx.x, 1u);
+            } else {
+              for (int s2 = sk.first; s2 < sk.slot; ++s2) st_release_gpu(p.sk_flags + s2, 0u);
+            }
+          }
+        }
+      }
+    } else {
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        SDB_DECODE_TILE(tile)
+        (void)kb0; (void)nkb;
+        epilogue_segment(m0, n0, z, zs, SkEpi{0, 0, 0});
+      }
     }
   }
 #undef SDB_DECODE_TILE

@@ -168,6 +168,9 @@ SIGNATURES = {
                                          _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(RenderTapeC), _P],
     "sdb_render_orient_forward": [C.POINTER(FieldC), _P, _I, C.POINTER(RenderTapeC), _P, _P, _P],
     "sdb_render_orient_backward": [C.POINTER(FieldC), C.POINTER(FieldGradsC), _I, C.POINTER(RenderTapeC), _P, _P, _P],
+    "sdb_hypernet_forward": [_P, _I, _I, _P, _P, _P, _F, _P, _P, _I, _P, _P, _P],
+    "sdb_hypernet_scratch_floats": [_I, _I],
+    "sdb_hypernet_backward": [_P, _I, _I, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "sdb_hyper_field_tape_floats": [_I, _I],
     "sdb_hyper_field_forward": [C.POINTER(GridCfgC), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "sdb_hyper_field_backward": [C.POINTER(GridCfgC), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -237,7 +240,7 @@ def _declare(lib: C.CDLL) -> None:
         fn.argtypes = args
         if name == "sdb_net_destroy":
             fn.restype = None
-        elif name in ("sdb_groupnorm_workspace_floats", "sdb_hyper_field_tape_floats"):
+        elif name in ("sdb_groupnorm_workspace_floats", "sdb_hyper_field_tape_floats", "sdb_hypernet_scratch_floats"):
             fn.restype = C.c_longlong
         elif name != "sdb_grid_num_entries":
             fn.restype = C.c_int

@@ -150,6 +150,41 @@ def _write_library(tmp_path, prompts):
     json.dump({"train": prompts, "val": prompts[:1], "test": prompts[:1]}, open(tmp_path / "load" / "lib.json", "w"))
 
 
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_native_hypernetwork_matches_torch_modules(cuda_device, B):
+    """sdb_hypernet_forward / backward (csrc/hypernet.cu) against the torch modules of the same LinearHyperNetwork
+    (Linear -> LayerNorm -> SiLU -> Linear; hyper_iNGP.py:18-111, pinned to the reference class in
+    test_amortized_golden_cpu.py): outputs 1e-5, every parameter gradient 1e-4; bitwise reproducible."""
+    from scaledreamer_b200.amortized import LinearHyperNetwork
+
+    torch.manual_seed(B)
+    net = LinearHyperNetwork(32, {"c_dim": 1024, "out_dims": {"sdf_weights": [64, 1], "feature_weights": [64, 3]},
+                                  "spectral_norm": False, "n_neurons": 64, "n_hidden_layers": 1}).to(cuda_device)
+    with torch.no_grad():
+        net.layers[1].weight.add_(0.1 * torch.randn(64, device=cuda_device))
+        net.layers[1].bias.add_(0.1 * torch.randn(64, device=cuda_device))
+        net.layers[3].bias.add_(0.1 * torch.randn(4352, device=cuda_device))
+    x = torch.randn(B, 1024, device=cuda_device)
+    g = torch.randn(B, 4352, device=cuda_device)
+    assert net._native_layout(x)
+    out = net(x)
+    flat = torch.cat([m.reshape(B, -1) for ms in out.values() for m in ms], 1)
+    (flat * g).sum().backward()
+    got = {n: p.grad.clone() for n, p in net.named_parameters()}
+    net.zero_grad()
+    ref = net.layers(x)
+    (ref * g).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_l2(flat, ref) < 1e-5
+    for n, p in net.named_parameters():
+        assert rel_l2(got[n], p.grad) < 1e-4, n
+    net.zero_grad()
+    out2 = net(x)
+    flat2 = torch.cat([m.reshape(B, -1) for ms in out2.values() for m in ms], 1)
+    (flat2 * g).sum().backward()
+    assert torch.equal(flat2, flat) and all(torch.equal(got[n], p.grad) for n, p in net.named_parameters())
+
+
 @pytest.mark.parametrize("kind", ["hyper", "triplane"])
 def test_chunked_training_render_equals_unchunked(cuda_device, kind):
     """`train_chunk_size` (generative_space_volsdf_volume_renderer.py:241-250; here: chunks recomputed in the backward so
