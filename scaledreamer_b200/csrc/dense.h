@@ -27,7 +27,8 @@ struct OperandGeom {
   int heads;       // kHeads
   int mn_major;    // B only: tile is [K rows][64 MN] (e.g. V of attention); requires BN == 64
   int W, H;        // kConv3x3 image size
-  int bw, bh, bn;  // kConv3x3 box (bw*bh*bn == 128)
+  int bw, bh, bn;  // kConv3x3: the 128 pixels of a tile are bw x bh x bn (columns, rows, images)
+  int split_dim;   // kConv3x3: the tile is fetched as two 64-pixel boxes, halved along w (1), h (2) or n (3)
   int cin_blocks;  // kConv3x3: Cin / 64
 };
 
@@ -54,12 +55,6 @@ struct GemmParams {
   int tiles_m, tiles_n, tiles_z;  // tile grid walked by the persistent CTAs (filled at launch)
   unsigned long long* dbg;  // optional [gridDim.x][4] globaltimer stamps: entry, setup done, first accumulator, exit
   int row_softmax;     // BN == 80 only: the epilogue applies softmax over the (single-tile) row of N <= 80 scores
-  // Stream-K (z == 1 launches whose tile count does not fill the CTA slots evenly): the tiles x k-blocks iteration space
-  // is cut into gridDim.x equal ranges; a CTA whose range ends inside a tile leaves an fp32 partial accumulator in its
-  // workspace slot, the CTA that owns the tile's last k-block adds the partials (fixed order) and runs the epilogue.
-  int streamk;
-  float* sk_ws;          // [gridDim.x][BN/32 chunks][128 rows][32] fp32
-  unsigned int* sk_flags;  // [gridDim.x] 0 = empty, 1 = partial ready (reset by the consumer)
 };
 
 struct GemmPlan {

@@ -39,7 +39,9 @@ struct Cfg {
   static constexpr int kStages = DEEP ? (BN <= 80 ? 8 : (BN <= 160 ? 6 : 4)) : (BN <= 80 ? 4 : 3);
   // DEEP: two accumulators in tensor memory (the MMA warp fills one while the epilogue drains the other) and two sets
   // of four epilogue warps that take alternate 32-column chunks of a tile.
-  static constexpr int kAccBufs = DEEP ? 2 : 1;
+  // (round 2) also with two CTAs per SM when both CTAs' accumulator pairs fit the 512 tensor-memory columns (BN <= 128):
+  // short-K layers spend longer in the epilogue than in the main loop, and a single accumulator serialises the two
+  static constexpr int kAccBufs = (DEEP || BN <= 128) ? 2 : 1;
   static constexpr int kEpiSets = DEEP ? 2 : 1;
   static constexpr int kThreads = 128 + 128 * kEpiSets;
   static constexpr int kAccStride = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
@@ -62,57 +64,18 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* tm, const Operan
     const int hw = g.H * g.W;
     const int n0 = r0 / hw, rem = r0 - n0 * hw;
     const int h0 = rem / g.W, w0 = rem - h0 * g.W;
+    // two 64-pixel boxes (8 KB each) instead of one of 128: the copy engine works on them concurrently, which is what
+    // keeps a lone CTA per SM fed (measured: 425 -> see profiles/r2i_conv_split_timeline.log ns per k-block)
+    const int hw_ = g.split_dim == 1 ? g.bw / 2 : 0, hh_ = g.split_dim == 2 ? g.bh / 2 : 0, hn_ = g.split_dim == 3 ? g.bn / 2 : 0;
     ptx::tma_load_4d(smem, tm, bar, cb * kBK, w0 + dx, h0 + dy, n0);
+    ptx::tma_load_4d(static_cast<uint8_t*>(smem) + kATileBytes / 2, tm, bar, cb * kBK, w0 + dx + hw_, h0 + dy + hh_, n0 + hn_);
   }
 }
 
 // Epilogue of one 128 x BN tile for the 32 rows of TMEM lane quadrant wq (one row per thread).
-// Stream-K bookkeeping of one segment's epilogue: sk_mode 0 = ordinary tile; 1 = leave the raw accumulator in workspace slot
-// `sk_slot`; 2 = add the partials of slots [sk_first, sk_slot) before the ordinary epilogue.
-struct SkEpi {
-  int mode, slot, first;
-};
-
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// barrier over the epilogue warps of one set only (ids 1, 2; barrier 0 is __syncthreads)
-__device__ __forceinline__ void epi_bar_sync(int set) {
-  asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
-}
-
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int wq, int lane, int m0, int n0,
-                                              int z, int zsplit, int set, int nsets, const SkEpi sk = SkEpi{0, 0, 0}) {
-  constexpr int kChunks = (BN + 31) / 32;
-  const size_t sk_slot_floats = (size_t)kChunks * kBM * 32;
-  if (sk.mode == 1) {  // raw fp32 accumulator -> this CTA's workspace slot, chunk-major: a warp writes 4 KB contiguous
-    float* dst = p.sk_ws + (size_t)sk.slot * sk_slot_floats + (size_t)(wq * 32 + lane) * 32;
-#pragma unroll 1
-    for (int c = 32 * set; c < BN; c += 32 * nsets) {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, v);
-      ptx::tmem_ld_wait();
-      float* o = dst + (size_t)(c >> 5) * kBM * 32;
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        __stcg(reinterpret_cast<uint4*>(o) + q, make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-    }
-    __threadfence();
-    return;
-  }
-  if (sk.mode == 2) {  // wait for every contributor once (lane 0 polls, the warp follows)
-    for (int s = sk.first; s < sk.slot; ++s) {
-      if (lane == 0)
-        while (ld_acquire_gpu(p.sk_flags + s) == 0u) __nanosleep(64);
-      __syncwarp();
-    }
-  }
+                                              int z, int zsplit, int set, int nsets) {
   const int m = m0 + wq * 32 + lane;
   const bool m_ok = m < p.M;
   const long long zoff = (long long)(z / p.out_zdiv) * p.out_zs_hi + (long long)(z % p.out_zdiv) * p.out_zs_lo;
@@ -218,19 +181,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       if (c + cstep < BN) load_res(c + cstep, rnext);
     }
     ptx::tmem_ld_wait();
-    if (sk.mode == 2) {  // partial accumulators of the CTAs that own the tile's earlier k-blocks, in slot order
-      for (int s = sk.first; s < sk.slot; ++s) {
-        const float* src = p.sk_ws + (size_t)s * sk_slot_floats + ((size_t)(c >> 5) * kBM + wq * 32 + lane) * 32;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t = __ldcg(reinterpret_cast<const float4*>(src) + q);
-          v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + t.x);
-          v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + t.y);
-          v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + t.z);
-          v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + t.w);
-        }
-      }
-    }
     if (!m_ok || nb >= p.N) continue;
     if (p.splits > 1) {  // raw fp32 partial sums; splitk_finalize_kernel applies the epilogue
       float* o = p.ws + ((long long)zsplit * p.M + m) * p.N + nb;
@@ -383,50 +333,65 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int kb0 = zs * per_split;                                                    \
   const int nkb = p.splits > 1 ? min(per_split, p.num_k_blocks - kb0) : p.num_k_blocks;
 
-  // Stream-K: this CTA's share of the tiles x k-blocks iteration space, walked from its END towards its beginning, so
-  // that the piece of a tile it shares with the next CTA (a partial accumulator another CTA is waiting for) is produced
-  // first and the tile it finishes itself (which waits for the previous CTAs' partials) comes last.
-  const long long sk_iters = (long long)tiles_mn * p.num_k_blocks;
-  const long long sk_begin = p.streamk ? sk_iters * blockIdx.x / gridDim.x : 0;
-  const long long sk_end = p.streamk ? sk_iters * (blockIdx.x + 1) / gridDim.x : 0;
-  struct SkSeg {
-    long long cur_end, begin;
-    int nkb_tile, tile, kb0, kb1;
-    __device__ __forceinline__ bool next() {
-      if (cur_end <= begin) return false;
-      tile = (int)((cur_end - 1) / nkb_tile);
-      const long long first = (long long)tile * nkb_tile;
-      const long long sb = begin > first ? begin : first;
-      kb0 = (int)(sb - first);
-      kb1 = (int)(cur_end - first);
-      cur_end = sb;
-      return true;
-    }
-  };
-
   if (warp == 0) {
     if (ptx::elect_one()) {
       uint32_t it = 0;
-      auto produce = [&](int m0, int n0, int z, int kb_first, int count) {
-        for (int kb = 0; kb < count; ++kb, ++it) {
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        SDB_DECODE_TILE(tile)
+        (void)zs;
+        if (p.a.mode == kConv3x3 && p.b.mode == kMatrix) {
+          // implicit 3x3 convolution: everything that depends on the tile only (image / row / column of its first pixel)
+          // is worked out once, the (tap, channel block) walk is two counters -- the producer is ONE thread, and four
+          // integer divisions per k-block were enough to make it the slowest stage of a single-CTA-per-SM launch
+          const OperandGeom& g = p.a;
+          const int hw = g.H * g.W;
+          const int img = m0 / hw, rem = m0 - img * hw;
+          const int h0 = rem / g.W, w0 = rem - h0 * g.W;
+          const int hw_ = g.split_dim == 1 ? g.bw / 2 : 0, hh_ = g.split_dim == 2 ? g.bh / 2 : 0,
+                    hn_ = g.split_dim == 3 ? g.bn / 2 : 0;
+          int tap = kb0 / g.cin_blocks, cb = kb0 - tap * g.cin_blocks;
+          int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          int s = it % C::kStages;
+          uint32_t ph = (it / C::kStages) & 1;
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(&empty[s], ph ^ 1u);
+            ptx::mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+            uint8_t* sa = base + s * C::kStageBytes;
+            ptx::tma_load_4d(sa, &tmA, &full[s], cb * kBK, w0 + dx, h0 + dy, img);
+            ptx::tma_load_4d(sa + kATileBytes / 2, &tmA, &full[s], cb * kBK, w0 + dx + hw_, h0 + dy + hh_, img + hn_);
+            ptx::tma_load_3d(sa + kATileBytes, &tmB, &full[s], (kb0 + kb) * kBK, n0, 0);
+            if (++cb == g.cin_blocks) {
+              cb = 0;
+              if (++dx == 2) dx = -1, ++dy;
+            }
+            if (++s == C::kStages) s = 0, ph ^= 1u;
+          }
+          it += nkb;
+          continue;
+        }
+        if (p.a.mode == kMatrix && p.b.mode == kMatrix) {  // plain (batched) matrices: no per-k-block decisions at all
+          const int za = p.a.batched ? z : 0, zb = p.b.batched ? z : 0;
+          int s = it % C::kStages;
+          uint32_t ph = (it / C::kStages) & 1;
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(&empty[s], ph ^ 1u);
+            ptx::mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+            uint8_t* sa = base + s * C::kStageBytes;
+            ptx::tma_load_3d(sa, &tmA, &full[s], (kb0 + kb) * kBK, m0, za);
+            ptx::tma_load_3d(sa + kATileBytes, &tmB, &full[s], (kb0 + kb) * kBK, n0, zb);
+            if (++s == C::kStages) s = 0, ph ^= 1u;
+          }
+          it += nkb;
+          continue;
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1u);
           ptx::mbar_arrive_expect_tx(&full[s], C::kStageBytes);
           uint8_t* sa = base + s * C::kStageBytes;
-          load_operand(&tmA, p.a, sa, &full[s], kb_first + kb, m0, z);
-          load_operand(&tmB, p.b, sa + kATileBytes, &full[s], kb_first + kb, n0, z);
-        }
-      };
-      if (p.streamk) {
-        SkSeg sg{sk_end, sk_begin, p.num_k_blocks, 0, 0, 0};
-        while (sg.next())
-          produce((sg.tile % p.tiles_m) * kBM, (sg.tile / p.tiles_m) * BN, 0, sg.kb0, sg.kb1 - sg.kb0);
-      } else {
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-          SDB_DECODE_TILE(tile)
-          (void)zs;
-          produce(m0, n0, z, kb0, nkb);
+          load_operand(&tmA, p.a, sa, &full[s], kb0 + kb, m0, z);
+          load_operand(&tmB, p.b, sa + kATileBytes, &full[s], kb0 + kb, n0, z);
         }
       }
     }
@@ -434,14 +399,16 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_f16(kBM, BN, 0, 0, p.b.mn_major);
       uint32_t it = 0, tcount = 0;
-      auto mma_segment = [&](int count) {
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
+        SDB_DECODE_TILE(tile)
+        (void)m0; (void)n0; (void)z; (void)zs; (void)kb0;
         const uint32_t buf = tcount % C::kAccBufs, use = tcount / C::kAccBufs;
         const uint32_t tmem_acc = tmem_base + buf * C::kAccStride;
         ptx::mbar_wait(&accum_empty[buf], (use & 1) ^ 1u);  // the epilogue warps drained this accumulator
         ptx::tc_fence_after();
-        for (int kb = 0; kb < count; ++kb, ++it) {
-          const int s = it % C::kStages;
-          const uint32_t ph = (it / C::kStages) & 1;
+        int s = it % C::kStages;
+        uint32_t ph = (it / C::kStages) & 1;
+        for (int kb = 0; kb < nkb; ++kb, ++it, s = (s + 1 == C::kStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(base + s * C::kStageBytes);
@@ -458,65 +425,21 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::umma_commit(&empty[s]);
         }
         ptx::umma_commit(&accum_full[buf]);
-        ++tcount;
-      };
-      if (p.streamk) {
-        SkSeg sg{sk_end, sk_begin, p.num_k_blocks, 0, 0, 0};
-        while (sg.next()) mma_segment(sg.kb1 - sg.kb0);
-      } else {
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-          SDB_DECODE_TILE(tile)
-          (void)m0; (void)n0; (void)z; (void)zs; (void)kb0;
-          mma_segment(nkb);
-        }
       }
     }
   } else if (warp >= 4) {
     const int wq = warp & 3, set = (warp - 4) >> 2;
     uint32_t tcount = 0;
-    auto epilogue_segment = [&](int m0, int n0, int z, int zs, const SkEpi sk) {
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
+      SDB_DECODE_TILE(tile)
+      (void)kb0; (void)nkb;
       const uint32_t buf = tcount % C::kAccBufs, use = tcount / C::kAccBufs;
       ptx::mbar_wait(&accum_full[buf], use & 1);
       ptx::tc_fence_after();
       if (tcount == 0) stamp(2);
-      epilogue_tile<BN>(p, tmem_base + buf * C::kAccStride, wq, lane, m0, n0, z, zs, set, C::kEpiSets, sk);
+      epilogue_tile<BN>(p, tmem_base + buf * C::kAccStride, wq, lane, m0, n0, z, zs, set, C::kEpiSets);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&accum_empty[buf]);
-      ++tcount;
-    };
-    if (p.streamk) {
-      SkSeg sg{sk_end, sk_begin, p.num_k_blocks, 0, 0, 0};
-      while (sg.next()) {
-        const int m0 = (sg.tile % p.tiles_m) * kBM, n0 = (sg.tile / p.tiles_m) * BN;
-        SkEpi sk{0, (int)blockIdx.x, 0};
-        if (sg.kb1 < p.num_k_blocks) {
-          sk.mode = 1;  // the tile's last k-blocks belong to a later CTA: leave a partial
-        } else if (sg.kb0 > 0) {
-          sk.mode = 2;  // this CTA finishes the tile: contributors are the CTAs from the owner of its first k-block on
-          const long long first = (long long)sg.tile * p.num_k_blocks;
-          long long ga = first * gridDim.x / sk_iters;
-          while (ga > 0 && sk_iters * ga / gridDim.x > first) --ga;
-          while (sk_iters * (ga + 1) / gridDim.x <= first) ++ga;
-          sk.first = (int)ga;
-        }
-        epilogue_segment(m0, n0, 0, 0, sk);
-        if (sk.mode != 0) {  // publish / retire flags once every epilogue warp is done with the workspace
-          asm volatile("bar.sync 1, %0;" ::"n"(128 * C::kEpiSets) : "memory");
-          if (threadIdx.x == 128) {
-            if (sk.mode == 1) {
-              st_release_gpu(p.sk_flags + blockIdx.x, 1u);
-            } else {
-              for (int s2 = sk.first; s2 < sk.slot; ++s2) st_release_gpu(p.sk_flags + s2, 0u);
-            }
-          }
-        }
-      }
-    } else {
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        SDB_DECODE_TILE(tile)
-        (void)kb0; (void)nkb;
-        epilogue_segment(m0, n0, z, zs, SkEpi{0, 0, 0});
-      }
     }
   }
 #undef SDB_DECODE_TILE
@@ -625,12 +548,14 @@ bool wide_tile(int M, int N, int K) {
 
 int gemm_splits(int M, int N, int K) {
   const bool wide = wide_tile(M, N, K);
-  const int bn = wide ? 256 : (N % 160 == 0 ? 160 : (N <= 64 ? 64 : 128));
+  const int bn = wide ? 256 : (N <= 64 ? 64 : 128);
   const int slots = wide ? kNumSMs : 2 * kNumSMs;  // the wide tile runs one CTA per SM
   const int tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
   const int nkb = (K + kBK - 1) / kBK;
-  // below one CTA per SM the TMA ring of a lone CTA is latency-bound: split K until the CTA slots are filled
-  if (tiles >= kNumSMs || nkb < 48) return 1;
+  // A lone CTA per SM streams a k-block in ~200 ns since the producer thread stopped dividing (round 2), so a launch of
+  // 80-128 tiles is better left whole (1280 x 1280 x 11520: 45 us whole, 59 us as three splits + finalize); only
+  // launches that would leave three quarters of the SMs idle are split along K.
+  if (tiles * 4 > kNumSMs || nkb < 48) return 1;
   int sp = std::min(std::min(slots / tiles, nkb / 4), 16);
   if (sp <= 1) return 1;
   const int per = (nkb + sp - 1) / sp;
@@ -645,7 +570,10 @@ int pick_bn(int M, int N, int K) {
     if (bn == 64 || bn == 80 || bn == 128 || bn == 160) return bn;
   }
   if (wide_tile(M, N, K)) return 256;
-  if (N % 160 == 0) return 160;
+  // 160-wide tiles divide the UNet's channel counts exactly, but only 128-wide ones leave room for two accumulators per
+  // CTA with two CTAs per SM (the epilogue of one tile then overlaps the main loop of the next): measured faster on
+  // every UNet / VAE shape despite the padded last tile of N = 320 / 960 (profiles/r2l_gemm_shapes_acc2_bn128.log).
+  // SDB_GEMM_BN=160 still selects the old tiling.
   if (N <= 64) return 64;
   return 128;
 }
@@ -851,7 +779,9 @@ int plan_conv3x3(GemmPlan* plan, const __half* x, int N, int H, int W, int Cin, 
   fill_epilogue(p, ep);
   uint64_t da[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
   uint64_t sa[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-  uint32_t ba[4] = {kBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  p.a.split_dim = bn >= 2 ? 3 : (bh >= 2 ? 2 : 1);
+  uint32_t ba[4] = {kBK, (uint32_t)(p.a.split_dim == 1 ? bw / 2 : bw), (uint32_t)(p.a.split_dim == 2 ? bh / 2 : bh),
+                    (uint32_t)(p.a.split_dim == 3 ? bn / 2 : bn)};
   int rc = make_tmap(&plan->ta, x, 4, da, sa, ba);
   if (rc) return rc;
   uint64_t db[3] = {(uint64_t)p.K, (uint64_t)Cout, 1};

@@ -53,6 +53,45 @@ def test_gemm_epilogue_and_fp32_out(cuda_device, M, N, K):
     assert rel(out, F.gelu(a.float() @ b.float().T + bias.float())) < 1e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 4608),     # 128 tiles of 72 k-blocks: fewer tiles than CTA slots
+                                   (20480, 320, 2880),    # 320 tiles on 296 slots: a nearly empty second wave
+                                   (1280, 1280, 11520),   # 80 tiles, long K: several CTAs per tile
+                                   (5000, 600, 2000),     # ragged M, N and K tails
+                                   (320, 1280, 11520)])   # 24 tiles cut into 296 pieces: ~12 contributors per tile
+def test_gemm_stream_k(cuda_device, M, N, K):
+    """Shapes whose tiles fill the CTA slots unevenly run as stream-K launches (csrc/gemm_sm100.cu::streamk_ctas): CTAs
+    share tiles along K through fp32 partial accumulators summed in a fixed order. Results match fp32 torch, are bitwise
+    reproducible, equal the ordinary launch up to fp32 summation order, and every epilogue feature still applies."""
+    from scaledreamer_b200 import nn_ops as O
+
+    a, b = rnd(M, K, dev=cuda_device, seed=1, scale=0.5), rnd(N, K, dev=cuda_device, seed=2, scale=0.1)
+    bias, res = rnd(N, dev=cuda_device, seed=3), rnd(M, N, dev=cuda_device, seed=4)
+    ref = a.float() @ b.float().T
+    out = O.gemm(a, b)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-3
+    for _ in range(3):
+        assert torch.equal(O.gemm(a, b), out)
+    out2 = O.gemm(a, b, bias=bias, residual=res, alpha=0.7, act="silu", out_fp32=True)
+    assert rel(out2, F.silu(ref * 0.7 + bias.float()) + res.float()) < 1e-4
+    # back-to-back launches reuse the same workspace slots and flags
+    outs = [O.gemm(a, b, bias=bias) for _ in range(4)]
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, outs[0]) for o in outs) and rel(outs[0], ref + bias.float()) < 1e-3
+
+
+def test_conv3x3_stream_k(cuda_device):
+    from scaledreamer_b200 import nn_ops as O
+
+    x = rnd(5, 32, 32, 640, dev=cuda_device, seed=1)
+    w = rnd(640, 3, 3, 640, dev=cuda_device, seed=2, scale=0.02)
+    bias = rnd(640, dev=cuda_device, seed=3)
+    out = O.conv3x3(x, w, bias=bias)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias.float(), padding=1).permute(0, 2, 3, 1)
+    assert rel(out, ref) < 1e-3
+    assert torch.equal(O.conv3x3(x, w, bias=bias), out)
+
+
 def test_gemm_batched(cuda_device):
     from scaledreamer_b200 import nn_ops as O
 
