@@ -5,10 +5,16 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "../../include/sdb200.h"
 #include "render_tape.cuh"
 
 unsigned long long g_sdb_launch_count = 0ull;
+bool sdb_pdl_enabled() {
+  static const bool on = !(getenv("SDB_PDL") && atoi(getenv("SDB_PDL")) == 0);
+  return on;
+}
 static thread_local char g_err[512] = "";
 
 void sdb_set_error(const char* fmt, ...) {

@@ -33,6 +33,39 @@ void sdb_set_error(const char* fmt, ...);
 extern unsigned long long g_sdb_launch_count;
 #define SDB_COUNT_LAUNCH() (++g_sdb_launch_count)
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// A training step is ~700 dependent launches of 5-100 us each. With programmatic stream serialisation the CTAs of
+// kernel i+1 are scheduled (and run their set-up: barrier / tensor-memory allocation, descriptor prefetch, index
+// arithmetic) while kernel i drains; `griddepcontrol.wait` then blocks until kernel i has completed and its writes are
+// visible. Every kernel launched through sdb_launch() therefore calls pdl_wait() before its first access to global
+// memory and pdl_launch_dependents() as early as it can. Both instructions are no-ops in a kernel launched the ordinary
+// way; SDB_PDL=0 launches everything the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+bool sdb_pdl_enabled();  // capi.cu
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t sdb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = sdb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static constexpr int kNumSMs = 148;
 static constexpr unsigned kFullMask = 0xffffffffu;
 

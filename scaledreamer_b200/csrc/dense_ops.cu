@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(512)
 gn_reduce_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
                  const __half* __restrict__ beta, const float* __restrict__ stats, float* __restrict__ out, int HW,
                  int C, int groups, int C8N, int PL, int pix_per_block, float eps, int act_silu) {
+  pdl_prologue();
   extern __shared__ float sm[];  // [PL][C/2][2]
   const int n = blockIdx.y;
   const int c8 = threadIdx.x % C8N, pl = threadIdx.x / C8N;
@@ -136,6 +137,7 @@ gn_reduce_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, co
 // statistics stay bitwise reproducible run to run.
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblk, int groups,
                                    int total) {
+  pdl_prologue();
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // (n, g, k)
   const int lane = threadIdx.x & 31;
   if (i >= total) return;
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(512)
 gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
                 const __half* __restrict__ beta, const float* __restrict__ stats, const float* __restrict__ red,
                 __half* __restrict__ y, int HW, int C, int groups, int C8N, int PL, float eps, int act_silu) {
+  pdl_prologue();
   const int n = blockIdx.y;
   const int c8 = threadIdx.x % C8N, pl = threadIdx.x / C8N;
   const int cpg = C / groups;
@@ -232,6 +235,7 @@ gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, con
 __global__ void __launch_bounds__(256)
 gn_fused_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                 __half* __restrict__ y, float* __restrict__ stats, int HW, int C, int groups, float eps, int act_silu) {
+  pdl_prologue();
   __shared__ float red[2][8];
   __shared__ float s_mean, s_rstd;
   const int n = blockIdx.x / groups, g = blockIdx.x % groups;
@@ -308,6 +312,7 @@ void gn_geometry(int HW, int C, int N, int* C8N, int* PL, int* ppb, int* nblk) {
 constexpr int LN_ITEMS = 5;  // 1280 channels
 __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                                  const __half* __restrict__ beta, __half* __restrict__ y, int rows, int C, float eps) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -387,6 +392,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __r
 // the row stays in registers between the max / sum / normalise passes. cols <= 256 * WARPS * ITEMS.
 template <int WARPS, int ITEMS>
 __global__ void __launch_bounds__(32 * WARPS) softmax_kernel(__half* __restrict__ x, int cols, long long ld) {
+  pdl_prologue();
   __shared__ float red[WARPS];
   __half* row = x + (size_t)blockIdx.x * ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -446,6 +452,7 @@ __global__ void __launch_bounds__(32 * WARPS) softmax_kernel(__half* __restrict_
 }
 
 __global__ void geglu_kernel(const __half* __restrict__ xg, __half* __restrict__ y, long long rows, int inner) {
+  pdl_prologue();
   const int i2 = inner / 2;
   const long long total = rows * i2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -460,6 +467,7 @@ __global__ void geglu_kernel(const __half* __restrict__ xg, __half* __restrict__
 }
 
 __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W, int C8) {
+  pdl_prologue();
   const long long total = (long long)N * 2 * H * 2 * W * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -476,6 +484,7 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restri
 
 __global__ void concat_kernel(const __half* __restrict__ a, int Ca8, const __half* __restrict__ b, int Cb8,
                               __half* __restrict__ y, long long rows) {
+  pdl_prologue();
   const int C8 = Ca8 + Cb8;
   const long long total = rows * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -489,12 +498,14 @@ __global__ void concat_kernel(const __half* __restrict__ a, int Ca8, const __hal
 
 __global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ y,
                            long long n2) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
     reinterpret_cast<__half2*>(y)[i] =
         __hadd2(reinterpret_cast<const __half2*>(a)[i], reinterpret_cast<const __half2*>(b)[i]);
 }
 
 __global__ void transpose_kernel(const __half* __restrict__ x, __half* __restrict__ y, int rows, int cols) {
+  pdl_prologue();
   __shared__ __half tile[32][34];
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -511,6 +522,7 @@ __global__ void transpose_kernel(const __half* __restrict__ x, __half* __restric
 // col[(n,oy,ox), (kh,kw,c)] = x[n, 2*oy + kh - pad_lo, 2*ox + kw - pad_lo, c] (zero outside)
 __global__ void im2col_s2_kernel(const __half* __restrict__ x, __half* __restrict__ col, int N, int H, int W, int C8,
                                  int pad_lo) {
+  pdl_prologue();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * Ho * Wo * 9 * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -534,6 +546,7 @@ __global__ void im2col_s2_kernel(const __half* __restrict__ x, __half* __restric
 // dx[n,iy,ix,c] = sum over (oy,ox,tap) with 2*oy + kh - pad_lo == iy, 2*ox + kw - pad_lo == ix of col[...]
 __global__ void col2im_s2_kernel(const __half* __restrict__ col, __half* __restrict__ dx, int N, int H, int W, int C8,
                                  int pad_lo) {
+  pdl_prologue();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * H * W * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -582,6 +595,7 @@ template <typename TIn, int CIN, int PX>
 __global__ void __launch_bounds__(128)
 conv_small_cin_kernel(const TIn* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                       void* __restrict__ y, int y_fp32, int N, int H, int W, int Cout, int CT) {
+  pdl_prologue();
   extern __shared__ float swf[];  // [9*CIN][CT]: the CT output channels of slice blockIdx.y
   constexpr int K = 9 * CIN;
   const int co0 = blockIdx.y * CT;
@@ -662,6 +676,7 @@ template <int COUT, int PX>
 __global__ void __launch_bounds__(128)
 conv_small_cout_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                        void* __restrict__ y, int y_fp32, int N, int H, int W, int Cin) {
+  pdl_prologue();
   extern __shared__ float swo[];  // [9][Cin][COUT] fp32
   const int K = 9 * Cin;
   for (int i = threadIdx.x; i < COUT * K; i += blockDim.x) {
@@ -735,6 +750,7 @@ template <int COUT>
 __global__ void conv_small_cout_warp_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
                                             const __half* __restrict__ bias, void* __restrict__ y, int y_fp32, int N,
                                             int H, int W, int Cin) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -777,6 +793,7 @@ __global__ void conv_small_cout_warp_kernel(const __half* __restrict__ x, const 
 
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, __half* __restrict__ out, int n, int dim,
                                           float max_period) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (i >= n * half) return;
@@ -791,6 +808,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, __half* _
 __global__ void linear_small_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
                                     const __half* __restrict__ bias, void* __restrict__ y, int y_fp32, int rows, int N,
                                     int K, int silu_in) {
+  pdl_prologue();
   extern __shared__ float sx[];  // [rows][K]
   for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
     float v = __half2float(x[i]);
@@ -824,6 +842,7 @@ __global__ void linear_small_kernel(const __half* __restrict__ x, const __half* 
 }
 
 __global__ void silu_f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2half_rn(silu(x[i]));
 }
@@ -866,7 +885,7 @@ int groupnorm_forward(const __half* x, const __half* gamma, const __half* beta, 
   // (C2 step: 30.0 ms with everything fused, 29.5 ms with nothing fused, 28.0 ms with the 8 MB switch).
   static const long long fused_max = getenv("SDB_GN_FUSED_MAX") ? atoll(getenv("SDB_GN_FUSED_MAX")) : (8ll << 20);
   if (N * groups >= 128 && cpg / 2 <= 256 && (long long)N * HW * C * 2 <= fused_max) {
-    gn_fused_kernel<<<N * groups, 256, 0, s>>>(x, gamma, beta, y, stats, HW, C, groups, eps, act_silu);
+    sdb_launch(gn_fused_kernel, N * groups, 256, 0, s, x, gamma, beta, y, stats, HW, C, groups, eps, act_silu);
     SDB_COUNT_LAUNCH();
     SDB_CHECK_LAUNCH("gn_fused");
     return SDB_OK;
@@ -876,13 +895,13 @@ int groupnorm_forward(const __half* x, const __half* gamma, const __half* beta, 
   float* partial = stats + (size_t)N * groups * 2;
   const int threads = c8n * pl;
   const size_t smem = sizeof(float) * (size_t)pl * C;
-  (gn_un8() ? gn_reduce_kernel<0, 8> : gn_reduce_kernel<0, 4>)<<<dim3(nblk, N), threads, smem, s>>>(x, nullptr, nullptr, nullptr, nullptr, partial, HW, C, groups,
+  sdb_launch((gn_un8() ? gn_reduce_kernel<0, 8> : gn_reduce_kernel<0, 4>), dim3(nblk, N), threads, smem, s, x, nullptr, nullptr, nullptr, nullptr, partial, HW, C, groups,
                                                            c8n, pl, ppb, eps, 0);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_stats");
-  gn_finalize_kernel<<<(N * groups * 2 + 3) / 4, 128, 0, s>>>(partial, stats, nblk, groups, N * groups * 2);
+  sdb_launch(gn_finalize_kernel, (N * groups * 2 + 3) / 4, 128, 0, s, partial, stats, nblk, groups, N * groups * 2);
   SDB_COUNT_LAUNCH();
-  (gn_un8() ? gn_apply_kernel<0, 8> : gn_apply_kernel<0, 4>)<<<dim3(gn_apply_blocks(HW, pl, N), N), threads, 0, s>>>(x, nullptr, gamma, beta, stats, nullptr, y,
+  sdb_launch((gn_un8() ? gn_apply_kernel<0, 8> : gn_apply_kernel<0, 4>), dim3(gn_apply_blocks(HW, pl, N), N), threads, 0, s, x, nullptr, gamma, beta, stats, nullptr, y,
                                                                              HW, C, groups, c8n, pl, eps, act_silu);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_apply");
@@ -897,13 +916,13 @@ int groupnorm_backward(const __half* x, const __half* gamma, const __half* beta,
   float* partial = scratch2 + (size_t)N * groups * 2;
   const int threads = c8n * pl;
   const size_t smem = sizeof(float) * (size_t)pl * C;
-  (gn_un8() ? gn_reduce_kernel<1, 8> : gn_reduce_kernel<1, 4>)<<<dim3(nblk, N), threads, smem, s>>>(x, dy, gamma, beta, stats, partial, HW, C, groups, c8n, pl,
+  sdb_launch((gn_un8() ? gn_reduce_kernel<1, 8> : gn_reduce_kernel<1, 4>), dim3(nblk, N), threads, smem, s, x, dy, gamma, beta, stats, partial, HW, C, groups, c8n, pl,
                                                            ppb, eps, act_silu);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_bwd_reduce");
-  gn_finalize_kernel<<<(N * groups * 2 + 3) / 4, 128, 0, s>>>(partial, scratch2, nblk, groups, N * groups * 2);
+  sdb_launch(gn_finalize_kernel, (N * groups * 2 + 3) / 4, 128, 0, s, partial, scratch2, nblk, groups, N * groups * 2);
   SDB_COUNT_LAUNCH();
-  (gn_un8() ? gn_apply_kernel<1, 8> : gn_apply_kernel<1, 4>)<<<dim3(gn_apply_blocks(HW, pl, N), N), threads, 0, s>>>(x, dy, gamma, beta, stats, scratch2, dx, HW,
+  sdb_launch((gn_un8() ? gn_apply_kernel<1, 8> : gn_apply_kernel<1, 4>), dim3(gn_apply_blocks(HW, pl, N), N), threads, 0, s, x, dy, gamma, beta, stats, scratch2, dx, HW,
                                                                              C, groups, c8n, pl, eps, act_silu);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gn_bwd_apply");
@@ -912,7 +931,7 @@ int groupnorm_backward(const __half* x, const __half* gamma, const __half* beta,
 
 int layernorm_forward(const __half* x, const __half* gamma, const __half* beta, __half* y, int rows, int C, float eps,
                       cudaStream_t s) {
-  layernorm_kernel<<<(rows + 3) / 4, 128, 0, s>>>(x, gamma, beta, y, rows, C, eps);
+  sdb_launch(layernorm_kernel, (rows + 3) / 4, 128, 0, s, x, gamma, beta, y, rows, C, eps);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("layernorm");
   return SDB_OK;
@@ -925,59 +944,59 @@ int softmax_rows(__half* x, long long rows, int cols, long long ld, cudaStream_t
     return SDB_ERR_UNSUPPORTED;
   }
   const unsigned g = (unsigned)rows;
-  if (ld <= 256) softmax_kernel<1, 1><<<g, 32, 0, s>>>(x, cols, ld);
-  else if (ld <= 1024) softmax_kernel<4, 1><<<g, 128, 0, s>>>(x, cols, ld);
-  else if (ld <= 2048) softmax_kernel<4, 2><<<g, 128, 0, s>>>(x, cols, ld);
-  else softmax_kernel<4, 4><<<g, 128, 0, s>>>(x, cols, ld);
+  if (ld <= 256) sdb_launch(softmax_kernel<1, 1>, g, 32, 0, s, x, cols, ld);
+  else if (ld <= 1024) sdb_launch(softmax_kernel<4, 1>, g, 128, 0, s, x, cols, ld);
+  else if (ld <= 2048) sdb_launch(softmax_kernel<4, 2>, g, 128, 0, s, x, cols, ld);
+  else sdb_launch(softmax_kernel<4, 4>, g, 128, 0, s, x, cols, ld);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("softmax");
   return SDB_OK;
 }
 
 int geglu(const __half* xg, __half* y, long long rows, int inner, cudaStream_t s) {
-  geglu_kernel<<<ew_grid(rows * inner / 2), 256, 0, s>>>(xg, y, rows, inner);
+  sdb_launch(geglu_kernel, ew_grid(rows * inner / 2), 256, 0, s, xg, y, rows, inner);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("geglu");
   return SDB_OK;
 }
 
 int silu_f32_to_f16(const float* x, __half* y, long long n, cudaStream_t s) {
-  silu_f32_to_f16_kernel<<<ew_grid(n), 256, 0, s>>>(x, y, n);
+  sdb_launch(silu_f32_to_f16_kernel, ew_grid(n), 256, 0, s, x, y, n);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("silu");
   return SDB_OK;
 }
 
 int upsample_nearest2x(const __half* x, __half* y, int N, int H, int W, int C, cudaStream_t s) {
-  upsample2x_kernel<<<ew_grid((long long)N * 4 * H * W * C / 8), 256, 0, s>>>(x, y, N, H, W, C / 8);
+  sdb_launch(upsample2x_kernel, ew_grid((long long)N * 4 * H * W * C / 8), 256, 0, s, x, y, N, H, W, C / 8);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("upsample2x");
   return SDB_OK;
 }
 
 int concat_channels(const __half* a, int Ca, const __half* b, int Cb, __half* y, long long rows, cudaStream_t s) {
-  concat_kernel<<<ew_grid(rows * (Ca + Cb) / 8), 256, 0, s>>>(a, Ca / 8, b, Cb / 8, y, rows);
+  sdb_launch(concat_kernel, ew_grid(rows * (Ca + Cb) / 8), 256, 0, s, a, Ca / 8, b, Cb / 8, y, rows);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("concat");
   return SDB_OK;
 }
 
 int add_f16(const __half* a, const __half* b, __half* y, long long n, cudaStream_t s) {
-  add_kernel<<<ew_grid(n / 2), 256, 0, s>>>(a, b, y, n / 2);
+  sdb_launch(add_kernel, ew_grid(n / 2), 256, 0, s, a, b, y, n / 2);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("add");
   return SDB_OK;
 }
 
 int transpose_f16(const __half* x, __half* y, int rows, int cols, cudaStream_t s) {
-  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, s>>>(x, y, rows, cols);
+  sdb_launch(transpose_kernel, dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, s, x, y, rows, cols);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("transpose");
   return SDB_OK;
 }
 
 int im2col_3x3_s2(const __half* x, __half* col, int N, int H, int W, int C, int pad_lo, cudaStream_t s) {
-  im2col_s2_kernel<<<ew_grid((long long)N * (H / 2) * (W / 2) * 9 * C / 8), 256, 0, s>>>(x, col, N, H, W, C / 8,
+  sdb_launch(im2col_s2_kernel, ew_grid((long long)N * (H / 2) * (W / 2) * 9 * C / 8), 256, 0, s, x, col, N, H, W, C / 8,
                                                                                         pad_lo);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("im2col_s2");
@@ -985,7 +1004,7 @@ int im2col_3x3_s2(const __half* x, __half* col, int N, int H, int W, int C, int 
 }
 
 int col2im_3x3_s2(const __half* col, __half* dx, int N, int H, int W, int C, int pad_lo, cudaStream_t s) {
-  col2im_s2_kernel<<<ew_grid((long long)N * H * W * C / 8), 256, 0, s>>>(col, dx, N, H, W, C / 8, pad_lo);
+  sdb_launch(col2im_s2_kernel, ew_grid((long long)N * H * W * C / 8), 256, 0, s, col, dx, N, H, W, C / 8, pad_lo);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("col2im_s2");
   return SDB_OK;
@@ -1001,7 +1020,7 @@ int conv3x3_small(const void* x, int x_fp32, const __half* w, const __half* bias
     const long long total = (long long)N * H * ((W + px - 1) / px) * (CT / 8);
     const dim3 grid(ew_grid(total, 128), Cout / CT);
 #define SDB_SMALL_CIN(T, CI, PX) \
-  conv_small_cin_kernel<T, CI, PX><<<grid, 128, smem, s>>>(reinterpret_cast<const T*>(x), w, bias, y, y_fp32, N, H, W, Cout, CT)
+  sdb_launch(conv_small_cin_kernel<T, CI, PX>, grid, 128, smem, s, reinterpret_cast<const T*>(x), w, bias, y, y_fp32, N, H, W, Cout, CT)
     if (x_fp32) {
       if (Cin == 3) SDB_SMALL_CIN(float, 3, 4);
       else if (Cin == 4) SDB_SMALL_CIN(float, 4, 4);
@@ -1023,7 +1042,7 @@ int conv3x3_small(const void* x, int x_fp32, const __half* w, const __half* bias
 #define SDB_SMALL_COUT(CO, PX)                                                                                     \
   do {                                                                                                             \
     cudaFuncSetAttribute(conv_small_cout_kernel<CO, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    conv_small_cout_kernel<CO, PX><<<grid, 128, smem, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin);                  \
+    sdb_launch(conv_small_cout_kernel<CO, PX>, grid, 128, smem, s, xh, w, bias, y, y_fp32, N, H, W, Cin);                  \
   } while (0)
     switch (Cout * 10 + px) {
       case 32: SDB_SMALL_COUT(3, 2); break;
@@ -1042,9 +1061,9 @@ int conv3x3_small(const void* x, int x_fp32, const __half* w, const __half* bias
     const int grid = ew_grid(total * 32);
     const __half* xh = reinterpret_cast<const __half*>(x);
     switch (Cout) {
-      case 3: conv_small_cout_warp_kernel<3><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
-      case 4: conv_small_cout_warp_kernel<4><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
-      case 8: conv_small_cout_warp_kernel<8><<<grid, 256, 0, s>>>(xh, w, bias, y, y_fp32, N, H, W, Cin); break;
+      case 3: sdb_launch(conv_small_cout_warp_kernel<3>, grid, 256, 0, s, xh, w, bias, y, y_fp32, N, H, W, Cin); break;
+      case 4: sdb_launch(conv_small_cout_warp_kernel<4>, grid, 256, 0, s, xh, w, bias, y, y_fp32, N, H, W, Cin); break;
+      case 8: sdb_launch(conv_small_cout_warp_kernel<8>, grid, 256, 0, s, xh, w, bias, y, y_fp32, N, H, W, Cin); break;
       default:
         sdb_set_error("conv3x3_small: Cout=%d not instantiated", Cout);
         return SDB_ERR_UNSUPPORTED;
@@ -1059,7 +1078,7 @@ int conv3x3_small(const void* x, int x_fp32, const __half* w, const __half* bias
 }
 
 int timestep_embedding(const float* t, __half* out, int n, int dim, float max_period, cudaStream_t s) {
-  timestep_embedding_kernel<<<(n * dim / 2 + 127) / 128, 128, 0, s>>>(t, out, n, dim, max_period);
+  sdb_launch(timestep_embedding_kernel, (n * dim / 2 + 127) / 128, 128, 0, s, t, out, n, dim, max_period);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("timestep_embedding");
   return SDB_OK;
@@ -1077,7 +1096,7 @@ int linear_small(const __half* x, const __half* w, const __half* bias, void* y, 
     cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr = true;
   }
-  linear_small_kernel<<<(N + 7) / 8, 256, smem, s>>>(x, w, bias, y, y_fp32, rows, N, K, silu_in);
+  sdb_launch(linear_small_kernel, (N + 7) / 8, 256, smem, s, x, w, bias, y, y_fp32, rows, N, K, silu_in);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("linear_small");
   return SDB_OK;
@@ -1091,6 +1110,7 @@ namespace {
 
 // wr[ci, kh, kw, co] = w[co, 2-kh, 2-kw, ci]: weights of the data-gradient convolution.
 __global__ void rotate_w3x3_kernel(const __half* __restrict__ w, __half* __restrict__ wr, int Cout, int Cin) {
+  pdl_prologue();
   const long long total = (long long)Cout * 9 * Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1105,6 +1125,7 @@ __global__ void rotate_w3x3_kernel(const __half* __restrict__ w, __half* __restr
 // dS = P * (dP - sum_j dP_j P_j) * scale, in place on dP. One 128-thread block per row, cols <= 4096.
 __global__ void __launch_bounds__(128) softmax_bwd_kernel(const __half* __restrict__ P, __half* __restrict__ dP,
                                                           int cols, long long ld, float scale) {
+  pdl_prologue();
   __shared__ float red[4];
   const __half* pr = P + (size_t)blockIdx.x * ld;
   __half* dr = dP + (size_t)blockIdx.x * ld;
@@ -1131,6 +1152,7 @@ __global__ void __launch_bounds__(128) softmax_bwd_kernel(const __half* __restri
 
 __global__ void add_silu_kernel(const float* __restrict__ a, const float* __restrict__ b, __half* __restrict__ y,
                                 long long n) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = a[i] + (b ? b[i] : 0.f);
     y[i] = __float2half_rn(v / (1.f + __expf(-v)));
@@ -1142,6 +1164,7 @@ __global__ void add_silu_kernel(const float* __restrict__ a, const float* __rest
 namespace {
 __global__ void interleave_geglu_rows_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int half_rows,
                                              int cols) {
+  pdl_prologue();
   const long long total = 2LL * half_rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % cols);
@@ -1158,14 +1181,14 @@ int interleave_geglu_rows(const __half* src, __half* dst, int half_rows, int col
     sdb_set_error("geglu interleave: inner width %d must be a multiple of 16", half_rows);
     return SDB_ERR_UNSUPPORTED;
   }
-  interleave_geglu_rows_kernel<<<ew_grid(2LL * half_rows * cols), 256, 0, s>>>(src, dst, half_rows, cols);
+  sdb_launch(interleave_geglu_rows_kernel, ew_grid(2LL * half_rows * cols), 256, 0, s, src, dst, half_rows, cols);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("interleave_geglu_rows");
   return SDB_OK;
 }
 
 int rotate_w3x3(const __half* w, __half* wr, int Cout, int Cin, cudaStream_t s) {
-  rotate_w3x3_kernel<<<ew_grid((long long)Cout * 9 * Cin), 256, 0, s>>>(w, wr, Cout, Cin);
+  sdb_launch(rotate_w3x3_kernel, ew_grid((long long)Cout * 9 * Cin), 256, 0, s, w, wr, Cout, Cin);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("rotate_w3x3");
   return SDB_OK;
@@ -1177,14 +1200,14 @@ int softmax_rows_backward(const __half* P, __half* dP, long long rows, int cols,
     sdb_set_error("softmax_backward: at most 4096 columns");
     return SDB_ERR_UNSUPPORTED;
   }
-  softmax_bwd_kernel<<<(unsigned)rows, 128, 0, s>>>(P, dP, cols, ld, scale);
+  sdb_launch(softmax_bwd_kernel, (unsigned)rows, 128, 0, s, P, dP, cols, ld, scale);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("softmax_bwd");
   return SDB_OK;
 }
 
 int add_silu_f32_to_f16(const float* a, const float* b, __half* y, long long n, cudaStream_t s) {
-  add_silu_kernel<<<ew_grid(n), 256, 0, s>>>(a, b, y, n);
+  sdb_launch(add_silu_kernel, ew_grid(n), 256, 0, s, a, b, y, n);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("add_silu");
   return SDB_OK;

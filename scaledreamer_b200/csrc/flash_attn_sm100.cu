@@ -63,6 +63,7 @@ flash_attn_f16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
   const int nblk = (p.Lk + kKV - 1) / kKV;
 
+  pdl_launch_dependents();
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
@@ -84,6 +85,7 @@ flash_attn_f16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ptx::tmem_alloc<256>(tmem_slot);
     ptx::tmem_relinquish();
   }
+  pdl_wait();  // set-up above touched no global memory; q / k / v come from the preceding kernel
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -304,7 +306,7 @@ int run_flash_attn(const FlashPlan& plan, cudaStream_t stream) {
   FlashParams p;
   p.Lq = plan.Lq, p.Lk = plan.Lk, p.heads = plan.heads, p.scale_log2 = plan.scale_log2, p.out = plan.out, p.ldo = plan.ldo;
   const int rec = profile_mark_begin(plan.flops, plan.Lq, plan.Lk, kD, (int)plan.grid.y, stream);
-  flash_attn_f16_kernel<<<plan.grid, kFaThreads, kFaSmem, stream>>>(plan.tq, plan.tk, plan.tv, p);
+  sdb_launch(flash_attn_f16_kernel, plan.grid, kFaThreads, kFaSmem, stream, plan.tq, plan.tk, plan.tv, p);
   profile_mark_end(rec, stream);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("flash_attn_f16");

@@ -296,6 +296,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   };
   stamp(0);
+  pdl_launch_dependents();  // the next kernel may start its own set-up; its data dependency is its pdl_wait()
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
@@ -316,6 +317,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
     ptx::tmem_relinquish();
   }
+  pdl_wait();  // everything above touched only shared / tensor memory and the kernel's own parameters
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -506,11 +508,11 @@ int launch_v(const GemmPlan& plan, cudaStream_t stream) {
   prm.tiles_m = (int)plan.grid.x, prm.tiles_n = (int)plan.grid.y, prm.tiles_z = (int)plan.grid.z;
   const long long total_tiles = (long long)plan.grid.x * plan.grid.y * plan.grid.z;
   const int ctas = (int)std::min<long long>(total_tiles, DEEP ? (long long)kNumSMs : 2LL * kNumSMs);
-  gemm_f16_kernel<BN, DEEP><<<ctas, Cfg<BN, DEEP>::kThreads, Cfg<BN, DEEP>::kSmemBytes, stream>>>(plan.ta, plan.tb, prm);
+  sdb_launch(gemm_f16_kernel<BN, DEEP>, ctas, Cfg<BN, DEEP>::kThreads, Cfg<BN, DEEP>::kSmemBytes, stream, plan.ta, plan.tb, prm);
   if (plan.p.splits > 1) {
     const long long total = (long long)plan.p.M * ((plan.p.N + 3) / 4);
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 8);
-    splitk_finalize_kernel<<<grid, 256, 0, stream>>>(prm);
+    sdb_launch(splitk_finalize_kernel, grid, 256, 0, stream, prm);
     SDB_COUNT_LAUNCH();
   }
   if (g_prof) {
@@ -601,6 +603,7 @@ void fill_epilogue(GemmParams& p, const Epilogue& ep) {
 
 // thread per 4 output columns: sums the split planes in fixed order (bitwise reproducible), then the GEMM epilogue
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const GemmParams p) {
+  pdl_prologue();
   const int n4 = (p.N + 3) / 4;
   const long long total = (long long)p.M * n4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
