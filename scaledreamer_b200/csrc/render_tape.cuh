@@ -138,6 +138,9 @@ int launch_render_fwd2(const FieldMeta& f, const FieldPtrs& p, const MarchMeta& 
                        const RenderTape* tape, cudaStream_t stream);
 int launch_render_bwd2(const FieldMeta& f, const FieldPtrs& p, const FieldGrads& g, const MarchMeta& m, const RayIO& io,
                        const RenderTape& tape, cudaStream_t stream);
+// Field backward with the MLP contractions on the tensor cores (render_bwd_tc.cu); same contract as the fp32 kernel.
+int launch_render_field_bwd_tc(const FieldMeta& f, const FieldPtrs& p, const FieldGrads& g, const RenderTape& tape,
+                               int scatter_on, cudaStream_t stream);
 // Orientation term on the taped samples (render_orient.cu): orient[ray] = sum_i w_i relu(n_i . d)^2 with finite-difference
 // normals; og [4][capacity] receives d term / d raw density at the sample and its three offset points.
 int launch_render_orient_fwd(const FieldMeta& f, const FieldPtrs& p, const float* rays_d, int n_rays,
