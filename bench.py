@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # no checkpoints on the box: the benchmark runs on seeded synthetic weights and says so in its JSON line
 os.environ.setdefault("SDB_SYNTHETIC_WEIGHTS", "1")
+os.environ.setdefault("SDB_NO_TRIAL_DIRS", "1")
 
 METRIC = "ASD steps/sec (256^2 render->UNet)"
 H = W = 256

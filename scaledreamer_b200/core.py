@@ -245,8 +245,20 @@ def load_config(*yamls: str, cli_args: Optional[List[str]] = None, from_string=F
     if not scfg.tag and not scfg.use_timestamp:
         raise ValueError("Either tag is specified or use_timestamp is True.")
     scfg.trial_name = scfg.tag
+    # threestudio/utils/config.py:86-101: a run without an explicit `timestamp` gets "@%Y%m%d-%H%M%S" appended to its trial
+    # name (single-GPU runs only: ranks of one job must agree on the directory), so successive runs never share
+    # ckpts/last.ckpt or save/, and "@LAST" has timestamped directories to choose from; the directory is created here
+    if scfg.timestamp is None:
+        scfg.timestamp = ""
+        if scfg.use_timestamp and n_gpus <= 1:
+            from datetime import datetime
+
+            scfg.timestamp = datetime.now().strftime("@%Y%m%d-%H%M%S")
+    scfg.trial_name += scfg.timestamp
     scfg.exp_dir = os.path.join(scfg.exp_root_dir, scfg.name)
     scfg.trial_dir = os.path.join(scfg.exp_dir, scfg.trial_name)
+    if os.environ.get("SDB_NO_TRIAL_DIRS") != "1":  # the test-suite parses dozens of configs and wants no directories
+        os.makedirs(scfg.trial_dir, exist_ok=True)
     return scfg
 
 

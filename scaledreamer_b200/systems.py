@@ -104,18 +104,34 @@ class FusedAdan(torch.optim.Optimizer):
                 if p.grad is None:
                     continue
                 state = self.state[p]
-                if not state:
-                    for k in ("exp_avg", "exp_avg_sq", "exp_avg_diff", "prev_grad"):
-                        state[k] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                elif "prev_grad" not in state:  # optimizer state of the reference's Adan (it keeps minus the gradient)
-                    state["prev_grad"] = state.pop("neg_pre_grad").neg_()
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                if not state:
+                    for k in ("exp_avg", "exp_avg_sq", "exp_avg_diff"):
+                        state[k] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    # optimizers.py:277-281: a parameter's first update sees neg_pre_grad = -grad, i.e. a zero gradient
+                    # difference, whatever the group's step count is by then
+                    state["prev_grad"] = (g * scale).to(torch.float32).clone(memory_format=torch.preserve_format)
                 L.check(lib.sdb_adan_step(L.ptr(p.data), L.ptr(g), L.ptr(state["exp_avg"]), L.ptr(state["exp_avg_sq"]),
                                           L.ptr(state["exp_avg_diff"]), L.ptr(state["prev_grad"]), p.numel(),
                                           float(group["lr"]), float(b1), float(b2), float(b3), float(group["eps"]),
                                           float(group["weight_decay"]), int(group["step"]), float(scale),
                                           int(bool(group["no_prox"])), st), "sdb_adan_step")
         return None
+
+
+    # The reference keeps MINUS the previous gradient under `neg_pre_grad` (optimizers.py:277-281, 307); checkpoints use
+    # its name and sign so that either side resumes the other's optimizer state.
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["state"] = {k: {("neg_pre_grad" if n == "prev_grad" else n): (-v if n == "prev_grad" else v)
+                           for n, v in st.items()} for k, st in sd["state"].items()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        sd = dict(state_dict)
+        sd["state"] = {k: {("prev_grad" if n == "neg_pre_grad" else n): (-v if n == "neg_pre_grad" else v)
+                           for n, v in st.items()} for k, st in state_dict["state"].items()}
+        super().load_state_dict(sd)
 
 
 def parse_optimizer(config: dict, model: nn.Module) -> torch.optim.Optimizer:
@@ -264,7 +280,8 @@ class StableDreamer(BaseSystem):
 
     def training_step(self, batch, batch_idx):
         # the fused renderer evaluates the orientation term itself (no per-sample normal / weights / t_dirs tensors)
-        self.renderer.orient_loss = self.C(self.cfg.loss.get("lambda_orient", 0.0)) > 0
+        if getattr(self, "renderer", None) is not None:
+            self.renderer.orient_loss = self.C(self.cfg.loss.get("lambda_orient", 0.0)) > 0
         out = self(batch)
         guidance_out = self.guidance(out["comp_rgb"], self.prompt_utils, **batch, rgb_as_latents=False)
         loss = 0.0

@@ -5,6 +5,7 @@ import pytest
 
 # no checkpoints / CLIP caches exist on the box: the tests opt in to seeded synthetic weights (core.synthetic_or_raise)
 os.environ.setdefault("SDB_SYNTHETIC_WEIGHTS", "1")
+os.environ.setdefault("SDB_NO_TRIAL_DIRS", "1")  # load_config() would create outputs/<name>/<tag>@<timestamp>/ otherwise
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

@@ -69,3 +69,43 @@ def test_unknown_keys_and_missing_prompt_are_refused():
         parse_structured(sd.find("stable-diffusion-prompt-processor").Config, {"prompt": "???"})
     with pytest.raises(ValueError):
         sd.load_config(path, cli_args=["not-an-override"])
+
+
+def test_trial_name_carries_a_timestamp_like_the_reference(tmp_path, monkeypatch):
+    """threestudio/utils/config.py:86-101: single-GPU runs append "@%Y%m%d-%H%M%S" to the trial name and create the trial
+    directory; multi-GPU runs (ranks must agree) and runs with an explicit timestamp do not invent one."""
+    import os
+    import re
+
+    import scaledreamer_b200 as sd
+
+    cfg_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs", "asd_sd_nerf.yaml")
+    cli = ["system.prompt_processor.prompt=a hamburger", f"exp_root_dir={tmp_path}/outputs"]
+    monkeypatch.delenv("SDB_NO_TRIAL_DIRS", raising=False)
+    cfg = sd.load_config(cfg_path, cli_args=cli)
+    assert re.fullmatch(r"a_hamburger@\d{8}-\d{6}", cfg.trial_name), cfg.trial_name
+    assert cfg.trial_dir == os.path.join(cfg.exp_dir, cfg.trial_name) and os.path.isdir(cfg.trial_dir)
+    assert sd.load_config(cfg_path, cli_args=cli, n_gpus=8).trial_name == "a_hamburger"
+    assert sd.load_config(cfg_path, cli_args=cli + ["timestamp=@fixed"]).trial_name == "a_hamburger@fixed"
+    assert sd.load_config(cfg_path, cli_args=cli + ["use_timestamp=false"]).trial_name == "a_hamburger"
+
+
+def test_adan_state_dict_uses_the_reference_key_and_sign():
+    """threestudio/systems/optimizers.py keeps MINUS the previous gradient under `neg_pre_grad`; FusedAdan keeps the
+    gradient itself and converts on the way out / in, so either side resumes the other's optimizer state."""
+    import torch
+
+    from scaledreamer_b200.systems import FusedAdan
+
+    p = torch.nn.Parameter(torch.zeros(5))
+    opt = FusedAdan([p], lr=1e-3)
+    g = torch.arange(5.0)
+    opt.state[p] = {"exp_avg": torch.ones(5), "exp_avg_sq": torch.ones(5), "exp_avg_diff": torch.zeros(5), "prev_grad": g.clone()}
+    sd = opt.state_dict()
+    st = sd["state"][0]
+    assert "prev_grad" not in st and torch.equal(st["neg_pre_grad"], -g)
+    assert torch.equal(opt.state[p]["prev_grad"], g)  # the live state is untouched
+    opt2 = FusedAdan([torch.nn.Parameter(torch.zeros(5))], lr=1e-3)
+    opt2.load_state_dict(sd)
+    st2 = next(iter(opt2.state.values()))
+    assert "neg_pre_grad" not in st2 and torch.equal(st2["prev_grad"], g)
