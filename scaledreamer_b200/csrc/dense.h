@@ -55,10 +55,12 @@ struct GemmParams {
   int tiles_m, tiles_n, tiles_z;  // tile grid walked by the persistent CTAs (filled at launch)
   unsigned long long* dbg;  // optional [gridDim.x][4] globaltimer stamps: entry, setup done, first accumulator, exit
   int row_softmax;     // BN == 80 only: the epilogue applies softmax over the (single-tile) row of N <= 80 scores
+  int tma_store;       // fp16 results leave through shared memory + cp.async.bulk.tensor stores (plan->tc)
 };
 
 struct GemmPlan {
   CUtensorMap ta, tb;
+  CUtensorMap tc;  // output [M, N] fp16 as 16-column x 32-row boxes (32-byte swizzle), valid when p.tma_store
   GemmParams p;
   dim3 grid;
   int bn;  // 64, 128 or 160
@@ -66,7 +68,7 @@ struct GemmPlan {
 
 // dtype: 0 = fp16 (the only one wired today). dims/box innermost first; strides in BYTES for dims 1..rank-1.
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box);
+              const uint32_t* box, int swizzle_bytes = 128);
 
 struct Epilogue {
   void* out = nullptr;

@@ -46,7 +46,15 @@ struct Cfg {
   static constexpr int kThreads = 128 + 128 * kEpiSets;
   static constexpr int kAccStride = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   static constexpr int kTmemCols = kAccStride * kAccBufs;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // per epilogue warp: the tile's BN bias values (fp16), fetched once per tile before the accumulator is ready instead
+  // of once per 32-column chunk with the load latency exposed (ncu source view, round 2: the bias conversion was the
+  // hottest stall of the epilogue warps)
+  static constexpr int kBiasBytes = (BN == 64 || BN == 128 || BN == 256) ? BN * 2 * 4 * kEpiSets : 0;
+  // per epilogue warp: two 32-row x 32-byte staging tiles for the TMA stores of the fp16 results (one 32-byte sector
+  // per row and store instead of a 16-byte piece per thread: the per-thread stores cost one L2 request per piece and
+  // bounded short-K layers at 14 GB/s per SM)
+  static constexpr int kStoreBytes = BN == 80 ? 0 : 2048 * 4 * kEpiSets;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 1024 /*barriers + pad*/ + kBiasBytes + kStoreBytes;
 };
 
 __device__ __forceinline__ void load_operand(const CUtensorMap* tm, const OperandGeom& g, void* smem, uint64_t* bar,
@@ -72,10 +80,183 @@ __device__ __forceinline__ void load_operand(const CUtensorMap* tm, const Operan
   }
 }
 
+// The common epilogue (no split-K partials, no GEGLU pairing, no row softmax) in 16-column steps with the tensor-memory
+// read of the NEXT step in flight while the current one is converted and stored: the ncu source view of round 2 put the
+// wait on tcgen05.ld first among the epilogue warps' stalls, and short-K layers are bounded by these four warps, not
+// by the main loop. v = act(alpha * acc + bias + rowbias) + residual, one output row per thread.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_pipelined(const GemmParams& p, uint32_t tm_row, int lane, int m, int n0,
+                                                        long long zoff, int set, int nsets, const __half* sbias,
+                                                        const CUtensorMap* tmC, uint8_t* stage) {
+  const bool m_ok = m < p.M;
+  const bool tma = stage != nullptr;  // launch-uniform: fp16 output through shared memory + TMA stores
+  const int m_row0 = m - lane;        // first row of this warp's 32
+  int nstore = 0;                     // stores issued by lane 0 so far (staging tile = nstore & 1)
+  const float* rowb = p.rowbias ? p.rowbias + (long long)(m_ok ? m / p.rows_per_group : 0) * p.rowbias_ld : nullptr;
+  const bool res_vec = p.residual && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
+  const bool bias_vec = p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+  const bool rowb_vec = rowb && (reinterpret_cast<uintptr_t>(rowb) & 15) == 0 && (p.rowbias_ld & 3) == 0;
+  const __half* rrow = p.residual ? p.residual + (long long)m * p.ldr : nullptr;
+  const int cstep = 16 * nsets;
+  auto load_res = [&](int c, uint4(&rv)[2]) {
+    const bool on = res_vec && m_ok && n0 + c + 16 <= p.N;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      rv[q] = on ? __ldg(reinterpret_cast<const uint4*>(rrow + n0 + c) + q) : make_uint4(0, 0, 0, 0);
+  };
+  auto finish = [&](const uint32_t(&v)[16], const uint4(&res)[2], int c) {
+    const int nb = n0 + c;
+    if (nb >= p.N) return;         // warp-uniform
+    if (!tma && !m_ok) return;     // rows past M: nothing to store (the TMA path clips them and stays warp-collective)
+    const bool full = nb + 16 <= p.N;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = 0.f;
+    if (p.bias) {
+      if (sbias || (bias_vec && full)) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint4 bv = sbias ? *(reinterpret_cast<const uint4*>(sbias + c) + q)
+                                 : __ldg(reinterpret_cast<const uint4*>(p.bias + nb) + q);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 t = __half22float2(h2[e]);
+            f[q * 8 + 2 * e] = t.x;
+            f[q * 8 + 2 * e + 1] = t.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < p.N) f[j] = __half2float(__ldg(p.bias + nb + j));
+      }
+    }
+    if (rowb) {
+      if (rowb_vec && full) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(rowb + nb) + q);
+          f[4 * q] += t.x, f[4 * q + 1] += t.y, f[4 * q + 2] += t.z, f[4 * q + 3] += t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < p.N) f[j] += __ldg(rowb + nb + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), p.alpha, f[j]);
+    if (p.act == kActSilu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+    } else if (p.act == kActGelu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
+    }
+    if (p.residual) {
+      if (res_vec && full) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&res[q]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 t = __half22float2(h2[e]);
+            f[q * 8 + 2 * e] += t.x;
+            f[q * 8 + 2 * e + 1] += t.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < p.N) f[j] += __half2float(__ldg(rrow + nb + j));
+      }
+    }
+    if (p.out_fp32) {
+      float* o = reinterpret_cast<float*>(p.out) + zoff + (long long)m * p.ldc + nb;
+      if (full && (p.ldc & 3) == 0 && (zoff & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < p.N) o[j] = f[j];
+      }
+    } else if (tma) {
+      // 32 rows x 32 bytes, 16-byte halves swapped on rows with bit 2 set (the 32-byte swizzle of the tensor map)
+      uint8_t* tile = stage + (nstore & 1) * 1024;
+      if (nstore >= 2) {  // the store that last read this tile must have drained it
+        if (lane == 0) ptx::tma_store_wait_read<1>();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint4 ov;
+        __half2* h2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(tile + lane * 32 + ((q ^ ((lane >> 2) & 1)) << 4)) = ov;
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d(tmC, tile, nb, m_row0);
+        ptx::tma_store_commit();
+      }
+      ++nstore;
+    } else {
+      __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc + nb;
+      if (full && (p.ldc & 7) == 0 && (zoff & 7) == 0) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint4 ov;
+          __half2* h2 = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
+          reinterpret_cast<uint4*>(o)[q] = ov;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < p.N) o[j] = __float2half_rn(f[j]);
+      }
+    }
+  };
+  uint32_t va[16], vb[16];
+  uint4 ra[2], rb[2];
+  int c = 16 * set;
+  if (c >= BN) return;
+  ptx::tmem_ld_32x16(tm_row + (uint32_t)c, va);
+  load_res(c, ra);
+#pragma unroll 1
+  for (; c < BN; c += 2 * cstep) {
+    ptx::tmem_ld_wait();  // va
+    const bool more1 = c + cstep < BN;
+    if (more1) {
+      ptx::tmem_ld_32x16(tm_row + (uint32_t)(c + cstep), vb);
+      load_res(c + cstep, rb);
+    }
+    finish(va, ra, c);
+    if (!more1) break;
+    ptx::tmem_ld_wait();  // vb
+    if (c + 2 * cstep < BN) {
+      ptx::tmem_ld_32x16(tm_row + (uint32_t)(c + 2 * cstep), va);
+      load_res(c + 2 * cstep, ra);
+    }
+    finish(vb, rb, c + cstep);
+  }
+  if (tma && nstore > 0) {  // the next tile starts with both staging tiles free
+    if (lane == 0) ptx::tma_store_wait_read<0>();
+    __syncwarp();
+  }
+}
+
 // Epilogue of one 128 x BN tile for the 32 rows of TMEM lane quadrant wq (one row per thread).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int wq, int lane, int m0, int n0,
-                                              int z, int zsplit, int set, int nsets) {
+                                              int z, int zsplit, int set, int nsets, const __half* sbias,
+                                              const CUtensorMap* tmC, uint8_t* stage) {
   const int m = m0 + wq * 32 + lane;
   const bool m_ok = m < p.M;
   const long long zoff = (long long)(z / p.out_zdiv) * p.out_zs_hi + (long long)(z % p.out_zdiv) * p.out_zs_lo;
@@ -121,70 +302,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       return;
     }
   }
-  // Latency matters more than bandwidth here (4 warps, one row per thread): every global load of a chunk is issued
-  // BEFORE the wait on the tensor-memory read, and the residual of the next chunk is prefetched a chunk ahead.
-  const bool res_vec = p.residual && (p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
+  if (p.splits == 1 && p.act != kActGeglu) {
+    uint32_t tm = tmem_base + ((uint32_t)(wq * 32) << 16);
+    asm volatile("" : "+r"(tm));  // keep it in a register: the compiler otherwise re-derives it from %tid every step
+    epilogue_tile_pipelined<BN>(p, tm, lane, m, n0, zoff, set, nsets, sbias, tmC,
+                                (p.tma_store && !p.out_fp32) ? stage : nullptr);
+    return;
+  }
+  // Left for the 32-column loop: split-K partial planes (raw fp32 accumulators, the epilogue runs in
+  // splitk_finalize_kernel) and GEGLU projections (bias only; a chunk holds 16 values followed by their 16 gates).
   const bool bias_vec = p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
-  const bool rowb_vec = rowb && (reinterpret_cast<uintptr_t>(rowb) & 15) == 0;
-  const __half* rrow = p.residual ? p.residual + (long long)m * p.ldr : nullptr;
-  uint4 rcur[4], rnext[4];
-  auto load_res = [&](int c, uint4(&rv)[4]) {
-    const bool on = res_vec && m_ok && n0 + c + 32 <= p.N;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      rv[q] = on ? __ldg(reinterpret_cast<const uint4*>(rrow + n0 + c) + q) : make_uint4(0, 0, 0, 0);
-  };
-  const int cstep = 32 * nsets;
-  if (p.splits == 1) load_res(32 * set, rcur);
+  uint32_t tm_row = tmem_base + ((uint32_t)(wq * 32) << 16);
+  asm volatile("" : "+r"(tm_row));
 #pragma unroll 1
-  for (int c = 32 * set; c < BN; c += cstep) {
+  for (int c = 32 * set; c < BN; c += 32 * nsets) {
     uint32_t v[32];
-    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, v);
-    const int nb = n0 + c;
-    const bool full_chunk = nb + 32 <= p.N;
-    float f[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = 0.f;
-    if (p.splits == 1 && nb < p.N) {
-      if (p.bias) {
-        if (bias_vec && full_chunk) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + nb) + q);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 t = __half22float2(h2[e]);
-              f[q * 8 + 2 * e] = t.x;
-              f[q * 8 + 2 * e + 1] = t.y;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) f[j] = __half2float(__ldg(p.bias + nb + j));
-        }
-      }
-      if (rowb) {
-        if (rowb_vec && full_chunk && (p.rowbias_ld & 3) == 0) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(rowb + nb) + q);
-            f[4 * q] += t.x, f[4 * q + 1] += t.y, f[4 * q + 2] += t.z, f[4 * q + 3] += t.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) f[j] += __ldg(rowb + nb + j);
-        }
-      }
-      if (c + cstep < BN) load_res(c + cstep, rnext);
-    }
+    ptx::tmem_ld_32x32(tm_row + (uint32_t)c, v);
     ptx::tmem_ld_wait();
+    const int nb = n0 + c;
     if (!m_ok || nb >= p.N) continue;
-    if (p.splits > 1) {  // raw fp32 partial sums; splitk_finalize_kernel applies the epilogue
+    const bool full_chunk = nb + 32 <= p.N;
+    if (p.splits > 1) {
       float* o = p.ws + ((long long)zsplit * p.M + m) * p.N + nb;
-      if (nb + 32 <= p.N && (p.N & 3) == 0) {
+      if (full_chunk && (p.N & 3) == 0) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           reinterpret_cast<uint4*>(o)[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -195,79 +335,43 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       }
       continue;
     }
+    // GEGLU: value * gelu(gate) -> 16 outputs
+    float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), p.alpha, f[j]);
-    if (p.act == kActSilu) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
-    } else if (p.act == kActGelu) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
-    }
-    if (p.act == kActGeglu) {  // chunk = 16 values | 16 gates (interleaved weight rows): value * gelu(gate)
-      __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc + (nb >> 1);
-      uint4 ov[2];
-      __half2* h2 = reinterpret_cast<__half2*>(ov);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float g0 = f[16 + 2 * e], g1 = f[17 + 2 * e];
-        h2[e] = __floats2half2_rn(f[2 * e] * (0.5f * g0 * (1.f + erff(g0 * 0.70710678118654752f))),
-                                  f[2 * e + 1] * (0.5f * g1 * (1.f + erff(g1 * 0.70710678118654752f))));
-      }
-      reinterpret_cast<uint4*>(o)[0] = ov[0];
-      reinterpret_cast<uint4*>(o)[1] = ov[1];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
-      continue;
-    }
-    if (p.residual) {
-      if (res_vec && full_chunk) {
+    for (int j = 0; j < 32; ++j) f[j] = 0.f;
+    if (p.bias) {
+      if (sbias || (bias_vec && full_chunk)) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const __half2* h2 = reinterpret_cast<const __half2*>(&rcur[q]);
+          const uint4 bv = sbias ? *(reinterpret_cast<const uint4*>(sbias + c) + q)
+                                 : __ldg(reinterpret_cast<const uint4*>(p.bias + nb) + q);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&bv);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 t = __half22float2(h2[e]);
-            f[q * 8 + 2 * e] += t.x;
-            f[q * 8 + 2 * e + 1] += t.y;
+            f[q * 8 + 2 * e] = t.x;
+            f[q * 8 + 2 * e + 1] = t.y;
           }
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (nb + j < p.N) f[j] += __half2float(__ldg(rrow + nb + j));
+          if (nb + j < p.N) f[j] = __half2float(__ldg(p.bias + nb + j));
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
-    if (p.out_fp32) {
-      float* o = reinterpret_cast<float*>(p.out) + zoff + (long long)m * p.ldc + nb;
-      if (full_chunk && (p.ldc & 3) == 0) {
+    for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), p.alpha, f[j]);
+    __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc + (nb >> 1);
+    uint4 ov[2];
+    __half2* h2 = reinterpret_cast<__half2*>(ov);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nb + j < p.N) o[j] = f[j];
-      }
-    } else {
-      __half* o = reinterpret_cast<__half*>(p.out) + zoff + (long long)m * p.ldc + nb;
-      if (full_chunk && (p.ldc & 7) == 0 && (zoff & 7) == 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 ov;
-          __half2* h2 = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
-          reinterpret_cast<uint4*>(o)[q] = ov;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nb + j < p.N) o[j] = __float2half_rn(f[j]);
-      }
+    for (int e = 0; e < 8; ++e) {
+      const float g0 = f[16 + 2 * e], g1 = f[17 + 2 * e];
+      h2[e] = __floats2half2_rn(f[2 * e] * (0.5f * g0 * (1.f + erff(g0 * 0.70710678118654752f))),
+                                f[2 * e + 1] * (0.5f * g1 * (1.f + erff(g1 * 0.70710678118654752f))));
     }
+    reinterpret_cast<uint4*>(o)[0] = ov[0];
+    reinterpret_cast<uint4*>(o)[1] = ov[1];
   }
 }
 
@@ -277,7 +381,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 template <int BN, bool DEEP>
 __global__ void __launch_bounds__(Cfg<BN, DEEP>::kThreads, DEEP ? 1 : 2)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ GemmParams p) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, DEEP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -286,6 +390,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* accum_full = empty + C::kStages;        // [kAccBufs]
   uint64_t* accum_empty = accum_full + C::kAccBufs;  // [kAccBufs]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + C::kAccBufs);
+  uint8_t* store_smem = base + C::kStages * C::kStageBytes + 1024;  // [epilogue warp][2][1 KB] (kStoreBytes), 1 KB aligned
+  uint8_t* bias_smem = store_smem + C::kStoreBytes;                 // [epilogue warp][BN] fp16 (kBiasBytes)
+  (void)bias_smem;
+  (void)store_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto stamp = [&](int slot) {
@@ -301,6 +409,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    if (p.tma_store) ptx::prefetch_tmap(&tmC);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -436,10 +545,27 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       SDB_DECODE_TILE(tile)
       (void)kb0; (void)nkb;
       const uint32_t buf = tcount % C::kAccBufs, use = tcount / C::kAccBufs;
+      const __half* sbias = nullptr;
+      if constexpr (C::kBiasBytes > 0) {
+        if (p.bias && p.splits == 1 && !p.row_softmax && n0 + BN <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+          __half* mine = reinterpret_cast<__half*>(bias_smem) + (warp - 4) * BN;
+          __syncwarp();  // the previous tile's readers are done
+          constexpr int kPer = BN / 32;  // halfs per lane: 2, 4 or 8
+          if constexpr (kPer == 2)
+            *reinterpret_cast<uint32_t*>(mine + 2 * lane) = __ldg(reinterpret_cast<const uint32_t*>(p.bias + n0) + lane);
+          else if constexpr (kPer == 4)
+            *reinterpret_cast<uint2*>(mine + 4 * lane) = __ldg(reinterpret_cast<const uint2*>(p.bias + n0) + lane);
+          else
+            *reinterpret_cast<uint4*>(mine + 8 * lane) = __ldg(reinterpret_cast<const uint4*>(p.bias + n0) + lane);
+          __syncwarp();
+          sbias = mine;
+        }
+      }
       ptx::mbar_wait(&accum_full[buf], use & 1);
       ptx::tc_fence_after();
       if (tcount == 0) stamp(2);
-      epilogue_tile<BN>(p, tmem_base + buf * C::kAccStride, wq, lane, m0, n0, z, zs, set, C::kEpiSets);
+      epilogue_tile<BN>(p, tmem_base + buf * C::kAccStride, wq, lane, m0, n0, z, zs, set, C::kEpiSets, sbias, &tmC,
+                        C::kStoreBytes > 0 ? store_smem + (warp - 4) * 2048 : nullptr);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&accum_empty[buf]);
     }
@@ -508,7 +634,7 @@ int launch_v(const GemmPlan& plan, cudaStream_t stream) {
   prm.tiles_m = (int)plan.grid.x, prm.tiles_n = (int)plan.grid.y, prm.tiles_z = (int)plan.grid.z;
   const long long total_tiles = (long long)plan.grid.x * plan.grid.y * plan.grid.z;
   const int ctas = (int)std::min<long long>(total_tiles, DEEP ? (long long)kNumSMs : 2LL * kNumSMs);
-  sdb_launch(gemm_f16_kernel<BN, DEEP>, ctas, Cfg<BN, DEEP>::kThreads, Cfg<BN, DEEP>::kSmemBytes, stream, plan.ta, plan.tb, prm);
+  sdb_launch(gemm_f16_kernel<BN, DEEP>, ctas, Cfg<BN, DEEP>::kThreads, Cfg<BN, DEEP>::kSmemBytes, stream, plan.ta, plan.tb, plan.tc, prm);
   if (plan.p.splits > 1) {
     const long long total = (long long)plan.p.M * ((plan.p.N + 3) / 4);
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 8);
@@ -545,7 +671,8 @@ bool wide_tile(int M, int N, int K) {
   static const bool on = !(getenv("SDB_GEMM_BN256") && atoi(getenv("SDB_GEMM_BN256")) == 0);
   // only when the wider tiles still fill every SM: with fewer the extra CTAs of the narrow tiling win
   // (measured: 1280 x 1280 x 1280, 50 wide tiles, 0.54 ms vs 0.45 ms; 65536 x 256 x 2304, 512 tiles, 0.46 vs 0.53 ms)
-  return on && N % 256 == 0 && K >= 1024 && (long long)((M + kBM - 1) / kBM) * (N / 256) >= kNumSMs;
+  static const int min_k = getenv("SDB_GEMM_WIDE_MINK") ? atoi(getenv("SDB_GEMM_WIDE_MINK")) : 256;
+  return on && N % 256 == 0 && K >= min_k && (long long)((M + kBM - 1) / kBM) * (N / 256) >= kNumSMs;
 }
 
 int gemm_splits(int M, int N, int K) {
@@ -648,6 +775,24 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const GemmParams p
   }
 }
 
+// Output tensor map for the TMA-store epilogue: plain [M, N] fp16 with 16-byte-aligned rows, one launch plane.
+int plan_output_map(GemmPlan* plan) {
+  static const bool on = !(getenv("SDB_GEMM_TMA_STORE") && atoi(getenv("SDB_GEMM_TMA_STORE")) == 0);
+  GemmParams& p = plan->p;
+  p.tma_store = 0;
+  memset(&plan->tc, 0, sizeof(plan->tc));
+  if (!on || p.out_fp32 || p.splits > 1 || p.row_softmax || p.act == kActGeglu || plan->grid.z != 1 || plan->bn == 80 ||
+      (p.ldc & 7) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0 || p.out_zs_hi != 0 || p.out_zs_lo != 0)
+    return SDB_OK;
+  uint64_t dc[2] = {(uint64_t)p.N, (uint64_t)p.M};
+  uint64_t sc[1] = {(uint64_t)p.ldc * 2};
+  uint32_t bc[2] = {16, 32};
+  int rc = make_tmap(&plan->tc, p.out, 2, dc, sc, bc, 32);
+  if (rc) return rc;
+  p.tma_store = 1;
+  return SDB_OK;
+}
+
 void apply_splitk(GemmPlan* plan, const Epilogue& ep) {
   if (!ep.splitk_ws || plan->grid.z != 1) return;
   const int sp = gemm_splits(plan->p.M, plan->p.N, plan->p.K);
@@ -660,7 +805,7 @@ void apply_splitk(GemmPlan* plan, const Epilogue& ep) {
 }  // namespace
 
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box) {
+              const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     sdb_set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
@@ -685,7 +830,10 @@ int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
       return SDB_ERR_ARG;
     }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, b, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     sdb_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu box %u,%u,%u)", (int)r,
@@ -728,7 +876,7 @@ int plan_gemm(GemmPlan* plan, const __half* A, long long lda, const __half* B, l
   if (rc) return rc;
   plan->grid = dim3((M + kBM - 1) / kBM, (N + plan->bn - 1) / plan->bn, batch);
   apply_splitk(plan, ep);
-  return SDB_OK;
+  return plan_output_map(plan);
 }
 
 int plan_conv3x3(GemmPlan* plan, const __half* x, int N, int H, int W, int Cin, const __half* w, int Cout,
@@ -794,7 +942,7 @@ int plan_conv3x3(GemmPlan* plan, const __half* x, int N, int H, int W, int Cin, 
   if (rc) return rc;
   plan->grid = dim3((p.M + kBM - 1) / kBM, (Cout + plan->bn - 1) / plan->bn, 1);
   apply_splitk(plan, ep);
-  return SDB_OK;
+  return plan_output_map(plan);
 }
 
 int plan_attn_scores(GemmPlan* plan, const __half* Q, long long ldq, const __half* K, long long ldk, int B, int heads,

@@ -217,7 +217,12 @@ def test_launch_validate_writes_the_evaluation_views(cuda_device, tmp_path):
                         "data.eval_width=48", "data.n_val_views=2", f"exp_root_dir={tmp_path}"],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-3000:]
-    out_dir = os.path.join(str(tmp_path), "asd_sd_nerf", "a_DSLR_photo_of_a_hamburger", "save", "val")
+    # the trial directory carries the reference's timestamp suffix (threestudio/utils/config.py:86-101)
+    import glob
+
+    trials = glob.glob(os.path.join(str(tmp_path), "asd_sd_nerf", "a_DSLR_photo_of_a_hamburger@*"))
+    assert len(trials) == 1, trials
+    out_dir = os.path.join(trials[0], "save", "val")
     files = sorted(os.listdir(out_dir))
     assert files == ["0.png", "1.png"], files
     im = Image.open(os.path.join(out_dir, "0.png"))
