@@ -54,10 +54,20 @@ def ncu_traffic():
     one profiled step of the same workload). Empty when no capture is committed: traffic is then null."""
     import glob
 
-    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_traffic.json")))
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_traffic.json")),
+                   key=os.path.getmtime)
     if not files:
         return {}
     t = json.load(open(files[-1]))
+    # only a capture of THESE kernels counts: the file carries the hash of the CUDA sources it was taken from
+    # (tools/summarize_profiles.py); anything else reads as null rather than as a stale number
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        from summarize_profiles import lib_sources_sha
+        if t.get("_lib_sources_sha") != lib_sources_sha():
+            return {}
+    except Exception:
+        return {}
     out = {}
     fam = [t[k] for k in ("gemm", "flash_attn") if k in t]
     if fam:
@@ -68,6 +78,9 @@ def ncu_traffic():
     if "render_field_bwd" in t:
         out["render_bwd"] = t["render_field_bwd"]["dram_bytes_per_launch"] + t.get("render_composite_bwd", {}).get(
             "dram_bytes_per_launch", 0.0)
+    for k in ("hyper_field_fwd", "hyper_field_bwd"):
+        if k in t:
+            out[k] = t[k]["dram_bytes_per_launch"]
     return out
 
 
@@ -357,10 +370,13 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
     loss_pinned = torch.empty(2, dtype=torch.float32).pin_memory()
     loss_events = [torch.cuda.Event(), torch.cuda.Event()]
     losses_host = []
+    host_s = 0.0
     for i in range(args.steps):
+        t_host = time.perf_counter()
         hb = job.host_batch()
         h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
         loss = job.step(job.to_device(hb))
+        host_s += time.perf_counter() - t_host
         loss_pinned[i & 1].copy_(loss.detach(), non_blocking=True)
         loss_events[i & 1].record()
         if i > 0:
@@ -397,7 +413,7 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
     else:
         timeline = {"compute_ms_mean_over_ranks": float(tl[:, 0].mean()), "optimizer_ms_mean": float(tl[:, 2].mean())}
     return dict(ms=float(t[0]), ms_e2e=float(t[1]), launches=int(launches), h2d=h2d, d2h=d2h, clocks=clk,
-                timeline=timeline)
+                timeline=timeline, host_enqueue_ms=1e3 * host_s / args.steps)
 
 
 def profile_pass(job: Job, n_prof: int = 3):
@@ -411,20 +427,17 @@ def profile_pass(job: Job, n_prof: int = 3):
 
     lib = L.load()
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    acc = {"generator_render_fwd": 0.0, "guidance_fwd": 0.0, "backward": 0.0, "optimizer": 0.0}
+    acc = {"forward_render_and_guidance": 0.0, "backward": 0.0, "optimizer": 0.0}
     lib.sdb_gemm_profile_begin()
     if os.environ.get("SDB_GEMM_CSV"):
         lib.sdb_gemm_profile_dump(os.environ["SDB_GEMM_CSV"].encode())
     L.call_timer_begin()
     system, opt = job.system, job.opt
-    for _ in range(n_prof):
+    for i in range(n_prof):
         b = job.to_device(job.host_batch())
-        a0, a1, a2, a3, a4 = ev(), ev(), ev(), ev(), ev()
+        a0, a2, a3, a4 = ev(), ev(), ev(), ev()
         a0.record()
-        out = system(b)
-        a1.record()
-        g = system.guidance(out["comp_rgb"], system.prompt_utils, **b, rgb_as_latents=False)
-        lossp = g["loss_asd"] + 30.0 * (out["opacity"] ** 2 + 0.01).sqrt().mean()
+        lossp = system.training_step(b, job.step_no + i)["loss"]  # the yaml's own loss terms (eikonal, sparsity, ...)
         a2.record()
         lossp.backward()
         a3.record()
@@ -432,7 +445,7 @@ def profile_pass(job: Job, n_prof: int = 3):
         opt.zero_grad(set_to_none=False)
         a4.record()
         torch.cuda.synchronize()
-        for k, (x, y) in zip(acc, ((a0, a1), (a1, a2), (a2, a3), (a3, a4))):
+        for k, (x, y) in zip(acc, ((a0, a2), (a2, a3), (a3, a4))):
             acc[k] += x.elapsed_time(y) / n_prof
     calls = L.call_timer_end()
     gm, gf, gl = C.c_double(), C.c_double(), C.c_int()
@@ -482,7 +495,7 @@ def nerf_kernels_alone(job: Job):
 
 def rooflines(job: Job, prof: dict, pk: dict):
     """roofline objects, most expensive family first. Algorithmic units are SURVEY.md 8(d)'s."""
-    tr = ncu_traffic() if job.name == "C2" else {}
+    tr = ncu_traffic()
     n_rays = job.views * H * W
     gemm_tfs = prof["gemm_tflop_per_step"] / (prof["gemm_ms_per_step"] / 1e3)
     roofs = [{"kernel": "gemm_f16_kernel + flash_attn_f16_kernel (tcgen05 GEMM / implicit conv / fused attention, all "
@@ -514,10 +527,12 @@ def rooflines(job: Job, prof: dict, pk: dict):
         extra = n_rays if job.name == "C4" else 0
         if ms_f > 0:
             roofs.append(hbm(" + ".join(fwd_names) + " (field lookups of the VolSDF renderer: proposal, centres, three "
-                             "finite-difference offsets)", ((nc + 4 * S) * n_rays + extra) * per_point / 1e9, ms_f))
+                             "finite-difference offsets)", ((nc + 4 * S) * n_rays + extra) * per_point / 1e9, ms_f,
+                             tr.get("hyper_field_fwd") if job.name == "C4" else None))
         if ms_b > 0:
             roofs.append(hbm(" + ".join(bwd_names) + " (field backward: MLP contractions + scatter)",
-                             (4 * S * n_rays + extra) * per_point / 1e9, ms_b))
+                             (4 * S * n_rays + extra) * per_point / 1e9, ms_b,
+                             tr.get("hyper_field_bwd") if job.name == "C4" else None))
     return sorted(roofs, key=lambda r: -r["ms_per_step"])
 
 
@@ -593,7 +608,8 @@ def main() -> None:
                                   "optimizer step",
                    "l2": "no explicit flush: each step streams 1.73 GB of UNet weights + >1 GB activations (>> 126 MB L2)"},
         "e2e": {"value": world * steps / (ms_e2e / 1e3), "unit": "steps/s", "h2d_bytes_per_step": res["h2d"],
-                "d2h_bytes_per_step": res["d2h"], "ms_per_step": ms_e2e / steps},
+                "d2h_bytes_per_step": res["d2h"], "ms_per_step": ms_e2e / steps,
+                "host_enqueue_ms_per_step": res["host_enqueue_ms"]},
         "gpu_launches": res["launches"], "gpu_launches_per_step": res["launches"] // steps,
         "clocks": res["clocks"], "roofline": roofs[0], "roofline_other_kernels": roofs[1:], "profile": prof,
         "timeline": res["timeline"],

@@ -15,7 +15,24 @@ SRC, DST = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 FAMILIES = [("gemm", "gemm_f16_kernel"), ("flash_attn", "flash_attn_f16_kernel"), ("render_fwd", "render_nerf_fwd2_kernel"),
             ("render_field_bwd", "render_field_bwd_kernel"), ("render_composite_bwd", "render_composite_bwd_kernel"),
-            ("groupnorm", "gn_")]
+            ("groupnorm", "gn_"), ("render_orient_fwd", "render_orient_fwd_kernel"),
+            ("render_orient_bwd", "render_orient_bwd_kernel"), ("hyper_field_fwd", "hyper_field_fwd_kernel"),
+            ("hyper_field_bwd", "hyper_field_bwd_kernel"), ("volsdf", "volsdf_")]
+
+
+def lib_sources_sha() -> str:
+    """Hash of the CUDA sources the library is built from: bench.py only reports `roofline.traffic` from a capture whose
+    hash equals the one of the sources it runs (a stale capture reads as null instead of a wrong number)."""
+    import glob
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "scaledreamer_b200", "csrc", "*.cu")) +
+                    glob.glob(os.path.join(ROOT, "scaledreamer_b200", "csrc", "*.cuh")) +
+                    glob.glob(os.path.join(ROOT, "scaledreamer_b200", "csrc", "*.h"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
 
 
 def rows_of(path):
@@ -90,7 +107,22 @@ def main():
                 fam[key] = {"launches_per_step": len(sel), "ms_per_step_under_ncu": round(sum(d["ms"] for d in sel), 4),
                             "share_of_step": round(sum(d["ms"] for d in sel) / total, 4),
                             "dram_bytes_per_launch": round(sum(d["rd"] + d["wr"] for d in sel) / len(sel), 1)}
+        for extra, label in (("c4", "C4"), ("orient", "C2 with lambda_orient = 100, render kernels only")):
+            pe = os.path.join(SRC, f"{TAG}_{extra}_step_traffic.csv")
+            if not os.path.exists(pe):
+                continue
+            le = launches(pe)
+            _, tot_e = per_kernel(le, os.path.join(DST, f"{TAG}_{extra}_step_kernels_traffic.csv"), True)
+            print(f"one {label} step: {len(le)} launches, {tot_e:.1f} ms under ncu")
+            for key, pat in FAMILIES:
+                sel = [d for d in le if pat in d["name"]]
+                if sel and key not in fam:
+                    fam[key] = {"launches_per_step": len(sel), "ms_per_step_under_ncu": round(sum(d["ms"] for d in sel), 4),
+                                "share_of_step": round(sum(d["ms"] for d in sel) / tot_e, 4),
+                                "dram_bytes_per_launch": round(sum(d["rd"] + d["wr"] for d in sel) / len(sel), 1),
+                                "workload": label}
         fam["_source"] = f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one step of tools/profile_step.py ({TAG})"
+        fam["_lib_sources_sha"] = lib_sources_sha()
         json.dump(fam, open(os.path.join(DST, f"{TAG}_traffic.json"), "w"), indent=1)
         print("one step:", len(ls), "launches,", f"{total:.1f} ms under ncu")
         print(json.dumps(fam, indent=1))
