@@ -403,6 +403,9 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
             "compute_ms_mean_over_ranks": float(comp.mean()),
             "compute_ms_max_over_ranks_mean_over_steps": float(comp.max(0).values.mean()),
             "rank_skew_ms": float((comp.max(0).values - comp.mean(0)).mean()),
+            # a rank that is slow on EVERY step is slower hardware (power / thermals), step-to-step changes are data
+            "compute_ms_mean_per_rank": [round(float(v), 2) for v in comp.mean(1)],
+            "compute_ms_std_over_steps_per_rank": [round(float(v), 2) for v in comp.std(1)],
             "allreduce_ms_fastest_rank_mean": float(st[:, :, 1].min(0).values.mean()),  # the last rank to arrive: pure NCCL
             "allreduce_ms_mean": float(st[:, :, 1].mean()),
             "optimizer_ms_mean": float(st[:, :, 2].mean()),
