@@ -518,10 +518,10 @@ int launch_render_bwd2(const FieldMeta& f, const FieldPtrs& p, const FieldGrads&
   const int grid_b = max(1, min(kNumSMs * 2, max_tiles));
   static const int scatter_on = getenv("SDB_FB_NOSCATTER") ? 0 : 1;  // diagnostics: time the MLP part alone
   // SDB_FB_TC=1 runs the contractions on the tensor cores instead (tf32 mma.sync, render_bwd_tc.cu; same results). Measured
-  // round 2 at 6.4 M samples: its MLP part takes 2.6 ms against 4.3 ms here, but the trilinear scatter (about one
-  // red.v2 instruction per 45 clocks per SM, however many lanes are active) then stands alone at 4.2 ms instead of
-  // hiding behind the other CTA's FMA phase: 7.3 ms against 7.1 ms in total, so the fp32 kernel stays the default until
-  // the scatter is restructured.
+  // round 2 at 6.4 M samples: its MLP part takes 2.6 ms against 4.3 ms here, but the trilinear scatter (620 M scattered
+  // lane-ops at the chip's 193 G/s, tools/red_probe.cu) then stands alone at 4.2 ms instead of hiding behind the other
+  // CTA's FMA phase: 7.3 ms against 7.1 ms in total, so the fp32 kernel stays the default until the scatter is
+  // restructured.
   static const int use_tc = (getenv("SDB_FB_TC") && atoi(getenv("SDB_FB_TC")) == 1) ? 1 : 0;
   static const int level_mask = getenv("SDB_FB_LEVELS") ? (int)strtol(getenv("SDB_FB_LEVELS"), nullptr, 0) : 0xffff;
   if (use_tc) return launch_render_field_bwd_tc(f, p, g, tape, scatter_on ? level_mask : 0, stream);
