@@ -58,10 +58,11 @@ def test_gemm_epilogue_and_fp32_out(cuda_device, M, N, K):
                                    (1280, 1280, 11520),   # 80 tiles, long K: several CTAs per tile
                                    (5000, 600, 2000),     # ragged M, N and K tails
                                    (320, 1280, 11520)])   # 24 tiles cut into 296 pieces: ~12 contributors per tile
-def test_gemm_stream_k(cuda_device, M, N, K):
-    """Shapes whose tiles fill the CTA slots unevenly run as stream-K launches (csrc/gemm_sm100.cu::streamk_ctas): CTAs
-    share tiles along K through fp32 partial accumulators summed in a fixed order. Results match fp32 torch, are bitwise
-    reproducible, equal the ordinary launch up to fp32 summation order, and every epilogue feature still applies."""
+def test_gemm_uneven_tile_counts(cuda_device, M, N, K):
+    """Shapes whose tiles fill the CTA slots unevenly (fewer tiles than slots, a nearly empty last wave, long K with few
+    tiles -> split-K, ragged tails): the persistent tile walk, both accumulator buffers, the split-K planes and the TMA
+    store epilogue. Results match fp32 torch, are bitwise reproducible, and every epilogue feature still applies. (These
+    are also the shapes the stream-K experiment of round 2 was measured on, profiles/r2h_*.)"""
     from scaledreamer_b200 import nn_ops as O
 
     a, b = rnd(M, K, dev=cuda_device, seed=1, scale=0.5), rnd(N, K, dev=cuda_device, seed=2, scale=0.1)
@@ -74,13 +75,13 @@ def test_gemm_stream_k(cuda_device, M, N, K):
         assert torch.equal(O.gemm(a, b), out)
     out2 = O.gemm(a, b, bias=bias, residual=res, alpha=0.7, act="silu", out_fp32=True)
     assert rel(out2, F.silu(ref * 0.7 + bias.float()) + res.float()) < 1e-4
-    # back-to-back launches reuse the same workspace slots and flags
+    # back-to-back launches
     outs = [O.gemm(a, b, bias=bias) for _ in range(4)]
     torch.cuda.synchronize()
     assert all(torch.equal(o, outs[0]) for o in outs) and rel(outs[0], ref + bias.float()) < 1e-3
 
 
-def test_conv3x3_stream_k(cuda_device):
+def test_conv3x3_fewer_tiles_than_slots(cuda_device):
     from scaledreamer_b200 import nn_ops as O
 
     x = rnd(5, 32, 32, 640, dev=cuda_device, seed=1)
