@@ -341,6 +341,12 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
     sync_all()
     resident = [job.to_device(job.host_batch()) for _ in range(args.steps)]
     sync_all()
+    # The end-to-end leg keeps the host at most one step ahead of the GPU, so a host pause lands in the number: one
+    # generation-2 garbage collection (~90 ms with torch + the UNet executor's objects alive) showed up as a 26 ms
+    # average in one run out of five. Collect now and keep the collector off inside the timed regions.
+    import gc
+    gc.collect()
+    gc.disable()
     clocks = ClockSampler(job.dev.index or 0)
     if sample_clocks:
         clocks.start()
@@ -370,13 +376,15 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
     loss_pinned = torch.empty(2, dtype=torch.float32).pin_memory()
     loss_events = [torch.cuda.Event(), torch.cuda.Event()]
     losses_host = []
-    host_s = 0.0
+    host_s = host_max = 0.0
     for i in range(args.steps):
         t_host = time.perf_counter()
         hb = job.host_batch()
         h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
         loss = job.step(job.to_device(hb))
-        host_s += time.perf_counter() - t_host
+        dt_host = time.perf_counter() - t_host
+        host_s += dt_host
+        host_max = max(host_max, dt_host)
         loss_pinned[i & 1].copy_(loss.detach(), non_blocking=True)
         loss_events[i & 1].record()
         if i > 0:
@@ -389,6 +397,7 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
     e3.record()
     sync_all()
     ms_e2e = e2.elapsed_time(e3)
+    gc.enable()
     clk = clocks.stop() if sample_clocks else {}
 
     t = torch.tensor([ms, ms_e2e], device=job.dev, dtype=torch.float64)
@@ -416,7 +425,7 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
     else:
         timeline = {"compute_ms_mean_over_ranks": float(tl[:, 0].mean()), "optimizer_ms_mean": float(tl[:, 2].mean())}
     return dict(ms=float(t[0]), ms_e2e=float(t[1]), launches=int(launches), h2d=h2d, d2h=d2h, clocks=clk,
-                timeline=timeline, host_enqueue_ms=1e3 * host_s / args.steps)
+                timeline=timeline, host_enqueue_ms=1e3 * host_s / args.steps, host_enqueue_ms_max=1e3 * host_max)
 
 
 def profile_pass(job: Job, n_prof: int = 3):
@@ -612,7 +621,8 @@ def main() -> None:
                    "l2": "no explicit flush: each step streams 1.73 GB of UNet weights + >1 GB activations (>> 126 MB L2)"},
         "e2e": {"value": world * steps / (ms_e2e / 1e3), "unit": "steps/s", "h2d_bytes_per_step": res["h2d"],
                 "d2h_bytes_per_step": res["d2h"], "ms_per_step": ms_e2e / steps,
-                "host_enqueue_ms_per_step": res["host_enqueue_ms"]},
+                "host_enqueue_ms_per_step": res["host_enqueue_ms"], "host_enqueue_ms_max": res["host_enqueue_ms_max"],
+                "gc": "collected before, disabled inside the timed regions"},
         "gpu_launches": res["launches"], "gpu_launches_per_step": res["launches"] // steps,
         "clocks": res["clocks"], "roofline": roofs[0], "roofline_other_kernels": roofs[1:], "profile": prof,
         "timeline": res["timeline"],

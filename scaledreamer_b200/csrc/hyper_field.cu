@@ -202,17 +202,6 @@ hyper_field_bwd_kernel(const __grid_constant__ GridMeta gm, const HfArgs a) {
     for (int q = 0; q < 8; ++q) g2a[q] = g2b[0][q] = g2b[1][q] = g2b[2][q] = 0.f;
   };
   zero_acc();
-  float lv_scale[2];
-  uint32_t lv_res[2], lv_size[2], lv_off[2], lv_hashed[2];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int l = 2 * lj + q;
-    lv_scale[q] = gm.scale[l];
-    lv_res[q] = gm.res[l];
-    lv_size[q] = gm.size[l];
-    lv_off[q] = gm.offset[l];
-    lv_hashed[q] = gm.hashed[l];
-  }
 
   // weight gradients of prompt b: registers -> global (dW1 is [enc][hidden], dW2a [hidden], dW2b [hidden][3])
   auto flush = [&](int b) {
@@ -417,25 +406,11 @@ hyper_field_bwd_kernel(const __grid_constant__ GridMeta gm, const HfArgs a) {
 
     if (tile + (int)gridDim.x < total) issue_tile(tile + gridDim.x, buf ^ 1);
 
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int sl = warp * 32 + 8 * li + r;
-      if (t * kHfTile + sl >= a.N) continue;
-      const float x = s.pos[buf][0][sl], y = s.pos[buf][1][sl], z = s.pos[buf][2][sl];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const float gx = dE[r][2 * q], gy = dE[r][2 * q + 1];
-        if (gx == 0.f && gy == 0.f) continue;
-        const LevelCell c = level_cell(lv_scale[q], x, y, z);
-        float2* tl = g_table + lv_off[q];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t idx = grid_index(lv_hashed[q], lv_res[q], lv_size[q], c.ix + (k & 1), c.iy + ((k >> 1) & 1),
-                                          c.iz + ((k >> 2) & 1));
-          const float w = corner_weight(c, k);
-          atomicAdd(tl + idx, make_float2(w * gx, w * gy));
-        }
-      }
+    // scatter: lane pairs, x-neighbour corners in one instruction (scatter_encoding_grads, render_tape.cuh)
+    {
+      const int sl0 = warp * 32 + 8 * li;
+      scatter_encoding_grads(gm, g_table, dE, lj, &s.pos[buf][0][sl0], &s.pos[buf][1][sl0], &s.pos[buf][2][sl0],
+                             a.N - (t * kHfTile + sl0));
     }
   }
   if (cur_b >= 0) flush(cur_b);

@@ -258,19 +258,6 @@ render_field_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, 
 #pragma unroll
   for (int b = 0; b < 8; ++b) g2d[b] = g2f[0][b] = g2f[1][b] = g2f[2][b] = 0.f;
   const int hg = tid >> 3, eg = tid & 7;
-  // this lane scatters levels 2*lj and 2*lj+1
-  float lv_scale[2];
-  uint32_t lv_res[2], lv_size[2], lv_off[2], lv_hashed[2];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int l = 2 * lj + q;
-    lv_scale[q] = f.grid.scale[l];
-    lv_res[q] = f.grid.res[l];
-    lv_size[q] = f.grid.size[l];
-    lv_off[q] = f.grid.offset[l];
-    lv_hashed[q] = f.grid.hashed[l];
-  }
-
   // cp.async staging of one tile: encodings (16-byte copies, zero-filled past the end), positions, output grads
   auto issue_tile = [&](int tile, int buf) {
     const int base = tile * kFbTile;
@@ -418,51 +405,11 @@ render_field_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p, 
     // the tile buffers are free (every thread passed the barrier above): stream the next tile in behind the scatter
     if (tile + (int)gridDim.x < n_tiles) issue_tile(tile + gridDim.x, buf ^ 1);
 
-    // ---- scatter: this lane owns levels 2 lj, 2 lj + 1 of samples 8 li + a ----
-    // The lane's eight samples are consecutive kept samples of (almost always) one ray, a step apart: on the coarse
-    // levels they fall into the same cell several times in a row. Contributions are summed per corner in registers
-    // and sent as one red.v2 per corner when the cell changes (levels 0-5 send 2-4 runs instead of 8 samples; the
-    // fine levels change cell every sample and behave as before).
+    // ---- scatter: lane pairs, x-neighbour corners in one instruction (scatter_encoding_grads, render_tape.cuh) ----
     if (scatter_on) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        float2* tl = g_table + lv_off[q];
-        uint32_t cx = 0u, cy = 0u, cz = 0u;
-        float ax[8], ay[8];
-        bool open = false;
-        auto flush = [&]() {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t idx = grid_index(lv_hashed[q], lv_res[q], lv_size[q], cx + (k & 1), cy + ((k >> 1) & 1),
-                                            cz + ((k >> 2) & 1));
-            atomicAdd(tl + idx, make_float2(ax[k], ay[k]));  // red.global.add.v2.f32
-          }
-        };
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          const int sl = warp * 32 + 8 * li + a;
-          const float gx = dE[a][2 * q], gy = dE[a][2 * q + 1];
-          if (base + sl >= n || (gx == 0.f && gy == 0.f)) continue;
-          const LevelCell c = level_cell(lv_scale[q], s.pos[buf][0][sl], s.pos[buf][1][sl], s.pos[buf][2][sl]);
-          if (open && (c.ix != cx || c.iy != cy || c.iz != cz)) {
-            flush();
-            open = false;
-          }
-          if (!open) {
-            cx = c.ix, cy = c.iy, cz = c.iz;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) ax[k] = ay[k] = 0.f;
-            open = true;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float w = corner_weight(c, k);
-            ax[k] = fmaf(w, gx, ax[k]);
-            ay[k] = fmaf(w, gy, ay[k]);
-          }
-        }
-        if (open) flush();
-      }
+      const int sl0 = warp * 32 + 8 * li;
+      scatter_encoding_grads(f.grid, g_table, dE, lj, &s.pos[buf][0][sl0], &s.pos[buf][1][sl0], &s.pos[buf][2][sl0],
+                             n - (base + sl0));
     }
   }
 
@@ -517,12 +464,11 @@ int launch_render_bwd2(const FieldMeta& f, const FieldPtrs& p, const FieldGrads&
   const int max_tiles = (tape.capacity + kFbTile - 1) / kFbTile;
   const int grid_b = max(1, min(kNumSMs * 2, max_tiles));
   static const int scatter_on = getenv("SDB_FB_NOSCATTER") ? 0 : 1;  // diagnostics: time the MLP part alone
-  // SDB_FB_TC=1 runs the contractions on the tensor cores instead (tf32 mma.sync, render_bwd_tc.cu; same results). Measured
-  // round 2 at 6.4 M samples: its MLP part takes 2.6 ms against 4.3 ms here, but the trilinear scatter (620 M scattered
-  // lane-ops at the chip's 193 G/s, tools/red_probe.cu) then stands alone at 4.2 ms instead of hiding behind the other
-  // CTA's FMA phase: 7.3 ms against 7.1 ms in total, so the fp32 kernel stays the default until the scatter is
-  // restructured.
-  static const int use_tc = (getenv("SDB_FB_TC") && atoi(getenv("SDB_FB_TC")) == 1) ? 1 : 0;
+  // The contractions run on the tensor cores by default (tf32 mma.sync with 3xTF32 where a ReLU mask depends on it,
+  // render_bwd_tc.cu; same gradients within the tests' tolerances). SDB_FB_TC=0 selects the fp32 CUDA-core kernel below,
+  // kept as the cross-check. Measured round 2 at 5.3 M kept samples, both with the lane-pair scatter: 4.45 ms (tensor
+  // cores) against 6.35 ms (this kernel) for the two backward kernels alone.
+  static const int use_tc = (getenv("SDB_FB_TC") && atoi(getenv("SDB_FB_TC")) == 0) ? 0 : 1;
   static const int level_mask = getenv("SDB_FB_LEVELS") ? (int)strtol(getenv("SDB_FB_LEVELS"), nullptr, 0) : 0xffff;
   if (use_tc) return launch_render_field_bwd_tc(f, p, g, tape, scatter_on ? level_mask : 0, stream);
   render_field_bwd_kernel<<<grid_b, kFbThreads, sizeof(FbSmem), stream>>>(f, p, g, tape, scatter_on);

@@ -359,27 +359,35 @@ render_field_bwd_tc_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs 
     if (tile + (int)gridDim.x < n_tiles) issue_tile(tile + gridDim.x, buf ^ 1);
 
     if (scatter_on) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (!((scatter_on >> (2 * lj + q)) & 1)) continue;  // diagnostics: SDB_FB_LEVELS masks levels out
-        float2* tl = (rep && 2 * lj + q < kRepLevels ? rep + (size_t)(blockIdx.x % n_rep) * rep_entries : g_table) + lv_off[q];
+      // Lane PAIRS: both lanes of a pair walk the same 8 consecutive samples x 4 levels, one takes the four corners with
+      // x = cx, the other those with x = cx + 1. The two entries are neighbours in the table three times out of four
+      // (dense levels: idx, idx + 1; hashed levels: the hash only XORs x in), and two lanes of ONE instruction on one
+      // 32-byte sector cost one sector operation: 327 G lane-ops/s instead of 193 G/s (tools/red_probe.cu, mode 3).
+      const int xp = lane & 1, pr = lane >> 1;
+      const int sg = pr >> 2, lq = pr & 3;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        const int lvl = 4 * lq + q;
+        if (!((scatter_on >> lvl) & 1)) continue;  // diagnostics: SDB_FB_LEVELS masks levels out
+        const float sc = f.grid.scale[lvl];
+        const uint32_t res = f.grid.res[lvl], size = f.grid.size[lvl], hashed = f.grid.hashed[lvl];
+        float2* tl = (rep && lvl < kRepLevels ? rep + (size_t)(blockIdx.x % n_rep) * rep_entries : g_table) + f.grid.offset[lvl];
         uint32_t cx = 0u, cy = 0u, cz = 0u;
-        float ax[8], ay[8];
+        float ax[4], ay[4];
         bool open = false;
         auto flush = [&]() {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t idx = grid_index(lv_hashed[q], lv_res[q], lv_size[q], cx + (k & 1), cy + ((k >> 1) & 1),
-                                            cz + ((k >> 2) & 1));
-            atomicAdd(tl + idx, make_float2(ax[k], ay[k]));  // red.global.add.v2.f32
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t idx = grid_index(hashed, res, size, cx + xp, cy + (j & 1), cz + (j >> 1));
+            atomicAdd(tl + idx, make_float2(ax[j], ay[j]));  // red.global.add.v2.f32
           }
         };
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
-          const int sl = warp * 32 + 8 * li + a;
-          const float2 gxy = *reinterpret_cast<const float2*>(s.dh + sl * kTcDh + 2 * (2 * lj + q));
+          const int sl = warp * 32 + 8 * sg + a;
+          const float2 gxy = *reinterpret_cast<const float2*>(s.dh + sl * kTcDh + 2 * lvl);
           if (base + sl >= n || (gxy.x == 0.f && gxy.y == 0.f)) continue;
-          const LevelCell c = level_cell(lv_scale[q], s.pos[buf][0][sl], s.pos[buf][1][sl], s.pos[buf][2][sl]);
+          const LevelCell c = level_cell(sc, s.pos[buf][0][sl], s.pos[buf][1][sl], s.pos[buf][2][sl]);
           if (open && (c.ix != cx || c.iy != cy || c.iz != cz)) {
             flush();
             open = false;
@@ -387,14 +395,14 @@ render_field_bwd_tc_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs 
           if (!open) {
             cx = c.ix, cy = c.iy, cz = c.iz;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) ax[k] = ay[k] = 0.f;
+            for (int j = 0; j < 4; ++j) ax[j] = ay[j] = 0.f;
             open = true;
           }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float w = corner_weight(c, k);
-            ax[k] = fmaf(w, gxy.x, ax[k]);
-            ay[k] = fmaf(w, gxy.y, ay[k]);
+          for (int j = 0; j < 4; ++j) {
+            const float w = corner_weight(c, xp | (j << 1));
+            ax[j] = fmaf(w, gxy.x, ax[j]);
+            ay[j] = fmaf(w, gxy.y, ay[j]);
           }
         }
         if (open) flush();

@@ -193,17 +193,6 @@ render_orient_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p,
   float w2[8];
 #pragma unroll
   for (int b = 0; b < 8; ++b) w2[b] = s.w2d[hidden_of(lj, b)];
-  float lv_scale[2];
-  uint32_t lv_res[2], lv_size[2], lv_off[2], lv_hashed[2];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int l = 2 * lj + q;
-    lv_scale[q] = f.grid.scale[l];
-    lv_res[q] = f.grid.res[l];
-    lv_size[q] = f.grid.size[l];
-    lv_off[q] = f.grid.offset[l];
-    lv_hashed[q] = f.grid.hashed[l];
-  }
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int base = tile * kObTile;
@@ -308,46 +297,10 @@ render_orient_bwd_kernel(const __grid_constant__ FieldMeta f, const FieldPtrs p,
             }
         }
       }
-      // ---- scatter: this lane owns levels 2 lj, 2 lj + 1 of samples 8 li + a (runs in one cell merged, as in
-      // render_field_bwd_kernel)
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        float2* tl = g_table + lv_off[q];
-        uint32_t cx = 0u, cy = 0u, cz = 0u;
-        float ax[8], ay[8];
-        bool open = false;
-        auto flush = [&]() {
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t idx = grid_index(lv_hashed[q], lv_res[q], lv_size[q], cx + (kk & 1), cy + ((kk >> 1) & 1),
-                                            cz + ((kk >> 2) & 1));
-            atomicAdd(tl + idx, make_float2(ax[kk], ay[kk]));
-          }
-        };
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          const int sl = warp * 32 + 8 * li + a;
-          const float gx = dE[a][2 * q], gy = dE[a][2 * q + 1];
-          if (base + sl >= n || (gx == 0.f && gy == 0.f)) continue;
-          const LevelCell c = level_cell(lv_scale[q], s.pos[0][sl], s.pos[1][sl], s.pos[2][sl]);
-          if (open && (c.ix != cx || c.iy != cy || c.iz != cz)) {
-            flush();
-            open = false;
-          }
-          if (!open) {
-            cx = c.ix, cy = c.iy, cz = c.iz;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) ax[kk] = ay[kk] = 0.f;
-            open = true;
-          }
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const float wgt = corner_weight(c, kk);
-            ax[kk] = fmaf(wgt, gx, ax[kk]);
-            ay[kk] = fmaf(wgt, gy, ay[kk]);
-          }
-        }
-        if (open) flush();
+      // ---- scatter: lane pairs, x-neighbour corners in one instruction (scatter_encoding_grads, render_tape.cuh)
+      {
+        const int sl0 = warp * 32 + 8 * li;
+        scatter_encoding_grads(f.grid, g_table, dE, lj, &s.pos[0][sl0], &s.pos[1][sl0], &s.pos[2][sl0], n - (base + sl0));
       }
       __syncthreads();  // pos / dout / et / dht are rewritten by the next pass
     }

@@ -106,6 +106,71 @@ __device__ __forceinline__ float corner_weight(const LevelCell& c, int k) {
   return ((k & 1) ? c.wx : 1.f - c.wx) * (((k >> 1) & 1) ? c.wy : 1.f - c.wy) * (((k >> 2) & 1) ? c.wz : 1.f - c.wz);
 }
 
+// Hash-table gradient scatter for the field backward kernels. Lane (li, lj) of a warp holds dE[a][c] = d loss / d encoding
+// feature 4 lj + c (levels 2 lj, 2 lj + 1) of its eight samples a; px/py/pz point at those samples' positions (shared
+// memory), the first n_valid of them exist. Lane PAIRS (lj, lj ^ 1) walk levels 4 (lj >> 1) .. + 3 together: one lane
+// sends the four corners with x = cx, the other those with x = cx + 1 (the partner's half of dE arrives by shuffle).
+// The two entries are neighbours in the table (dense levels: idx, idx + 1; hashed levels: x enters the hash
+// un-multiplied), and two lanes of ONE red.v2 on one 32-byte sector cost one sector operation: 327 G lane-ops/s
+// against 193 G/s for lanes on their own sectors (tools/red_probe.cu mode 3, profiles/r2t_red_probe.log).
+// Consecutive samples that stay in one cell (coarse levels, samples a step apart on one ray) are summed per corner in
+// registers and sent once when the cell changes. Must be called by all 32 lanes (it shuffles). level_mask: bit l = send
+// level l.
+__device__ __forceinline__ void scatter_encoding_grads(const GridMeta& gm, float2* __restrict__ g_table,
+                                                       const float (&dE)[8][4], int lj, const float* px, const float* py,
+                                                       const float* pz, int n_valid, uint32_t level_mask = 0xFFFFu) {
+  const int xp = lj & 1;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int lvl = 4 * (lj >> 1) + q;
+    const bool mine = (q >> 1) == xp;  // this lane computed dE for level lvl (else the partner did)
+    float gxs[8], gys[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const float ox = __shfl_xor_sync(kFullMask, dE[a][2 * (q & 1)], 1);
+      const float oy = __shfl_xor_sync(kFullMask, dE[a][2 * (q & 1) + 1], 1);
+      gxs[a] = mine ? dE[a][2 * (q & 1)] : ox;
+      gys[a] = mine ? dE[a][2 * (q & 1) + 1] : oy;
+    }
+    if (!((level_mask >> lvl) & 1u)) continue;
+    const float sc = gm.scale[lvl];
+    const uint32_t res = gm.res[lvl], size = gm.size[lvl], hashed = gm.hashed[lvl];
+    float2* tl = g_table + gm.offset[lvl];
+    uint32_t cx = 0u, cy = 0u, cz = 0u;
+    float ax[4], ay[4];
+    bool open = false;
+    auto flush = [&]() {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t idx = grid_index(hashed, res, size, cx + xp, cy + (j & 1), cz + (j >> 1));
+        atomicAdd(tl + idx, make_float2(ax[j], ay[j]));  // red.global.add.v2.f32
+      }
+    };
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      if (a >= n_valid || (gxs[a] == 0.f && gys[a] == 0.f)) continue;
+      const LevelCell c = level_cell(sc, px[a], py[a], pz[a]);
+      if (open && (c.ix != cx || c.iy != cy || c.iz != cz)) {
+        flush();
+        open = false;
+      }
+      if (!open) {
+        cx = c.ix, cy = c.iy, cz = c.iz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ax[j] = ay[j] = 0.f;
+        open = true;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w = corner_weight(c, xp | (j << 1));
+        ax[j] = fmaf(w, gxs[a], ax[j]);
+        ay[j] = fmaf(w, gys[a], ay[j]);
+      }
+    }
+    if (open) flush();
+  }
+}
+
 // Encodes this lane's point through all levels straight into column `lane` of the warp's tile.
 // `kStride` = floats per feature row of the tile (32 for the forward's per-warp tile).
 template <int kStride = 32>

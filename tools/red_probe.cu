@@ -11,7 +11,8 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
 }
 
 // mode 0: every active lane a random entry; mode 1: active lanes in groups of 4 consecutive entries (one 32-B sector
-// per group of 4... entries are 8 B, so 4 entries = one sector); mode 2: all active lanes the same random entry
+// per group of 4... entries are 8 B, so 4 entries = one sector); mode 2: all active lanes the same random entry;
+// mode 3: lane pairs on adjacent entries e, e + 1 (the two x-corners of a grid cell: same sector three times out of four)
 template <int VEC>
 __global__ void red_kernel(float2* table, uint32_t n_entries, int iters, int active, int mode) {
   const int lane = threadIdx.x & 31;
@@ -22,6 +23,7 @@ __global__ void red_kernel(float2* table, uint32_t n_entries, int iters, int act
     uint32_t idx;
     if (mode == 0) idx = hash32(base + lane * 7919u) % n_entries;
     else if (mode == 1) idx = ((hash32(base + (lane >> 2) * 7919u) % (n_entries / 4)) * 4 + (lane & 3));
+    else if (mode == 3) idx = (hash32(base + (lane >> 1) * 7919u) % (n_entries - 1)) + (lane & 1);  // lane pairs on entries e, e + 1
     else idx = base % n_entries;
     if (VEC == 2) atomicAdd(table + idx, make_float2(1.f, 2.f));
     else atomicAdd(reinterpret_cast<float*>(table + idx), 1.f);
@@ -37,8 +39,8 @@ int main() {
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
   printf("warps/SM  active  mode  ns per warp-instruction per SM   G lane-ops/s\n");
-  for (int wps : {8, 16, 32, 64})
-    for (int mode : {0, 1, 2})
+  for (int wps : {8, 32})
+    for (int mode : {0, 1, 3, 2})
       for (int active : {4, 8, 16, 32}) {
         const int blocks = 148 * wps / 4;  // 4 warps per block
         red_kernel<2><<<blocks, 128>>>(table, n_entries, 50, active, mode);
