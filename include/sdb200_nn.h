@@ -106,6 +106,59 @@ int sdb_col2im3x3s2_f16(const void* col, void* dx, int n, int h, int w, int c, i
  *   [out,in], vectors [n]. */
 typedef struct sdb_net sdb_net;
 
+/* ---- fp32 / tf32 kernels of the trained Triplane-Transformer generator ---------------------------------------
+ * custom/amortized/extern/triplane_transformer_modules.py:33-71 (ConditionModulationBlock: LayerNorm ->
+ * diffusers Attention -> residual, x3) and :115-187 (TriplaneTransformer: pos_embed, 12 blocks, LayerNorm,
+ * ConvTranspose2d). The reference runs them through torch.nn.functional / cuBLAS at `precision: 32`
+ * (configs/multi-prompt_benchmark/asd_mv_triplane_transformer_10k.yaml:127); here every contraction is
+ * sdb_gemm_tf32 (tcgen05 kind::tf32, fp32 accumulate) and the rest are the fp32 kernels below. */
+typedef struct {
+  const float* A;              /* [M, K] rows `lda` floats apart (multiple of 4) */
+  long long lda, a_zs_hi, a_zs_lo; /* batch strides in floats; 0 = shared along that batch coordinate */
+  const float* B;              /* [N, K] */
+  long long ldb, b_zs_hi, b_zs_lo;
+  int M, N, K;
+  int batch, zdiv;             /* batch index z = hi * zdiv + lo */
+  float* out;                  /* out[hi*out_zs_hi + lo*out_zs_lo + m*ldc + n] */
+  long long ldc, out_zs_hi, out_zs_lo;
+  const float* bias;           /* [N] or NULL */
+  const float* residual;       /* added after the activation, indexed like `out` with its own strides; or NULL */
+  long long ldr, res_zs_hi, res_zs_lo;
+  float alpha;
+  int act;                     /* SDB_ACT_NONE | SDB_ACT_GELU */
+} sdb_gemm_tf32_args;
+/* out = act(alpha * A B^T + bias) + residual, fp32 in / out, tf32 products. K, M, N need no padding. */
+int sdb_gemm_tf32(const sdb_gemm_tf32_args* a, void* stream);
+/* out[z][c][r] = in[z][r][c] */
+int sdb_transpose_f32(const float* in, long long ld_in, long long zs_in, float* out, long long ld_out, long long zs_out,
+                      int rows, int cols, int batch, void* stream);
+/* torch.nn.LayerNorm over the last dimension (C multiple of 32, <= 1024); mean / rstd [rows] are kept for the backward */
+int sdb_layernorm_f32_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                              int rows, int C, float eps, void* stream);
+long long sdb_layernorm_f32_backward_ws_floats(int rows, int C);
+/* dx = dLayerNorm(dy) + dskip (dskip NULL: no skip branch); d_gamma / d_beta [C] are written, fixed summation order */
+int sdb_layernorm_f32_backward(const float* x, const float* gamma, const float* mean, const float* rstd, const float* dy,
+                               const float* dskip, float* dx, float* ws, float* d_gamma, float* d_beta, int rows, int C,
+                               void* stream);
+/* in-place row softmax of the first `cols` (<= 4096) entries of each row; lse[row] = log sum exp */
+int sdb_softmax_f32_forward(float* x, long long rows, int cols, long long ld, float* lse, void* stream);
+/* X <- P = exp(X - lse), Y <- P * (Y - delta): X holds scores [batch][rows][cols] and Y d loss / d P; the statistics
+ * are indexed by row (by_col 0) or by column (by_col 1: X holds the TRANSPOSED scores) */
+int sdb_softmax_f32_backward_stats(float* X, float* Y, int batch, int rows, int cols, long long ld, const float* lse,
+                                   const float* delta, int by_col, void* stream);
+/* delta[(b*heads + h)*L + q] = sum_j dO[b,q,h*d+j] * O[b,q,h*d+j] */
+int sdb_attn_delta_f32(const float* dO, const float* O, float* delta, int B, int L, int heads, int head_dim, void* stream);
+int sdb_gelu_f32_forward(const float* h, float* g, long long n, void* stream);
+int sdb_gelu_f32_backward(const float* h, float* dg_inout, long long n, void* stream);
+long long sdb_colsum_f32_ws_floats(long long rows, int cols);
+/* out[c] = sum_r x[r, c] (bias gradients; position-embedding gradient), fixed summation order */
+int sdb_colsum_f32(const float* x, long long rows, int cols, long long ld, float* ws, float* out, void* stream);
+/* out[k][i] = src[i], k < copies (pos_embed.repeat(N, 1, 1), triplane_transformer_modules.py:172) */
+int sdb_broadcast_f32(const float* src, long long n, float* out, int copies, void* stream);
+/* ConvTranspose2d(k 2, s 2) written as a GEMM leaves t[(plane,h,w)][d*4 + a*2 + b]; this moves it to the channels-last
+ * plane p[plane][2h+a][2w+b][d] the triplane sampler reads (inverse 1: plane gradient -> GEMM layout) */
+int sdb_deconv_shuffle_f32(const float* in, float* out, int planes, int H, int W, int D, int inverse, void* stream);
+
 typedef struct {
   int in_channels, out_channels, model_channels;
   int num_levels;

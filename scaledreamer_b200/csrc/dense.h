@@ -66,9 +66,9 @@ struct GemmPlan {
   int bn;  // 64, 128 or 160
 };
 
-// dtype: 0 = fp16 (the only one wired today). dims/box innermost first; strides in BYTES for dims 1..rank-1.
+// dtype: 0 = fp16, 1 = fp32 (the tf32 GEMM). dims/box innermost first; strides in BYTES for dims 1..rank-1.
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int swizzle_bytes = 128);
+              const uint32_t* box, int swizzle_bytes = 128, int dtype = 0);
 
 struct Epilogue {
   void* out = nullptr;
@@ -123,6 +123,45 @@ void debug_timeline(unsigned long long* device_buf);  // non-null: every GEMM la
 void profile_begin();
 void profile_dump_to(const char* path);  // the next profile_end() also writes one CSV row per launch
 int profile_end(double* ms, double* flops, int* launches);
+
+// ---- fp32-in / fp32-out GEMM on tcgen05 kind::tf32 (gemm_tf32_sm100.cu): the trained Triplane-Transformer -----------
+// One operand of out[z][M, N] = alpha * A[z][M, K] * B[z][N, K]^T: row-major fp32, `ld` floats between rows (multiple of
+// 4), batch index z = hi * zdiv + lo with element strides zs_hi / zs_lo (0 = the operand is shared along that index).
+struct Tf32Operand {
+  const float* ptr;
+  long long ld, zs_hi, zs_lo;
+};
+struct Tf32Epilogue {
+  const float* bias = nullptr;      // [N]
+  const float* residual = nullptr;  // added after the activation; indexed like the output with its own strides
+  long long ldr = 0, res_zs_hi = 0, res_zs_lo = 0;
+  float alpha = 1.f;
+  int act = kActNone;  // kActNone | kActGelu
+};
+// out[(z / zdiv) * out_zs_hi + (z % zdiv) * out_zs_lo + m * ldc + n], z < batch.
+int gemm_tf32(const Tf32Operand& A, const Tf32Operand& B, int M, int N, int K, float* out, long long ldc, int batch,
+              int zdiv, long long out_zs_hi, long long out_zs_lo, const Tf32Epilogue& ep, cudaStream_t stream);
+
+// fp32 companions of the tf32 GEMM (transformer_ops.cu); every reduction has a fixed order.
+int transpose_f32(const float* in, long long ld_in, long long zs_in, float* out, long long ld_out, long long zs_out, int R,
+                  int C, int Z, cudaStream_t s);  // out[z][c][r] = in[z][r][c]
+int layernorm_f32_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                          int rows, int C, float eps, cudaStream_t s);
+long long layernorm_f32_backward_ws_floats(int rows, int C);
+// dx = LayerNorm'(dy) + dskip (dskip may be null); dgamma / dbeta are WRITTEN
+int layernorm_f32_backward(const float* x, const float* gamma, const float* mean, const float* rstd, const float* dy,
+                           const float* dskip, float* dx, float* ws, float* dgamma, float* dbeta, int rows, int C,
+                           cudaStream_t s);
+int softmax_f32_forward(float* x, long long rows, int cols, long long ld, float* lse, cudaStream_t s);
+int softmax_f32_backward_stats(float* X, float* Y, int Z, int R, int cols, long long ld, const float* lse,
+                               const float* delta, int by_col, cudaStream_t s);
+int attn_delta_f32(const float* dO, const float* O, float* delta, int B, int L, int heads, int d, cudaStream_t s);
+int gelu_f32_forward(const float* h, float* g, long long n, cudaStream_t s);
+int gelu_f32_backward(const float* h, float* dg, long long n, cudaStream_t s);  // dg *= gelu'(h)
+long long colsum_f32_ws_floats(long long rows, int cols);
+int colsum_f32(const float* x, long long rows, int cols, long long ld, float* ws, float* out, cudaStream_t s);
+int broadcast_f32(const float* src, long long n, float* out, int copies, cudaStream_t s);
+int deconv_shuffle_f32(const float* in, float* out, int planes, int H, int W, int D, int inverse, cudaStream_t s);
 
 // ---- normalisation / element-wise kernels (dense_ops.cu) ------------------------------------------------
 // Size (floats) of the `stats` / `scratch2` buffers below: [N,groups,2] results followed by per-block partials

@@ -805,7 +805,7 @@ void apply_splitk(GemmPlan* plan, const Epilogue& ep) {
 }  // namespace
 
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int swizzle_bytes) {
+              const uint32_t* box, int swizzle_bytes, int dtype) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     sdb_set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
@@ -829,7 +829,7 @@ int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
       sdb_set_error("tensor map: stride %d (%llu bytes) must be a multiple of 16", i, (unsigned long long)st[i]);
       return SDB_ERR_ARG;
     }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, b, es,
+  CUresult r = enc(out, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, b, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                        : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),

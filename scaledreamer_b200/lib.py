@@ -60,6 +60,15 @@ class GemmArgsC(C.Structure):
                 ("batch", C.c_int), ("a_zs", C.c_longlong), ("b_zs", C.c_longlong), ("out_zs", C.c_longlong)]
 
 
+class GemmTf32ArgsC(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_longlong), ("a_zs_hi", C.c_longlong), ("a_zs_lo", C.c_longlong),
+                ("B", C.c_void_p), ("ldb", C.c_longlong), ("b_zs_hi", C.c_longlong), ("b_zs_lo", C.c_longlong),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int), ("zdiv", C.c_int),
+                ("out", C.c_void_p), ("ldc", C.c_longlong), ("out_zs_hi", C.c_longlong), ("out_zs_lo", C.c_longlong),
+                ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_longlong), ("res_zs_hi", C.c_longlong),
+                ("res_zs_lo", C.c_longlong), ("alpha", C.c_float), ("act", C.c_int)]
+
+
 class UNetCfgC(C.Structure):
     _fields_ = [("in_channels", C.c_int), ("out_channels", C.c_int), ("model_channels", C.c_int),
                 ("num_levels", C.c_int), ("channel_mult", C.c_int * 4), ("num_res_blocks", C.c_int),
@@ -210,6 +219,20 @@ SIGNATURES = {
     "sdb_upsample2x_f16": [_P, _P, _I, _I, _I, _I, _P],
     "sdb_im2col3x3s2_f16": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sdb_col2im3x3s2_f16": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "sdb_gemm_tf32": [C.POINTER(GemmTf32ArgsC), _P],
+    "sdb_transpose_f32": [_P, _LL, _LL, _P, _LL, _LL, _I, _I, _I, _P],
+    "sdb_layernorm_f32_forward": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "sdb_layernorm_f32_backward_ws_floats": [_I, _I],
+    "sdb_layernorm_f32_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "sdb_softmax_f32_forward": [_P, _LL, _I, _LL, _P, _P],
+    "sdb_softmax_f32_backward_stats": [_P, _P, _I, _I, _I, _LL, _P, _P, _I, _P],
+    "sdb_attn_delta_f32": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "sdb_gelu_f32_forward": [_P, _P, _LL, _P],
+    "sdb_gelu_f32_backward": [_P, _P, _LL, _P],
+    "sdb_colsum_f32_ws_floats": [_LL, _I],
+    "sdb_colsum_f32": [_P, _LL, _I, _LL, _P, _P, _P],
+    "sdb_broadcast_f32": [_P, _LL, _P, _I, _P],
+    "sdb_deconv_shuffle_f32": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sdb_unet_create": [C.POINTER(UNetCfgC), _I, _I, _I, C.POINTER(C.c_void_p)],
     "sdb_unet_forward": [_P, _P, _P, _P, _P, _P, _P],
     "sdb_vae_encoder_create": [C.POINTER(VaeCfgC), _I, _I, _I, C.POINTER(C.c_void_p)],
@@ -240,7 +263,8 @@ def _declare(lib: C.CDLL) -> None:
         fn.argtypes = args
         if name == "sdb_net_destroy":
             fn.restype = None
-        elif name in ("sdb_groupnorm_workspace_floats", "sdb_hyper_field_tape_floats", "sdb_hypernet_scratch_floats"):
+        elif name in ("sdb_groupnorm_workspace_floats", "sdb_hyper_field_tape_floats", "sdb_hypernet_scratch_floats",
+                      "sdb_layernorm_f32_backward_ws_floats", "sdb_colsum_f32_ws_floats"):
             fn.restype = C.c_longlong
         elif name != "sdb_grid_num_entries":
             fn.restype = C.c_int
