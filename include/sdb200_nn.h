@@ -126,30 +126,40 @@ typedef struct {
   long long ldr, res_zs_hi, res_zs_lo;
   float alpha;
   int act;                     /* SDB_ACT_NONE | SDB_ACT_GELU */
+  int round_out;               /* 1: results are rounded to the nearest tf32 (outputs that only feed further GEMMs) */
 } sdb_gemm_tf32_args;
-/* out = act(alpha * A B^T + bias) + residual, fp32 in / out, tf32 products. K, M, N need no padding. */
+/* out = act(alpha * A B^T + bias) + residual, fp32 in / out, tf32 products. K, M, N need no padding.
+ * The tensor core IGNORES the low 13 mantissa bits of its fp32 operands (truncation, a bias that compounds through
+ * chained GEMMs): producers therefore write GEMM-only tensors already rounded to the nearest tf32 -- the `round_out`
+ * flags below and sdb_round_tf32_f32 -- which is the rounding cuBLAS' tf32 path applies to its operands. */
 int sdb_gemm_tf32(const sdb_gemm_tf32_args* a, void* stream);
+/* out = nearest tf32 of in (in place allowed) */
+int sdb_round_tf32_f32(const float* in, float* out, long long n, void* stream);
 /* out[z][c][r] = in[z][r][c] */
 int sdb_transpose_f32(const float* in, long long ld_in, long long zs_in, float* out, long long ld_out, long long zs_out,
-                      int rows, int cols, int batch, void* stream);
+                      int rows, int cols, int batch, int round_out, void* stream);
 /* torch.nn.LayerNorm over the last dimension (C multiple of 32, <= 1024); mean / rstd [rows] are kept for the backward */
 int sdb_layernorm_f32_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
-                              int rows, int C, float eps, void* stream);
+                              int rows, int C, float eps, int round_out, void* stream);
 long long sdb_layernorm_f32_backward_ws_floats(int rows, int C);
 /* dx = dLayerNorm(dy) + dskip (dskip NULL: no skip branch); d_gamma / d_beta [C] are written, fixed summation order */
 int sdb_layernorm_f32_backward(const float* x, const float* gamma, const float* mean, const float* rstd, const float* dy,
                                const float* dskip, float* dx, float* ws, float* d_gamma, float* d_beta, int rows, int C,
                                void* stream);
 /* in-place row softmax of the first `cols` (<= 4096) entries of each row; lse[row] = log sum exp */
-int sdb_softmax_f32_forward(float* x, long long rows, int cols, long long ld, float* lse, void* stream);
+int sdb_softmax_f32_forward(float* x, long long rows, int cols, long long ld, float* lse, int round_out, void* stream);
+/* Row form of the softmax backward: X holds scores [rows][cols] and Y d loss / d P. X <- P = exp(X - lse[row]),
+ * delta[row] = sum_k P dP (WRITTEN), Y <- dS = P (dP - delta) */
+int sdb_softmax_f32_backward_rows(float* X, float* Y, long long rows, int cols, long long ld, const float* lse,
+                                  float* delta, int round_out, void* stream);
 /* X <- P = exp(X - lse), Y <- P * (Y - delta): X holds scores [batch][rows][cols] and Y d loss / d P; the statistics
  * are indexed by row (by_col 0) or by column (by_col 1: X holds the TRANSPOSED scores) */
 int sdb_softmax_f32_backward_stats(float* X, float* Y, int batch, int rows, int cols, long long ld, const float* lse,
-                                   const float* delta, int by_col, void* stream);
+                                   const float* delta, int by_col, int round_out, void* stream);
 /* delta[(b*heads + h)*L + q] = sum_j dO[b,q,h*d+j] * O[b,q,h*d+j] */
 int sdb_attn_delta_f32(const float* dO, const float* O, float* delta, int B, int L, int heads, int head_dim, void* stream);
-int sdb_gelu_f32_forward(const float* h, float* g, long long n, void* stream);
-int sdb_gelu_f32_backward(const float* h, float* dg_inout, long long n, void* stream);
+int sdb_gelu_f32_forward(const float* h, float* g, long long n, int round_out, void* stream);
+int sdb_gelu_f32_backward(const float* h, float* dg_inout, long long n, int round_out, void* stream);
 long long sdb_colsum_f32_ws_floats(long long rows, int cols);
 /* out[c] = sum_r x[r, c] (bias gradients; position-embedding gradient), fixed summation order */
 int sdb_colsum_f32(const float* x, long long rows, int cols, long long ld, float* ws, float* out, void* stream);

@@ -387,8 +387,9 @@ class _BlockConcat(nn.Module):  # ConditionModulationBlockwoCrossAttn (global te
 
 class TriplaneTransformer(nn.Module):
     """custom/amortized/extern/triplane_transformer_modules.py:115-187 (state-dict compatible). A TRAINED dense network
-    ("next"): it runs on torch / cuBLAS / SDPA for now; everything downstream of its output
-    planes is this repo's CUDA."""
+    (SURVEY.md §8f rank 1). With `local_text: true` (the C5 yaml) forward and backward run on this library's kernels
+    (triplane_native.py: tcgen05 kind::tf32 GEMMs + fp32 LayerNorm / softmax / GELU); `forward_torch` is the same network
+    in plain torch, kept as the comparison for the tests and for the `local_text: false` variant no benchmark selects."""
 
     def __init__(self, inner_dim: int, condition_dim: int, triplane_low_res: int, triplane_high_res: int,
                  triplane_dim: int, num_layers: int, num_heads: int, local_text: bool, mlp_ratio: float = 4.0,
@@ -405,6 +406,13 @@ class TriplaneTransformer(nn.Module):
             self.proj = nn.Linear(condition_dim, inner_dim)
 
     def forward(self, text_embed: torch.Tensor) -> torch.Tensor:
+        if self.needs_local_text:
+            from .triplane_native import generate_planes
+
+            return generate_planes(self, text_embed)  # raises off-CUDA: no CPU path
+        return self.forward_torch(text_embed)
+
+    def forward_torch(self, text_embed: torch.Tensor) -> torch.Tensor:
         N, H = text_embed.shape[0], self.triplane_low_res
         if not self.needs_local_text:
             text_embed = self.proj(text_embed).unsqueeze(1)

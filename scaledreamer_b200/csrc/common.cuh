@@ -66,6 +66,15 @@ inline cudaError_t sdb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 #endif
 
+// fp32 -> nearest tf32 (10 mantissa bits), returned as fp32 bits. tcgen05 kind::tf32 IGNORES the low 13 mantissa bits of
+// its fp32 operands (truncation: a bias of ~3e-4 per operand that compounds through chained GEMMs); every tensor that
+// only feeds GEMMs is therefore written already rounded by its producer.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 static constexpr int kNumSMs = 148;
 static constexpr unsigned kFullMask = 0xffffffffu;
 

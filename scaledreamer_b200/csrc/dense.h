@@ -137,27 +137,33 @@ struct Tf32Epilogue {
   long long ldr = 0, res_zs_hi = 0, res_zs_lo = 0;
   float alpha = 1.f;
   int act = kActNone;  // kActNone | kActGelu
+  int round_out = 0;   // write results rounded to tf32 (for outputs that only feed further tf32 GEMMs)
 };
 // out[(z / zdiv) * out_zs_hi + (z % zdiv) * out_zs_lo + m * ldc + n], z < batch.
 int gemm_tf32(const Tf32Operand& A, const Tf32Operand& B, int M, int N, int K, float* out, long long ldc, int batch,
               int zdiv, long long out_zs_hi, long long out_zs_lo, const Tf32Epilogue& ep, cudaStream_t stream);
 
 // fp32 companions of the tf32 GEMM (transformer_ops.cu); every reduction has a fixed order.
+// out[z][c][r] = in[z][r][c]; round_out: values rounded to tf32 on the way
 int transpose_f32(const float* in, long long ld_in, long long zs_in, float* out, long long ld_out, long long zs_out, int R,
-                  int C, int Z, cudaStream_t s);  // out[z][c][r] = in[z][r][c]
+                  int C, int Z, int round_out, cudaStream_t s);
+int round_tf32_f32(const float* in, float* out, long long n, cudaStream_t s);  // out = nearest tf32 of in (in == out allowed)
 int layernorm_f32_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
-                          int rows, int C, float eps, cudaStream_t s);
+                          int rows, int C, float eps, int round_out, cudaStream_t s);
 long long layernorm_f32_backward_ws_floats(int rows, int C);
 // dx = LayerNorm'(dy) + dskip (dskip may be null); dgamma / dbeta are WRITTEN
 int layernorm_f32_backward(const float* x, const float* gamma, const float* mean, const float* rstd, const float* dy,
                            const float* dskip, float* dx, float* ws, float* dgamma, float* dbeta, int rows, int C,
                            cudaStream_t s);
-int softmax_f32_forward(float* x, long long rows, int cols, long long ld, float* lse, cudaStream_t s);
+// the softmax kernels write P / dS rounded to tf32 when round_out is set (they only feed GEMMs)
+int softmax_f32_forward(float* x, long long rows, int cols, long long ld, float* lse, int round_out, cudaStream_t s);
+int softmax_f32_backward_rows(float* X, float* Y, long long rows, int cols, long long ld, const float* lse, float* delta,
+                              int round_out, cudaStream_t s);
 int softmax_f32_backward_stats(float* X, float* Y, int Z, int R, int cols, long long ld, const float* lse,
-                               const float* delta, int by_col, cudaStream_t s);
+                               const float* delta, int by_col, int round_out, cudaStream_t s);
 int attn_delta_f32(const float* dO, const float* O, float* delta, int B, int L, int heads, int d, cudaStream_t s);
-int gelu_f32_forward(const float* h, float* g, long long n, cudaStream_t s);
-int gelu_f32_backward(const float* h, float* dg, long long n, cudaStream_t s);  // dg *= gelu'(h)
+int gelu_f32_forward(const float* h, float* g, long long n, int round_out, cudaStream_t s);
+int gelu_f32_backward(const float* h, float* dg, long long n, int round_out, cudaStream_t s);  // dg *= gelu'(h)
 long long colsum_f32_ws_floats(long long rows, int cols);
 int colsum_f32(const float* x, long long rows, int cols, long long ld, float* ws, float* out, cudaStream_t s);
 int broadcast_f32(const float* src, long long n, float* out, int copies, cudaStream_t s);

@@ -47,6 +47,7 @@ struct Tf32Params {
   long long ldr, res_zs_hi, res_zs_lo;
   float alpha;
   int act;
+  int round_out;  // results are rounded to tf32: the output only feeds further GEMMs
   int tiles_m, tiles_n, tiles_z;
 };
 
@@ -187,13 +188,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f[4 * q] += t.x, f[4 * q + 1] += t.y, f[4 * q + 2] += t.z, f[4 * q + 3] += t.w;
             }
           }
+          if (p.round_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = round_tf32(f[j]);
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             reinterpret_cast<float4*>(orow + nb)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (nb + j < p.N) orow[nb + j] = f[j] + (rrow ? rrow[nb + j] : 0.f);
+            if (nb + j < p.N) {
+              const float v = f[j] + (rrow ? rrow[nb + j] : 0.f);
+              orow[nb + j] = p.round_out ? round_tf32(v) : v;
+            }
         }
       };
       uint32_t va[16], vb[16];
@@ -272,7 +280,7 @@ int gemm_tf32(const Tf32Operand& A, const Tf32Operand& B, int M, int N, int K, f
   p.zdiv = zdiv;
   p.out = out, p.ldc = ldc, p.out_zs_hi = out_zs_hi, p.out_zs_lo = out_zs_lo;
   p.bias = ep.bias, p.residual = ep.residual, p.ldr = ep.ldr, p.res_zs_hi = ep.res_zs_hi, p.res_zs_lo = ep.res_zs_lo;
-  p.alpha = ep.alpha, p.act = ep.act;
+  p.alpha = ep.alpha, p.act = ep.act, p.round_out = ep.round_out;
   p.tiles_m = (M + kBM - 1) / kBM, p.tiles_n = (N + bn - 1) / bn, p.tiles_z = batch;
   CUtensorMap ta, tb;
   int rc = operand_map(&ta, A, M, K, batch / zdiv, zdiv, kBM, &p.a_hi, &p.a_lo, "A");

@@ -15,7 +15,7 @@ namespace {
 // out[z][c][r] = in[z][r][c]; 32 x 32 tiles through shared memory (+1 padding), both sides coalesced.
 __global__ void __launch_bounds__(256)
 transpose_f32_kernel(const float* __restrict__ in, long long ld_in, long long zs_in, float* __restrict__ out,
-                     long long ld_out, long long zs_out, int R, int C) {
+                     long long ld_out, long long zs_out, int R, int C, int round_out) {
   pdl_prologue();
   __shared__ float tile[32][33];
   const int z = blockIdx.z;
@@ -26,7 +26,10 @@ transpose_f32_kernel(const float* __restrict__ in, long long ld_in, long long zs
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int r = r0 + ty + 8 * j, c = c0 + tx;
-    if (r < R && c < C) tile[ty + 8 * j][tx] = src[(long long)r * ld_in + c];
+    if (r < R && c < C) {
+      const float v = src[(long long)r * ld_in + c];
+      tile[ty + 8 * j][tx] = round_out ? round_tf32(v) : v;
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -44,7 +47,7 @@ template <int PER>
 __global__ void __launch_bounds__(256)
 layernorm_f32_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                          float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
-                         int C, float eps) {
+                         int C, float eps, int round_out) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -73,7 +76,8 @@ layernorm_f32_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
   for (int i = 0; i < PER; ++i)
     if (i < per) {
       const int c = i * 32 + lane;
-      yr[c] = fmaf((v[i] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c));
+      const float o = fmaf((v[i] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c));
+      yr[c] = round_out ? round_tf32(o) : o;
     }
   if (lane == 0) {
     mean_out[row] = mean;
@@ -169,7 +173,8 @@ __global__ void ln_param_finalize_kernel(const float* __restrict__ partial, int 
 // T = 256: the block); lse[row] = max + log(sum exp(x - max)). Up to 16 * T columns stay in registers.
 template <int T>
 __global__ void __launch_bounds__(256)
-softmax_f32_fwd_kernel(float* __restrict__ x, long long rows, int cols, long long ld, float* __restrict__ lse) {
+softmax_f32_fwd_kernel(float* __restrict__ x, long long rows, int cols, long long ld, float* __restrict__ lse,
+                       int round_out) {
   pdl_prologue();
   constexpr int kRowsPerBlock = 256 / T;
   __shared__ float red[8];
@@ -213,16 +218,65 @@ softmax_f32_fwd_kernel(float* __restrict__ x, long long rows, int cols, long lon
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int c = i * T + t;
-    if (c < cols) xr[c] = v[i] * inv;
+    if (c < cols) xr[c] = round_out ? round_tf32(v[i] * inv) : v[i] * inv;
   }
   if (t == 0) lse[row] = mx + __logf(s);
+}
+
+// Row form of the softmax backward: X holds the scores S of one row, Y holds dP. X <- P = exp(S - lse[row]),
+// delta[row] = sum_k P dP, Y <- dS = P (dP - delta). delta is reduced from the SAME dP the row is corrected with, so
+// sum_k dS = 0 holds to fp32 rounding (with delta taken from dO . O instead, the tf32 rounding of the two products
+// differs and leaves a per-row offset that the key / query projections' gradients amplify tenfold).
+template <int T>
+__global__ void __launch_bounds__(256)
+softmax_f32_bwd_rows_kernel(float* __restrict__ X, float* __restrict__ Y, long long rows, int cols, long long ld,
+                            const float* __restrict__ lse, float* __restrict__ delta, int round_out) {
+  pdl_prologue();
+  constexpr int kRowsPerBlock = 256 / T;
+  __shared__ float red[8];
+  const int t = threadIdx.x % T;
+  const long long row = (long long)blockIdx.x * kRowsPerBlock + threadIdx.x / T;
+  const bool on = row < rows;
+  float* xr = X + (on ? row : 0) * ld;
+  float* yr = Y + (on ? row : 0) * ld;
+  const float l = on ? lse[row] : 0.f;
+  float pv[16], dv[16];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = i * T + t;
+    const bool in = on && c < cols;
+    pv[i] = in ? __expf(xr[c] - l) : 0.f;
+    dv[i] = in ? yr[c] : 0.f;
+    s = fmaf(pv[i], dv[i], s);
+  }
+  s = warp_sum(s);
+  if (T == 256) {
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+  }
+  if (!on) return;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = i * T + t;
+    if (c < cols) {
+      const float ds = pv[i] * (dv[i] - s);
+      xr[c] = round_out ? round_tf32(pv[i]) : pv[i];
+      yr[c] = round_out ? round_tf32(ds) : ds;
+    }
+  }
+  if (t == 0) delta[row] = s;
 }
 
 // X <- P = exp(X - lse[i]);  Y <- dS = P * (Y - delta[i]) over [Z][R][cols] (row stride ld), i = z*R + r (by_col = 0:
 // X holds scores S) or i = z*cols + c (by_col = 1: X holds S^T, the statistics belong to the columns).
 __global__ void __launch_bounds__(256)
 softmax_f32_bwd_stats_kernel(float* __restrict__ X, float* __restrict__ Y, int R, int cols, long long ld,
-                             const float* __restrict__ lse, const float* __restrict__ delta, int by_col, long long total4) {
+                             const float* __restrict__ lse, const float* __restrict__ delta, int by_col, long long total4,
+                             int round_out) {
   pdl_prologue();
   const int c4n = (cols + 3) >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
@@ -245,14 +299,19 @@ softmax_f32_bwd_stats_kernel(float* __restrict__ X, float* __restrict__ Y, int R
       }
       xv.x = __expf(xv.x - l[0]), xv.y = __expf(xv.y - l[1]), xv.z = __expf(xv.z - l[2]), xv.w = __expf(xv.w - l[3]);
       yv.x = xv.x * (yv.x - d[0]), yv.y = xv.y * (yv.y - d[1]), yv.z = xv.z * (yv.z - d[2]), yv.w = xv.w * (yv.w - d[3]);
+      if (round_out) {
+        xv.x = round_tf32(xv.x), xv.y = round_tf32(xv.y), xv.z = round_tf32(xv.z), xv.w = round_tf32(xv.w);
+        yv.x = round_tf32(yv.x), yv.y = round_tf32(yv.y), yv.z = round_tf32(yv.z), yv.w = round_tf32(yv.w);
+      }
       *reinterpret_cast<float4*>(xp) = xv;
       *reinterpret_cast<float4*>(yp) = yv;
     } else {
       for (int j = 0; j < 4 && c + j < cols; ++j) {
         const long long si = by_col ? z * cols + c + j : row;
         const float pv = __expf(xp[j] - lse[si]);
-        xp[j] = pv;
-        yp[j] = pv * (yp[j] - delta[si]);
+        const float ds = pv * (yp[j] - delta[si]);
+        xp[j] = round_out ? round_tf32(pv) : pv;
+        yp[j] = round_out ? round_tf32(ds) : ds;
       }
     }
   }
@@ -278,7 +337,7 @@ __global__ void attn_delta_f32_kernel(const float* __restrict__ dO, const float*
 }
 
 // ---------------------------------------------------------------------------------------------- GELU (erf form)
-__global__ void gelu_f32_fwd_kernel(const float* __restrict__ h, float* __restrict__ g, long long n4) {
+__global__ void gelu_f32_fwd_kernel(const float* __restrict__ h, float* __restrict__ g, long long n4, int round_out) {
   pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(h)[i];
@@ -286,18 +345,20 @@ __global__ void gelu_f32_fwd_kernel(const float* __restrict__ h, float* __restri
     v.y = 0.5f * v.y * (1.f + erff(v.y * 0.70710678118654752f));
     v.z = 0.5f * v.z * (1.f + erff(v.z * 0.70710678118654752f));
     v.w = 0.5f * v.w * (1.f + erff(v.w * 0.70710678118654752f));
+    if (round_out) v.x = round_tf32(v.x), v.y = round_tf32(v.y), v.z = round_tf32(v.z), v.w = round_tf32(v.w);
     reinterpret_cast<float4*>(g)[i] = v;
   }
 }
 __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
-__global__ void gelu_f32_bwd_kernel(const float* __restrict__ h, float* __restrict__ dg, long long n4) {
+__global__ void gelu_f32_bwd_kernel(const float* __restrict__ h, float* __restrict__ dg, long long n4, int round_out) {
   pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(h)[i];
     float4 d = reinterpret_cast<float4*>(dg)[i];
     d.x *= gelu_grad(v.x), d.y *= gelu_grad(v.y), d.z *= gelu_grad(v.z), d.w *= gelu_grad(v.w);
+    if (round_out) d.x = round_tf32(d.x), d.y = round_tf32(d.y), d.z = round_tf32(d.z), d.w = round_tf32(d.w);
     reinterpret_cast<float4*>(dg)[i] = d;
   }
 }
@@ -340,6 +401,17 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nb
   out[c] = a;
 }
 
+__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  pdl_prologue();
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    v.x = round_tf32(v.x), v.y = round_tf32(v.y), v.z = round_tf32(v.z), v.w = round_tf32(v.w);
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[n4 * 4 + threadIdx.x] = round_tf32(in[n4 * 4 + threadIdx.x]);
+}
+
 // out[k][i] = src[i] for k < copies (the position embedding repeated over the prompts of the batch)
 __global__ void broadcast_f32_kernel(const float* __restrict__ src, long long n4, float* __restrict__ out, int copies) {
   pdl_prologue();
@@ -378,28 +450,28 @@ int ew_blocks(long long n) {
 }  // namespace
 
 int transpose_f32(const float* in, long long ld_in, long long zs_in, float* out, long long ld_out, long long zs_out, int R,
-                  int C, int Z, cudaStream_t s) {
+                  int C, int Z, int round_out, cudaStream_t s) {
   if (R <= 0 || C <= 0 || Z <= 0 || Z > 65535) {
     sdb_set_error("transpose_f32: bad shape R=%d C=%d Z=%d", R, C, Z);
     return SDB_ERR_ARG;
   }
   sdb_launch(transpose_f32_kernel, dim3((C + 31) / 32, (R + 31) / 32, Z), dim3(256), 0, s, in, ld_in, zs_in, out, ld_out,
-             zs_out, R, C);
+             zs_out, R, C, round_out);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("transpose_f32");
   return SDB_OK;
 }
 
 int layernorm_f32_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
-                          int rows, int C, float eps, cudaStream_t s) {
+                          int rows, int C, float eps, int round_out, cudaStream_t s) {
   if (C % 32 || C > 32 * kLnMaxPerLane) {
     sdb_set_error("layernorm_f32: C=%d must be a multiple of 32, at most %d", C, 32 * kLnMaxPerLane);
     return SDB_ERR_UNSUPPORTED;
   }
   if (C <= 768)
-    sdb_launch(layernorm_f32_fwd_kernel<24>, dim3((rows + 7) / 8), dim3(256), 0, s, x, gamma, beta, y, mean, rstd, rows, C, eps);
+    sdb_launch(layernorm_f32_fwd_kernel<24>, dim3((rows + 7) / 8), dim3(256), 0, s, x, gamma, beta, y, mean, rstd, rows, C, eps, round_out);
   else
-    sdb_launch(layernorm_f32_fwd_kernel<32>, dim3((rows + 7) / 8), dim3(256), 0, s, x, gamma, beta, y, mean, rstd, rows, C, eps);
+    sdb_launch(layernorm_f32_fwd_kernel<32>, dim3((rows + 7) / 8), dim3(256), 0, s, x, gamma, beta, y, mean, rstd, rows, C, eps, round_out);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("layernorm_f32_fwd");
   return SDB_OK;
@@ -445,23 +517,40 @@ int layernorm_f32_backward(const float* x, const float* gamma, const float* mean
   return SDB_OK;
 }
 
-int softmax_f32_forward(float* x, long long rows, int cols, long long ld, float* lse, cudaStream_t s) {
+int softmax_f32_forward(float* x, long long rows, int cols, long long ld, float* lse, int round_out, cudaStream_t s) {
   if (cols <= 0 || cols > 4096) {
     sdb_set_error("softmax_f32: cols=%d must be in [1, 4096]", cols);
     return SDB_ERR_UNSUPPORTED;
   }
   if (cols <= 512) {
-    sdb_launch(softmax_f32_fwd_kernel<32>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, x, rows, cols, ld, lse);
+    sdb_launch(softmax_f32_fwd_kernel<32>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, x, rows, cols, ld, lse, round_out);
   } else {
-    sdb_launch(softmax_f32_fwd_kernel<256>, dim3((unsigned)rows), dim3(256), 0, s, x, rows, cols, ld, lse);
+    sdb_launch(softmax_f32_fwd_kernel<256>, dim3((unsigned)rows), dim3(256), 0, s, x, rows, cols, ld, lse, round_out);
   }
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("softmax_f32_fwd");
   return SDB_OK;
 }
 
+int softmax_f32_backward_rows(float* X, float* Y, long long rows, int cols, long long ld, const float* lse, float* delta,
+                              int round_out, cudaStream_t s) {
+  if (cols <= 0 || cols > 4096) {
+    sdb_set_error("softmax_f32: cols=%d must be in [1, 4096]", cols);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  if (cols <= 512)
+    sdb_launch(softmax_f32_bwd_rows_kernel<32>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, X, Y, rows, cols, ld, lse,
+               delta, round_out);
+  else
+    sdb_launch(softmax_f32_bwd_rows_kernel<256>, dim3((unsigned)rows), dim3(256), 0, s, X, Y, rows, cols, ld, lse, delta,
+               round_out);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("softmax_f32_bwd_rows");
+  return SDB_OK;
+}
+
 int softmax_f32_backward_stats(float* X, float* Y, int Z, int R, int cols, long long ld, const float* lse,
-                               const float* delta, int by_col, cudaStream_t s) {
+                               const float* delta, int by_col, int round_out, cudaStream_t s) {
   if ((ld & 3) || (by_col && (cols & 3))) {
     sdb_set_error("softmax_f32_backward_stats: ld=%lld (and cols=%d when the statistics run along columns) must be multiples of 4",
                   ld, cols);
@@ -469,7 +558,7 @@ int softmax_f32_backward_stats(float* X, float* Y, int Z, int R, int cols, long 
   }
   const long long total4 = (long long)Z * R * ((cols + 3) >> 2);
   sdb_launch(softmax_f32_bwd_stats_kernel, dim3(ew_blocks(total4)), dim3(256), 0, s, X, Y, R, cols, ld, lse, delta, by_col,
-             total4);
+             total4, round_out);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("softmax_f32_bwd_stats");
   return SDB_OK;
@@ -487,22 +576,22 @@ int attn_delta_f32(const float* dO, const float* O, float* delta, int B, int L, 
   return SDB_OK;
 }
 
-int gelu_f32_forward(const float* h, float* g, long long n, cudaStream_t s) {
+int gelu_f32_forward(const float* h, float* g, long long n, int round_out, cudaStream_t s) {
   if (n % 4) {
     sdb_set_error("gelu_f32: n=%lld must be a multiple of 4", n);
     return SDB_ERR_ARG;
   }
-  sdb_launch(gelu_f32_fwd_kernel, dim3(ew_blocks(n / 4)), dim3(256), 0, s, h, g, n / 4);
+  sdb_launch(gelu_f32_fwd_kernel, dim3(ew_blocks(n / 4)), dim3(256), 0, s, h, g, n / 4, round_out);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gelu_f32_fwd");
   return SDB_OK;
 }
-int gelu_f32_backward(const float* h, float* dg, long long n, cudaStream_t s) {
+int gelu_f32_backward(const float* h, float* dg, long long n, int round_out, cudaStream_t s) {
   if (n % 4) {
     sdb_set_error("gelu_f32: n=%lld must be a multiple of 4", n);
     return SDB_ERR_ARG;
   }
-  sdb_launch(gelu_f32_bwd_kernel, dim3(ew_blocks(n / 4)), dim3(256), 0, s, h, dg, n / 4);
+  sdb_launch(gelu_f32_bwd_kernel, dim3(ew_blocks(n / 4)), dim3(256), 0, s, h, dg, n / 4, round_out);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gelu_f32_bwd");
   return SDB_OK;
@@ -527,6 +616,13 @@ int colsum_f32(const float* x, long long rows, int cols, long long ld, float* ws
   sdb_launch(colsum_finalize_kernel, dim3((cols + 255) / 256), dim3(256), 0, s, (const float*)ws, nblk, cols, out);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("colsum_finalize");
+  return SDB_OK;
+}
+
+int round_tf32_f32(const float* in, float* out, long long n, cudaStream_t s) {
+  sdb_launch(round_tf32_kernel, dim3(ew_blocks((n + 3) / 4)), dim3(256), 0, s, in, out, n);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("round_tf32");
   return SDB_OK;
 }
 

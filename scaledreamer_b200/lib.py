@@ -66,7 +66,7 @@ class GemmTf32ArgsC(C.Structure):
                 ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int), ("zdiv", C.c_int),
                 ("out", C.c_void_p), ("ldc", C.c_longlong), ("out_zs_hi", C.c_longlong), ("out_zs_lo", C.c_longlong),
                 ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_longlong), ("res_zs_hi", C.c_longlong),
-                ("res_zs_lo", C.c_longlong), ("alpha", C.c_float), ("act", C.c_int)]
+                ("res_zs_lo", C.c_longlong), ("alpha", C.c_float), ("act", C.c_int), ("round_out", C.c_int)]
 
 
 class UNetCfgC(C.Structure):
@@ -220,15 +220,17 @@ SIGNATURES = {
     "sdb_im2col3x3s2_f16": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sdb_col2im3x3s2_f16": [_P, _P, _I, _I, _I, _I, _I, _P],
     "sdb_gemm_tf32": [C.POINTER(GemmTf32ArgsC), _P],
-    "sdb_transpose_f32": [_P, _LL, _LL, _P, _LL, _LL, _I, _I, _I, _P],
-    "sdb_layernorm_f32_forward": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "sdb_round_tf32_f32": [_P, _P, _LL, _P],
+    "sdb_transpose_f32": [_P, _LL, _LL, _P, _LL, _LL, _I, _I, _I, _I, _P],
+    "sdb_layernorm_f32_forward": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
     "sdb_layernorm_f32_backward_ws_floats": [_I, _I],
     "sdb_layernorm_f32_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
-    "sdb_softmax_f32_forward": [_P, _LL, _I, _LL, _P, _P],
-    "sdb_softmax_f32_backward_stats": [_P, _P, _I, _I, _I, _LL, _P, _P, _I, _P],
+    "sdb_softmax_f32_forward": [_P, _LL, _I, _LL, _P, _I, _P],
+    "sdb_softmax_f32_backward_rows": [_P, _P, _LL, _I, _LL, _P, _P, _I, _P],
+    "sdb_softmax_f32_backward_stats": [_P, _P, _I, _I, _I, _LL, _P, _P, _I, _I, _P],
     "sdb_attn_delta_f32": [_P, _P, _P, _I, _I, _I, _I, _P],
-    "sdb_gelu_f32_forward": [_P, _P, _LL, _P],
-    "sdb_gelu_f32_backward": [_P, _P, _LL, _P],
+    "sdb_gelu_f32_forward": [_P, _P, _LL, _I, _P],
+    "sdb_gelu_f32_backward": [_P, _P, _LL, _I, _P],
     "sdb_colsum_f32_ws_floats": [_LL, _I],
     "sdb_colsum_f32": [_P, _LL, _I, _LL, _P, _P, _P],
     "sdb_broadcast_f32": [_P, _LL, _P, _I, _P],

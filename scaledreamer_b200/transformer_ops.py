@@ -34,8 +34,9 @@ def mat(t: torch.Tensor) -> Operand:
 
 def gemm(A: Operand, B: Operand, M: int, N: int, K: int, out: Operand, batch: int = 1, zdiv: int = 1,
          bias: Optional[torch.Tensor] = None, residual: Optional[Operand] = None, alpha: float = 1.0,
-         act: int = ACT_NONE) -> None:
-    """out[z] = act(alpha * A[z] B[z]^T + bias) + residual[z]; z = hi * zdiv + lo < batch."""
+         act: int = ACT_NONE, round_out: bool = False) -> None:
+    """out[z] = act(alpha * A[z] B[z]^T + bias) + residual[z]; z = hi * zdiv + lo < batch. round_out: the result is
+    written rounded to the nearest tf32 (for tensors that only feed further GEMMs; the tensor core truncates otherwise)."""
     a = L.GemmTf32ArgsC()
     a.A, a.lda, a.a_zs_hi, a.a_zs_lo = A.ptr, A.ld, A.zs_hi, A.zs_lo
     a.B, a.ldb, a.b_zs_hi, a.b_zs_lo = B.ptr, B.ld, B.zs_hi, B.zs_lo
@@ -44,20 +45,29 @@ def gemm(A: Operand, B: Operand, M: int, N: int, K: int, out: Operand, batch: in
     a.bias = bias.data_ptr() if bias is not None else None
     if residual is not None:
         a.residual, a.ldr, a.res_zs_hi, a.res_zs_lo = residual.ptr, residual.ld, residual.zs_hi, residual.zs_lo
-    a.alpha, a.act = alpha, act
+    a.alpha, a.act, a.round_out = alpha, act, 1 if round_out else 0
     L.check(L.load().sdb_gemm_tf32(a, L.stream_ptr()), "sdb_gemm_tf32")
 
 
-def transpose(src: torch.Tensor, rows: int, cols: int, batch: int = 1, ld_out: Optional[int] = None) -> torch.Tensor:
-    """[batch, rows, cols] contiguous -> [batch, cols, ld_out >= rows] (ld_out: rows rounded up to a multiple of 4)."""
-    ld_out = ld_out or (rows + 3) // 4 * 4
-    out = torch.empty(batch, cols, ld_out, device=src.device, dtype=torch.float32)
-    L.check(L.load().sdb_transpose_f32(src.data_ptr(), cols, rows * cols, out.data_ptr(), ld_out, cols * ld_out, rows,
-                                       cols, batch, L.stream_ptr()), "sdb_transpose_f32")
+def round_tf32(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Nearest-tf32 copy of a contiguous fp32 tensor (out=src rounds in place)."""
+    out = torch.empty_like(src) if out is None else out
+    L.check(L.load().sdb_round_tf32_f32(src.data_ptr(), out.data_ptr(), src.numel(), L.stream_ptr()), "sdb_round_tf32_f32")
     return out
 
 
-def layernorm_forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float
+def transpose(src: torch.Tensor, rows: int, cols: int, batch: int = 1, ld_out: Optional[int] = None,
+              round_out: bool = True) -> torch.Tensor:
+    """[batch, rows, cols] contiguous -> [batch, cols, ld_out >= rows] (ld_out: rows rounded up to a multiple of 4).
+    Transposes exist to feed GEMMs, so the values are rounded to tf32 on the way unless round_out is False."""
+    ld_out = ld_out or (rows + 3) // 4 * 4
+    out = torch.empty(batch, cols, ld_out, device=src.device, dtype=torch.float32)
+    L.check(L.load().sdb_transpose_f32(src.data_ptr(), cols, rows * cols, out.data_ptr(), ld_out, cols * ld_out, rows,
+                                       cols, batch, 1 if round_out else 0, L.stream_ptr()), "sdb_transpose_f32")
+    return out
+
+
+def layernorm_forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, round_out: bool = False
                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     C = x.shape[-1]
     rows = x.numel() // C
@@ -65,7 +75,8 @@ def layernorm_forward(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, 
     mean = torch.empty(rows, device=x.device, dtype=torch.float32)
     rstd = torch.empty_like(mean)
     L.check(L.load().sdb_layernorm_f32_forward(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
-                                               mean.data_ptr(), rstd.data_ptr(), rows, C, eps, L.stream_ptr()),
+                                               mean.data_ptr(), rstd.data_ptr(), rows, C, eps, 1 if round_out else 0,
+                                               L.stream_ptr()),
             "sdb_layernorm_f32_forward")
     return y, mean, rstd
 
@@ -86,19 +97,30 @@ def layernorm_backward(x, gamma, mean, rstd, dy, dskip: Optional[torch.Tensor]
     return dx, dgb[0], dgb[1]
 
 
-def softmax_forward_(x: torch.Tensor, rows: int, cols: int, ld: int) -> torch.Tensor:
+def softmax_forward_(x: torch.Tensor, rows: int, cols: int, ld: int, round_out: bool = False) -> torch.Tensor:
     """In place over x viewed as [rows, ld]; -> lse [rows]."""
     lse = torch.empty(rows, device=x.device, dtype=torch.float32)
-    L.check(L.load().sdb_softmax_f32_forward(x.data_ptr(), rows, cols, ld, lse.data_ptr(), L.stream_ptr()),
+    L.check(L.load().sdb_softmax_f32_forward(x.data_ptr(), rows, cols, ld, lse.data_ptr(), 1 if round_out else 0,
+                                             L.stream_ptr()),
             "sdb_softmax_f32_forward")
     return lse
 
 
+def softmax_backward_rows_(X: torch.Tensor, Y: torch.Tensor, rows: int, cols: int, ld: int, lse: torch.Tensor,
+                           round_out: bool = False) -> torch.Tensor:
+    """X (scores) <- P, Y (dP) <- dS, -> delta [rows] = sum_k P dP."""
+    delta = torch.empty(rows, device=X.device, dtype=torch.float32)
+    L.check(L.load().sdb_softmax_f32_backward_rows(X.data_ptr(), Y.data_ptr(), rows, cols, ld, lse.data_ptr(),
+                                                   delta.data_ptr(), 1 if round_out else 0, L.stream_ptr()),
+            "sdb_softmax_f32_backward_rows")
+    return delta
+
+
 def softmax_backward_stats_(X: torch.Tensor, Y: torch.Tensor, batch: int, rows: int, cols: int, ld: int,
-                            lse: torch.Tensor, delta: torch.Tensor, by_col: bool) -> None:
+                            lse: torch.Tensor, delta: torch.Tensor, by_col: bool, round_out: bool = False) -> None:
     L.check(L.load().sdb_softmax_f32_backward_stats(X.data_ptr(), Y.data_ptr(), batch, rows, cols, ld, lse.data_ptr(),
-                                                    delta.data_ptr(), 1 if by_col else 0, L.stream_ptr()),
-            "sdb_softmax_f32_backward_stats")
+                                                    delta.data_ptr(), 1 if by_col else 0, 1 if round_out else 0,
+                                                    L.stream_ptr()), "sdb_softmax_f32_backward_stats")
 
 
 def attn_delta(dO: torch.Tensor, O: torch.Tensor, B: int, Lq: int, heads: int, d: int) -> torch.Tensor:
@@ -108,14 +130,16 @@ def attn_delta(dO: torch.Tensor, O: torch.Tensor, B: int, Lq: int, heads: int, d
     return delta
 
 
-def gelu_forward(h: torch.Tensor) -> torch.Tensor:
+def gelu_forward(h: torch.Tensor, round_out: bool = False) -> torch.Tensor:
     g = torch.empty_like(h)
-    L.check(L.load().sdb_gelu_f32_forward(h.data_ptr(), g.data_ptr(), h.numel(), L.stream_ptr()), "sdb_gelu_f32_forward")
+    L.check(L.load().sdb_gelu_f32_forward(h.data_ptr(), g.data_ptr(), h.numel(), 1 if round_out else 0, L.stream_ptr()),
+            "sdb_gelu_f32_forward")
     return g
 
 
-def gelu_backward_(h: torch.Tensor, dg: torch.Tensor) -> torch.Tensor:
-    L.check(L.load().sdb_gelu_f32_backward(h.data_ptr(), dg.data_ptr(), h.numel(), L.stream_ptr()), "sdb_gelu_f32_backward")
+def gelu_backward_(h: torch.Tensor, dg: torch.Tensor, round_out: bool = False) -> torch.Tensor:
+    L.check(L.load().sdb_gelu_f32_backward(h.data_ptr(), dg.data_ptr(), h.numel(), 1 if round_out else 0, L.stream_ptr()),
+            "sdb_gelu_f32_backward")
     return dg
 
 

@@ -77,7 +77,7 @@ def test_transpose_layernorm_softmax_gelu_colsum_shuffle():
     T = _ops()
     g = torch.Generator(device="cuda").manual_seed(7)
     x = torch.randn(3, 70, 45, device="cuda", generator=g)
-    xt = T.transpose(x, 70, 45, batch=3)
+    xt = T.transpose(x, 70, 45, batch=3, round_out=False)
     assert xt.shape == (3, 45, 72) and torch.equal(xt[:, :, :70], x.transpose(1, 2))
 
     C = 768
@@ -108,6 +108,10 @@ def test_transpose_layernorm_softmax_gelu_colsum_shuffle():
         T.softmax_backward_stats_(X, Y, 1, rows, cols, ld, lse, delta.contiguous(), by_col=False)
         ref_ds = ref * (dP[:, :cols] - delta[:, None])
         assert _rel(X[:, :cols], ref) < 1e-5 and _rel(Y[:, :cols], ref_ds) < 1e-4
+        X, Y = s.clone(), dP.clone()
+        dl = T.softmax_backward_rows_(X, Y, rows, cols, ld, lse)
+        assert _rel(dl, delta) < 1e-5 and _rel(X[:, :cols], ref) < 1e-5 and _rel(Y[:, :cols], ref_ds) < 1e-4
+        assert float(Y[:, :cols].sum(-1).abs().max()) < 1e-5  # rows of dS sum to zero
     # column-indexed statistics on the transposed scores
     Z, R, Cc = 2, 40, 64
     s = torch.randn(Z, R, Cc, device="cuda", generator=g)
@@ -130,6 +134,11 @@ def test_transpose_layernorm_softmax_gelu_colsum_shuffle():
     m = torch.randn(12288, 96, device="cuda", generator=g)
     assert _rel(T.colsum(m, 12288, 96), m.double().sum(0)) < 1e-5
     assert _rel(T.colsum(m[:3].contiguous(), 3, 96), m[:3].double().sum(0)) < 1e-6
+
+    # nearest-tf32 rounding: 10 mantissa bits, ties away from zero; transposes round on the way by default
+    r = T.round_tf32(m)
+    assert (r.view(torch.int32) & 0x1FFF).eq(0).all() and float((r - m).abs().max() / m.abs().max()) < 2.0 ** -11
+    assert torch.equal(T.transpose(x, 70, 45, batch=3)[:, :, :70], T.round_tf32(x).transpose(1, 2))
 
     pe = torch.randn(50, 64, device="cuda", generator=g)
     assert torch.equal(T.broadcast(pe, 3), pe.expand(3, 50, 64))
