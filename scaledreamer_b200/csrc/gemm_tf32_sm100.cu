@@ -9,10 +9,15 @@
 //   warp 0   : TMA producer  (4-D maps {K, rows, z_lo, z_hi}, 128-byte swizzle: a row of a tile is 32 floats)
 //   warp 1   : MMA issuer    (128 x BN x 8 per instruction, four per 32-float k-block; two accumulators in tensor memory)
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue      (tcgen05.ld 16 columns at a time, next read in flight while this one is stored)
+//   warps 4-7: epilogue      (tcgen05.ld 32 columns at a time, next read in flight while this one leaves: each warp stages
+//                             its 32 rows x 128 bytes in shared memory (128-byte swizzle) and one lane issues a TMA store,
+//                             three staging tiles per warp so that 48 KB of stores are in flight per SM. Per-thread
+//                             16-byte stores cost one L2 request each and held the 3072 x 3072 x 48 score products at
+//                             2.3 TB/s of output; two 2 KB stores in flight per warp at 3.1 TB/s: the store latency)
 // A partial last k-block and rows past M / N are zero-filled by TMA (out-of-bounds fill), so K needs no padding:
 // the attention products run with K = head_dim = 48 and K = 77 text tokens.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "dense.h"
@@ -29,11 +34,13 @@ template <int BN>
 struct TCfg {
   static constexpr int kBTile = BN * 128;
   static constexpr int kStage = kATile + kBTile;
-  static constexpr int kStages = BN <= 64 ? 8 : 6;
+  static constexpr int kStages = BN <= 64 ? 6 : 5;
   static constexpr int kAccStride = BN <= 64 ? 64 : 128;
   static constexpr int kTmemCols = 2 * kAccStride;
   static constexpr int kThreads = 256;
-  static constexpr int kSmem = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStoreTiles = 3;                      // staging tiles per epilogue warp
+  static constexpr int kStoreBytes = 4 * kStoreTiles * 4096;  // each 32 rows x 128 bytes
+  static constexpr int kSmem = kStages * kStage + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct Tf32Params {
@@ -48,17 +55,20 @@ struct Tf32Params {
   float alpha;
   int act;
   int round_out;  // results are rounded to tf32: the output only feeds further GEMMs
+  int tma_store;  // results leave through shared memory + cp.async.bulk.tensor (tmC); c_hi / c_lo as for the operands
+  int c_hi, c_lo;
   int tiles_m, tiles_n, tiles_z;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ Tf32Params p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ Tf32Params p) {
   using C = TCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + C::kStages * C::kStage);
+  uint8_t* store_smem = base + C::kStages * C::kStage;  // 1024-byte aligned
+  uint64_t* full = reinterpret_cast<uint64_t*>(store_smem + C::kStoreBytes);
   uint64_t* empty = full + C::kStages;
   uint64_t* accum_full = empty + C::kStages;  // [2]
   uint64_t* accum_empty = accum_full + 2;     // [2]
@@ -69,6 +79,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    if (p.tma_store) ptx::prefetch_tmap(&tmC);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -141,6 +152,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 4) {
     const int wq = warp & 3;
     uint32_t tcount = 0;
+    uint8_t* stage = store_smem + wq * (C::kStoreTiles * 4096);
+    int nstore = 0;  // TMA stores issued by this warp's lane 0 so far (staging tile = nstore % kStoreTiles)
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
       const int t_mn = tile % tiles_mn, z = tile / tiles_mn;
       const int m0 = (t_mn % p.tiles_m) * kBM, n0 = (t_mn / p.tiles_m) * BN;
@@ -153,70 +166,97 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           p.residual ? p.residual + (long long)zh * p.res_zs_hi + (long long)zl * p.res_zs_lo + (long long)m * p.ldr : nullptr;
       const bool vec_ok = ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
                           (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+      const int c3 = p.c_hi ? zh : 0, c2 = p.c_lo ? zl : 0;
       ptx::mbar_wait(&accum_full[buf], use & 1u);
       ptx::tc_fence_after();
       uint32_t tm_row = tmem_base + buf * C::kAccStride + ((uint32_t)(wq * 32) << 16);
-      auto finish = [&](const uint32_t(&v)[16], int c) {
+      auto finish = [&](const uint32_t(&v)[32], int c) {
         const int nb = n0 + c;
-        if (!m_ok || nb >= p.N) return;
-        const bool fullc = nb + 16 <= p.N;
-        float f[16];
+        if (nb >= p.N) return;              // warp-uniform
+        if (!p.tma_store && !m_ok) return;  // rows past M: nothing to store (the TMA path clips them, stays collective)
+        const bool fullc = nb + 32 <= p.N;
+        float f[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
         if (p.bias) {
           if (fullc && (reinterpret_cast<uintptr_t>(p.bias + nb) & 15) == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
               const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + q);
               f[4 * q] += t.x, f[4 * q + 1] += t.y, f[4 * q + 2] += t.z, f[4 * q + 3] += t.w;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < 32; ++j)
               if (nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
           }
         }
         if (p.act == kActGelu) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
+          for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
         }
-        if (fullc && vec_ok && (nb & 3) == 0) {
-          if (rrow) {
+        if (rrow && m_ok) {
+          if (fullc && vec_ok && (nb & 3) == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
               const float4 t = *(reinterpret_cast<const float4*>(rrow + nb) + q);
               f[4 * q] += t.x, f[4 * q + 1] += t.y, f[4 * q + 2] += t.z, f[4 * q + 3] += t.w;
             }
-          }
-          if (p.round_out) {
+          } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = round_tf32(f[j]);
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) f[j] += rrow[nb + j];
+          }
+        }
+        if (p.round_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
+        }
+        if (p.tma_store) {
+          // 32 rows x 128 bytes; the 16-byte piece q of row r sits at piece q ^ (r & 7) (128-byte swizzle of tmC)
+          uint8_t* tile_s = stage + (nstore % C::kStoreTiles) * 4096;
+          if (nstore >= C::kStoreTiles) {  // the store that last read this staging tile must have drained it
+            if (lane == 0) ptx::tma_store_wait_read<C::kStoreTiles - 1>();
+            __syncwarp();
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(tile_s + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_4d(&tmC, tile_s, nb, m - lane, c2, c3);  // columns past N / rows past M are clipped
+            ptx::tma_store_commit();
+          }
+          ++nstore;
+        } else if (fullc && vec_ok && (nb & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
             reinterpret_cast<float4*>(orow + nb)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < p.N) {
-              const float v = f[j] + (rrow ? rrow[nb + j] : 0.f);
-              orow[nb + j] = p.round_out ? round_tf32(v) : v;
-            }
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) orow[nb + j] = f[j];
         }
       };
-      uint32_t va[16], vb[16];
-      ptx::tmem_ld_32x16(tm_row, va);
+      uint32_t va[32], vb[32];
+      ptx::tmem_ld_32x32(tm_row, va);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = 0; c < BN; c += 64) {
         ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x16(tm_row + (uint32_t)(c + 16), vb);
+        ptx::tmem_ld_32x32(tm_row + (uint32_t)(c + 32), vb);
         finish(va, c);
         ptx::tmem_ld_wait();
-        if (c + 32 < BN) ptx::tmem_ld_32x16(tm_row + (uint32_t)(c + 32), va);
-        finish(vb, c + 16);
+        if (c + 64 < BN) ptx::tmem_ld_32x32(tm_row + (uint32_t)(c + 64), va);
+        finish(vb, c + 32);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&accum_empty[buf]);
+    }
+    if (p.tma_store && nstore > 0) {
+      if (lane == 0) ptx::tma_store_wait_read<0>();
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -244,7 +284,8 @@ int operand_map(CUtensorMap* tm, const Tf32Operand& o, int rows, int K, int z_hi
 }
 
 template <int BN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Tf32Params& p, int grid, cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const Tf32Params& p, int grid,
+           cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCfg<BN>::kSmem);
@@ -254,7 +295,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Tf32Params& p, in
     }
     attr = true;
   }
-  sdb_launch(gemm_tf32_kernel<BN>, dim3(grid), dim3(256), (size_t)TCfg<BN>::kSmem, stream, ta, tb, p);
+  sdb_launch(gemm_tf32_kernel<BN>, dim3(grid), dim3(256), (size_t)TCfg<BN>::kSmem, stream, ta, tb, tc, p);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("gemm_tf32");
   return SDB_OK;
@@ -287,9 +328,28 @@ int gemm_tf32(const Tf32Operand& A, const Tf32Operand& B, int M, int N, int K, f
   if (rc) return rc;
   rc = operand_map(&tb, B, N, K, batch / zdiv, zdiv, bn, &p.b_hi, &p.b_lo, "B");
   if (rc) return rc;
+  // output map {N, M, z_lo, z_hi}, 32-column x 32-row boxes, 128-byte swizzle
+  CUtensorMap tc;
+  memset(&tc, 0, sizeof(tc));
+  static const int tma_store_on = getenv("SDB_TF32_TMA_STORE") ? atoi(getenv("SDB_TF32_TMA_STORE")) : 1;
+  // (N % 4 != 0 keeps the per-thread stores: the bulk store writes whole 16-byte granules, i.e. it would also write the
+  // columns between N and the next multiple of 4 -- measured with N = 5, ldc = 8)
+  if (tma_store_on && (N & 3) == 0 && (ldc & 3) == 0 && (out_zs_hi & 3) == 0 && (out_zs_lo & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int z_hi = batch / zdiv, z_lo = zdiv;
+    p.c_hi = (z_hi > 1 && out_zs_hi != 0) ? 1 : 0;
+    p.c_lo = (z_lo > 1 && out_zs_lo != 0) ? 1 : 0;
+    const uint64_t dflt = (uint64_t)ldc * 4 * (uint64_t)M;
+    uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, (uint64_t)(p.c_lo ? z_lo : 1), (uint64_t)(p.c_hi ? z_hi : 1)};
+    uint64_t strides[3] = {(uint64_t)ldc * 4, p.c_lo ? (uint64_t)out_zs_lo * 4 : dflt, p.c_hi ? (uint64_t)out_zs_hi * 4 : dflt};
+    uint32_t box[4] = {32, 32, 1, 1};
+    rc = make_tmap(&tc, out, 4, dims, strides, box, 128, 1);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
   const long long total = (long long)p.tiles_m * p.tiles_n * p.tiles_z;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  return bn == 64 ? launch<64>(ta, tb, p, grid, stream) : launch<128>(ta, tb, p, grid, stream);
+  return bn == 64 ? launch<64>(ta, tb, tc, p, grid, stream) : launch<128>(ta, tb, tc, p, grid, stream);
 }
 
 }  // namespace dense

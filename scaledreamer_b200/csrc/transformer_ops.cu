@@ -85,66 +85,75 @@ layernorm_f32_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
-// dx = rstd * (dy*g - mean_c(dy*g) - xhat * mean_c(dy*g*xhat)) (+ dskip); each CTA walks a contiguous slab of rows and
-// writes its partial (d gamma, d beta) to partial[blk][2][C]; ln_param_finalize sums the slabs in order.
+// dx = rstd * (dy*g - mean_c(dy*g) - xhat * mean_c(dy*g*xhat)) (+ dskip), warp per row like the forward.
+// (A first version also accumulated d gamma / d beta per lane over a slab of rows: 175 registers, one CTA per SM, 277 us
+// for 151 MB. Split in two, the row kernel streams at the forward's rate and the parameter sums are a column reduction.)
 template <int PER>
 __global__ void __launch_bounds__(256)
-layernorm_f32_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean_in,
-                         const float* __restrict__ rstd_in, const float* __restrict__ dy, const float* __restrict__ dskip,
-                         float* __restrict__ dx, float* __restrict__ partial, int rows, int C, int rows_per_block) {
+layernorm_f32_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                            const float* __restrict__ rstd_in, const float* __restrict__ dy, const float* __restrict__ dskip,
+                            float* __restrict__ dx, int rows, int C) {
   pdl_prologue();
-  extern __shared__ float sm[];  // [8 warps][2][C]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int per = C / 32;
-  float g[PER], dg[PER], db[PER];
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    g[i] = i < per ? __ldg(gamma + i * 32 + lane) : 0.f;
-    dg[i] = db[i] = 0.f;
-  }
-  const int r_begin = blockIdx.x * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
-  for (int row = r_begin + warp; row < r_end; row += 8) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const float* xr = x + (long long)row * C;
-    const float* dr = dy + (long long)row * C;
-    float xh[PER], dz[PER];
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      if (i < per) {
-        const float d = dr[i * 32 + lane];
-        xh[i] = (xr[i * 32 + lane] - mean) * rstd;
-        dz[i] = d * g[i];
-        s0 += dz[i];
-        s1 = fmaf(dz[i], xh[i], s1);
-        dg[i] = fmaf(d, xh[i], dg[i]);
-        db[i] += d;
-      }
-    s0 = warp_sum(s0) / (float)C;
-    s1 = warp_sum(s1) / (float)C;
-    float* o = dx + (long long)row * C;
-    const float* sk = dskip ? dskip + (long long)row * C : nullptr;
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      if (i < per) {
-        float v = rstd * (dz[i] - s0 - xh[i] * s1);
-        if (sk) v += sk[i * 32 + lane];
-        o[i * 32 + lane] = v;
-      }
-  }
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  const float* xr = x + (long long)row * C;
+  const float* dr = dy + (long long)row * C;
+  const float* sk = dskip ? dskip + (long long)row * C : nullptr;
+  float xh[PER], dz[PER], skv[PER];
+  float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i)
     if (i < per) {
-      sm[(warp * 2) * C + i * 32 + lane] = dg[i];
-      sm[(warp * 2 + 1) * C + i * 32 + lane] = db[i];
+      const int c = i * 32 + lane;
+      xh[i] = (xr[c] - mean) * rstd;
+      dz[i] = dr[c] * __ldg(gamma + c);
+      skv[i] = sk ? sk[c] : 0.f;
+      s0 += dz[i];
+      s1 = fmaf(dz[i], xh[i], s1);
     }
+  s0 = warp_sum(s0) / (float)C;
+  s1 = warp_sum(s1) / (float)C;
+  float* o = dx + (long long)row * C;
+#pragma unroll
+  for (int i = 0; i < PER; ++i)
+    if (i < per) o[i * 32 + lane] = fmaf(rstd, dz[i] - s0 - xh[i] * s1, skv[i]);
+}
+
+// partial[blk][0][c] = sum_r dy[r][c] * xhat[r][c], partial[blk][1][c] = sum_r dy[r][c] over the block's rows; 32 columns
+// x 8 row lanes per CTA (every warp reads 128 contiguous bytes per operand), ln_param_finalize sums the blocks in order.
+__global__ void __launch_bounds__(256)
+ln_param_partial_kernel(const float* __restrict__ x, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                        const float* __restrict__ dy, float* __restrict__ partial, int rows, int C, int rows_per_block) {
+  pdl_prologue();
+  __shared__ float sm[2][8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
+  int r = r0 + ty;
+  for (; r + 8 < r1; r += 16) {
+    const float d0 = dy[(long long)r * C + c], d1 = dy[(long long)(r + 8) * C + c];
+    const float x0 = (x[(long long)r * C + c] - mean_in[r]) * rstd_in[r];
+    const float x1 = (x[(long long)(r + 8) * C + c] - mean_in[r + 8]) * rstd_in[r + 8];
+    g0 = fmaf(d0, x0, g0), g1 = fmaf(d1, x1, g1);
+    b0 += d0, b1 += d1;
+  }
+  if (r < r1) {
+    const float d0 = dy[(long long)r * C + c];
+    g0 = fmaf(d0, (x[(long long)r * C + c] - mean_in[r]) * rstd_in[r], g0);
+    b0 += d0;
+  }
+  sm[0][ty][tx] = g0 + g1;
+  sm[1][ty][tx] = b0 + b1;
   __syncthreads();
-  for (int t = threadIdx.x; t < 2 * C; t += 256) {
-    const int k = t / C, c = t - k * C;
+  if (ty < 2) {
     float a = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) a += sm[(w * 2 + k) * C + c];
-    partial[((long long)blockIdx.x * 2 + k) * C + c] = a;
+    for (int w = 0; w < 8; ++w) a += sm[ty][w][tx];
+    partial[((long long)blockIdx.y * 2 + ty) * C + c] = a;
   }
 }
 
@@ -392,6 +401,20 @@ colsum_f32_kernel(const float* __restrict__ x, long long rows, int cols, long lo
     partial[(long long)blockIdx.y * cols + c] = a;
   }
 }
+// few rows (the slices of a split weight-gradient product, the prompts of the position-embedding gradient): one thread
+// per four columns sums the rows in order
+__global__ void colsum_small_kernel(const float* __restrict__ x, int rows, long long cols4, long long ld4,
+                                    float* __restrict__ out) {
+  pdl_prologue();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cols4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(x)[i];
+    for (int r = 1; r < rows; ++r) {
+      const float4 v = reinterpret_cast<const float4*>(x)[(long long)r * ld4 + i];
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+}
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int cols, float* __restrict__ out) {
   pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -478,8 +501,8 @@ int layernorm_f32_forward(const float* x, const float* gamma, const float* beta,
 }
 
 static int ln_bwd_blocks(int rows, int* rpb) {
-  int r = (rows + kNumSMs * 2 - 1) / (kNumSMs * 2);
-  if (r < 8) r = 8;
+  int r = (rows + 63) / 64;
+  if (r < 16) r = 16;
   *rpb = r;
   return (rows + r - 1) / r;
 }
@@ -494,22 +517,19 @@ int layernorm_f32_backward(const float* x, const float* gamma, const float* mean
     sdb_set_error("layernorm_f32: C=%d must be a multiple of 32, at most %d", C, 32 * kLnMaxPerLane);
     return SDB_ERR_UNSUPPORTED;
   }
+  if (C <= 768)
+    sdb_launch(layernorm_f32_bwd_dx_kernel<24>, dim3((rows + 7) / 8), dim3(256), 0, s, x, gamma, mean, rstd, dy, dskip, dx,
+               rows, C);
+  else
+    sdb_launch(layernorm_f32_bwd_dx_kernel<32>, dim3((rows + 7) / 8), dim3(256), 0, s, x, gamma, mean, rstd, dy, dskip, dx,
+               rows, C);
+  SDB_COUNT_LAUNCH();
+  SDB_CHECK_LAUNCH("layernorm_f32_bwd_dx");
   int rpb;
   const int nblk = ln_bwd_blocks(rows, &rpb);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(layernorm_f32_bwd_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4);
-    cudaFuncSetAttribute(layernorm_f32_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4);
-    attr = true;
-  }
-  if (C <= 768)
-    sdb_launch(layernorm_f32_bwd_kernel<24>, dim3(nblk), dim3(256), sizeof(float) * 16 * (size_t)C, s, x, gamma, mean, rstd,
-               dy, dskip, dx, ws, rows, C, rpb);
-  else
-    sdb_launch(layernorm_f32_bwd_kernel<32>, dim3(nblk), dim3(256), sizeof(float) * 16 * (size_t)C, s, x, gamma, mean, rstd,
-               dy, dskip, dx, ws, rows, C, rpb);
+  sdb_launch(ln_param_partial_kernel, dim3(C / 32, nblk), dim3(256), 0, s, x, mean, rstd, dy, ws, rows, C, rpb);
   SDB_COUNT_LAUNCH();
-  SDB_CHECK_LAUNCH("layernorm_f32_bwd");
+  SDB_CHECK_LAUNCH("ln_param_partial");
   sdb_launch(ln_param_finalize_kernel, dim3((2 * C + 255) / 256), dim3(256), 0, s, (const float*)ws, nblk, 2 * C, dgamma,
              dbeta, C);
   SDB_COUNT_LAUNCH();
@@ -608,6 +628,14 @@ long long colsum_f32_ws_floats(long long rows, int cols) {
   return (long long)colsum_blocks(rows, &rpb) * cols;
 }
 int colsum_f32(const float* x, long long rows, int cols, long long ld, float* ws, float* out, cudaStream_t s) {
+  if (rows <= 16 && (cols & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    sdb_launch(colsum_small_kernel, dim3(ew_blocks(cols / 4)), dim3(256), 0, s, x, (int)rows, (long long)(cols / 4), ld / 4,
+               out);
+    SDB_COUNT_LAUNCH();
+    SDB_CHECK_LAUNCH("colsum_small");
+    return SDB_OK;
+  }
   int rpb;
   const int nblk = colsum_blocks(rows, &rpb);
   sdb_launch(colsum_f32_kernel, dim3((cols + 31) / 32, nblk), dim3(256), 0, s, x, rows, cols, ld, rpb, ws);

@@ -61,3 +61,38 @@ print(f"one native step by entry point ({tot:.2f} ms on the device, {sum(v['laun
 for k, v in sorted(rec.items(), key=lambda kv: -kv[1]["ms"]):
     print(f"  {k:36s} {v['calls']:5d} calls {v['ms']:8.2f} ms")
 print(f"peak memory {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+
+# ---- per-shape GEMM times of one native step (CUDA events around every sdb_gemm_tf32 call)
+from collections import defaultdict  # noqa: E402
+
+from scaledreamer_b200 import transformer_ops as TO  # noqa: E402
+
+_orig = TO.gemm
+_recs = []
+
+
+def _timed(A, B, M, N, K, out, batch=1, zdiv=1, **kw):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _orig(A, B, M, N, K, out, batch=batch, zdiv=zdiv, **kw)
+    b.record()
+    _recs.append(((M, N, K, batch), a, b))
+
+
+TO.gemm = _timed
+import scaledreamer_b200.triplane_native as TN  # noqa: E402
+
+TN.T.gemm = _timed
+for p in gen.parameters():
+    p.grad = None
+gen(emb).backward(d)
+torch.cuda.synchronize()
+agg = defaultdict(lambda: [0, 0.0])
+for shp, a, b in _recs:
+    agg[shp][0] += 1
+    agg[shp][1] += a.elapsed_time(b)
+print("GEMM shapes of one step (M, N, K, batch): calls, total ms, TFLOP/s, output GB/s")
+for shp, (n, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    M_, N_, K_, Bz = shp
+    fl = 2.0 * M_ * N_ * K_ * Bz * n
+    print(f"  {str(shp):28s} {n:4d} {ms_:8.2f} ms {fl / ms_ / 1e9:8.1f} TF/s {4.0 * M_ * N_ * Bz * n / ms_ / 1e6:8.0f} GB/s")
