@@ -545,6 +545,25 @@ def rooflines(job: Job, prof: dict, pk: dict):
             roofs.append(hbm(" + ".join(bwd_names) + " (field backward: MLP contractions + scatter)",
                              (4 * S * n_rays + extra) * per_point / 1e9, ms_b,
                              tr.get("hyper_field_bwd") if job.name == "C4" else None))
+        if job.name == "C5" and "sdb_gemm_tf32" in calls:
+            # the trained generator's contractions: 2 * M * N * K of every sdb_gemm_tf32 of one step (forward 3.87 TFLOP at
+            # 4 prompts (0.97 at the one prompt x 4 views of a C5 step), backward twice that plus the recomputed score products). tf32 runs at half the bf16 rate: the
+            # peak is half the measured bf16 figure (no tf32 number in MEASURED_PEAKS.json).
+            gen = job.system.geometry.space_generator
+            L_, Cg = gen.pos_embed.shape[1], gen.pos_embed.shape[2]
+            Hh, nl, nb = gen.layers[0].self_attn.heads, len(gen.layers), max(1, int(job.cfg.data["batch_size"]) // int(job.cfg.data.get("n_view", 1)))
+            lin = lambda m, n, k: 2.0 * m * n * k
+            fwd = nl * nb * (6 * lin(L_, Cg, Cg) + 2 * lin(77, Cg, 1024) + 2 * lin(L_, 4 * Cg, Cg)
+                             + Hh * 2 * (lin(L_, L_, Cg // Hh) + lin(L_, 77, Cg // Hh)))
+            score = nl * nb * Hh * (lin(L_, L_, Cg // Hh) + lin(L_, 77, Cg // Hh))
+            tfl = (3 * fwd + 3 * score) / 1e12  # backward = 2 x forward + S, S^T, dP^T recomputed / extra score-shaped products
+            ms_g = calls["sdb_gemm_tf32"]["ms_per_step"]
+            roofs.append({"kernel": "gemm_tf32_kernel (Triplane-Transformer generator, forward + backward)", "bound": "tensor",
+                          "achieved": tfl / (ms_g / 1e3), "peak": pk["tf_sustained"] / 2, "unit": "TFLOP/s",
+                          "frac": tfl / (ms_g / 1e3) / (pk["tf_sustained"] / 2), "traffic": None, "ms_per_step": ms_g,
+                          "peak_source": pk["src"] + " sustained bf16 / 2 (tf32)",
+                          "note": "60 of the step's products are 3072 x 3072 x 48 score matrices written in fp32: those "
+                                  "are bound by their 2.4 GB outputs (4.3 TB/s), not by the tensor pipe"})
     return sorted(roofs, key=lambda r: -r["ms_per_step"])
 
 

@@ -148,10 +148,10 @@ int sdb_layernorm_f32_backward(const float* x, const float* gamma, const float* 
                                void* stream);
 /* in-place row softmax of the first `cols` (<= 4096) entries of each row; lse[row] = log sum exp */
 int sdb_softmax_f32_forward(float* x, long long rows, int cols, long long ld, float* lse, int round_out, void* stream);
-/* Row form of the softmax backward: X holds scores [rows][cols] and Y d loss / d P. X <- P = exp(X - lse[row]),
- * delta[row] = sum_k P dP (WRITTEN), Y <- dS = P (dP - delta) */
+/* Row form of the softmax backward: X holds scores [rows][cols] and Y d loss / d P. X <- P = exp(X - lse[row]) (only
+ * when write_p is set), delta[row] = sum_k P dP (WRITTEN), Y <- dS = P (dP - delta) */
 int sdb_softmax_f32_backward_rows(float* X, float* Y, long long rows, int cols, long long ld, const float* lse,
-                                  float* delta, int round_out, void* stream);
+                                  float* delta, int round_out, int write_p, void* stream);
 /* X <- P = exp(X - lse), Y <- P * (Y - delta): X holds scores [batch][rows][cols] and Y d loss / d P; the statistics
  * are indexed by row (by_col 0) or by column (by_col 1: X holds the TRANSPOSED scores) */
 int sdb_softmax_f32_backward_stats(float* X, float* Y, int batch, int rows, int cols, long long ld, const float* lse,

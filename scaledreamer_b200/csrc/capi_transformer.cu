@@ -54,9 +54,9 @@ int sdb_softmax_f32_forward(float* x, long long rows, int cols, long long ld, fl
 }
 
 int sdb_softmax_f32_backward_rows(float* X, float* Y, long long rows, int cols, long long ld, const float* lse,
-                                  float* delta, int round_out, void* stream) {
+                                  float* delta, int round_out, int write_p, void* stream) {
   SDB_CHECK_ARG(X && Y && lse && delta && rows > 0 && cols > 0, "softmax_f32_backward_rows: bad arguments");
-  return softmax_f32_backward_rows(X, Y, rows, cols, ld, lse, delta, round_out, (cudaStream_t)stream);
+  return softmax_f32_backward_rows(X, Y, rows, cols, ld, lse, delta, round_out, write_p, (cudaStream_t)stream);
 }
 
 int sdb_softmax_f32_backward_stats(float* X, float* Y, int batch, int rows, int cols, long long ld, const float* lse,

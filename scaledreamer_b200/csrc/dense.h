@@ -157,8 +157,9 @@ int layernorm_f32_backward(const float* x, const float* gamma, const float* mean
                            cudaStream_t s);
 // the softmax kernels write P / dS rounded to tf32 when round_out is set (they only feed GEMMs)
 int softmax_f32_forward(float* x, long long rows, int cols, long long ld, float* lse, int round_out, cudaStream_t s);
+// write_p = 0: X (the scores) is only read -- the caller does not need P afterwards
 int softmax_f32_backward_rows(float* X, float* Y, long long rows, int cols, long long ld, const float* lse, float* delta,
-                              int round_out, cudaStream_t s);
+                              int round_out, int write_p, cudaStream_t s);
 int softmax_f32_backward_stats(float* X, float* Y, int Z, int R, int cols, long long ld, const float* lse,
                                const float* delta, int by_col, int round_out, cudaStream_t s);
 int attn_delta_f32(const float* dO, const float* O, float* delta, int B, int L, int heads, int d, cudaStream_t s);

@@ -239,7 +239,7 @@ softmax_f32_fwd_kernel(float* __restrict__ x, long long rows, int cols, long lon
 template <int T>
 __global__ void __launch_bounds__(256)
 softmax_f32_bwd_rows_kernel(float* __restrict__ X, float* __restrict__ Y, long long rows, int cols, long long ld,
-                            const float* __restrict__ lse, float* __restrict__ delta, int round_out) {
+                            const float* __restrict__ lse, float* __restrict__ delta, int round_out, int write_p) {
   pdl_prologue();
   constexpr int kRowsPerBlock = 256 / T;
   __shared__ float red[8];
@@ -273,7 +273,7 @@ softmax_f32_bwd_rows_kernel(float* __restrict__ X, float* __restrict__ Y, long l
     const int c = i * T + t;
     if (c < cols) {
       const float ds = pv[i] * (dv[i] - s);
-      xr[c] = round_out ? round_tf32(pv[i]) : pv[i];
+      if (write_p) xr[c] = round_out ? round_tf32(pv[i]) : pv[i];
       yr[c] = round_out ? round_tf32(ds) : ds;
     }
   }
@@ -553,17 +553,17 @@ int softmax_f32_forward(float* x, long long rows, int cols, long long ld, float*
 }
 
 int softmax_f32_backward_rows(float* X, float* Y, long long rows, int cols, long long ld, const float* lse, float* delta,
-                              int round_out, cudaStream_t s) {
+                              int round_out, int write_p, cudaStream_t s) {
   if (cols <= 0 || cols > 4096) {
     sdb_set_error("softmax_f32: cols=%d must be in [1, 4096]", cols);
     return SDB_ERR_UNSUPPORTED;
   }
   if (cols <= 512)
     sdb_launch(softmax_f32_bwd_rows_kernel<32>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, X, Y, rows, cols, ld, lse,
-               delta, round_out);
+               delta, round_out, write_p);
   else
     sdb_launch(softmax_f32_bwd_rows_kernel<256>, dim3((unsigned)rows), dim3(256), 0, s, X, Y, rows, cols, ld, lse, delta,
-               round_out);
+               round_out, write_p);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("softmax_f32_bwd_rows");
   return SDB_OK;

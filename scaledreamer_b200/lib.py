@@ -226,7 +226,7 @@ SIGNATURES = {
     "sdb_layernorm_f32_backward_ws_floats": [_I, _I],
     "sdb_layernorm_f32_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "sdb_softmax_f32_forward": [_P, _LL, _I, _LL, _P, _I, _P],
-    "sdb_softmax_f32_backward_rows": [_P, _P, _LL, _I, _LL, _P, _P, _I, _P],
+    "sdb_softmax_f32_backward_rows": [_P, _P, _LL, _I, _LL, _P, _P, _I, _I, _P],
     "sdb_softmax_f32_backward_stats": [_P, _P, _I, _I, _I, _LL, _P, _P, _I, _I, _P],
     "sdb_attn_delta_f32": [_P, _P, _P, _I, _I, _I, _I, _P],
     "sdb_gelu_f32_forward": [_P, _P, _LL, _I, _P],

@@ -107,12 +107,12 @@ def softmax_forward_(x: torch.Tensor, rows: int, cols: int, ld: int, round_out: 
 
 
 def softmax_backward_rows_(X: torch.Tensor, Y: torch.Tensor, rows: int, cols: int, ld: int, lse: torch.Tensor,
-                           round_out: bool = False) -> torch.Tensor:
-    """X (scores) <- P, Y (dP) <- dS, -> delta [rows] = sum_k P dP."""
+                           round_out: bool = False, write_p: bool = True) -> torch.Tensor:
+    """X (scores) <- P (unless write_p is False), Y (dP) <- dS, -> delta [rows] = sum_k P dP."""
     delta = torch.empty(rows, device=X.device, dtype=torch.float32)
     L.check(L.load().sdb_softmax_f32_backward_rows(X.data_ptr(), Y.data_ptr(), rows, cols, ld, lse.data_ptr(),
-                                                   delta.data_ptr(), 1 if round_out else 0, L.stream_ptr()),
-            "sdb_softmax_f32_backward_rows")
+                                                   delta.data_ptr(), 1 if round_out else 0, 1 if write_p else 0,
+                                                   L.stream_ptr()), "sdb_softmax_f32_backward_rows")
     return delta
 
 

@@ -158,7 +158,7 @@ def _attn_backward(dy, saved, xn, ctx, Wq, Wk, Wv, Wo, heads, self_attn):
     dP = _empty(B * heads, L, Lkp, like=xn)
     T.gemm(hv.act(dO, L), hv.act(v, Lk), L, Lk, d, hv.scores(dP, L, Lkp), batch=B * heads, zdiv=heads)
     # delta = sum_k P dP from the very dP the rows are corrected with (not dO . O: see softmax_f32_bwd_rows_kernel)
-    delta = T.softmax_backward_rows_(S, dP, B * heads * L, Lk, Lkp, lse, round_out=True)
+    delta = T.softmax_backward_rows_(S, dP, B * heads * L, Lk, Lkp, lse, round_out=True, write_p=False)  # P is not used again here
     kT = T.transpose(k, Lk, C, batch=B, ld_out=Lkp)  # [B, C, Lkp]
     dq = _empty(B, L, C, like=xn)
     T.gemm(hv.scores(dP, L, Lkp), hv.act_T(kT, Lkp), L, d, Lk, hv.act(dq, L), batch=B * heads, zdiv=heads, alpha=scale,

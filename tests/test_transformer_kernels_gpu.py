@@ -112,6 +112,9 @@ def test_transpose_layernorm_softmax_gelu_colsum_shuffle():
         dl = T.softmax_backward_rows_(X, Y, rows, cols, ld, lse)
         assert _rel(dl, delta) < 1e-5 and _rel(X[:, :cols], ref) < 1e-5 and _rel(Y[:, :cols], ref_ds) < 1e-4
         assert float(Y[:, :cols].sum(-1).abs().max()) < 1e-5  # rows of dS sum to zero
+        X2, Y2 = s.clone(), dP.clone()
+        T.softmax_backward_rows_(X2, Y2, rows, cols, ld, lse, write_p=False)
+        assert torch.equal(X2, s) and torch.equal(Y2, Y)
     # column-indexed statistics on the transposed scores
     Z, R, Cc = 2, 40, 64
     s = torch.randn(Z, R, Cc, device="cuda", generator=g)
