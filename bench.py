@@ -93,18 +93,57 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons sampled every 200 ms during the timed region. NVML is read in-process from a thread
+    (two driver queries per sample); the `nvidia-smi -lms` subprocess this replaces takes a driver-wide lock for tens of
+    milliseconds per sample, which showed up as 65 ms host stalls in the end-to-end leg and as 10-15 ms per step on the
+    host-paced C4 workload (step times without a sampler: 66.1-70.4 ms, tools/step_times.py). nvidia-smi stays as the
+    fallback when NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index: int):
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         self.gpu = gpu_index
+        self.thread = None
+        self.samples = []  # (sm_mhz, reasons bitmask)
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
 
     def start(self):
+        import threading
+
+        try:
+            nv, h = self._nvml_handle()
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.stop_flag = threading.Event()
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons_fn(h))))
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(0.2)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                           str(self.gpu), "-lms", "200"], stdout=open(self.path, "w"),
@@ -113,6 +152,15 @@ class ClockSampler:
             self.proc = None
 
     def stop(self) -> dict:
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            sm = sorted(v for v, _ in self.samples)
+            mask = 0
+            for _, m in self.samples:
+                mask |= m
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max,
+                    "reasons": sorted(k for k, b in self.BITS.items() if mask & b), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -136,7 +184,7 @@ class ClockSampler:
         os.unlink(self.path)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------- CPU baseline
@@ -367,14 +415,21 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
                       device=job.dev, dtype=torch.float64)
 
     h2d = d2h = 0
-    sync_all()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
     # The loss of step i is copied to pinned host memory asynchronously and read on the host one step later (after
     # step i+1 has been enqueued), the way a logging trainer consumes it: every step still pays its H2D inputs and a
     # D2H result, but the host never drains the GPU queue between steps.
     loss_pinned = torch.empty(2, dtype=torch.float32).pin_memory()
     loss_events = [torch.cuda.Event(), torch.cuda.Event()]
+    # one untimed step through exactly this path: the first pinned allocation / first D2H read of a process cost 97 ms of
+    # host time on a fresh box (page-ins), which landed in step 0 of the timed leg
+    loss = job.step(job.to_device(job.host_batch()))
+    loss_pinned[0].copy_(loss.detach(), non_blocking=True)
+    loss_events[0].record()
+    loss_events[0].synchronize()
+    float(loss_pinned[0])
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
     losses_host = []
     host_s = host_max = 0.0
     for i in range(args.steps):

@@ -7,7 +7,9 @@
 // Forward: rolled 16-level encode into a per-warp tile + register-tiled hidden layers (render_tape.cuh), optional
 // tape of the encodings. Backward: the tape-based field backward of render_bwd2.cu generalised to per-prompt
 // weights: hidden recompute, dE = dH W1^T, dW1 += E^T dH, dW2 += H^T d out, trilinear scatter into the table gradient.
-#include "render_tape.cuh"
+#include <cstdlib>
+
+#include "field_bwd_tc.cuh"
 
 namespace {
 
@@ -416,6 +418,128 @@ hyper_field_bwd_kernel(const __grid_constant__ GridMeta gm, const HfArgs a) {
   if (cur_b >= 0) flush(cur_b);
 }
 
+// The same backward with the contractions on the tensor cores (field_bwd_tc.cuh: mma.sync tf32, 3xTF32 for the hidden
+// recompute) and the lane-pair scatter reading dE from shared memory; the default. Per-prompt weights are re-staged
+// (transposed to [hidden][feature]) and the register accumulators flushed whenever a CTA crosses a prompt boundary.
+__global__ void __launch_bounds__(fbtc::kTcThreads, 2)
+hyper_field_bwd_tc_kernel(const __grid_constant__ GridMeta gm, const HfArgs a) {
+  using namespace fbtc;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int hb = warp * 16;
+  const int tiles_per_b = a.n_pad / kTcTile;
+  const int total = a.B * tiles_per_b;
+  float2* g_table = reinterpret_cast<float2*>(a.g_table);
+  const bool has0 = a.w1a != nullptr && a.d_a != nullptr, has1 = a.w1b != nullptr && a.d_b != nullptr;
+
+  float accw1[2][2][2][4];  // [net][feature block of 16][hidden block of 8][c]: dW1^T[e][h]
+  float accw2[2][2][4];     // [net][hidden block of 8][c]: dW2^T[o][h], rows o = gq
+  auto zero_acc = [&]() {
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          accw1[q][0][b][c] = accw1[q][1][b][c] = 0.f;
+          accw2[q][b][c] = 0.f;
+        }
+  };
+  zero_acc();
+
+  // weight gradients of prompt b: registers -> global (dW1 is [feature][hidden], dW2a [hidden], dW2b [hidden][3])
+  auto flush = [&](int b) {
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      if (!(net == 0 ? has0 : has1)) continue;
+      float* gw1 = (net == 0 ? a.g_w1a : a.g_w1b) + (size_t)b * kWpSize;
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int e = 16 * mb + gq + 8 * (c >> 1), h = hb + 8 * nb + 2 * tq + (c & 1);
+            atomicAdd(gw1 + e * kHidden + h, accw1[net][mb][nb][c]);
+          }
+      if (gq < (net == 0 ? 1 : 3)) {
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int h = hb + 8 * nb + 2 * tq + c;
+            if (net == 0) atomicAdd(a.g_w2a + (size_t)b * kHidden + h, accw2[0][nb][c]);
+            else atomicAdd(a.g_w2b + (size_t)b * 3 * kHidden + h * 3 + gq, accw2[1][nb][c]);
+          }
+      }
+    }
+    zero_acc();
+  };
+
+  auto issue_tile = [&](int tile, int buf) {
+    const int b = tile / tiles_per_b, t = tile - b * tiles_per_b;
+    const float* src = a.tape + ((size_t)b * a.n_pad + (size_t)t * kTcTile) * kEncDim;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int q = tid + kTcThreads * r;
+      const int sub = q >> 8, k = (q & 255) >> 3, s4 = q & 7;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s.et[sub][k * kTcEt + s4 * 4]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)q * 4) : "memory");
+    }
+    const int i = t * kTcTile + tid;
+    const int valid = i < a.N ? 4 : 0;
+    const size_t pi = (size_t)b * a.N + (i < a.N ? i : 0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s.pos[buf][c][tid]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(a.pts + pi * 3 + c), "r"(valid)
+                   : "memory");
+    }
+    {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s.dout[buf][0][tid]);
+      const float* sp = a.d_a ? a.d_a + pi : a.pts;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(sp), "r"(a.d_a ? valid : 0)
+                   : "memory");
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s.dout[buf][1 + c][tid]);
+      const float* sp = a.d_b ? a.d_b + pi * 3 + c : a.pts;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(sp), "r"(a.d_b ? valid : 0)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0, cur_b = -1;
+  if ((int)blockIdx.x < total) issue_tile(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, buf ^= 1) {
+    const int b = tile / tiles_per_b, t = tile - b * tiles_per_b;
+    if (b != cur_b) {
+      if (cur_b >= 0) flush(cur_b);
+      // (every warp is past the last barrier of the previous tile's contractions: nobody reads the old weights any more)
+      for (int i = tid; i < kWpSize; i += kTcThreads) {
+        const int e = i >> 6, h = i & 63;  // w1 [feature][hidden]
+        if (a.w1a) s.w1[0][h * kTcW1 + e] = a.w1a[(size_t)b * kWpSize + i];
+        if (a.w1b) s.w1[1][h * kTcW1 + e] = a.w1b[(size_t)b * kWpSize + i];
+      }
+      if (a.w1a)
+        for (int i = tid; i < kHidden; i += kTcThreads) s.w2d[i] = a.w2a[(size_t)b * kHidden + i];
+      if (a.w1b)
+        for (int i = tid; i < 3 * kHidden; i += kTcThreads) s.w2f[(i % 3) * kHidden + i / 3] = a.w2b[(size_t)b * 3 * kHidden + i];
+      cur_b = b;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    contract_tile(s, buf, warp, lane, has0, has1, accw1, accw2);
+    if (tile + (int)gridDim.x < total) issue_tile(tile + gridDim.x, buf ^ 1);
+    scatter_tile(gm, g_table, s, buf, warp, lane, a.N - t * kTcTile, 0xffff, nullptr, 0, 0, 1);
+  }
+  if (cur_b >= 0) flush(cur_b);
+}
+
 }  // namespace
 
 int launch_hyper_field_fwd(const GridMeta& gm, const float* table, const float* pts, int B, int N, const float* w1a,
@@ -446,6 +570,9 @@ int launch_hyper_field_bwd(const GridMeta& gm, const float* pts, int B, int N, c
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(hyper_field_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(HfBwdSmem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(hyper_field_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(fbtc::TcSmem));
     if (e != cudaSuccess) {
       sdb_set_error("hyper_field_bwd: smem attribute: %s", cudaGetErrorString(e));
       return SDB_ERR_CUDA;
@@ -459,7 +586,10 @@ int launch_hyper_field_bwd(const GridMeta& gm, const float* pts, int B, int N, c
   a.d_a = d_a, a.d_b = d_b, a.g_table = g_table, a.g_w1a = g_w1a, a.g_w2a = g_w2a, a.g_w1b = g_w1b, a.g_w2b = g_w2b;
   const int total = B * (a.n_pad / kHfTile);
   const int grid = max(1, min(kNumSMs * 2, total));
-  hyper_field_bwd_kernel<<<grid, kHfThreads, sizeof(HfBwdSmem), stream>>>(gm, a);
+  // tensor-core contractions by default; SDB_HF_TC=0 selects the fp32 CUDA-core kernel (the cross-check)
+  static const int use_tc = (getenv("SDB_HF_TC") && atoi(getenv("SDB_HF_TC")) == 0) ? 0 : 1;
+  if (use_tc) hyper_field_bwd_tc_kernel<<<grid, fbtc::kTcThreads, sizeof(fbtc::TcSmem), stream>>>(gm, a);
+  else hyper_field_bwd_kernel<<<grid, kHfThreads, sizeof(HfBwdSmem), stream>>>(gm, a);
   SDB_COUNT_LAUNCH();
   SDB_CHECK_LAUNCH("hyper_field_bwd");
   return SDB_OK;
