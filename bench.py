@@ -59,27 +59,27 @@ def ncu_traffic():
     if not files:
         return {}
     t = json.load(open(files[-1]))
-    # only a capture of THESE kernels counts: the file carries the hash of the CUDA sources it was taken from
-    # (tools/summarize_profiles.py); anything else reads as null rather than as a stale number
+    # only a capture of THESE kernels counts: the file carries hashes of the CUDA sources each kernel group was built from
+    # (tools/summarize_profiles.py); a group whose sources changed since reads as null rather than as a stale number
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     try:
-        from summarize_profiles import lib_sources_sha
-        if t.get("_lib_sources_sha") != lib_sources_sha():
-            return {}
+        from summarize_profiles import SOURCE_GROUPS, lib_sources_sha
+        shas = t.get("_group_sources_sha", {})
+        ok = {g: shas.get(g) == lib_sources_sha(g) for g in SOURCE_GROUPS}
     except Exception:
         return {}
     out = {}
     fam = [t[k] for k in ("gemm", "flash_attn") if k in t]
-    if fam:
+    if fam and ok["tensor"]:
         n = sum(f["launches_per_step"] for f in fam)
         out["tensor"] = sum(f["dram_bytes_per_launch"] * f["launches_per_step"] for f in fam) / n
-    if "render_fwd" in t:
+    if "render_fwd" in t and ok["render"]:
         out["render_fwd"] = t["render_fwd"]["dram_bytes_per_launch"]
-    if "render_field_bwd" in t:
+    if "render_field_bwd" in t and ok["render"]:
         out["render_bwd"] = t["render_field_bwd"]["dram_bytes_per_launch"] + t.get("render_composite_bwd", {}).get(
             "dram_bytes_per_launch", 0.0)
     for k in ("hyper_field_fwd", "hyper_field_bwd"):
-        if k in t:
+        if k in t and ok["hyper_field"]:
             out[k] = t[k]["dram_bytes_per_launch"]
     return out
 

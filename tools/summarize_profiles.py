@@ -14,22 +14,38 @@ TAG = sys.argv[1] if len(sys.argv) > 1 else "r1f"
 SRC, DST = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 FAMILIES = [("gemm", "gemm_f16_kernel"), ("flash_attn", "flash_attn_f16_kernel"), ("render_fwd", "render_nerf_fwd2_kernel"),
-            ("render_field_bwd", "render_field_bwd_kernel"), ("render_composite_bwd", "render_composite_bwd_kernel"),
+            ("render_field_bwd", "render_field_bwd"), ("render_composite_bwd", "render_composite_bwd_kernel"),
             ("groupnorm", "gn_"), ("render_orient_fwd", "render_orient_fwd_kernel"),
             ("render_orient_bwd", "render_orient_bwd_kernel"), ("hyper_field_fwd", "hyper_field_fwd_kernel"),
-            ("hyper_field_bwd", "hyper_field_bwd_kernel"), ("volsdf", "volsdf_")]
+            ("hyper_field_bwd", "hyper_field_bwd"), ("volsdf", "volsdf_"), ("gemm_tf32", "gemm_tf32_kernel"),
+            ("softmax_f32", "softmax_f32_")]
 
 
-def lib_sources_sha() -> str:
-    """Hash of the CUDA sources the library is built from: bench.py only reports `roofline.traffic` from a capture whose
-    hash equals the one of the sources it runs (a stale capture reads as null instead of a wrong number)."""
+# CUDA sources each group of kernel families is built from: a capture counts for a group only while these files are
+# unchanged (editing the transformer kernels does not invalidate the render or tensor numbers)
+SOURCE_GROUPS = {
+    "tensor": ["gemm_sm100.cu", "flash_attn_sm100.cu", "ptx_sm100.cuh", "dense.h", "common.cuh"],
+    "render": ["render_fwd2.cu", "render_bwd2.cu", "render_bwd_tc.cu", "field_bwd_tc.cuh", "render_tape.cuh",
+               "render_types.cuh", "field.cuh", "common.cuh"],
+    "hyper_field": ["hyper_field.cu", "field_bwd_tc.cuh", "render_tape.cuh", "render_types.cuh", "field.cuh", "common.cuh"],
+}
+
+
+def lib_sources_sha(group: str = None) -> str:
+    """Hash of the CUDA sources a group of kernels is built from (all sources when group is None): bench.py only reports
+    `roofline.traffic` from a capture whose hash equals the one of the sources it runs (a stale capture reads as null
+    instead of a wrong number)."""
     import glob
     import hashlib
 
+    base = os.path.join(ROOT, "scaledreamer_b200", "csrc")
+    if group is None:
+        files = sorted(glob.glob(os.path.join(base, "*.cu")) + glob.glob(os.path.join(base, "*.cuh")) +
+                       glob.glob(os.path.join(base, "*.h")))
+    else:
+        files = [os.path.join(base, f) for f in SOURCE_GROUPS[group]]
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "scaledreamer_b200", "csrc", "*.cu")) +
-                    glob.glob(os.path.join(ROOT, "scaledreamer_b200", "csrc", "*.cuh")) +
-                    glob.glob(os.path.join(ROOT, "scaledreamer_b200", "csrc", "*.h"))):
+    for f in files:
         h.update(os.path.basename(f).encode())
         h.update(open(f, "rb").read())
     return h.hexdigest()[:16]
@@ -107,7 +123,8 @@ def main():
                 fam[key] = {"launches_per_step": len(sel), "ms_per_step_under_ncu": round(sum(d["ms"] for d in sel), 4),
                             "share_of_step": round(sum(d["ms"] for d in sel) / total, 4),
                             "dram_bytes_per_launch": round(sum(d["rd"] + d["wr"] for d in sel) / len(sel), 1)}
-        for extra, label in (("c4", "C4"), ("orient", "C2 with lambda_orient = 100, render kernels only")):
+        for extra, label in (("c4", "C4"), ("orient", "C2 with lambda_orient = 100, render kernels only"),
+                             ("generator", "Triplane-Transformer generator, 2 of 12 blocks, 4 prompts, forward + backward")):
             pe = os.path.join(SRC, f"{TAG}_{extra}_step_traffic.csv")
             if not os.path.exists(pe):
                 continue
@@ -123,6 +140,7 @@ def main():
                                 "workload": label}
         fam["_source"] = f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one step of tools/profile_step.py ({TAG})"
         fam["_lib_sources_sha"] = lib_sources_sha()
+        fam["_group_sources_sha"] = {g: lib_sources_sha(g) for g in SOURCE_GROUPS}
         json.dump(fam, open(os.path.join(DST, f"{TAG}_traffic.json"), "w"), indent=1)
         print("one step:", len(ls), "launches,", f"{total:.1f} ms under ncu")
         print(json.dumps(fam, indent=1))
