@@ -22,7 +22,8 @@ METRICS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_p
 
 def short(name):
     name = re.sub(r"\(.*", "", name)
-    return re.sub(r"^(void )?((dense::)?(<unnamed>|\(anonymous namespace\))::)*", "", name)[:80]
+    name = re.sub(r"^(void )?((dense::)?(<unnamed>|\(anonymous namespace\))::)*", "", name)
+    return re.sub(r"^(void )?unnamed>::", "", name)[:80]  # ncu prints `dense::<unnamed>::f<...>` as `unnamed>::f<...>`
 
 
 out = [["capture", "kernel"] + METRICS]

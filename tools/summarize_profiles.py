@@ -69,7 +69,8 @@ def to_bytes(v, unit):
 
 def short(name):
     name = re.sub(r"\(.*", "", name)
-    return re.sub(r"^(void )?((dense::)?(<unnamed>|\(anonymous namespace\))::)*", "", name)[:80]
+    name = re.sub(r"^(void )?((dense::)?(<unnamed>|\(anonymous namespace\))::)*", "", name)
+    return re.sub(r"^(void )?unnamed>::", "", name)[:80]  # ncu prints `dense::<unnamed>::f<...>` as `unnamed>::f<...>`
 
 
 def launches(path):
