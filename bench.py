@@ -577,7 +577,7 @@ def rooflines(job: Job, prof: dict, pk: dict):
 
     if "render_samples_kept" in prof:  # NeRF path: samples x 16 levels x 8 corners x 2 features x 4 B, E = 1
         ns = prof["render_samples_kept"]
-        roofs.append(hbm("render_composite_bwd_kernel + render_field_bwd_kernel (tape backward)",
+        roofs.append(hbm("render_composite_bwd_kernel + render_field_bwd_tc_kernel (tape backward)",
                          (2 * ns * 1024 + n_rays * 52) / 1e9, prof["render_bwd_kernel_ms"], tr.get("render_bwd")))
         roofs.append(hbm("render_bg_kernel + render_nerf_fwd2_kernel (march + encode + MLPs + composite + tape)",
                          (ns * 1024 + n_rays * 52) / 1e9, prof["render_fwd_kernel_ms"], tr.get("render_fwd")))
