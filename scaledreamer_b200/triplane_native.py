@@ -20,7 +20,7 @@ Supported variant: `local_text: true` (ConditionModulationBlock: cross-attention
 the C5 yaml selects (configs/multi-prompt_benchmark/asd_mv_triplane_transformer_10k.yaml:52)."""
 from __future__ import annotations
 
-from typing import List, Sequence
+from typing import List
 
 import torch
 
