@@ -8,6 +8,8 @@
 // tile is written back over it (unit-major) -> layer 2 -> ReLU -> layer 3 by a reduce-scatter.
 // Backward (128-row CTA tiles): hidden recompute with ReLU masks, dH2 = mask2 * W3^T dY, dH1 = mask1 * dH2 W2,
 // dX = dH1 W1, and the three weight gradients as CTA-level register tiles accumulated across tiles.
+#include <cstdlib>
+
 #include "../../include/sdb200.h"
 #include "render_tape.cuh"
 
@@ -360,6 +362,12 @@ size_t bwd_smem(int D, int k) {
 
 }  // namespace
 
+// mlp3_tc.cu: the same forward on the tensor cores (3xTF32), the default
+int launch_mlp3_fwd_tc(const float* x, long long n, int D, const float* w1, const float* w2, const float* w3, int n_out,
+                       float* y, cudaStream_t s);
+int launch_mlp3_bwd_tc(const float* x, long long n, int D, const float* w1, const float* w2, const float* w3, int n_out,
+                       const float* dy, float* dx, int accumulate, float* g_w1, float* g_w2, float* g_w3, cudaStream_t s);
+
 extern "C" {
 
 int sdb_mlp3_forward(const float* x, long long n, int d_in, const float* w1, const float* w2, const float* w3,
@@ -368,6 +376,8 @@ int sdb_mlp3_forward(const float* x, long long n, int d_in, const float* w1, con
   SDB_CHECK_ARG(d_in >= 8 && d_in <= 96 && d_in % 8 == 0, "mlp3: d_in must be a multiple of 8 in [8, 96]");
   SDB_CHECK_ARG(n_out == 1 || n_out == 3, "mlp3: n_out must be 1 or 3");
   if (n == 0) return SDB_OK;
+  static const int use_tc = (getenv("SDB_MLP3_TC") && atoi(getenv("SDB_MLP3_TC")) == 0) ? 0 : 1;
+  if (use_tc) return launch_mlp3_fwd_tc(x, n, d_in, w1, w2, w3, n_out, y, (cudaStream_t)stream);
   const size_t smem = fwd_smem(d_in, n_out);
   const long long tiles = (n + kTile - 1) / kTile;
   const int grid = (int)(tiles < 2LL * kNumSMs ? tiles : 2LL * kNumSMs);
@@ -392,6 +402,9 @@ int sdb_mlp3_backward(const float* x, long long n, int d_in, const float* w1, co
   SDB_CHECK_ARG(d_in >= 8 && d_in <= 96 && d_in % 8 == 0, "mlp3: d_in must be a multiple of 8 in [8, 96]");
   SDB_CHECK_ARG(n_out == 1 || n_out == 3, "mlp3: n_out must be 1 or 3");
   if (n == 0) return SDB_OK;
+  static const int use_tc = (getenv("SDB_MLP3_TC") && atoi(getenv("SDB_MLP3_TC")) == 0) ? 0 : 1;
+  if (use_tc)
+    return launch_mlp3_bwd_tc(x, n, d_in, w1, w2, w3, n_out, d_y, d_x, accumulate_dx, g_w1, g_w2, g_w3, (cudaStream_t)stream);
   const size_t smem = bwd_smem(d_in, n_out);
   const long long tiles = (n + kTile - 1) / kTile;
   const int grid = (int)(tiles < (long long)kNumSMs ? tiles : (long long)kNumSMs);

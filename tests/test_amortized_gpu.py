@@ -391,12 +391,16 @@ def test_tiny_mlp_forward_backward(cuda_device, n, d_in, k):
     assert rel_l2(y.detach().cpu().double(), ref.detach()) < 1e-5
     (y * go.float().to(cuda_device)).sum().backward()
     # A pre-activation within fp32 rounding of zero flips its ReLU mask against the fp64 oracle and changes that ROW's
-    # gradient by O(1): all but a handful of rows must agree to 1e-4, the whole to 5e-3.
+    # gradient by O(1): all but a handful of rows must agree to the row bound, the whole to 5e-3. The default kernels run
+    # the gradient products on tf32 operands (2^-11 operand rounding; the hidden recompute is 3xTF32, so the masks are the
+    # forward's): row bound 2e-3, weight gradients 1e-3. SDB_MLP3_TC=0 (the fp32 CUDA-core kernels) keeps 1e-4 / 1e-4.
+    tc = os.environ.get("SDB_MLP3_TC", "1") != "0"
+    row_tol, w_tol = (2e-3, 1e-3) if tc else (1e-4, 1e-4)
     row_err = (xd.grad.cpu().double() - x.grad).norm(dim=1) / x.grad.norm(dim=1).clamp_min(1e-12)
-    assert (row_err > 1e-4).sum().item() <= max(2, n // 2000), row_err.max()
+    assert (row_err > row_tol).sum().item() <= max(2, n // 2000), row_err.max()
     assert rel_l2(xd.grad.cpu().double(), x.grad) < 5e-3
     for a, b in zip(wd, ws):
-        assert rel_l2(a.grad.cpu().double(), b.grad) < (1e-4 if n <= 1000 else 5e-3)
+        assert rel_l2(a.grad.cpu().double(), b.grad) < (w_tol if n <= 1000 else 5e-3)
 
 
 def test_tiny_mlp_accumulates_input_gradient(cuda_device):
