@@ -384,6 +384,12 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # the sampler starts BEFORE the warm-up: the first NVML queries of a process take tens of milliseconds with a driver
+    # lock held (one run in three showed 97 ms of stalled launches at the start of the timed region otherwise); its
+    # samples are discarded when the timed region begins
+    clocks = ClockSampler(job.dev.index or 0)
+    if sample_clocks:
+        clocks.start()
     for _ in range(args.warmup):
         job.step(job.to_device(job.host_batch()))
     sync_all()
@@ -395,9 +401,7 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
     import gc
     gc.collect()
     gc.disable()
-    clocks = ClockSampler(job.dev.index or 0)
-    if sample_clocks:
-        clocks.start()
+    clocks.samples.clear()
     n0 = L.launch_count()
     job.marks = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
