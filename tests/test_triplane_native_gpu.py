@@ -88,6 +88,27 @@ def test_c5_width_generator_forward_backward(cuda_device):
     _compare(cfg, 2, cuda_device, 1e-3, 3e-3)
 
 
+def test_generator_step_is_bitwise_reproducible(cuda_device):
+    """No atomics anywhere in the generator: every reduction (LayerNorm / bias / position-embedding gradients, split
+    weight-gradient products, softmax statistics) has a fixed order, so two runs on the same inputs agree bit for bit."""
+    cfg = {"inner_dim": 128, "condition_dim": 1024, "triplane_low_res": 8, "triplane_high_res": 16, "triplane_dim": 32,
+           "num_layers": 2, "num_heads": 4, "flash_attention": False, "local_text": True}
+    gen = _build(cfg, cuda_device)
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    emb = torch.randn(3, 77, 1024, device=cuda_device, generator=g)
+    d = torch.randn(3, 3, 32, 16, 16, device=cuda_device, generator=g)
+    runs = []
+    for _ in range(2):
+        for p in gen.parameters():
+            p.grad = None
+        out = gen(emb)
+        out.backward(d)
+        runs.append((out.detach().clone(), [p.grad.clone() for p in gen.parameters()]))
+    assert torch.equal(runs[0][0], runs[1][0])
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert torch.equal(a, b)
+
+
 def test_no_torch_kernels_between_embeddings_and_planes(cuda_device):
     """Every kernel of the generator's forward + backward is this library's: the profiler sees no at:: / cuBLAS / SDPA
     kernel apart from the loss the test itself builds."""
