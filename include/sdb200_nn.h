@@ -113,7 +113,7 @@ typedef struct sdb_net sdb_net;
  * (configs/multi-prompt_benchmark/asd_mv_triplane_transformer_10k.yaml:127); here every contraction is
  * sdb_gemm_tf32 (tcgen05 kind::tf32, fp32 accumulate) and the rest are the fp32 kernels below. */
 typedef struct {
-  const float* A;              /* [M, K] rows `lda` floats apart (multiple of 4) */
+  const float* A;              /* [M, K] rows `lda` floats apart (multiple of 4); with a_mn_major: stored [K, M] */
   long long lda, a_zs_hi, a_zs_lo; /* batch strides in floats; 0 = shared along that batch coordinate */
   const float* B;              /* [N, K] */
   long long ldb, b_zs_hi, b_zs_lo;
@@ -127,6 +127,7 @@ typedef struct {
   float alpha;
   int act;                     /* SDB_ACT_NONE | SDB_ACT_GELU */
   int round_out;               /* 1: results are rounded to the nearest tf32 (outputs that only feed further GEMMs) */
+  int a_mn_major;              /* 1: A is given transposed, [K rows][M] with lda floats between K rows: out = A^T-free A B^T */
 } sdb_gemm_tf32_args;
 /* out = act(alpha * A B^T + bias) + residual, fp32 in / out, tf32 products. K, M, N need no padding.
  * The tensor core IGNORES the low 13 mantissa bits of its fp32 operands (truncation, a bias that compounds through

@@ -9,7 +9,7 @@ extern "C" {
 int sdb_gemm_tf32(const sdb_gemm_tf32_args* a, void* stream) {
   SDB_CHECK_ARG(a && a->A && a->B && a->out, "gemm_tf32: NULL argument");
   SDB_CHECK_ARG((a->ldc & 3) == 0 || a->N < 4, "gemm_tf32: ldc=%lld should be a multiple of 4", a->ldc);
-  Tf32Operand A{a->A, a->lda, a->a_zs_hi, a->a_zs_lo}, B{a->B, a->ldb, a->b_zs_hi, a->b_zs_lo};
+  Tf32Operand A{a->A, a->lda, a->a_zs_hi, a->a_zs_lo, a->a_mn_major}, B{a->B, a->ldb, a->b_zs_hi, a->b_zs_lo, 0};
   Tf32Epilogue ep;
   ep.bias = a->bias;
   ep.residual = a->residual;

@@ -130,6 +130,9 @@ int profile_end(double* ms, double* flops, int* launches);
 struct Tf32Operand {
   const float* ptr;
   long long ld, zs_hi, zs_lo;
+  // A only: the matrix is stored TRANSPOSED, [K rows][M] with `ld` floats between K rows (M contiguous): the product
+  // reads A^T without a transpose pass (MN-major shared-memory tiles). dV = P^T dO and dK = dS^T Q of the attention backward.
+  int mn_major = 0;
 };
 struct Tf32Epilogue {
   const float* bias = nullptr;      // [N]

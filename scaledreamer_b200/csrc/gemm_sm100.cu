@@ -832,7 +832,9 @@ int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
   CUresult r = enc(out, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, b, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
-                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                   : swizzle_bytes == 12832 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B  /* 128-byte swizzle, 32-byte atoms */
+                                         : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

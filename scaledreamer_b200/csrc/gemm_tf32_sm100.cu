@@ -47,6 +47,7 @@ struct Tf32Params {
   int M, N, K, num_k_blocks;
   int zdiv;
   int a_hi, a_lo, b_hi, b_lo;  // 1: the operand is indexed along that batch coordinate
+  int a_mn;                    // A is stored [K][M] (M contiguous): MN-major tiles, four 32-wide M chunks per k-block
   float* out;
   long long ldc, out_zs_hi, out_zs_lo;
   const float* bias;
@@ -118,7 +119,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mbar_wait(&empty[s], ph ^ 1u);
           ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
           uint8_t* sa = base + s * C::kStage;
-          ptx::tma_load_4d(sa, &tmA, &full[s], kb * kBKf, m0, a2, a3);
+          if (p.a_mn) {  // [32 K rows][32 M floats] boxes: chunk c holds M = m0 + 32 c .. + 31, 4 KB each
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ptx::tma_load_4d(sa + c * 4096, &tmA, &full[s], m0 + 32 * c, kb * kBKf, a2, a3);
+          } else {
+            ptx::tma_load_4d(sa, &tmA, &full[s], kb * kBKf, m0, a2, a3);
+          }
           ptx::tma_load_4d(sa + kATile, &tmB, &full[s], kb * kBKf, n0, b2, b3);
           if (++s == C::kStages) s = 0, ph ^= 1u;
         }
@@ -126,7 +132,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_tf32(kBM, BN);
+      const uint32_t idesc = ptx::make_idesc_tf32(kBM, BN, p.a_mn);
       int s = 0;
       uint32_t ph = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
@@ -138,11 +144,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(base + s * C::kStage);
-          const uint64_t da = ptx::smem_desc_k_sw128(sa);
+          // MN-major A (stored [K][M]): 32-bit operands transpose only in the "128-byte swizzle, 32-byte atom" layout
+          // (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, descriptor layout type 1): atoms of 4 K rows x 128 bytes, 512 bytes
+          // apart along K (SBO), the 32-wide M chunks 4096 bytes apart (LBO). With the plain 128-byte swizzle (type 2) the
+          // product came back as zeros.
+          const uint64_t da = p.a_mn ? ptx::smem_desc_mn_sw128(sa, 4096, 1, 512) : ptx::smem_desc_k_sw128(sa);
           const uint64_t db = ptx::smem_desc_k_sw128(sa + kATile);
 #pragma unroll
           for (int k = 0; k < kBKf / 8; ++k)  // 8 tf32 = 32 bytes further along the swizzled row
-            ptx::umma_tf32(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_tf32(tmem_acc, da + (uint64_t)(p.a_mn ? k * 64 : k * 2), db + (uint64_t)(k * 2), idesc,
+                           (kb | k) != 0 ? 1u : 0u);  // 8 K rows further: 1024 bytes (MN-major) or 32 bytes along the row
           ptx::umma_commit(&empty[s]);
           if (++s == C::kStages) s = 0, ph ^= 1u;
         }
@@ -280,7 +291,7 @@ int operand_map(CUtensorMap* tm, const Tf32Operand& o, int rows, int K, int z_hi
   uint64_t dims[4] = {(uint64_t)K, (uint64_t)rows, (uint64_t)(*use_lo ? z_lo : 1), (uint64_t)(*use_hi ? z_hi : 1)};
   uint64_t strides[3] = {(uint64_t)o.ld * 4, *use_lo ? (uint64_t)o.zs_lo * 4 : dflt, *use_hi ? (uint64_t)o.zs_hi * 4 : dflt};
   uint32_t box[4] = {(uint32_t)kBKf, (uint32_t)box_rows, 1, 1};
-  return make_tmap(tm, o.ptr, 4, dims, strides, box, 128, 1);
+  return make_tmap(tm, o.ptr, 4, dims, strides, box, o.mn_major ? 12832 : 128, 1);
 }
 
 template <int BN>
@@ -324,7 +335,9 @@ int gemm_tf32(const Tf32Operand& A, const Tf32Operand& B, int M, int N, int K, f
   p.alpha = ep.alpha, p.act = ep.act, p.round_out = ep.round_out;
   p.tiles_m = (M + kBM - 1) / kBM, p.tiles_n = (N + bn - 1) / bn, p.tiles_z = batch;
   CUtensorMap ta, tb;
-  int rc = operand_map(&ta, A, M, K, batch / zdiv, zdiv, kBM, &p.a_hi, &p.a_lo, "A");
+  p.a_mn = A.mn_major ? 1 : 0;
+  int rc = A.mn_major ? operand_map(&ta, A, K, M, batch / zdiv, zdiv, kBKf, &p.a_hi, &p.a_lo, "A (MN-major)")
+                      : operand_map(&ta, A, M, K, batch / zdiv, zdiv, kBM, &p.a_hi, &p.a_lo, "A");
   if (rc) return rc;
   rc = operand_map(&tb, B, N, K, batch / zdiv, zdiv, bn, &p.b_hi, &p.b_lo, "B");
   if (rc) return rc;

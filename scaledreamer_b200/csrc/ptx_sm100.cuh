@@ -165,13 +165,14 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
 
 // MN-major operand tile: rows of K, each 128 bytes = 64 contiguous MN elements, 8 K-rows per swizzle group
 // (1024 bytes, SBO); successive 64-wide MN chunks are `lbo_bytes` apart.
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t layout_type = 2,
+                                                       uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B with 32-byte atoms (MN-major 32-bit operands)
   return d;
 }
 
@@ -181,9 +182,10 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int ab_fmt, 
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// Instruction descriptor for kind::tf32: fp32 accumulate, A/B format 2 (tf32), both K-major.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// Instruction descriptor for kind::tf32: fp32 accumulate, A/B format 2 (tf32), B K-major, A K-major or MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, int a_mn_major = 0) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 
 }  // namespace ptx

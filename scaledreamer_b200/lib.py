@@ -66,7 +66,8 @@ class GemmTf32ArgsC(C.Structure):
                 ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int), ("zdiv", C.c_int),
                 ("out", C.c_void_p), ("ldc", C.c_longlong), ("out_zs_hi", C.c_longlong), ("out_zs_lo", C.c_longlong),
                 ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_longlong), ("res_zs_hi", C.c_longlong),
-                ("res_zs_lo", C.c_longlong), ("alpha", C.c_float), ("act", C.c_int), ("round_out", C.c_int)]
+                ("res_zs_lo", C.c_longlong), ("alpha", C.c_float), ("act", C.c_int), ("round_out", C.c_int),
+                ("a_mn_major", C.c_int)]
 
 
 class UNetCfgC(C.Structure):

@@ -34,9 +34,10 @@ def mat(t: torch.Tensor) -> Operand:
 
 def gemm(A: Operand, B: Operand, M: int, N: int, K: int, out: Operand, batch: int = 1, zdiv: int = 1,
          bias: Optional[torch.Tensor] = None, residual: Optional[Operand] = None, alpha: float = 1.0,
-         act: int = ACT_NONE, round_out: bool = False) -> None:
+         act: int = ACT_NONE, round_out: bool = False, a_mn_major: bool = False) -> None:
     """out[z] = act(alpha * A[z] B[z]^T + bias) + residual[z]; z = hi * zdiv + lo < batch. round_out: the result is
-    written rounded to the nearest tf32 (for tensors that only feed further GEMMs; the tensor core truncates otherwise)."""
+    written rounded to the nearest tf32 (for tensors that only feed further GEMMs; the tensor core truncates otherwise).
+    a_mn_major: A is handed over TRANSPOSED, [K rows][M] with A.ld floats between K rows (no transpose pass)."""
     a = L.GemmTf32ArgsC()
     a.A, a.lda, a.a_zs_hi, a.a_zs_lo = A.ptr, A.ld, A.zs_hi, A.zs_lo
     a.B, a.ldb, a.b_zs_hi, a.b_zs_lo = B.ptr, B.ld, B.zs_hi, B.zs_lo
@@ -46,6 +47,7 @@ def gemm(A: Operand, B: Operand, M: int, N: int, K: int, out: Operand, batch: in
     if residual is not None:
         a.residual, a.ldr, a.res_zs_hi, a.res_zs_lo = residual.ptr, residual.ld, residual.zs_hi, residual.zs_lo
     a.alpha, a.act, a.round_out = alpha, act, 1 if round_out else 0
+    a.a_mn_major = 1 if a_mn_major else 0
     L.check(L.load().sdb_gemm_tf32(a, L.stream_ptr()), "sdb_gemm_tf32")
 
 

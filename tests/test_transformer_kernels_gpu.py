@@ -59,6 +59,22 @@ def test_gemm_tf32_heads_batched():
     assert _rel(O, ref_o) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K,Z", [(128, 48, 64, 1), (200, 48, 300, 3), (77, 48, 3072, 2), (3072, 48, 77, 2)])
+def test_gemm_tf32_mn_major_a(M, N, K, Z):
+    """A handed over transposed ([K rows][M], M contiguous): out = A^T-free product through MN-major shared-memory tiles
+    (dV = P^T dO, dK = dS^T Q of the attention backward read P / dS [q][k] as they are)."""
+    T = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    ldm = (M + 3) // 4 * 4
+    At = torch.randn(Z, K, ldm, device="cuda", generator=g)  # A^T: [K][M]
+    B = torch.randn(Z, N, (K + 3) // 4 * 4, device="cuda", generator=g)
+    out = torch.zeros(Z, M, N, device="cuda")
+    T.gemm(T.Operand(At, ldm, K * ldm), T.Operand(B, B.shape[-1], N * B.shape[-1]), M, N, K, T.Operand(out, N, M * N),
+           batch=Z, a_mn_major=True)
+    ref = torch.einsum("zkm,znk->zmn", At[:, :, :M].double(), B[:, :, :K].double())
+    assert _rel(out, ref) < 2e-3
+
+
 def test_gemm_tf32_shared_weight_batched_output():
     """V^T[b] = W_v ctx[b]^T: A shared by the batch, B batched, one output matrix per prompt."""
     T = _ops()
