@@ -7,8 +7,8 @@ nothing (no gradient-accumulation adds, no permute copies) between the text embe
 Layout: activations are [N prompts, L = 3 * low_res^2 tokens, C] fp32; attention heads are strided views of them
 (row stride C, head stride d, prompt stride L*C) passed to the GEMM as 4-D tensor maps, scores are [N*heads][Lq][Lk]
 fp32 matrices that live only inside one attention call. The backward recomputes the scores and never transposes them:
-P^T and dS^T come from the operand-swapped products S^T = K Q^T, dP^T = V dO^T and the per-query statistics
-(log-sum-exp from the forward, delta = sum_k P dP from the query-major pass).
+dV = P^T dO and dK = dS^T Q hand P / dS to the GEMM as they are ([query][key]) with `a_mn_major`, i.e. the tensor core
+reads its A operand MN-major; delta = sum_k P dP comes from the same pass that turns dP into dS.
 
 Rounding: tcgen05 kind::tf32 ignores the low 13 mantissa bits of its fp32 operands (truncation; measured here as 5x the
 error of torch's tf32 path after two blocks, because the bias compounds through chained GEMMs). Every GEMM operand is
@@ -152,32 +152,28 @@ def _attn_backward(dy, saved, xn, ctx, Wq, Wk, Wv, Wo, heads, self_attn):
     dbo = T.colsum(dy2, M, C)
     dO = _dgrad(T.round_tf32(dy2), Wo, round_out=True).view(B, L, C)
     Lkp, Lp = _ceil4(Lk), _ceil4(L)
-    # query-major: S -> P, dP -> dS, dq = scale * dS k
+    # S -> P, dP -> dS (row form: delta = sum_k P dP from the very dP the rows are corrected with, see
+    # softmax_f32_bwd_rows_kernel), dq = scale * dS k
     S = _empty(B * heads, L, Lkp, like=xn)
     T.gemm(hv.act(q, L), hv.act(k, Lk), L, Lk, d, hv.scores(S, L, Lkp), batch=B * heads, zdiv=heads, alpha=scale)
     dP = _empty(B * heads, L, Lkp, like=xn)
     T.gemm(hv.act(dO, L), hv.act(v, Lk), L, Lk, d, hv.scores(dP, L, Lkp), batch=B * heads, zdiv=heads)
-    # delta = sum_k P dP from the very dP the rows are corrected with (not dO . O: see softmax_f32_bwd_rows_kernel)
-    delta = T.softmax_backward_rows_(S, dP, B * heads * L, Lk, Lkp, lse, round_out=True, write_p=False)  # P is not used again here
+    T.softmax_backward_rows_(S, dP, B * heads * L, Lk, Lkp, lse, round_out=True)
     kT = T.transpose(k, Lk, C, batch=B, ld_out=Lkp)  # [B, C, Lkp]
     dq = _empty(B, L, C, like=xn)
     T.gemm(hv.scores(dP, L, Lkp), hv.act_T(kT, Lkp), L, d, Lk, hv.act(dq, L), batch=B * heads, zdiv=heads, alpha=scale,
            round_out=True)
-    del S, dP, kT
-    # key-major: S^T -> P^T, dP^T -> dS^T, dv = P^T dO, dk = scale * dS^T q
-    ST = _empty(B * heads, Lk, Lp, like=xn)
-    T.gemm(hv.act(k, Lk), hv.act(q, L), Lk, L, d, hv.scores(ST, Lk, Lp), batch=B * heads, zdiv=heads, alpha=scale)
-    dPT = _empty(B * heads, Lk, Lp, like=xn)
-    T.gemm(hv.act(v, Lk), hv.act(dO, L), Lk, L, d, hv.scores(dPT, Lk, Lp), batch=B * heads, zdiv=heads)
-    T.softmax_backward_stats_(ST, dPT, B * heads, Lk, L, Lp, lse, delta, by_col=True, round_out=True)
+    # dv = P^T dO and dk = scale * dS^T q read P / dS [query][key] as they are: the GEMM takes A transposed (MN-major
+    # tiles), so neither the 2.4 GB score matrices nor their gradients are transposed or recomputed key-major
     dOT = T.transpose(dO, L, C, batch=B, ld_out=Lp)
     dv = _empty(B, Lk, C, like=xn)
-    T.gemm(hv.scores(ST, Lk, Lp), hv.act_T(dOT, Lp), Lk, d, L, hv.act(dv, Lk), batch=B * heads, zdiv=heads, round_out=True)
+    T.gemm(hv.scores(S, L, Lkp), hv.act_T(dOT, Lp), Lk, d, L, hv.act(dv, Lk), batch=B * heads, zdiv=heads, round_out=True,
+           a_mn_major=True)
     qT = T.transpose(q, L, C, batch=B, ld_out=Lp)
     dk = _empty(B, Lk, C, like=xn)
-    T.gemm(hv.scores(dPT, Lk, Lp), hv.act_T(qT, Lp), Lk, d, L, hv.act(dk, Lk), batch=B * heads, zdiv=heads, alpha=scale,
-           round_out=True)
-    del ST, dPT, dOT, qT
+    T.gemm(hv.scores(dP, L, Lkp), hv.act_T(qT, Lp), Lk, d, L, hv.act(dk, Lk), batch=B * heads, zdiv=heads, alpha=scale,
+           round_out=True, a_mn_major=True)
+    del S, dP, kT, dOT, qT
     # projections
     xnT = _tr(xn.view(M, C), M, C)
     ctxT = xnT if self_attn else _tr(ctx.view(Mk, Cc), Mk, Cc)
