@@ -615,7 +615,7 @@ def rooflines(job: Job, prof: dict, pk: dict):
             fwd = nl * nb * (6 * lin(L_, Cg, Cg) + 2 * lin(77, Cg, 1024) + 2 * lin(L_, 4 * Cg, Cg)
                              + Hh * 2 * (lin(L_, L_, Cg // Hh) + lin(L_, 77, Cg // Hh)))
             score = nl * nb * Hh * (lin(L_, L_, Cg // Hh) + lin(L_, 77, Cg // Hh))
-            tfl = (3 * fwd + 3 * score) / 1e12  # backward = 2 x forward + S, S^T, dP^T recomputed / extra score-shaped products
+            tfl = (3 * fwd + score) / 1e12  # backward = 2 x forward + the recomputed score product S
             ms_g = calls["sdb_gemm_tf32"]["ms_per_step"]
             roofs.append({"kernel": "gemm_tf32_kernel (Triplane-Transformer generator, forward + backward)", "bound": "tensor",
                           "achieved": tfl / (ms_g / 1e3), "peak": pk["tf_sustained"] / 2, "unit": "TFLOP/s",
