@@ -390,8 +390,12 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
     clocks = ClockSampler(job.dev.index or 0)
     if sample_clocks:
         clocks.start()
-    for _ in range(args.warmup):
+    for w in range(args.warmup):
+        # the last warm-up step also records the per-step timeline events, so that nothing (timing-enabled events, the
+        # all-reduce side stream) is created for the first time inside the timed region
+        job.marks = [] if w == args.warmup - 1 else None
         job.step(job.to_device(job.host_batch()))
+    job.marks = None
     sync_all()
     resident = [job.to_device(job.host_batch()) for _ in range(args.steps)]
     sync_all()
@@ -482,7 +486,11 @@ def timed_regions(job: Job, args, dist, sample_clocks: bool):
                    "optimizer waits on; its time on a rank includes waiting for the slowest rank's backward",
         }
     else:
-        timeline = {"compute_ms_mean_over_ranks": float(tl[:, 0].mean()), "optimizer_ms_mean": float(tl[:, 2].mean())}
+        timeline = {"compute_ms_mean_over_ranks": float(tl[:, 0].mean()), "optimizer_ms_mean": float(tl[:, 2].mean()),
+                    # every step of the timed region (camera-dependent: 18-25 ms on C2); a single step far outside that
+                    # range is a stall of the box, not of the step
+                    "compute_ms_per_step": [round(float(v), 2) for v in tl[:, 0]],
+                    "compute_ms_median": float(tl[:, 0].median())}
     return dict(ms=float(t[0]), ms_e2e=float(t[1]), launches=int(launches), h2d=h2d, d2h=d2h, clocks=clk,
                 timeline=timeline, host_enqueue_ms=1e3 * host_s / args.steps, host_enqueue_ms_max=1e3 * host_max)
 
