@@ -1,6 +1,8 @@
 """Host side of the native Triplane-Transformer (no GPU): the flat parameter list the autograd node works on covers every
 parameter of the state-dict-compatible module exactly once, in the documented order, and the product path refuses to
 run without CUDA instead of falling back to torch."""
+import os
+
 import pytest
 import torch
 
@@ -34,3 +36,22 @@ def test_no_cpu_path():
         gen(torch.randn(1, 77, 1024))
     # the plain-torch restatement (tests' comparison, and the local_text = False variant) does run anywhere
     assert gen.forward_torch(torch.randn(1, 77, 1024)).shape == (1, 3, 32, 16, 16)
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "triplane_generator_golden.pt")
+
+
+@pytest.mark.parametrize("tag", ["local_text", "global_text"])
+def test_forward_torch_matches_the_reference_module(tag):
+    """`TriplaneTransformer.forward_torch` (the comparison the GPU parity tests use, and the path of the local_text = False
+    variant) against planes computed by the REFERENCE's own triplane_transformer_modules.py, executed unchanged by
+    tests/golden/make_triplane_generator_golden.py (diffusers' Attention restated there: it is not installed). The strict
+    state-dict load also pins every parameter name and shape to the reference's."""
+    g = torch.load(GOLD)[tag]
+    gen = TriplaneTransformer(**g["cfg"])
+    gen.load_state_dict(g["state_dict"], strict=True)
+    with torch.no_grad():
+        out = gen.forward_torch(g["text_embed"])
+    assert out.shape == g["planes"].shape
+    err = float((out - g["planes"]).norm() / g["planes"].norm())
+    assert err < 1e-5, err

@@ -88,6 +88,23 @@ def test_c5_width_generator_forward_backward(cuda_device):
     _compare(cfg, 2, cuda_device, 1e-3, 3e-3)
 
 
+def test_native_generator_matches_reference_module_golden(cuda_device):
+    """The native path against planes computed by the reference's own module (tests/golden/triplane_generator_golden.pt,
+    see make_triplane_generator_golden.py): 64 channels, 4 heads of 16, 48 tokens, 7 x 48 text tokens, two blocks."""
+    import os
+
+    from scaledreamer_b200.amortized import TriplaneTransformer
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "triplane_generator_golden.pt"))["local_text"]
+    gen = TriplaneTransformer(**g["cfg"]).to(cuda_device)
+    gen.load_state_dict(g["state_dict"], strict=True)
+    with torch.no_grad():
+        out = gen(g["text_embed"].to(cuda_device))
+    e = _rel(out.cpu(), g["planes"])
+    print(f"planes vs reference module rel_l2 {e:.2e}")
+    assert e < 1e-3
+
+
 def test_generator_step_is_bitwise_reproducible(cuda_device):
     """No atomics anywhere in the generator: every reduction (LayerNorm / bias / position-embedding gradients, split
     weight-gradient products, softmax statistics) has a fixed order, so two runs on the same inputs agree bit for bit."""
