@@ -47,3 +47,31 @@ def test_reference_arm_never_maps_the_product_library():
 
 def test_reference_arm_is_silent_on_other_ranks():
     assert _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_roofline_traffic_is_keyed_to_the_sources_it_was_captured_from(tmp_path, monkeypatch):
+    """`roofline.traffic` comes from the committed ncu capture only for kernel groups whose CUDA sources still hash to what
+    the capture recorded; a group whose sources changed reads as absent (null in the JSON line), never as a stale number."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import glob
+
+    import bench
+    import summarize_profiles as sp
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), key=os.path.getmtime)
+    assert files, "no committed traffic capture"
+    t = json.load(open(files[-1]))
+    assert set(t["_group_sources_sha"]) == set(sp.SOURCE_GROUPS)
+    now = bench.ncu_traffic()
+    for group, keys in (("tensor", ["tensor"]), ("render", ["render_fwd", "render_bwd"]),
+                        ("hyper_field", ["hyper_field_fwd", "hyper_field_bwd"])):
+        same = t["_group_sources_sha"][group] == sp.lib_sources_sha(group)
+        for k in keys:
+            assert (k in now) == same, (group, k, same)
+    # a group whose hash no longer matches disappears, the others stay
+    real = sp.lib_sources_sha
+    monkeypatch.setattr(sp, "lib_sources_sha", lambda g=None: "0" * 16 if g == "render" else real(g))
+    changed = bench.ncu_traffic()
+    assert "render_fwd" not in changed and "render_bwd" not in changed
+    assert ("tensor" in changed) == ("tensor" in now)
